@@ -1,0 +1,100 @@
+/* In-memory stand-in for the handful of EXODUS II read calls the reference's
+ * rd_exo() makes (rd_exo.c:202-728 in /root/reference/src).  The oracle driver
+ * registers a structured mesh here, then the reference's own read_mesh_exoII()
+ * runs unmodified on top of it.  TEST INFRASTRUCTURE ONLY. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "exodusII.h"
+
+struct fake_mesh {
+  int dim, num_nodes, num_elems, npe;
+  char elem_type[33];
+  const double *x, *y, *z;
+  const int *conn; /* 1-based, num_elems*npe */
+  int num_ns;
+  const int *ns_ids, *ns_ptr, *ns_nodes; /* 1-based node ids */
+} g_fake;
+
+void fake_exodus_set_mesh(int dim, int num_nodes, const double *x, const double *y, const double *z,
+                          int num_elems, int npe, const char *elem_type, const int *conn,
+                          int num_ns, const int *ns_ids, const int *ns_ptr, const int *ns_nodes) {
+  g_fake.dim = dim; g_fake.num_nodes = num_nodes; g_fake.x = x; g_fake.y = y; g_fake.z = z;
+  g_fake.num_elems = num_elems; g_fake.npe = npe; g_fake.conn = conn;
+  strncpy(g_fake.elem_type, elem_type, 32);
+  g_fake.num_ns = num_ns; g_fake.ns_ids = ns_ids; g_fake.ns_ptr = ns_ptr; g_fake.ns_nodes = ns_nodes;
+}
+
+int ex_open_int(const char *path, int mode, int *comp_ws, int *io_ws, float *version, int run_version) {
+  (void)path; (void)mode; (void)run_version;
+  *comp_ws = 8; *io_ws = 8; *version = 8.03f;
+  return 1;
+}
+int ex_open(const char *path, int mode, int *comp_ws, int *io_ws, float *version) {
+  return ex_open_int(path, mode, comp_ws, io_ws, version, 0);
+}
+int ex_close(int id) { (void)id; return 0; }
+int ex_opts(int o) { (void)o; return 0; }
+int ex_get_init(int id, char *title, int *num_dim, int *num_nodes, int *num_elems, int *num_eb,
+                int *num_ns, int *num_ss) {
+  (void)id;
+  strcpy(title, "goma_b200 oracle in-memory mesh");
+  *num_dim = g_fake.dim; *num_nodes = g_fake.num_nodes; *num_elems = g_fake.num_elems;
+  *num_eb = 1; *num_ns = g_fake.num_ns; *num_ss = 0;
+  return 0;
+}
+int ex_inquire(int id, int what, int *ri, float *rf, char *rc) {
+  (void)id; (void)rc;
+  *ri = 0; *rf = 0.f;
+  switch (what) {
+  case EX_INQ_API_VERS: case EX_INQ_DB_VERS: *rf = 8.03f; break;
+  case EX_INQ_NS_NODE_LEN: *ri = g_fake.num_ns ? g_fake.ns_ptr[g_fake.num_ns] : 0; break;
+  default: break; /* no QA, info, dist-factors, side sets, properties, time planes */
+  }
+  return 0;
+}
+int ex_get_coord(int id, double *x, double *y, double *z) {
+  (void)id;
+  size_t n = (size_t)g_fake.num_nodes * sizeof(double);
+  if (x && g_fake.x) memcpy(x, g_fake.x, n);
+  if (y && g_fake.y) memcpy(y, g_fake.y, n);
+  if (z && g_fake.z) memcpy(z, g_fake.z, n);
+  return 0;
+}
+int ex_get_coord_names(int id, char **names) {
+  (void)id;
+  const char *nm[3] = {"x", "y", "z"};
+  for (int i = 0; i < g_fake.dim; i++) strcpy(names[i], nm[i]);
+  return 0;
+}
+int ex_get_ids(int id, int type, int *ids) {
+  (void)id;
+  if (type == EX_ELEM_BLOCK) ids[0] = 1;
+  else if (type == EX_NODE_SET) for (int i = 0; i < g_fake.num_ns; i++) ids[i] = g_fake.ns_ids[i];
+  return 0;
+}
+int ex_get_block(int id, int type, int blk, char *etype, int *nel, int *npe, int *nedge, int *nface, int *nattr) {
+  (void)id; (void)type; (void)blk; (void)nedge; (void)nface;
+  strcpy(etype, g_fake.elem_type);
+  *nel = g_fake.num_elems; *npe = g_fake.npe; *nattr = 0;
+  return 0;
+}
+int ex_get_conn(int id, int type, int blk, int *conn, int *e, int *f) {
+  (void)id; (void)type; (void)blk; (void)e; (void)f;
+  memcpy(conn, g_fake.conn, (size_t)g_fake.num_elems * g_fake.npe * sizeof(int));
+  return 0;
+}
+int ex_get_concat_sets(int id, int type, ex_set_specs *s) {
+  (void)id;
+  if (type != EX_NODE_SET) return 0;
+  int *ids = s->sets_ids, *cnt = s->num_entries_per_set, *ndf = s->num_dist_per_set;
+  int *idx = s->sets_entry_index, *dfi = s->sets_dist_index, *lst = s->sets_entry_list;
+  for (int i = 0; i < g_fake.num_ns; i++) {
+    ids[i] = g_fake.ns_ids[i];
+    cnt[i] = g_fake.ns_ptr[i + 1] - g_fake.ns_ptr[i];
+    ndf[i] = 0; idx[i] = g_fake.ns_ptr[i]; dfi[i] = 0;
+  }
+  if (g_fake.num_ns) memcpy(lst, g_fake.ns_nodes, (size_t)g_fake.ns_ptr[g_fake.num_ns] * sizeof(int));
+  return 0;
+}
+int ex_get_variable_param(int id, int type, int *n) { (void)id; (void)type; *n = 0; return 0; }
