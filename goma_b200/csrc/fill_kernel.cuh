@@ -1,0 +1,460 @@
+// Element assembly kernel for sm_100a: one CTA per element, persistent over the element list.
+//
+// What it replaces in the reference, per element (src/mm_fill.c:317 matrix_fill):
+//   BLOCK 1   load_elem_dofptr / load_ei          -> phase 0 gather through prebuilt tables
+//   per Gauss point (mm_fill.c:1253-2665):
+//     load_basis_functions (mm_fill_util.c:2608)  -> constant tables staged once per CTA by TMA
+//     beer_belly           (mm_fill_util.c:140)   -> phases 1-2 (J, detJ, B = J^-1 by cofactors)
+//     load_bf_grad         (mm_fill_util.c:1634)  -> phase 3  (grad_phi = B . dphi/dxi)
+//     load_fv / load_fv_grads (load_field_variables.c:128,2049) -> phase 4
+//     assemble_momentum    (mm_fill_momentum.c:100)   residual :534-662, J_m_v :1564-1735,
+//                                                     J_m_T :746-915, J_m_P :2052-2117
+//     assemble_continuity  (mm_fill_continuity.c:119) residual :435-613, J_c_v :665-761
+//     assemble_energy      (mm_fill_energy.c:109)     residual :322-381, J_e_T :425-487, J_e_v :628-692
+//   BLOCK 8   put_dirichlet_in_matrix (bc_dirich.c:44)
+//   load_lec  (mm_fill.c:5175, MSR branch :5241-5483) -> slot-mapped fp64 atomic scatter
+//
+// The Jacobian uses the Cartesian closed forms of SURVEY.md App. A instead of the reference's
+// zero-padded grad_phi_e / d_Pi tensors; the per-(i,j) node-pair block is accumulated in
+// registers over the Gauss points and written once.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/goma_gpu_fill.h"
+
+namespace goma_b200 {
+
+struct FillParams {
+  // mesh / maps
+  const int *conn;
+  const double *coord[3];
+  const int *first_unknown;
+  const unsigned char *node_kind;
+  int kind_slot[GOMA_GPU_MAX_KINDS][GOMA_NSLOT];
+  const long long *rowstart;
+  const unsigned short *pair_full;
+  const unsigned short *pair_p;
+  const unsigned char *dbc_flag;
+  const double *dbc_value;
+  const int *elem_list;  // optional indirection (colour classes); nullptr = identity
+  int elem_begin, elem_end;
+  int num_owned_nodes;
+  // state
+  const double *x, *x_old, *xdot;
+  double *a;
+  double *resid;
+  int *flags;
+  const double *tables;
+  // switches
+  int assemble_residual, assemble_jacobian, transient, use_atomics;
+  // constants
+  double etm_mom[6], etm_cont[2], etm_energy[5], etm_species[5], etm_mesh[5];
+  double rho, mu, k, Cp, beta, Tref, heat_source;
+  double g[3];
+  int source_model;  // 0 CONSTANT, 1 BOUSS (hydrostatic), 2 BOUSSINESQ
+  double diffusivity[4];
+  double delta_t, theta, time_value, h_elem_avg, U_norm;
+  double lame_mu, lame_lambda;
+};
+
+template <int DIM_, int NN_, int NGP_, bool P1_, bool ENERGY_, int NSPEC_, bool ALE_, int TPE_>
+struct Cfg {
+  static constexpr int DIM = DIM_, NN = NN_, NGP = NGP_, TPE = TPE_, NSPEC = NSPEC_;
+  static constexpr bool P1 = P1_, ENERGY = ENERGY_, ALE = ALE_;
+  static constexpr int F_V = 0;
+  static constexpr int F_T = DIM;
+  static constexpr int F_Y = DIM + (ENERGY ? 1 : 0);
+  static constexpr int F_D = F_Y + NSPEC;
+  static constexpr int F_P = F_D + (ALE ? DIM : 0);
+  static constexpr int NF = F_P + (P1 ? 0 : 1);
+  static constexpr int NP = P1 ? DIM + 1 : 0;
+  static constexpr int CEN = NN == 9 ? 8 : (NN == 27 ? 20 : 0);
+  static constexpr int TBL = NGP + NGP * NN + NGP * NN * DIM + NGP * (DIM + 1);
+  static constexpr int TBL_PAD = (TBL + 1) & ~1;  // 16-byte multiple for the bulk copy
+  static constexpr int T_WT = 0, T_PHI = NGP, T_DPHI = T_PHI + NGP * NN, T_PSI = T_DPHI + NGP * NN * DIM;
+  __host__ __device__ static constexpr int slot(int f) {
+    return f < DIM                       ? GOMA_SLOT_U + f
+           : (ENERGY && f == F_T)        ? GOMA_SLOT_T
+           : (f >= F_Y && f < F_Y + NSPEC) ? GOMA_SLOT_Y0 + (f - F_Y)
+           : (ALE && f >= F_D && f < F_D + DIM) ? GOMA_SLOT_DX + (f - F_D)
+                                         : GOMA_SLOT_P;
+  }
+};
+
+template <class C>
+struct alignas(16) Smem {
+  double tbl[C::TBL_PAD];
+  double X[C::DIM][C::NN];
+  double U[C::NF][C::NN];
+  double Udot[C::NF][C::NN];
+  double Pd[C::NP > 0 ? C::NP : 1];
+  double G[C::NGP][C::NN][C::DIM];
+  double w[C::NGP];
+  double B[C::NGP][C::DIM * C::DIM];
+  double F[C::NGP][C::NF][C::DIM + 2];  // value, grad[DIM], time derivative
+  double Pgp[C::NGP];
+  long long rs[C::NF][C::NN];  // MSR row start of (field,node); -1 = not written here (ghost/Dirichlet)
+  long long rsP[C::NP > 0 ? C::NP : 1];
+  int node[C::NN];
+  int fu[C::NN];
+  int kind[C::NN];
+  int gun[C::NF][C::NN];
+  unsigned long long mbar;
+};
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a),
+      "r"(phase)
+      : "memory");
+}
+// TMA bulk copy global -> shared (SASS: UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+               "l"(src), "r"(bytes), "r"(b)
+               : "memory");
+}
+
+template <class C>
+__device__ __forceinline__ void mat_add(const FillParams &P, const Smem<C> &s, long long rowstart, int row, int elem,
+                                        int li, int lj, int col_off, bool row_is_T, double val) {
+  int col = s.fu[lj] + col_off;
+  long long pos;
+  if (row == col) {
+    pos = row;
+  } else {
+    size_t pq = ((size_t)elem * C::NN + li) * C::NN + lj;
+    int off = (int)P.pair_full[pq] + col_off;
+    if (C::ENERGY && row_is_T) off -= (int)P.pair_p[pq];
+    pos = rowstart + off - (col > row ? 1 : 0);
+  }
+  if (P.use_atomics)
+    atomicAdd(&P.a[pos], val);
+  else
+    P.a[pos] += val;
+}
+
+template <class C>
+__device__ __forceinline__ void momentum_source(const FillParams &P, double T, double f[3], double dfdT[3]) {
+  // momentum_source_term (mm_fill_momentum.c:3738) CONSTANT branch and
+  // bouss_momentum_source (mm_std_models.c:125-360), temperature piece only
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    f[a] = 0.0;
+    dfdT[a] = 0.0;
+  }
+  if (P.etm_mom[4] == 0.0) return;
+#pragma unroll
+  for (int a = 0; a < C::DIM; a++) {
+    if (P.source_model == 0) {
+      f[a] = P.g[a];
+    } else if (C::ENERGY) {
+      double d = -P.beta * (T - P.Tref);
+      f[a] = P.rho * P.g[a] * (P.source_model == 1 ? (1.0 + d) : d);
+      dfdT[a] = -P.g[a] * P.rho * P.beta;
+    }
+  }
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::TPE) fill_kernel(const __grid_constant__ FillParams P) {
+  constexpr int DIM = C::DIM, NN = C::NN, NGP = C::NGP, NF = C::NF, NP = C::NP, TPE = C::TPE;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<C> &s = *reinterpret_cast<Smem<C> *>(smem_raw);
+  const int tid = threadIdx.x;
+
+  // ---- stage the quadrature/basis tables once per CTA with a TMA bulk copy
+  if (tid == 0) {
+    mbar_init(&s.mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&s.mbar, C::TBL_PAD * 8);
+    tma_bulk_g2s(s.tbl, P.tables, C::TBL_PAD * 8, &s.mbar);
+  }
+  mbar_wait(&s.mbar, 0);
+  const double *t_wt = s.tbl + C::T_WT;
+  const double *t_phi = s.tbl + C::T_PHI;    // [gp][NN]
+  const double *t_dphi = s.tbl + C::T_DPHI;  // [gp][NN][DIM]
+  const double *t_psi = s.tbl + C::T_PSI;    // [gp][DIM+1]
+
+  const double tfac = P.transient ? (1.0 + 2.0 * P.theta) / P.delta_t : 0.0;
+
+  for (int ee = P.elem_begin + blockIdx.x; ee < P.elem_end; ee += gridDim.x) {
+    const int elem = P.elem_list ? P.elem_list[ee] : ee;
+
+    // ---- phase 0: connectivity, coordinates, unknown indices, nodal values
+    for (int k = tid; k < NN; k += TPE) {
+      int nd = P.conn[(size_t)elem * NN + k];
+      s.node[k] = nd;
+      s.fu[k] = P.first_unknown[nd];
+      s.kind[k] = P.node_kind[nd];
+#pragma unroll
+      for (int d = 0; d < DIM; d++) s.X[d][k] = P.coord[d][nd];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < NF * NN; idx += TPE) {
+      int f = idx / NN, k = idx - f * NN;
+      int gun = s.fu[k] + P.kind_slot[s.kind[k]][C::slot(f)];
+      s.gun[f][k] = gun;
+      s.U[f][k] = P.x[gun];
+      s.Udot[f][k] = P.transient ? P.xdot[gun] : 0.0;
+      bool owned = s.node[k] < P.num_owned_nodes;
+      s.rs[f][k] = (owned && P.dbc_flag[gun] == 0) ? P.rowstart[gun] : -1;
+    }
+    if (C::P1 && tid < NP) {
+      int gun = s.fu[C::CEN] + P.kind_slot[s.kind[C::CEN]][GOMA_SLOT_P] + tid;
+      s.Pd[tid] = P.x[gun];
+      bool owned = s.node[C::CEN] < P.num_owned_nodes;
+      s.rsP[tid] = (owned && P.dbc_flag[gun] == 0) ? P.rowstart[gun] : -1;
+    }
+    __syncthreads();
+
+    // ---- phase 1: J[a][b] = sum_k x_b,k dphi_k/dxi_a   (beer_belly, mm_fill_util.c:258-276)
+    for (int idx = tid; idx < NGP * DIM * DIM; idx += TPE) {
+      int gp = idx / (DIM * DIM), ab = idx - gp * DIM * DIM;
+      int a = ab / DIM, b = ab - a * DIM;
+      double acc = 0.0;
+#pragma unroll 9
+      for (int k = 0; k < NN; k++) acc += s.X[b][k] * t_dphi[(gp * NN + k) * DIM + a];
+      s.B[gp][ab] = acc;
+    }
+    __syncthreads();
+    // ---- phase 2: detJ, B = J^-1 by cofactors (mm_fill_util.c:386-391, :450-480)
+    if (tid < NGP) {
+      double *J = s.B[tid];
+      double det;
+      if (DIM == 2) {
+        double j00 = J[0], j01 = J[1], j10 = J[2], j11 = J[3];
+        det = j00 * j11 - j01 * j10;
+        J[0] = j11 / det;
+        J[1] = -j01 / det;
+        J[2] = -j10 / det;
+        J[3] = j00 / det;
+      } else {
+        double j00 = J[0], j01 = J[1], j02 = J[2], j10 = J[3], j11 = J[4], j12 = J[5], j20 = J[6], j21 = J[7],
+               j22 = J[8];
+        det = j00 * (j11 * j22 - j12 * j21) - j01 * (j10 * j22 - j20 * j12) + j02 * (j10 * j21 - j20 * j11);
+        J[0] = (j11 * j22 - j21 * j12) / det;
+        J[1] = -(j01 * j22 - j21 * j02) / det;
+        J[2] = (j01 * j12 - j11 * j02) / det;
+        J[3] = -(j10 * j22 - j20 * j12) / det;
+        J[4] = (j00 * j22 - j20 * j02) / det;
+        J[5] = -(j00 * j12 - j10 * j02) / det;
+        J[6] = (j10 * j21 - j11 * j20) / det;
+        J[7] = -(j00 * j21 - j20 * j01) / det;
+        J[8] = (j00 * j11 - j10 * j01) / det;
+      }
+      s.w[tid] = det * t_wt[tid];  // d_area = detJ * wt * h3, h3 = 1 (Cartesian)
+    }
+    __syncthreads();
+    // ---- phase 3: grad_phi[i][p] = sum_q B[p][q] dphi_i/dxi_q  (load_bf_grad, mm_fill_util.c:1765-1776)
+    for (int idx = tid; idx < NGP * NN; idx += TPE) {
+      int gp = idx / NN, i = idx - gp * NN;
+      const double *B = s.B[gp];
+      const double *dp = &t_dphi[(gp * NN + i) * DIM];
+#pragma unroll
+      for (int p = 0; p < DIM; p++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < DIM; q++) acc += B[p * DIM + q] * dp[q];
+        s.G[gp][i][p] = acc;
+      }
+    }
+    __syncthreads();
+    // ---- phase 4: field values, gradients, time derivatives at the Gauss points
+    for (int idx = tid; idx < NGP * NF; idx += TPE) {
+      int gp = idx / NF, f = idx - gp * NF;
+      double val = 0.0, dot = 0.0, gr[DIM];
+#pragma unroll
+      for (int p = 0; p < DIM; p++) gr[p] = 0.0;
+      for (int k = 0; k < NN; k++) {
+        double u = s.U[f][k];
+        val += u * t_phi[gp * NN + k];
+        dot += s.Udot[f][k] * t_phi[gp * NN + k];
+#pragma unroll
+        for (int p = 0; p < DIM; p++) gr[p] += u * s.G[gp][k][p];
+      }
+      s.F[gp][f][0] = val;
+#pragma unroll
+      for (int p = 0; p < DIM; p++) s.F[gp][f][1 + p] = gr[p];
+      s.F[gp][f][1 + DIM] = dot;
+    }
+    if (C::P1) {
+      for (int gp = tid; gp < NGP; gp += TPE) {
+        double v = 0.0;
+#pragma unroll
+        for (int p = 0; p < NP; p++) v += s.Pd[p] * t_psi[gp * (DIM + 1) + p];
+        s.Pgp[gp] = v;
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 5: residual rows + Dirichlet rows (bc_dirich.c:130-140)
+    for (int idx = tid; idx < NF * NN + NP; idx += TPE) {
+      const bool prow = idx >= NF * NN;  // P1 continuity row
+      const int f = prow ? 0 : idx / NN;
+      const int i = prow ? C::CEN : idx - f * NN;
+      const int gun = prow ? s.fu[C::CEN] + P.kind_slot[s.kind[C::CEN]][GOMA_SLOT_P] + (idx - NF * NN) : s.gun[f][i];
+      if (s.node[i] >= P.num_owned_nodes) continue;
+      const int dbc = P.dbc_flag[gun];
+      if (dbc) {
+        if (P.assemble_residual) {
+          double r = dbc == 1 ? P.x[gun] - P.dbc_value[gun] : 0.0;
+          if (P.use_atomics) atomicAdd(&P.resid[gun], r); else P.resid[gun] += r;
+        }
+        if (P.assemble_jacobian) {
+          if (P.use_atomics) atomicAdd(&P.a[gun], 1.0); else P.a[gun] += 1.0;
+        }
+        continue;
+      }
+      if (!P.assemble_residual) continue;
+      double R = 0.0;
+      for (int gp = 0; gp < NGP; gp++) {
+        const double w = s.w[gp];
+        double v[DIM], gT[DIM];
+#pragma unroll
+        for (int p = 0; p < DIM; p++) v[p] = s.F[gp][C::F_V + p][0];
+        if (prow) {
+          double div = 0.0;
+#pragma unroll
+          for (int p = 0; p < DIM; p++) div += s.F[gp][C::F_V + p][1 + p];
+          R += P.etm_cont[0] * w * t_psi[gp * (DIM + 1) + (idx - NF * NN)] * div;
+          continue;
+        }
+        const double phi_i = t_phi[gp * NN + i];
+        const double *gi = s.G[gp][i];
+        const double T = C::ENERGY ? s.F[gp][C::F_T][0] : 0.0;
+        if (f < DIM) {
+          const int a = f;
+          double adv = 0.0, diff = 0.0;
+#pragma unroll
+          for (int p = 0; p < DIM; p++) adv += v[p] * s.F[gp][C::F_V + a][1 + p];
+          const double Pr = C::P1 ? s.Pgp[gp] : s.F[gp][C::F_P][0];
+#pragma unroll
+          for (int p = 0; p < DIM; p++) {
+            double Pi = P.mu * (s.F[gp][C::F_V + p][1 + a] + s.F[gp][C::F_V + a][1 + p]) - (p == a ? Pr : 0.0);
+            diff += gi[p] * Pi;
+          }
+          double fs[3], dfdT[3];
+          momentum_source<C>(P, T, fs, dfdT);
+          R += w * (-P.etm_mom[0] * P.rho * phi_i * s.F[gp][C::F_V + a][1 + DIM] - P.etm_mom[1] * P.rho * phi_i * adv -
+                    P.etm_mom[3] * diff + P.etm_mom[4] * phi_i * fs[a]);
+        } else if (C::ENERGY && f == C::F_T) {
+          double adv = 0.0, diff = 0.0;
+#pragma unroll
+          for (int p = 0; p < DIM; p++) {
+            gT[p] = s.F[gp][C::F_T][1 + p];
+            adv += v[p] * gT[p];
+            diff += gi[p] * (-P.k * gT[p]);
+          }
+          const double rcp = P.rho * P.Cp;
+          R += w * (-P.etm_energy[0] * rcp * phi_i * s.F[gp][C::F_T][1 + DIM] - P.etm_energy[1] * rcp * phi_i * adv +
+                    P.etm_energy[3] * diff + P.etm_energy[4] * phi_i * P.heat_source);
+        }
+      }
+      if (P.use_atomics) atomicAdd(&P.resid[gun], R); else P.resid[gun] += R;
+    }
+
+    if (P.assemble_jacobian) {
+      // ---- phase 6: node-pair blocks, accumulated in registers over the Gauss points
+      const double rcp = P.rho * P.Cp;
+      for (int pr = tid; pr < NN * NN; pr += TPE) {
+        const int i = pr / NN, j = pr - i * NN;
+        double acc[NF][NF];
+#pragma unroll
+        for (int r = 0; r < NF; r++)
+#pragma unroll
+          for (int c = 0; c < NF; c++) acc[r][c] = 0.0;
+        for (int gp = 0; gp < NGP; gp++) {
+          const double w = s.w[gp];
+          const double phi_i = t_phi[gp * NN + i], phi_j = t_phi[gp * NN + j];
+          const double *gi = s.G[gp][i], *gj = s.G[gp][j];
+          double gij = 0.0, vgj = 0.0;
+#pragma unroll
+          for (int p = 0; p < DIM; p++) {
+            gij += gi[p] * gj[p];
+            vgj += s.F[gp][C::F_V + p][0] * gj[p];
+          }
+          const double wphi_i = w * phi_i, pp = wphi_i * phi_j;
+          // J_m_v
+          const double base = -P.etm_mom[1] * P.rho * wphi_i * vgj - P.etm_mom[3] * P.mu * w * gij -
+                              P.etm_mom[0] * P.rho * tfac * pp;
+#pragma unroll
+          for (int a = 0; a < DIM; a++) {
+#pragma unroll
+            for (int b = 0; b < DIM; b++) {
+              double t = -P.etm_mom[1] * P.rho * pp * s.F[gp][C::F_V + a][1 + b] -
+                         P.etm_mom[3] * P.mu * w * gi[b] * gj[a];
+              acc[a][b] += (a == b) ? t + base : t;
+            }
+          }
+          if (C::ENERGY) {
+            double fs[3], dfdT[3];
+            momentum_source<C>(P, s.F[gp][C::F_T][0], fs, dfdT);
+#pragma unroll
+            for (int a = 0; a < DIM; a++) {
+              acc[a][C::F_T] += P.etm_mom[4] * pp * dfdT[a];                               // J_m_T
+              acc[C::F_T][a] += -P.etm_energy[1] * rcp * pp * s.F[gp][C::F_T][1 + a];      // J_e_v
+            }
+            acc[C::F_T][C::F_T] += -P.etm_energy[1] * rcp * wphi_i * vgj - P.etm_energy[3] * P.k * w * gij -
+                                   P.etm_energy[0] * rcp * tfac * pp;                      // J_e_T
+          }
+        }
+        // scatter the block through the slot map
+#pragma unroll
+        for (int r = 0; r < NF; r++) {
+          const long long rstart = s.rs[r][i];
+          if (rstart < 0) continue;
+          const int row = s.gun[r][i];
+          const bool rowT = C::ENERGY && r == C::F_T;
+#pragma unroll
+          for (int c = 0; c < NF; c++) {
+            if (rowT && !C::P1 && c == C::F_P) continue;  // Inter_Mask: energy rows carry no pressure columns
+            int col_off = P.kind_slot[s.kind[j]][C::slot(c)];
+            mat_add<C>(P, s, rstart, row, elem, i, j, col_off, rowT, acc[r][c]);
+          }
+        }
+      }
+      // ---- phase 7: P1 pressure coupling, S[i][a][p] = sum_gp w grad_phi_i[a] psi_p
+      //      J_m_P (mm_fill_momentum.c:2091-2104) and J_c_v (mm_fill_continuity.c:686-716) share it
+      if (C::P1) {
+        const int poff = P.kind_slot[s.kind[C::CEN]][GOMA_SLOT_P];
+        for (int idx = tid; idx < NN * DIM * NP; idx += TPE) {
+          int i = idx / (DIM * NP), r = idx - i * DIM * NP;
+          int a = r / NP, p = r - a * NP;
+          double S = 0.0;
+          for (int gp = 0; gp < NGP; gp++) S += s.w[gp] * s.G[gp][i][a] * t_psi[gp * (DIM + 1) + p];
+          if (s.rs[a][i] >= 0)
+            mat_add<C>(P, s, s.rs[a][i], s.gun[a][i], elem, i, C::CEN, poff + p, false, P.etm_mom[3] * S);
+          if (s.rsP[p] >= 0)
+            mat_add<C>(P, s, s.rsP[p], s.fu[C::CEN] + poff + p, elem, C::CEN, i,
+                       P.kind_slot[s.kind[i]][GOMA_SLOT_U + a], false, P.etm_cont[0] * S);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace goma_b200

@@ -1,0 +1,514 @@
+// C ABI of the sm_100a matrix_fill path (see include/goma_gpu_fill.h for the contract and
+// the reference call sites each entry point replaces).  No torch, no CPU fallback: every
+// failure is an error code plus goma_gpu_last_error().
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/goma_gpu_fill.h"
+#include "fill_kernel.cuh"
+#include "pattern.h"
+#include "tables.h"
+
+using namespace goma_b200;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                               \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(-3, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + \
+                          std::to_string(__LINE__));                                           \
+  } while (0)
+
+struct goma_gpu_ctx {
+  goma_gpu_problem prob;  // scalar members + kind tables only; pointers are not retained
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  Pattern pat;  // host copy kept for get_msr (nn lists) -- sized for test/bench meshes
+  // device arrays
+  int *d_conn = nullptr, *d_first = nullptr;
+  double *d_coord[3] = {nullptr, nullptr, nullptr};
+  unsigned char *d_kind = nullptr, *d_dbc_flag = nullptr;
+  double *d_dbc_value = nullptr;
+  long long *d_rowstart = nullptr;
+  unsigned short *d_pair_full = nullptr, *d_pair_p = nullptr;
+  double *d_tables = nullptr;
+  double *d_x = nullptr, *d_x_old = nullptr, *d_x_older = nullptr, *d_xdot = nullptr, *d_xdot_old = nullptr;
+  double *d_a = nullptr, *d_resid = nullptr;
+  int *d_flags = nullptr;
+  int *d_elem_list = nullptr;      // colour-ordered element list
+  std::vector<int> colour_begin;   // [ncolours+1]
+  int scatter_mode = 0;            // 0 atomics, 1 coloured
+  int grid_limit = 0;
+  double last_ms = 0.0;
+  int last_launches = 0;
+  size_t device_bytes = 0;
+};
+
+template <class T>
+static int upload(T **dst, const T *src, size_t n, goma_gpu_ctx *c) {
+  CU(cudaMalloc((void **)dst, std::max<size_t>(n, 1) * sizeof(T)));
+  c->device_bytes += n * sizeof(T);
+  if (n) CU(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+template <class T>
+static int dalloc(T **dst, size_t n, goma_gpu_ctx *c) {
+  CU(cudaMalloc((void **)dst, std::max<size_t>(n, 1) * sizeof(T)));
+  c->device_bytes += n * sizeof(T);
+  CU(cudaMemset(*dst, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  return 0;
+}
+
+extern "C" const char *goma_gpu_last_error(void) { return g_err.c_str(); }
+
+// ------------------------------------------------------------------ kernel dispatch
+namespace {
+
+struct KernelEntry {
+  void (*fn)(const FillParams);
+  int tpe;
+  size_t smem;
+  int tbl_pad;
+};
+
+template <class C>
+KernelEntry entry() {
+  return {fill_kernel<C>, C::TPE, sizeof(Smem<C>), C::TBL_PAD};
+}
+
+// the instantiated physics/element combinations
+int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
+  const bool p1 = p.pressure_interp == GOMA_PRESSURE_P1;
+  if (p.ale) return fail(-2, "ALE (mesh equations) path not built yet");
+  if (p.pspg || !p1) return fail(-2, "equal-order PSPG path not built yet");
+  if (p.num_species) return fail(-2, "species path not built yet");
+  if (p.elem_type == GOMA_GPU_QUAD9) {
+    k = p.energy ? entry<Cfg<2, 9, 9, true, true, 0, false, 96>>() : entry<Cfg<2, 9, 9, true, false, 0, false, 96>>();
+    return 0;
+  }
+  if (p.elem_type == GOMA_GPU_HEX27) {
+    k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256>>()
+                 : entry<Cfg<3, 27, 27, true, false, 0, false, 256>>();
+    return 0;
+  }
+  return fail(-2, "element type / interpolation combination not supported by the GPU fill");
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ init / destroy
+static int validate(const goma_gpu_problem &p) {
+  if (p.dim != 2 && p.dim != 3) return fail(-2, "dim must be 2 or 3");
+  const int et = p.elem_type;
+  if (et != GOMA_GPU_QUAD4 && et != GOMA_GPU_QUAD9 && et != GOMA_GPU_HEX8 && et != GOMA_GPU_HEX27)
+    return fail(-2, "element types other than QUAD4/QUAD9/HEX8/HEX27 are not supported");
+  if ((p.dim == 2) != (et == GOMA_GPU_QUAD4 || et == GOMA_GPU_QUAD9)) return fail(-2, "dim / element type mismatch");
+  if (p.num_kinds < 1 || p.num_kinds > GOMA_GPU_MAX_KINDS) return fail(-2, "num_kinds out of range");
+  if (p.num_species < 0 || p.num_species > 4) return fail(-2, "num_species out of range (MAX_CONC = 4)");
+  if (!p.elem_connect || !p.first_unknown || !p.node_kind || !p.dbc_flag || !p.dbc_value)
+    return fail(-2, "null array in goma_gpu_problem");
+  for (int d = 0; d < p.dim; d++)
+    if (!p.coord[d]) return fail(-2, "null coordinate array");
+  if (p.pressure_interp == GOMA_PRESSURE_P1 && !(et == GOMA_GPU_QUAD9 || et == GOMA_GPU_HEX27))
+    return fail(-2, "P1 pressure needs a centroid node (QUAD9/HEX27)");
+  if (p.num_owned_nodes < 0 || p.num_owned_nodes > p.num_nodes) return fail(-2, "num_owned_nodes out of range");
+  return 0;
+}
+
+// greedy element colouring: no two elements of a colour share a node (conflict-free plain stores)
+static void colour_elements(const goma_gpu_problem &p, std::vector<int> &order, std::vector<int> &begin) {
+  const int ne = p.num_elems, npe = p.elem_type;
+  std::vector<unsigned long long> node_mask(p.num_nodes, 0ull);
+  std::vector<int> colour(ne);
+  int ncol = 0;
+  for (int e = 0; e < ne; e++) {
+    unsigned long long used = 0;
+    for (int k = 0; k < npe; k++) used |= node_mask[p.elem_connect[(size_t)e * npe + k]];
+    int c = 0;
+    while (c < 63 && (used >> c) & 1ull) c++;
+    colour[e] = c;
+    ncol = std::max(ncol, c + 1);
+    for (int k = 0; k < npe; k++) node_mask[p.elem_connect[(size_t)e * npe + k]] |= 1ull << c;
+  }
+  begin.assign(ncol + 1, 0);
+  for (int e = 0; e < ne; e++) begin[colour[e] + 1]++;
+  for (int c = 0; c < ncol; c++) begin[c + 1] += begin[c];
+  order.resize(ne);
+  std::vector<int> fill(begin.begin(), begin.end() - 1);
+  for (int e = 0; e < ne; e++) order[fill[colour[e]]++] = e;
+}
+
+extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, goma_gpu_ctx **out) {
+  if (!problem || !out) return fail(-2, "null argument");
+  *out = nullptr;
+  const goma_gpu_problem &p = *problem;
+  if (int rc = validate(p)) return rc;
+  KernelEntry ke;
+  if (int rc = pick_kernel(p, ke)) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(-3, "no CUDA device: the goma_gpu_fill path has no CPU fallback");
+  CU(cudaSetDevice(device));
+
+  goma_gpu_ctx *c = new goma_gpu_ctx();
+  c->prob = p;
+  c->device = device;
+  int nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+  std::string perr = build_pattern(p, c->pat, std::min(nthreads, 32));
+  if (!perr.empty()) {
+    delete c;
+    return fail(-2, "sparsity pattern: " + perr);
+  }
+  // optional bit-exact check against the host's own MSR graph
+  if (p.ija) {
+    const int N = p.num_unknowns;
+    if (c->pat.nnz_plus > 2147483647LL) {
+      delete c;
+      return fail(-2, "host ija given but nnz exceeds the 32-bit MSR limit");
+    }
+    std::vector<int> mine((size_t)c->pat.nnz_plus + 1, 0);
+    emit_msr_columns(p, c->pat, mine.data());
+    (void)N;
+    for (long long k = 0; k < c->pat.nnz_plus; k++) {
+      if (mine[k] != p.ija[k]) {
+        delete c;
+        return fail(-2, "host MSR graph differs from the derived one at ija[" + std::to_string(k) + "]");
+      }
+    }
+  }
+
+  const int nn = p.num_nodes, ne = p.num_elems, npe = p.elem_type, N = p.num_unknowns;
+  int rc = 0;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&c->ev0));
+  CU(cudaEventCreate(&c->ev1));
+  rc |= upload(&c->d_conn, p.elem_connect, (size_t)ne * npe, c);
+  rc |= upload(&c->d_first, p.first_unknown, nn, c);
+  for (int d = 0; d < p.dim; d++) rc |= upload(&c->d_coord[d], p.coord[d], nn, c);
+  rc |= upload(&c->d_kind, p.node_kind, nn, c);
+  rc |= upload(&c->d_dbc_flag, p.dbc_flag, N, c);
+  rc |= upload(&c->d_dbc_value, p.dbc_value, N, c);
+  static_assert(sizeof(long long) == sizeof(int64_t), "64-bit row pointers");
+  rc |= upload(&c->d_rowstart, (const long long *)c->pat.rowstart.data(), (size_t)N + 1, c);
+  rc |= upload(&c->d_pair_full, (const unsigned short *)c->pat.pair_full.data(), c->pat.pair_full.size(), c);
+  rc |= upload(&c->d_pair_p, (const unsigned short *)c->pat.pair_p.data(), c->pat.pair_p.size(), c);
+  if (rc) {
+    goma_gpu_fill_destroy(c);
+    return -3;
+  }
+  // pair tables live on the device from here on
+  std::vector<uint16_t>().swap(c->pat.pair_full);
+  std::vector<uint16_t>().swap(c->pat.pair_p);
+
+  // quadrature / basis tables, packed in the order Smem<C>::tbl expects
+  ElemTables t = make_tables(p.elem_type);
+  std::vector<double> packed;
+  packed.insert(packed.end(), t.wt.begin(), t.wt.end());
+  packed.insert(packed.end(), t.phi.begin(), t.phi.end());
+  packed.insert(packed.end(), t.dphi.begin(), t.dphi.end());
+  packed.insert(packed.end(), t.psi.begin(), t.psi.end());
+  packed.resize(ke.tbl_pad, 0.0);
+  rc |= upload(&c->d_tables, packed.data(), packed.size(), c);
+
+  rc |= dalloc(&c->d_x, N, c);
+  rc |= dalloc(&c->d_x_old, N, c);
+  rc |= dalloc(&c->d_x_older, N, c);
+  rc |= dalloc(&c->d_xdot, N, c);
+  rc |= dalloc(&c->d_xdot_old, N, c);
+  rc |= dalloc(&c->d_resid, N, c);
+  rc |= dalloc(&c->d_a, (size_t)c->pat.nnz_plus + 1, c);
+  rc |= dalloc(&c->d_flags, 4, c);
+  if (rc) {
+    goma_gpu_fill_destroy(c);
+    return -3;
+  }
+
+  std::vector<int> order;
+  colour_elements(p, order, c->colour_begin);
+  if (upload(&c->d_elem_list, order.data(), order.size(), c)) {
+    goma_gpu_fill_destroy(c);
+    return -3;
+  }
+  if (ke.smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute((const void *)ke.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ke.smem);
+    if (e != cudaSuccess) {
+      goma_gpu_fill_destroy(c);
+      return fail(-3, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    }
+  }
+  *out = c;
+  return 0;
+}
+
+extern "C" void goma_gpu_fill_destroy(goma_gpu_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  void *ptrs[] = {c->d_conn, c->d_first, c->d_coord[0], c->d_coord[1], c->d_coord[2], c->d_kind, c->d_dbc_flag,
+                  c->d_dbc_value, c->d_rowstart, c->d_pair_full, c->d_pair_p, c->d_tables, c->d_x, c->d_x_old,
+                  c->d_x_older, c->d_xdot, c->d_xdot_old, c->d_a, c->d_resid, c->d_flags, c->d_elem_list};
+  for (void *q : ptrs)
+    if (q) cudaFree(q);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int goma_gpu_fill_get_msr(goma_gpu_ctx *c, long long *nnz_plus) {
+  if (!c) return fail(-2, "null context");
+  if (nnz_plus) *nnz_plus = c->pat.nnz_plus;
+  return 0;
+}
+
+// ija export needs the host arrays again (they are not retained in the context)
+extern "C" int goma_gpu_fill_export_msr(goma_gpu_ctx *c, const goma_gpu_problem *p, int *ija_out) {
+  if (!c || !p || !ija_out) return fail(-2, "null argument");
+  if (c->pat.nnz_plus > 2147483647LL) return fail(-2, "nnz exceeds the 32-bit MSR limit of ija");
+  emit_msr_columns(*p, c->pat, ija_out);
+  return 0;
+}
+
+// Host-only: derive the MSR graph (no device needed).  ija_out may be NULL to query nnz_plus.
+extern "C" int goma_gpu_pattern_msr(const goma_gpu_problem *p, long long *nnz_plus, int *ija_out) {
+  if (!p) return fail(-2, "null argument");
+  if (int rc = validate(*p)) return rc;
+  Pattern pat;
+  int nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+  std::string perr = build_pattern(*p, pat, std::min(nthreads, 32));
+  if (!perr.empty()) return fail(-2, "sparsity pattern: " + perr);
+  if (nnz_plus) *nnz_plus = pat.nnz_plus;
+  if (ija_out) {
+    if (pat.nnz_plus > 2147483647LL) return fail(-2, "nnz exceeds the 32-bit MSR limit of ija");
+    emit_msr_columns(*p, pat, ija_out);
+  }
+  return 0;
+}
+
+extern "C" int goma_gpu_fill_set_option(goma_gpu_ctx *c, const char *name, int value) {
+  if (!c || !name) return fail(-2, "null argument");
+  if (!strcmp(name, "scatter")) {
+    if (value != 0 && value != 1) return fail(-2, "scatter must be 0 (atomic) or 1 (coloured)");
+    c->scatter_mode = value;
+    return 0;
+  }
+  if (!strcmp(name, "grid_limit")) {
+    c->grid_limit = value;
+    return 0;
+  }
+  return fail(-2, std::string("unknown option ") + name);
+}
+
+extern "C" int goma_gpu_fill_device_buffers(goma_gpu_ctx *c, goma_gpu_device_buffers *o) {
+  if (!c || !o) return fail(-2, "null argument");
+  o->d_x = c->d_x;
+  o->d_x_old = c->d_x_old;
+  o->d_x_older = c->d_x_older;
+  o->d_xdot = c->d_xdot;
+  o->d_xdot_old = c->d_xdot_old;
+  o->d_a = c->d_a;
+  o->d_resid = c->d_resid;
+  o->stream = (void *)c->stream;
+  return 0;
+}
+
+// ------------------------------------------------------------------ the fill
+static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double time_value, double h_elem_avg,
+                       double U_norm, int assemble_residual, int assemble_jacobian) {
+  const goma_gpu_problem &p = c->prob;
+  KernelEntry ke;
+  if (int rc = pick_kernel(p, ke)) return rc;
+  FillParams P;
+  memset(&P, 0, sizeof(P));
+  P.conn = c->d_conn;
+  for (int d = 0; d < 3; d++) P.coord[d] = c->d_coord[d];
+  P.first_unknown = c->d_first;
+  P.node_kind = c->d_kind;
+  memcpy(P.kind_slot, p.kind_slot, sizeof(P.kind_slot));
+  P.rowstart = c->d_rowstart;
+  P.pair_full = c->d_pair_full;
+  P.pair_p = c->d_pair_p;
+  P.dbc_flag = c->d_dbc_flag;
+  P.dbc_value = c->d_dbc_value;
+  P.num_owned_nodes = p.num_owned_nodes;
+  P.x = c->d_x;
+  P.x_old = c->d_x_old;
+  P.xdot = c->d_xdot;
+  P.a = c->d_a;
+  P.resid = c->d_resid;
+  P.flags = c->d_flags;
+  P.tables = c->d_tables;
+  P.assemble_residual = assemble_residual;
+  P.assemble_jacobian = assemble_jacobian;
+  P.transient = p.transient;
+  memcpy(P.etm_mom, p.etm_momentum, sizeof(P.etm_mom));
+  memcpy(P.etm_cont, p.etm_continuity, sizeof(P.etm_cont));
+  memcpy(P.etm_energy, p.etm_energy, sizeof(P.etm_energy));
+  memcpy(P.etm_species, p.etm_species, sizeof(P.etm_species));
+  memcpy(P.etm_mesh, p.etm_mesh, sizeof(P.etm_mesh));
+  if (!p.transient) {  // steady: the *_dot terms are skipped
+    P.etm_mom[0] = 0.0;
+    P.etm_energy[0] = 0.0;
+    P.etm_species[0] = 0.0;
+  }
+  P.rho = p.rho;
+  P.mu = p.mu;
+  P.k = p.conductivity;
+  P.Cp = p.heat_capacity;
+  P.beta = p.volume_expansion;
+  P.Tref = p.reference_temperature;
+  P.heat_source = p.heat_source;
+  for (int d = 0; d < 3; d++) P.g[d] = p.momentum_source[d];
+  P.source_model = p.momentum_source_model;
+  for (int w = 0; w < 4; w++) P.diffusivity[w] = p.diffusivity[w];
+  P.delta_t = delta_t;
+  P.theta = theta;
+  P.time_value = time_value;
+  P.h_elem_avg = h_elem_avg;
+  P.U_norm = U_norm;
+  P.lame_mu = p.lame_mu;
+  P.lame_lambda = p.lame_lambda;
+  if (p.transient && !(delta_t > 0.0)) return fail(-2, "transient fill needs delta_t > 0");
+
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, c->device));
+  int per_sm = 1;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)ke.fn, ke.tpe, ke.smem));
+  if (per_sm < 1) return fail(-3, "fill kernel does not fit on an SM");
+  int max_grid = prop.multiProcessorCount * per_sm;
+  if (c->grid_limit > 0) max_grid = std::min(max_grid, c->grid_limit);
+
+  c->last_launches = 0;
+  CU(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int), c->stream));
+  CU(cudaEventRecord(c->ev0, c->stream));
+  if (assemble_residual) CU(cudaMemsetAsync(c->d_resid, 0, (size_t)p.num_unknowns * sizeof(double), c->stream));
+  if (assemble_jacobian) CU(cudaMemsetAsync(c->d_a, 0, ((size_t)c->pat.nnz_plus + 1) * sizeof(double), c->stream));
+  if (c->scatter_mode == 0) {
+    P.use_atomics = 1;
+    P.elem_list = nullptr;
+    P.elem_begin = 0;
+    P.elem_end = p.num_elems;
+    int grid = std::max(1, std::min(max_grid, p.num_elems));
+    ke.fn<<<grid, ke.tpe, ke.smem, c->stream>>>(P);
+    c->last_launches++;
+  } else {
+    P.use_atomics = 0;
+    P.elem_list = c->d_elem_list;
+    for (size_t col = 0; col + 1 < c->colour_begin.size(); col++) {
+      P.elem_begin = c->colour_begin[col];
+      P.elem_end = c->colour_begin[col + 1];
+      int n = P.elem_end - P.elem_begin;
+      if (n <= 0) continue;
+      int grid = std::max(1, std::min(max_grid, n));
+      ke.fn<<<grid, ke.tpe, ke.smem, c->stream>>>(P);
+      c->last_launches++;
+    }
+  }
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ev1, c->stream));
+  return 0;
+}
+
+static int finish_fill(goma_gpu_ctx *c, int flags_out[3]) {
+  int h_flags[4] = {0, 0, 0, 0};
+  CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->last_ms = ms;
+  if (flags_out) {
+    flags_out[0] = h_flags[0];  // neg_elem_volume
+    flags_out[1] = h_flags[1];  // neg_lub_height
+    flags_out[2] = h_flags[2];  // zero_detJ
+  }
+  // matrix_fill_full's return convention (mm_fill.c:285-311)
+  return (h_flags[0] || h_flags[1] || h_flags[2]) ? -1 : 0;
+}
+
+extern "C" int goma_gpu_fill_device(goma_gpu_ctx *c, double delta_t, double theta, double time_value,
+                                    double h_elem_avg, double U_norm, int assemble_residual, int assemble_jacobian,
+                                    int flags_out[3]) {
+  if (!c) return fail(-2, "null context");
+  CU(cudaSetDevice(c->device));
+  if (int rc = launch_fill(c, delta_t, theta, time_value, h_elem_avg, U_norm, assemble_residual, assemble_jacobian))
+    return rc;
+  return finish_fill(c, flags_out);
+}
+
+extern "C" int goma_gpu_fill(goma_gpu_ctx *c, const double *x, const double *x_old, const double *x_older,
+                             const double *xdot, const double *xdot_old, double delta_t, double theta,
+                             double time_value, double h_elem_avg, double U_norm, int assemble_residual,
+                             int assemble_jacobian, double *a, double *resid_vector, int flags_out[3]) {
+  if (!c) return fail(-2, "null context");
+  if (!x) return fail(-2, "x is null");
+  if (assemble_jacobian && !a) return fail(-2, "a is null");
+  if (assemble_residual && !resid_vector) return fail(-2, "resid_vector is null");
+  CU(cudaSetDevice(c->device));
+  const size_t nb = (size_t)c->prob.num_unknowns * sizeof(double);
+  CU(cudaMemcpyAsync(c->d_x, x, nb, cudaMemcpyHostToDevice, c->stream));
+  if (c->prob.transient) {
+    if (!xdot) return fail(-2, "transient fill needs xdot");
+    CU(cudaMemcpyAsync(c->d_xdot, xdot, nb, cudaMemcpyHostToDevice, c->stream));
+    if (x_old) CU(cudaMemcpyAsync(c->d_x_old, x_old, nb, cudaMemcpyHostToDevice, c->stream));
+    if (x_older) CU(cudaMemcpyAsync(c->d_x_older, x_older, nb, cudaMemcpyHostToDevice, c->stream));
+    if (xdot_old) CU(cudaMemcpyAsync(c->d_xdot_old, xdot_old, nb, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (int rc = launch_fill(c, delta_t, theta, time_value, h_elem_avg, U_norm, assemble_residual, assemble_jacobian))
+    return rc;
+  if (assemble_jacobian)
+    CU(cudaMemcpyAsync(a, c->d_a, ((size_t)c->pat.nnz_plus + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (assemble_residual) CU(cudaMemcpyAsync(resid_vector, c->d_resid, nb, cudaMemcpyDeviceToHost, c->stream));
+  return finish_fill(c, flags_out);
+}
+
+extern "C" int goma_gpu_fill_last_stats(goma_gpu_ctx *c, double *kernel_ms, int *launches) {
+  if (!c) return fail(-2, "null context");
+  if (kernel_ms) *kernel_ms = c->last_ms;
+  if (launches) *launches = c->last_launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------ exchange_dof halves
+__global__ void pack_dofs_kernel(const double *__restrict__ v, const int *__restrict__ list, int n,
+                                 double *__restrict__ buf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) buf[i] = v[list[i]];
+}
+__global__ void unpack_dofs_kernel(double *__restrict__ v, const int *__restrict__ list, int n,
+                                   const double *__restrict__ buf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[list[i]] = buf[i];
+}
+extern "C" int goma_gpu_pack_dofs(goma_gpu_ctx *c, const double *d_vec, const int *d_list, int n, double *d_buf) {
+  if (!c) return fail(-2, "null context");
+  if (n <= 0) return 0;
+  pack_dofs_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_vec, d_list, n, d_buf);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int goma_gpu_unpack_dofs(goma_gpu_ctx *c, double *d_vec, const int *d_list, int n, const double *d_buf) {
+  if (!c) return fail(-2, "null context");
+  if (n <= 0) return 0;
+  unpack_dofs_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_vec, d_list, n, d_buf);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int goma_gpu_global_h_U(goma_gpu_ctx *c, double sums_out[4]) {
+  (void)sums_out;
+  if (!c) return fail(-2, "null context");
+  return fail(-2, "global_h_elem_siz / global_velocity_norm: PSPG path not built yet");
+}

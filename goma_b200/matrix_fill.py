@@ -1,0 +1,122 @@
+"""Host-side mirror of the reference's assembly entry point.
+
+``MatrixFill.matrix_fill_full`` keeps the argument meaning and return convention of
+``int matrix_fill_full(ams, x, resid_vector, x_old, x_older, xdot, xdot_old, x_update,
+ptr_delta_t, ptr_theta, first_elem_side_BC_array, ptr_time_value, exo, dpi,
+ptr_num_total_nodes, ptr_h_elem_avg, ptr_U_norm, estifm)`` (reference
+``include/mm_fill.h:41-58``, ``src/mm_fill.c:158-312``): the state vectors go in, the MSR
+values ``a`` (``ams->val``) and ``resid_vector`` come out, the return value is 0 or -1 with
+the three domain-failure flags.  All compute happens in ``libgoma_gpu_fill.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class MatrixFill:
+    def __init__(self, problem, device: int = 0, ija=None, num_owned_nodes=None):
+        self.lib = capi.load_library()
+        self.problem = problem
+        self._struct, self._keep = capi.make_problem_struct(problem, ija=ija, num_owned_nodes=num_owned_nodes)
+        self._ctx = C.c_void_p()
+        capi.check(self.lib.goma_gpu_fill_init(C.byref(self._struct), device, C.byref(self._ctx)),
+                   "goma_gpu_fill_init")
+        nnz = C.c_longlong()
+        capi.check(self.lib.goma_gpu_fill_get_msr(self._ctx, C.byref(nnz)), "goma_gpu_fill_get_msr")
+        self.nnz_plus = int(nnz.value)
+        self.num_unknowns = int(self._struct.num_unknowns)
+        self.flags = np.zeros(3, np.int32)
+
+    # -- MSR graph (ams->bindx) as derived by the library
+    def export_msr(self) -> np.ndarray:
+        ija = np.zeros(self.nnz_plus + 1, np.int32)
+        capi.check(self.lib.goma_gpu_fill_export_msr(self._ctx, C.byref(self._struct),
+                                                     ija.ctypes.data_as(capi._ip)), "goma_gpu_fill_export_msr")
+        return ija[: self.nnz_plus]
+
+    def set_option(self, name: str, value: int):
+        capi.check(self.lib.goma_gpu_fill_set_option(self._ctx, name.encode(), int(value)), "set_option")
+
+    def matrix_fill_full(self, x, x_old=None, x_older=None, xdot=None, xdot_old=None, delta_t=0.0, theta=0.0,
+                         time_value=0.0, h_elem_avg=0.0, U_norm=0.0, assemble_residual=True,
+                         assemble_jacobian=True, a=None, resid_vector=None):
+        """Returns (err, a, resid_vector).  ``a`` has the MSR layout of ``ams->val`` (length nnz_plus+1)."""
+        n = self.num_unknowns
+
+        def prep(v):
+            if v is None:
+                return None
+            v = np.ascontiguousarray(v, np.float64)
+            if v.shape != (n,):
+                raise ValueError(f"state vector has shape {v.shape}, expected ({n},)")
+            return v
+
+        x, x_old, x_older, xdot, xdot_old = (prep(v) for v in (x, x_old, x_older, xdot, xdot_old))
+        if a is None and assemble_jacobian:
+            a = np.empty(self.nnz_plus + 1, np.float64)
+        if resid_vector is None and assemble_residual:
+            resid_vector = np.empty(n, np.float64)
+        p = lambda v: capi._ptr(v, capi._dp)
+        err = capi.check(self.lib.goma_gpu_fill(self._ctx, p(x), p(x_old), p(x_older), p(xdot), p(xdot_old),
+                                                float(delta_t), float(theta), float(time_value),
+                                                float(h_elem_avg), float(U_norm), int(assemble_residual),
+                                                int(assemble_jacobian), p(a), p(resid_vector),
+                                                self.flags.ctypes.data_as(capi._ip)), "goma_gpu_fill")
+        return err, a, resid_vector
+
+    def fill_raw(self, ptrs, delta_t=0.0, theta=0.0, time_value=0.0, h_elem_avg=0.0, U_norm=0.0,
+                 assemble_residual=True, assemble_jacobian=True):
+        """Host-buffer call on raw addresses (pinned buffers owned by the caller): ptrs =
+        (x, x_old, x_older, xdot, xdot_old, a, resid) as ints (0 = NULL)."""
+        cast = lambda v: C.cast(C.c_void_p(v or None), capi._dp)
+        x, xo, xoo, xd, xdo, a, r = ptrs
+        return capi.check(self.lib.goma_gpu_fill(self._ctx, cast(x), cast(xo), cast(xoo), cast(xd), cast(xdo),
+                                                 float(delta_t), float(theta), float(time_value),
+                                                 float(h_elem_avg), float(U_norm), int(assemble_residual),
+                                                 int(assemble_jacobian), cast(a), cast(r),
+                                                 self.flags.ctypes.data_as(capi._ip)), "goma_gpu_fill")
+
+    def device_buffers(self) -> capi.DeviceBuffers:
+        b = capi.DeviceBuffers()
+        capi.check(self.lib.goma_gpu_fill_device_buffers(self._ctx, C.byref(b)), "device_buffers")
+        return b
+
+    def fill_device(self, delta_t=0.0, theta=0.0, time_value=0.0, h_elem_avg=0.0, U_norm=0.0,
+                    assemble_residual=True, assemble_jacobian=True) -> int:
+        """Device-resident assembly: state already in the context's device buffers."""
+        return capi.check(self.lib.goma_gpu_fill_device(self._ctx, float(delta_t), float(theta), float(time_value),
+                                                        float(h_elem_avg), float(U_norm), int(assemble_residual),
+                                                        int(assemble_jacobian),
+                                                        self.flags.ctypes.data_as(capi._ip)), "goma_gpu_fill_device")
+
+    def last_stats(self):
+        ms, n = C.c_double(), C.c_int()
+        capi.check(self.lib.goma_gpu_fill_last_stats(self._ctx, C.byref(ms), C.byref(n)), "last_stats")
+        return float(ms.value), int(n.value)
+
+    def close(self):
+        if self._ctx:
+            self.lib.goma_gpu_fill_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def msr_to_csr(ija, a, n):
+    """MSR (diagonal first, reference ``mm_fill_util.c:2865-3031``) -> scipy CSR, for the host Newton loop."""
+    import scipy.sparse as sp
+
+    ija = np.asarray(ija)
+    rows = np.repeat(np.arange(n), np.diff(ija[: n + 1]))
+    cols = ija[n + 1: ija[n]]
+    vals = a[n + 1: ija[n]]
+    A = sp.csr_matrix((vals, (rows, cols)), shape=(n, n)) + sp.diags(a[:n])
+    return A.tocsr()

@@ -1,0 +1,174 @@
+/*
+ * goma_gpu_fill.h -- C ABI of the B200 (sm_100a) implementation of Goma's
+ * per-Newton-iteration assembly hot path.
+ *
+ * What each entry point replaces in the reference (paths under /root/reference):
+ *
+ *   goma_gpu_fill_init      one-off snapshot of the host globals the element loop reads
+ *                           (src/mm_fill.c:317-3785 reads pd/mp/upd/ei/Nodes/Coor/
+ *                           Proc_Elem_Connect; src/mm_fill_ptrs.c:170,1136 load_ei /
+ *                           load_elem_dofptr rebuild the gather tables per element, per
+ *                           iteration -- here they are built once) and of the MSR graph
+ *                           (src/mm_fill_util.c:2865 alloc_MSR_sparse_arrays, :3229
+ *                           find_MSR_problem_graph; src/exo_conn.c:204 build_node_node).
+ *   goma_gpu_fill           int matrix_fill_full(struct GomaLinearSolverData *ams, double x[],
+ *                           double resid_vector[], double x_old[], double x_older[],
+ *                           double xdot[], double xdot_old[], double x_update[],
+ *                           double *ptr_delta_t, double *ptr_theta, ..., double *ptr_time_value,
+ *                           Exo_DB *exo, Dpi *dpi, int *ptr_num_total_nodes,
+ *                           dbl *ptr_h_elem_avg, dbl *ptr_U_norm, dbl *estifm)
+ *                           include/mm_fill.h:41-58, src/mm_fill.c:158-312 (element loop,
+ *                           flags) + :317 matrix_fill (one element) + :5175 load_lec (scatter).
+ *   goma_gpu_fill_device    same, device-resident operands (hand-off to a GPU solver; the
+ *                           `value` leg of bench.py).
+ *   goma_gpu_global_h_U     global_h_elem_siz / global_velocity_norm,
+ *                           src/mm_fill_aux.c:1128 and :612 (PSPG only,
+ *                           src/mm_sol_nonlinear.c:1184-1192).
+ *   goma_gpu_pack_dofs /    the gather (src/dp_comm.c:77-80) and the contiguous receive
+ *   goma_gpu_ghost_tail     tail (src/dp_comm.c:86-96) of exchange_dof(); the transport
+ *                           itself is ncclSend/ncclRecv issued by the host on these buffers.
+ *   goma_gpu_fill_destroy   (no counterpart: the reference never frees lec/ei.)
+ *
+ * Conventions kept from the reference: return 0 on success, -1 on "domain failure"
+ * (neg_elem_volume / neg_lub_height / zero_detJ, src/mm_fill.c:285-311) with the
+ * three flags reported; any other problem is an error (<= -2) with a message from
+ * goma_gpu_last_error() -- there is NO CPU fallback.  resid_vector and the matrix
+ * values are what matrix_fill_full leaves in caller-zeroed storage
+ * (src/mm_sol_nonlinear.c:1109-1121): this library overwrites them.
+ * All indices are 0-based ints as in the reference; matrix positions are 64-bit.
+ */
+#ifndef GOMA_GPU_FILL_H
+#define GOMA_GPU_FILL_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element types (values = nodes per element; reference: include/el_elm.h) */
+#define GOMA_GPU_QUAD4 4
+#define GOMA_GPU_QUAD9 9
+#define GOMA_GPU_HEX8 8
+#define GOMA_GPU_HEX27 27
+
+/* per-node unknown "slots", in the order variables appear inside a node
+ * (increasing variable id, include/rf_fem_const.h:174-200; species expanded) */
+enum {
+  GOMA_SLOT_U = 0, GOMA_SLOT_V, GOMA_SLOT_W, GOMA_SLOT_T,
+  GOMA_SLOT_Y0, GOMA_SLOT_Y1, GOMA_SLOT_Y2, GOMA_SLOT_Y3,
+  GOMA_SLOT_DX, GOMA_SLOT_DY, GOMA_SLOT_DZ, GOMA_SLOT_P,
+  GOMA_NSLOT
+};
+
+#define GOMA_GPU_MAX_KINDS 4
+
+/* pressure interpolation */
+#define GOMA_PRESSURE_P1 1 /* discontinuous {1,s,t[,u]} on the centroid node (I_P1) */
+#define GOMA_PRESSURE_EQ 2 /* same basis as velocity (Q1/Q1, needs PSPG)            */
+
+/* Plain-C snapshot of the host state the element loop depends on. */
+struct goma_gpu_problem {
+  /* mesh: Exo_DB / rd_mesh.c:397-507 globals */
+  int dim;
+  int elem_type; /* GOMA_GPU_* */
+  int num_nodes; /* dpi->num_universe_nodes (owned + external)       */
+  int num_owned_nodes; /* internal + boundary; rows of nodes >= this are never written */
+  int num_elems; /* all local elements, owned and ghost (mm_fill.c:224) */
+  const int *elem_connect; /* Proc_Elem_Connect, [num_elems * npe] */
+  const double *coord[3]; /* Coor[dim][node] */
+
+  /* unknown map: Nodes[n]->First_Unknown and the nodal variable layout */
+  int num_unknowns; /* NumUnknowns + NumExtUnknowns */
+  const int *first_unknown; /* [num_nodes] */
+  int num_kinds; /* distinct nodal layouts (<= GOMA_GPU_MAX_KINDS) */
+  const unsigned char *node_kind; /* [num_nodes] */
+  /* kind_slot[k][s] = offset of slot s inside a node of kind k, or -1;
+   * for GOMA_PRESSURE_P1 the P slot is the first of dim+1 consecutive dofs */
+  int kind_slot[GOMA_GPU_MAX_KINDS][GOMA_NSLOT];
+  int kind_num_unknowns[GOMA_GPU_MAX_KINDS];
+
+  /* optional host MSR graph (ams->bindx); when given it must equal the one this
+   * library derives (checked bit-exactly) -- pass NULL to let the library build it */
+  const int *ija;
+
+  /* physics switches: pd->e / pd->v, upd */
+  int pressure_interp; /* GOMA_PRESSURE_* */
+  int energy; /* R_ENERGY active */
+  int num_species; /* upd->Max_Num_Species_Eqn */
+  int ale; /* mesh1..dim active, pd->MeshMotion == ARBITRARY */
+  int transient; /* pd->TimeIntegration != STEADY */
+  int pspg; /* 0 off, 1 global ("yes"), 2 local */
+  double ps_scaling;
+
+  /* pd->etm[imtrx][eqn][LOG2_*]; a zero multiplier means the term's bit is off */
+  double etm_momentum[6]; /* mass advection boundary diffusion source porous */
+  double etm_continuity[2]; /* advection(div) source */
+  double etm_energy[5]; /* mass advection boundary diffusion source */
+  double etm_species[5];
+  double etm_mesh[5];
+
+  /* mp / elc constants (CONSTANT models only) */
+  double rho, mu, conductivity, heat_capacity, volume_expansion, reference_temperature;
+  double diffusivity[4];
+  double momentum_source[3]; /* Navier-Stokes Source vector */
+  int momentum_source_model; /* 0 CONSTANT, 1 BOUSS */
+  double heat_source;
+  double lame_mu, lame_lambda;
+
+  /* Dirichlet table: Nodes[]->DBC, BC_Types[].BC_Data_Float[0], BC_relax (bc_dirich.c:86-140) */
+  const unsigned char *dbc_flag; /* [num_unknowns] 0 none, 1 residual = x - value, 2 hard set (residual 0) */
+  const double *dbc_value; /* [num_unknowns] */
+};
+
+typedef struct goma_gpu_ctx goma_gpu_ctx;
+
+int goma_gpu_fill_init(const struct goma_gpu_problem *problem, int device, goma_gpu_ctx **ctx);
+void goma_gpu_fill_destroy(goma_gpu_ctx *ctx);
+
+/* MSR graph as built by the library: nnz_plus = ija[num_unknowns].  export_msr writes the
+ * whole ija[0..nnz_plus) (needs the host arrays of `problem` again; fails beyond 2^31-1). */
+int goma_gpu_fill_get_msr(goma_gpu_ctx *ctx, long long *nnz_plus);
+int goma_gpu_fill_export_msr(goma_gpu_ctx *ctx, const struct goma_gpu_problem *problem, int *ija_out);
+
+/* Host-only (no device): the MSR graph the library derives from mesh + unknown map, i.e. what
+ * find_MSR_problem_graph (src/mm_fill_util.c:3229) builds; ija_out may be NULL to size it. */
+int goma_gpu_pattern_msr(const struct goma_gpu_problem *problem, long long *nnz_plus, int *ija_out);
+
+/* Host-buffer call: H2D of the state vectors, assembly, D2H of a[0..nnz_plus] and resid. */
+int goma_gpu_fill(goma_gpu_ctx *ctx, const double *x, const double *x_old, const double *x_older,
+                  const double *xdot, const double *xdot_old, double delta_t, double theta,
+                  double time_value, double h_elem_avg, double U_norm, int assemble_residual,
+                  int assemble_jacobian, double *a, double *resid_vector, int flags_out[3]);
+
+/* Device-resident call.  Pointers returned by goma_gpu_fill_device_buffers stay valid for the
+ * life of the context; the caller fills d_x (and friends) and reads d_a / d_resid. */
+struct goma_gpu_device_buffers {
+  double *d_x, *d_x_old, *d_x_older, *d_xdot, *d_xdot_old;
+  double *d_a; /* [nnz_plus + 1] MSR values */
+  double *d_resid; /* [num_unknowns] */
+  void *stream; /* cudaStream_t all work is ordered on */
+};
+int goma_gpu_fill_device_buffers(goma_gpu_ctx *ctx, struct goma_gpu_device_buffers *out);
+int goma_gpu_fill_device(goma_gpu_ctx *ctx, double delta_t, double theta, double time_value,
+                         double h_elem_avg, double U_norm, int assemble_residual,
+                         int assemble_jacobian, int flags_out[3]);
+
+/* global_h_elem_siz / global_velocity_norm local sums (owner-weighted); the host all-reduces. */
+int goma_gpu_global_h_U(goma_gpu_ctx *ctx, double sums_out[4]);
+
+/* exchange_dof halves: gather x[list[k]] into buf (device), and the ghost tail pointer */
+int goma_gpu_pack_dofs(goma_gpu_ctx *ctx, const double *d_vec, const int *d_list, int n, double *d_buf);
+int goma_gpu_unpack_dofs(goma_gpu_ctx *ctx, double *d_vec, const int *d_list, int n, const double *d_buf);
+
+/* timing / accounting of the last goma_gpu_fill*: device ms of the assembly kernel(s)
+ * (CUDA events on the context's stream) and number of kernel launches */
+int goma_gpu_fill_last_stats(goma_gpu_ctx *ctx, double *kernel_ms, int *launches);
+
+/* tuning knob: 0 = fp64 atomic scatter, 1 = coloured plain-store scatter */
+int goma_gpu_fill_set_option(goma_gpu_ctx *ctx, const char *name, int value);
+
+const char *goma_gpu_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,308 @@
+/* fill_port.c -- CPU restatement (the "port" oracle) of the reference's matrix_fill hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY: used by tests/, __graft_entry__.smoke() and bench.py's CPU
+ * baseline leg as a checker.  The product (goma_b200/) never links or calls it.
+ *
+ * Parity pinning: this restatement is checked against outputs of the reference itself
+ * (oracle/_ref = the reference's unmodified C sources, see oracle/ref_build/) through the
+ * committed fixtures tests/golden/*.npz and, where oracle/_ref is present, live.
+ *
+ * Structure follows the reference one element at a time, with a dense element block `lec`
+ * exactly as src/mm_fill.c:317 matrix_fill does:
+ *   gather             load_elem_dofptr        src/mm_fill_ptrs.c:1136
+ *   Gauss loop         src/mm_fill.c:1253      find_stu/Gq_weight src/el_elm_info.c:1615,3469
+ *   basis              shape()                 src/rf_shape.c:185,361,698,1105; P1 src/mm_fill_util.c:3802
+ *   map                beer_belly              src/mm_fill_util.c:258-276 (J), :386-480 (detJ, B)
+ *   gradients          load_bf_grad            src/mm_fill_util.c:1765-1776
+ *   fields             load_fv, load_fv_grads  src/load_field_variables.c:128,2049
+ *   momentum           assemble_momentum       src/mm_fill_momentum.c:534-662 (R), :1564-1735 (J_m_v),
+ *                                              :746-915 (J_m_T), :2052-2117 (J_m_P); fluid_stress :3268-3271,
+ *                                              :3458-3469, :3704; sources :3738, src/mm_std_models.c:125
+ *   continuity         assemble_continuity     src/mm_fill_continuity.c:435-444 (R), :665-761 (J_c_v)
+ *   energy             assemble_energy         src/mm_fill_energy.c:322-381 (R), :425-487 (J_e_T), :628-692 (J_e_v)
+ *   Dirichlet          put_dirichlet_in_matrix src/bc_dirich.c:44-151
+ *   scatter            load_lec (MSR)          src/mm_fill.c:5241-5483 (in_list search :5461)
+ * Cartesian coordinates only (h3 = 1, grad_phi_e[i][a][p][q] = delta_aq grad_phi[i][p],
+ * src/mm_fill_util.c:1838-1871).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/goma_gpu_fill.h"
+
+#define MAXN 27
+#define MAXF 12 /* phi-interpolated fields per node */
+#define MAXD (MAXN * MAXF + 4)
+
+static void lagrange1d(int order, double s, double *L, double *dL) {
+  if (order == 1) {
+    L[0] = 0.5 * (1.0 - s); L[1] = 0.5 * (1.0 + s);
+    dL[0] = -0.5; dL[1] = 0.5;
+  } else {
+    L[0] = -0.5 * s * (1.0 - s); L[1] = 1.0 - s * s; L[2] = 0.5 * s * (1.0 + s);
+    dL[0] = -0.5 * (1.0 - 2.0 * s); dL[1] = -2.0 * s; dL[2] = 0.5 * (1.0 + 2.0 * s);
+  }
+}
+
+/* lattice position (0..order per direction) of each local node, Exodus/PATRAN order */
+static const int LAT4[4][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}};
+static const int LAT9[9][3] = {{0, 0, 0}, {2, 0, 0}, {2, 2, 0}, {0, 2, 0}, {1, 0, 0}, {2, 1, 0}, {1, 2, 0}, {0, 1, 0}, {1, 1, 0}};
+static const int LAT8[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+static const int LAT27[27][3] = {
+    {0, 0, 0}, {2, 0, 0}, {2, 2, 0}, {0, 2, 0}, {0, 0, 2}, {2, 0, 2}, {2, 2, 2}, {0, 2, 2}, {1, 0, 0},
+    {2, 1, 0}, {1, 2, 0}, {0, 1, 0}, {0, 0, 1}, {2, 0, 1}, {2, 2, 1}, {0, 2, 1}, {1, 0, 2}, {2, 1, 2},
+    {1, 2, 2}, {0, 1, 2}, {1, 1, 1}, {1, 1, 0}, {1, 1, 2}, {0, 1, 1}, {2, 1, 1}, {1, 0, 1}, {1, 2, 1}};
+
+static void basis(int et, const double xi[3], double *phi, double (*dphi)[3]) {
+  int dim = (et == 4 || et == 9) ? 2 : 3, order = (et == 4 || et == 8) ? 1 : 2;
+  const int(*lat)[3] = et == 4 ? LAT4 : et == 9 ? LAT9 : et == 8 ? LAT8 : LAT27;
+  double L[3][3] = {{1, 0, 0}, {1, 0, 0}, {1, 0, 0}}, dL[3][3] = {{0}};
+  for (int d = 0; d < dim; d++) lagrange1d(order, xi[d], L[d], dL[d]);
+  for (int i = 0; i < et; i++) {
+    double l0 = L[0][lat[i][0]], l1 = L[1][lat[i][1]], l2 = dim == 3 ? L[2][lat[i][2]] : 1.0;
+    phi[i] = l0 * l1 * l2;
+    dphi[i][0] = dL[0][lat[i][0]] * l1 * l2;
+    dphi[i][1] = l0 * dL[1][lat[i][1]] * l2;
+    dphi[i][2] = dim == 3 ? l0 * l1 * dL[2][lat[i][2]] : 0.0;
+  }
+}
+
+static void gauss_point(int et, int ip, double xi[3], double *wt) {
+  /* find_stu / Gq_weight: s fastest, then t, then u; positive abscissa first */
+  static const double F1 = 0.57735026918962584208, F2 = 0.77459666924148340428;
+  static const double W1 = 0.55555555555555555556, W2 = 0.88888888888888888888;
+  int dim = (et == 4 || et == 9) ? 2 : 3, n1 = (et == 4 || et == 8) ? 2 : 3;
+  int idx[3] = {ip % n1, (ip / n1) % n1, ip / (n1 * n1)};
+  double w = 1.0;
+  xi[2] = 0.0;
+  for (int d = 0; d < dim; d++) {
+    if (n1 == 2) {
+      xi[d] = idx[d] == 0 ? F1 : -F1;
+    } else {
+      xi[d] = idx[d] == 0 ? F2 : idx[d] == 1 ? 0.0 : -F2;
+      w *= idx[d] == 1 ? W2 : W1;
+    }
+  }
+  *wt = w;
+}
+
+/* in_list over one MSR row, as load_lec does (mm_fill.c:5461) */
+static long msr_pos(const int *ija, int ie, int je) {
+  if (ie == je) return ie;
+  for (int k = ija[ie]; k < ija[ie + 1]; k++)
+    if (ija[k] == je) return k;
+  return -1;
+}
+
+/* Returns 0, or -2 if a (row,col) the element block touches is missing from ija. */
+int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const double *x, const double *x_old,
+                   const double *xdot, double delta_t, double theta, double time_value, double h_elem_avg,
+                   double U_norm, int assemble_residual, int assemble_jacobian, double *a, double *resid) {
+  (void)x_old; (void)time_value; (void)h_elem_avg; (void)U_norm;
+  const int dim = p->dim, et = p->elem_type, nn = et;
+  const int n1 = (et == 4 || et == 8) ? 2 : 3;
+  const int ngp = dim == 2 ? n1 * n1 : n1 * n1 * n1;
+  const int p1 = p->pressure_interp == GOMA_PRESSURE_P1;
+  const int cen = et == 9 ? 8 : et == 27 ? 20 : 0;
+  const int np = p1 ? dim + 1 : 0;
+  /* fields interpolated with phi, in nodal order */
+  int fslot[MAXF], nf = 0, fT = -1, fP = -1;
+  for (int d = 0; d < dim; d++) fslot[nf++] = GOMA_SLOT_U + d;
+  if (p->energy) { fT = nf; fslot[nf++] = GOMA_SLOT_T; }
+  for (int w = 0; w < p->num_species; w++) fslot[nf++] = GOMA_SLOT_Y0 + w;
+  if (p->ale) for (int d = 0; d < dim; d++) fslot[nf++] = GOMA_SLOT_DX + d;
+  if (!p1) { fP = nf; fslot[nf++] = GOMA_SLOT_P; }
+  (void)fP;
+  const int ndof = nf * nn + np; /* element block size; P1 dofs last */
+  const int transient = p->transient;
+  double em[6], ee[5];
+  memcpy(em, p->etm_momentum, sizeof(em));
+  memcpy(ee, p->etm_energy, sizeof(ee));
+  if (!transient) em[0] = ee[0] = 0.0;
+  const double ec0 = p->etm_continuity[0];
+  const double tfac = transient ? (1.0 + 2.0 * theta) / delta_t : 0.0;
+  const double rho = p->rho, mu = p->mu, rcp = p->rho * p->heat_capacity, kc = p->conductivity;
+
+  double *R = (double *)malloc(sizeof(double) * ndof);
+  double *J = (double *)malloc(sizeof(double) * ndof * ndof);
+  int *gun = (int *)malloc(sizeof(int) * ndof);
+  int *lnode = (int *)malloc(sizeof(int) * ndof);
+  int rc = 0;
+
+  for (int e = 0; e < p->num_elems; e++) {
+    const int *c = p->elem_connect + (size_t)e * nn;
+    double X[3][MAXN], U[MAXF][MAXN], Ud[MAXF][MAXN], Pd[4] = {0, 0, 0, 0};
+    /* local dof numbering: dof(f,i) = f*nn + i ; P1 dofs = nf*nn + q */
+    for (int i = 0; i < nn; i++) {
+      int kd = p->node_kind[c[i]];
+      for (int d = 0; d < dim; d++) X[d][i] = p->coord[d][c[i]];
+      for (int f = 0; f < nf; f++) {
+        int g = p->first_unknown[c[i]] + p->kind_slot[kd][fslot[f]];
+        gun[f * nn + i] = g;
+        lnode[f * nn + i] = i;
+        U[f][i] = x[g];
+        Ud[f][i] = transient ? xdot[g] : 0.0;
+      }
+    }
+    for (int q = 0; q < np; q++) {
+      int g = p->first_unknown[c[cen]] + p->kind_slot[p->node_kind[c[cen]]][GOMA_SLOT_P] + q;
+      gun[nf * nn + q] = g;
+      lnode[nf * nn + q] = cen;
+      Pd[q] = x[g];
+    }
+    memset(R, 0, sizeof(double) * ndof);
+    memset(J, 0, sizeof(double) * ndof * ndof);
+
+    for (int ip = 0; ip < ngp; ip++) {
+      double xi[3], wt, phi[MAXN], dphi[MAXN][3], g[MAXN][3], psi[4];
+      gauss_point(et, ip, xi, &wt);
+      basis(et, xi, phi, dphi);
+      psi[0] = 1.0;
+      for (int d = 0; d < dim; d++) psi[1 + d] = xi[d];
+      /* beer_belly */
+      double Jm[3][3] = {{0}}, B[3][3] = {{0}}, det;
+      for (int a_ = 0; a_ < dim; a_++)
+        for (int b = 0; b < dim; b++)
+          for (int k = 0; k < nn; k++) Jm[a_][b] += X[b][k] * dphi[k][a_];
+      if (dim == 2) {
+        det = Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0];
+        B[0][0] = Jm[1][1] / det; B[0][1] = -Jm[0][1] / det;
+        B[1][0] = -Jm[1][0] / det; B[1][1] = Jm[0][0] / det;
+      } else {
+        det = Jm[0][0] * (Jm[1][1] * Jm[2][2] - Jm[1][2] * Jm[2][1]) - Jm[0][1] * (Jm[1][0] * Jm[2][2] - Jm[2][0] * Jm[1][2]) +
+              Jm[0][2] * (Jm[1][0] * Jm[2][1] - Jm[2][0] * Jm[1][1]);
+        B[0][0] = (Jm[1][1] * Jm[2][2] - Jm[2][1] * Jm[1][2]) / det;
+        B[0][1] = -(Jm[0][1] * Jm[2][2] - Jm[2][1] * Jm[0][2]) / det;
+        B[0][2] = (Jm[0][1] * Jm[1][2] - Jm[1][1] * Jm[0][2]) / det;
+        B[1][0] = -(Jm[1][0] * Jm[2][2] - Jm[2][0] * Jm[1][2]) / det;
+        B[1][1] = (Jm[0][0] * Jm[2][2] - Jm[2][0] * Jm[0][2]) / det;
+        B[1][2] = -(Jm[0][0] * Jm[1][2] - Jm[1][0] * Jm[0][2]) / det;
+        B[2][0] = (Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0]) / det;
+        B[2][1] = -(Jm[0][0] * Jm[2][1] - Jm[2][0] * Jm[0][1]) / det;
+        B[2][2] = (Jm[0][0] * Jm[1][1] - Jm[1][0] * Jm[0][1]) / det;
+      }
+      const double d_area = det * wt; /* h3 = 1 */
+      for (int i = 0; i < nn; i++)
+        for (int q = 0; q < dim; q++) {
+          g[i][q] = 0.0;
+          for (int r = 0; r < dim; r++) g[i][q] += B[q][r] * dphi[i][r];
+        }
+      /* load_fv / load_fv_grads: grad[f][q] = d f / d x_q */
+      double val[MAXF], dot[MAXF], grad[MAXF][3];
+      for (int f = 0; f < nf; f++) {
+        val[f] = dot[f] = 0.0;
+        grad[f][0] = grad[f][1] = grad[f][2] = 0.0;
+        for (int k = 0; k < nn; k++) {
+          val[f] += U[f][k] * phi[k];
+          dot[f] += Ud[f][k] * phi[k];
+          for (int q = 0; q < dim; q++) grad[f][q] += U[f][k] * g[k][q];
+        }
+      }
+      double Pr = 0.0;
+      if (p1) for (int q = 0; q < np; q++) Pr += Pd[q] * psi[q];
+      const double T = p->energy ? val[fT] : 0.0;
+      /* momentum_source_term */
+      double fs[3] = {0, 0, 0}, dfdT[3] = {0, 0, 0};
+      if (em[4] != 0.0) {
+        for (int a_ = 0; a_ < dim; a_++) {
+          if (p->momentum_source_model == 0) {
+            fs[a_] = p->momentum_source[a_];
+          } else if (p->energy) {
+            double d = -p->volume_expansion * (T - p->reference_temperature);
+            fs[a_] = rho * p->momentum_source[a_] * (p->momentum_source_model == 1 ? 1.0 + d : d);
+            dfdT[a_] = -p->momentum_source[a_] * rho * p->volume_expansion;
+          }
+        }
+      }
+      double div_v = 0.0;
+      for (int q = 0; q < dim; q++) div_v += grad[q][q];
+
+      for (int i = 0; i < nn; i++) {
+        const double phi_i = phi[i];
+        /* ---- momentum rows */
+        for (int a_ = 0; a_ < dim; a_++) {
+          const int row = a_ * nn + i;
+          if (assemble_residual) {
+            double adv = 0.0, diff = 0.0;
+            for (int q = 0; q < dim; q++) adv += val[q] * grad[a_][q]; /* v_q d_q v_a */
+            for (int q = 0; q < dim; q++) {
+              double Pi = mu * (grad[q][a_] + grad[a_][q]) - (q == a_ ? Pr : 0.0);
+              diff += g[i][q] * Pi;
+            }
+            R[row] += -em[0] * rho * phi_i * dot[a_] * d_area - em[1] * rho * phi_i * adv * d_area -
+                      em[3] * diff * d_area + em[4] * phi_i * fs[a_] * d_area;
+          }
+          if (assemble_jacobian) {
+            for (int j = 0; j < nn; j++) {
+              double gij = 0.0, vgj = 0.0;
+              for (int q = 0; q < dim; q++) { gij += g[i][q] * g[j][q]; vgj += val[q] * g[j][q]; }
+              for (int b = 0; b < dim; b++) {
+                double mass = (a_ == b) ? -em[0] * rho * phi_i * phi[j] * tfac * d_area : 0.0;
+                double adv = -em[1] * rho * phi_i * (phi[j] * grad[a_][b] + (a_ == b ? vgj : 0.0)) * d_area;
+                double dif = -em[3] * mu * (g[i][b] * g[j][a_] + (a_ == b ? gij : 0.0)) * d_area;
+                J[row * ndof + b * nn + j] += mass + adv + dif;
+              }
+              if (p->energy) J[row * ndof + fT * nn + j] += em[4] * phi_i * dfdT[a_] * phi[j] * d_area;
+            }
+            for (int q = 0; q < np; q++) J[row * ndof + nf * nn + q] += em[3] * g[i][a_] * psi[q] * d_area;
+          }
+        }
+        /* ---- energy row */
+        if (p->energy) {
+          const int row = fT * nn + i;
+          if (assemble_residual) {
+            double adv = 0.0, diff = 0.0;
+            for (int q = 0; q < dim; q++) { adv += val[q] * grad[fT][q]; diff += g[i][q] * (-kc * grad[fT][q]); }
+            R[row] += -ee[0] * rcp * phi_i * dot[fT] * d_area - ee[1] * rcp * phi_i * adv * d_area +
+                      ee[3] * diff * d_area + ee[4] * phi_i * p->heat_source * d_area;
+          }
+          if (assemble_jacobian) {
+            for (int j = 0; j < nn; j++) {
+              double gij = 0.0, vgj = 0.0;
+              for (int q = 0; q < dim; q++) { gij += g[i][q] * g[j][q]; vgj += val[q] * g[j][q]; }
+              J[row * ndof + fT * nn + j] += (-ee[0] * rcp * phi_i * phi[j] * tfac - ee[1] * rcp * phi_i * vgj -
+                                              ee[3] * kc * gij) * d_area;
+              for (int b = 0; b < dim; b++)
+                J[row * ndof + b * nn + j] += -ee[1] * rcp * phi_i * phi[j] * grad[fT][b] * d_area;
+            }
+          }
+        }
+      }
+      /* ---- continuity rows (P1) */
+      for (int q = 0; q < np; q++) {
+        const int row = nf * nn + q;
+        if (assemble_residual) R[row] += ec0 * psi[q] * div_v * d_area;
+        if (assemble_jacobian)
+          for (int j = 0; j < nn; j++)
+            for (int b = 0; b < dim; b++) J[row * ndof + b * nn + j] += ec0 * psi[q] * g[j][b] * d_area;
+      }
+    }
+
+    /* put_dirichlet_in_matrix */
+    for (int r = 0; r < ndof; r++) {
+      int fl = p->dbc_flag[gun[r]];
+      if (!fl) continue;
+      for (int cidx = 0; cidx < ndof; cidx++) J[r * ndof + cidx] = 0.0;
+      J[r * ndof + r] = 1.0;
+      R[r] = fl == 1 ? x[gun[r]] - p->dbc_value[gun[r]] : 0.0;
+    }
+    /* load_lec, MSR */
+    for (int r = 0; r < ndof; r++) {
+      if (c[lnode[r]] >= p->num_owned_nodes) continue;
+      int ie = gun[r];
+      if (assemble_residual) resid[ie] += R[r];
+      if (!assemble_jacobian) continue;
+      int rowT = p->energy && r >= fT * nn && r < (fT + 1) * nn;
+      for (int cidx = 0; cidx < ndof; cidx++) {
+        if (rowT && cidx >= nf * nn) continue;           /* Inter_Mask[T][P] = 0 */
+        if (rowT && !p1 && cidx / nn == fP) continue;
+        long pos = msr_pos(ija, ie, gun[cidx]);
+        if (pos < 0) { rc = -2; continue; }
+        a[pos] += J[r * ndof + cidx];
+      }
+    }
+  }
+  free(R); free(J); free(gun); free(lnode);
+  return rc;
+}

@@ -225,6 +225,16 @@ int main(int argc, char **argv) {
   pg->matrices[imtrx].scale = scale;
   pg->matrices[imtrx].resid_vector = resid;
 
+  /* solve_problem always runs find_and_set_Dirichlet before the first fill (rf_solve.c:917): it
+   * builds Nodes[]->DBC, which put_dirichlet_in_matrix consumes.  Done here on scratch vectors so
+   * the caller's state is only touched when it asks for the preset. */
+  {
+    double *xs = alloc_dbl_1(numProcUnknowns, 0.0), *xds = alloc_dbl_1(numProcUnknowns, 0.0);
+    find_and_set_Dirichlet(xs, xds, exo, dpi);
+    free(xs);
+    free(xds);
+  }
+
   if (strcmp(mode, "map") == 0) {
     /* unknown map + sparsity + Dirichlet table: the bit-exact contract */
     FILE *f = fopen("map.bin", "wb");
@@ -264,6 +274,12 @@ int main(int argc, char **argv) {
       }
     }
     wr(f, dbc, numProcUnknowns, 4);
+    /* Inter_Mask rows/cols for variable ids 0..9 (v, T, Y, d, -, P) */
+    int im[100];
+    for (int r = 0; r < 10; r++)
+      for (int c = 0; c < 10; c++)
+        im[10 * r + c] = Inter_Mask[imtrx][r][c];
+    wr(f, im, 100, 4);
     fclose(f);
     printf("map: unknowns=%d N=%d nnz_plus=%d setup_s=%.3f\n", numProcUnknowns, N, nnz_plus, t_setup);
     return 0;

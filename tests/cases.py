@@ -1,0 +1,111 @@
+"""Parity cases shared by the golden-fixture generator and the tests.
+
+Each case is a small instance of one of the BASELINE.json configs: a perturbed structured
+mesh, material constants chosen so that every term has a distinct weight, Dirichlet rows of
+both kinds (hard-set and relaxed), and a smooth-plus-noise state so that every Jacobian
+term is exercised.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from goma_b200.mesh import box_mesh
+from goma_b200.problem import Dirichlet, Problem
+
+SEED = 20261017
+
+
+def make_state(problem, seed=SEED, transient=False, delta_t=0.01, theta=0.0):
+    """u = (sin pi x cos pi y, -cos pi x sin pi y[, 0.3 sin pi z]) + 0.05 N(0,1); P ~ N(0,1);
+    T = x + 0.1 N; Y_w = 0.5 + 0.05 N; d = 0.02 h N  (SURVEY.md §8d)."""
+    rng = np.random.default_rng(seed)
+    m = problem.mesh
+    first, node_kind, kinds = problem.unknown_map()
+    n = int(first[-1])
+    X = m.coords
+
+    def fill():
+        x = np.zeros(n)
+        for kind_id, slots in enumerate(kinds):
+            nodes = np.nonzero(node_kind == kind_id)[0]
+            for off, name in enumerate(slots):
+                idx = first[nodes] + off
+                cx, cy = X[0][nodes], X[1][nodes]
+                noise = rng.normal(size=len(nodes))
+                if name == "U":
+                    v = np.sin(np.pi * cx) * np.cos(np.pi * cy) + 0.05 * noise
+                elif name == "V":
+                    v = -np.cos(np.pi * cx) * np.sin(np.pi * cy) + 0.05 * noise
+                elif name == "W":
+                    v = 0.3 * np.sin(np.pi * X[2][nodes]) + 0.05 * noise
+                elif name == "T":
+                    v = cx + 0.1 * noise
+                elif name.startswith("Y"):
+                    v = 0.5 + 0.05 * noise
+                elif name.startswith("D"):
+                    h = 1.0 / max(m.lattice)
+                    v = 0.02 * h * noise
+                else:  # pressure dofs
+                    v = noise
+                x[idx] = v
+        return x
+
+    st = {"x": fill()}
+    if transient:
+        x_old = st["x"] + 0.03 * rng.normal(size=n)
+        xdot_old = rng.normal(size=n) * 0.1
+        # rf_solve.c:2848: xdot = (1+2 theta)/dt (x - x_old) - 2 theta xdot_old
+        st.update(x_old=x_old, x_older=x_old.copy(), xdot_old=xdot_old,
+                  xdot=(1 + 2 * theta) / delta_t * (st["x"] - x_old) - 2 * theta * xdot_old)
+    return st
+
+
+def _bcs(dim, energy=False):
+    bcs = [Dirichlet("U", 1, 1.0), Dirichlet("V", 1, 0.0), Dirichlet("U", 3, 0.0, relax=1.0),
+           Dirichlet("V", 3, 0.25, relax=1.0), Dirichlet("U", 4, 0.0), Dirichlet("V", 4, 0.0),
+           Dirichlet("V", 2, 0.0)]
+    if dim == 3:
+        bcs += [Dirichlet("W", 5, 0.0), Dirichlet("W", 6, 0.5, relax=1.0), Dirichlet("W", 1, 0.0)]
+    if energy:
+        bcs += [Dirichlet("T", 1, 1.0), Dirichlet("T", 2, 0.0, relax=1.0)]
+    return bcs
+
+
+def build_case(name):
+    """Returns (problem, fill kwargs)."""
+    if name == "c1_quad9_ns":
+        m = box_mesh("QUAD9", (6, 4), lo=(0, 0), hi=(2, 1), perturb=0.15, seed=1)
+        p = Problem(m, rho=1.3, mu=0.7, gravity=(0.3, -0.2, 0.0), bcs=_bcs(2) + [Dirichlet("P", 7, 0.5)])
+        return p, {}
+    if name == "c1_quad9_ns_transient":
+        m = box_mesh("QUAD9", (5, 3), lo=(0, 0), hi=(2, 1), perturb=0.15, seed=2)
+        p = Problem(m, rho=1.3, mu=0.7, gravity=(0.3, -0.2, 0.0), transient=True,
+                    etm_momentum=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0), bcs=_bcs(2))
+        return p, {"delta_t": 0.01, "theta": 0.5, "time": 0.2}
+    if name == "c2_hex27_ns":
+        m = box_mesh("HEX27", (2, 2, 2), perturb=0.12, seed=3)
+        p = Problem(m, rho=1.0, mu=0.01, gravity=(0.0, 0.0, -0.4), bcs=_bcs(3))
+        return p, {}
+    if name == "c3_hex27_boussinesq":
+        m = box_mesh("HEX27", (2, 2, 2), perturb=0.12, seed=4)
+        p = Problem(m, energy=True, rho=1.1, mu=0.05, k=0.07, Cp=1.4, beta=0.8, Tref=0.3,
+                    gravity=(0.0, 0.1, -1.0), ns_source="BOUSSINESQ", heat_source=0.6, bcs=_bcs(3, True))
+        return p, {}
+    if name == "c3_quad9_bouss_transient":
+        m = box_mesh("QUAD9", (4, 4), perturb=0.15, seed=5)
+        p = Problem(m, energy=True, rho=1.1, mu=0.05, k=0.07, Cp=1.4, beta=0.8, Tref=0.3,
+                    gravity=(0.2, -1.0, 0.0), ns_source="BOUSS", heat_source=0.6, transient=True,
+                    etm_momentum=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0), etm_energy=(1.0, 1.0, 1.0, 1.0, 1.0),
+                    bcs=_bcs(2, True))
+        return p, {"delta_t": 0.02, "theta": 0.0, "time": 0.1}
+    raise KeyError(name)
+
+
+GOLDEN_CASES = ["c1_quad9_ns", "c1_quad9_ns_transient", "c2_hex27_ns", "c3_hex27_boussinesq",
+                "c3_quad9_bouss_transient"]
+
+
+def case_state(name):
+    p, kw = build_case(name)
+    st = make_state(p, transient=p.transient, delta_t=kw.get("delta_t", 0.01), theta=kw.get("theta", 0.0))
+    return p, kw, st
