@@ -166,6 +166,26 @@ class Problem:
                 hard[idx] = 1 if bc.relax is None else 0
         return is_dbc, value, hard
 
+    def preset_dirichlet(self, x, xdot=None):
+        """find_and_set_Dirichlet (``mm_bc.c:480-585``): every hard-set card (no relax float)
+        overwrites ``x`` with its value and zeroes ``xdot``, card by card in deck order -- so at a
+        node shared by two node sets the value of the last *hard* card stays in ``x`` even when
+        a later relaxed card owns the row."""
+        first, node_kind, kinds = self.unknown_map()
+        for bc in self.bcs:
+            if bc.relax is not None:
+                continue
+            slot = f"Y{bc.species}" if bc.var == "Y" else bc.var
+            nodes = self.mesh.node_sets[bc.ns_id]
+            for kind_id, slots in enumerate(kinds):
+                if slot in slots:
+                    sel = nodes[node_kind[nodes] == kind_id]
+                    idx = first[sel] + slots.index(slot)
+                    x[idx] = bc.value
+                    if xdot is not None:
+                        xdot[idx] = 0.0
+        return x
+
     # ------------------------------------------------------------------- decks
     def deck(self) -> str:
         """Goma problem-description file for this problem (cards per SURVEY.md App. C)."""

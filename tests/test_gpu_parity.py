@@ -1,0 +1,157 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the oracle.
+
+Tolerance (BASELINE.json north_star): residual and Jacobian entries agree to 1e-12 relative in
+fp64 (summation order differs); sparsity pattern and unknown ordering bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from goma_b200 import capi
+from goma_b200.matrix_fill import MatrixFill, msr_to_csr
+from goma_b200.mesh import box_mesh
+from goma_b200.problem import Dirichlet, Problem
+from oracle import port, ref_driver
+from tests.cases import GOLDEN_CASES, case_state, make_state
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-12
+
+
+def golden(name):
+    return np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+
+
+def rel_err(got, ref):
+    return np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+def assert_close(got, ref, what):
+    e = rel_err(got, ref)
+    assert e < TOL, f"{what}: max rel err {e:.3e}"
+
+
+@pytest.mark.parametrize("scatter", [0, 1], ids=["atomic", "coloured"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_gpu_matches_reference_fixture(built, name, scatter):
+    """CUDA assembly == the reference's own matrix_fill_full output (committed fixture)."""
+    p, kw, st = case_state(name)
+    g = golden(name)
+    mf = MatrixFill(p, ija=g["ija"])  # the library also checks its derived graph against the host's
+    mf.set_option("scatter", scatter)
+    assert mf.nnz_plus == len(g["ija"])
+    np.testing.assert_array_equal(mf.export_msr(), g["ija"])
+    err, a, r = mf.matrix_fill_full(st["x"], st.get("x_old"), st.get("x_older"), st.get("xdot"), st.get("xdot_old"),
+                                    delta_t=kw.get("delta_t", 0.0), theta=kw.get("theta", 0.0),
+                                    time_value=kw.get("time", 0.0))
+    assert err == 0 and not mf.flags.any()
+    assert_close(a, g["a"], "Jacobian")
+    assert_close(r, g["resid"], "residual")
+    # residual-only call (modified Newton, mm_sol_nonlinear.c:1226-1231) leaves the same residual
+    err, _, r2 = mf.matrix_fill_full(st["x"], st.get("x_old"), st.get("x_older"), st.get("xdot"), st.get("xdot_old"),
+                                     delta_t=kw.get("delta_t", 0.0), theta=kw.get("theta", 0.0),
+                                     assemble_jacobian=False)
+    assert_close(r2, g["resid"], "residual-only")
+    mf.close()
+
+
+@pytest.mark.parametrize("et,n,energy", [("HEX27", (5, 4, 3), True), ("HEX27", (4, 4, 4), False),
+                                         ("QUAD9", (17, 9), True), ("QUAD9", (40, 10), False)])
+def test_gpu_matches_port_oracle_seeded(built, et, n, energy):
+    """Larger seeded cases than the fixtures, against the CPU restatement."""
+    m = box_mesh(et, n, perturb=0.1, seed=11)
+    dim = m.dim
+    bcs = [Dirichlet("U", 1, 1.0), Dirichlet("V", 3, 0.0, relax=1.0), Dirichlet("U", 4, 0.0)]
+    if energy:
+        bcs += [Dirichlet("T", 1, 1.0), Dirichlet("T", 2, 0.0, relax=1.0)]
+    p = Problem(m, energy=energy, rho=1.2, mu=0.03, k=0.05, Cp=1.3, beta=0.7, Tref=0.1,
+                gravity=(0.1, -1.0, 0.2)[:3], ns_source="BOUSSINESQ" if energy else "CONSTANT",
+                heat_source=0.3, bcs=bcs)
+    st = make_state(p, seed=5)
+    ija = capi.pattern_msr(p)
+    rc, a_ref, r_ref = port.port_fill(p, ija, st)
+    assert rc == 0
+    mf = MatrixFill(p)
+    for scatter in (0, 1):
+        mf.set_option("scatter", scatter)
+        err, a, r = mf.matrix_fill_full(st["x"])
+        assert err == 0
+        assert_close(a, a_ref, f"Jacobian scatter={scatter}")
+        assert_close(r, r_ref, f"residual scatter={scatter}")
+    mf.close()
+
+
+def test_gpu_ghost_rows_are_not_written(built):
+    """Rows of external (ghost) nodes stay zero: load_lec's owned_ledof test (mm_fill.c:5374)."""
+    m = box_mesh("QUAD9", (6, 5), perturb=0.1, seed=3)
+    p = Problem(m, bcs=[Dirichlet("U", 1, 1.0)])
+    st = make_state(p, seed=9)
+    owned = m.num_nodes - 40
+    ija = capi.pattern_msr(p)
+    rc, a_ref, r_ref = port.port_fill(p, ija, st, num_owned_nodes=owned)
+    mf = MatrixFill(p, num_owned_nodes=owned)
+    err, a, r = mf.matrix_fill_full(st["x"])
+    assert_close(a, a_ref, "Jacobian")
+    assert_close(r, r_ref, "residual")
+    first = p.unknown_map()[0]
+    assert not r[first[owned]:].any() and not a[first[owned]:len(r)].any()
+    mf.close()
+
+
+def test_gpu_jacobian_is_derivative_of_residual(built):
+    """The reference's own self-check (numerical_jacobian, mm_numjac.c:716): J d == dR/dx . d.
+    Size-independent property, run at a size the CPU oracle would take minutes for."""
+    m = box_mesh("HEX27", (12, 12, 12), perturb=0.08, seed=2)
+    p = Problem(m, energy=True, rho=1.0, mu=0.02, k=0.03, Cp=1.1, beta=0.5, Tref=0.0, gravity=(0, 0, -1.0),
+                ns_source="BOUSSINESQ")
+    st = make_state(p, seed=4)
+    mf = MatrixFill(p)
+    n = mf.num_unknowns
+    err, a, r0 = mf.matrix_fill_full(st["x"])
+    A = msr_to_csr(mf.export_msr(), a, n)
+    rng = np.random.default_rng(0)
+    d = rng.normal(size=n)
+    eps = 1e-6
+    _, _, rp = mf.matrix_fill_full(st["x"] + eps * d, assemble_jacobian=False)
+    rp = rp.copy()
+    _, _, rm = mf.matrix_fill_full(st["x"] - eps * d, assemble_jacobian=False)
+    fd = (rp - rm) / (2 * eps)
+    jd = A @ d
+    assert np.abs(fd - jd).max() / np.abs(jd).max() < 1e-7
+    mf.close()
+
+
+def test_gpu_stokes_residual_is_affine(built):
+    """With advection off the residual is affine in x: R(x) - R(0) == J x (exactly, to round-off)."""
+    m = box_mesh("HEX27", (8, 8, 8), perturb=0.05, seed=6)
+    p = Problem(m, rho=1.0, mu=0.5, etm_momentum=(0.0, 0.0, 1.0, 1.0, 1.0, 0.0), gravity=(0.1, 0.2, -0.3))
+    st = make_state(p, seed=8)
+    mf = MatrixFill(p)
+    n = mf.num_unknowns
+    _, a, r = mf.matrix_fill_full(st["x"])
+    A = msr_to_csr(mf.export_msr(), a, n)
+    _, _, r0 = mf.matrix_fill_full(np.zeros(n), assemble_jacobian=False)
+    lhs = r - r0
+    rhs = A @ st["x"]
+    assert np.abs(lhs - rhs).max() / np.abs(rhs).max() < 1e-11
+    mf.close()
+
+
+@pytest.mark.skipif(not ref_driver.ref_available(), reason="oracle/_ref binary not present on this box")
+def test_gpu_matches_reference_live(built):
+    """Where the reference binary travelled with the snapshot: run it live on a fresh case."""
+    m = box_mesh("HEX27", (3, 3, 3), perturb=0.1, seed=21)
+    p = Problem(m, energy=True, rho=0.9, mu=0.04, k=0.2, Cp=2.0, beta=0.3, Tref=0.5, gravity=(0.3, 0.0, -1.0),
+                ns_source="BOUSSINESQ", heat_source=0.1,
+                bcs=[Dirichlet("U", 5, 0.0), Dirichlet("V", 5, 0.0), Dirichlet("W", 5, 0.0), Dirichlet("U", 6, 1.0),
+                     Dirichlet("T", 1, 1.0), Dirichlet("T", 2, 0.0, relax=1.0), Dirichlet("P", 7, 0.0)])
+    st = make_state(p, seed=13)
+    ref = ref_driver.run_fill(p, [st])[0]
+    mf = MatrixFill(p)
+    err, a, r = mf.matrix_fill_full(st["x"])
+    assert err == ref["err"] == 0
+    assert_close(a, ref["a"], "Jacobian vs live reference")
+    assert_close(r, ref["resid"], "residual vs live reference")
+    mf.close()
