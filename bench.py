@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the matrix_fill hot path (BASELINE.json: Jacobian+residual elements/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle/_ref)
+
+One "step" = one matrix_fill_full over the whole local mesh (residual + Jacobian): zero the MSR
+values and residual, assemble every element, scatter.  At N=1 the workload is BASELINE.json
+configs[1]: 3-D lid-driven cavity, Q2/P1 hex27, 100^3 = 1M elements (SURVEY.md §8d "C2").  At
+N>1 every rank assembles its own 1M-element slab of an N-times longer box (weak scaling; the
+element loop has no data-path collective -- SURVEY.md §8e).
+
+`value`  : device-resident step (state already in HBM), elements/s over all ranks.
+`e2e`    : the same step through goma_gpu_fill() with HOST buffers: H2D of x, assembly, D2H of
+           the MSR values and the residual, all inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# SURVEY.md §8(d) / BASELINE.md §3 per-element algorithmic work, fixed per config
+ALG_FLOPS_PER_ELEM = {"c2_hex27_ns": 1.2e6, "c3_hex27_ns_energy": 1.85e6}
+FP64_PEAK_NOMINAL_TFLOPS = 40.0  # BASELINE.json north_star; replaced by the DFMA micro-benchmark when it runs
+
+
+def cavity_problem(n, energy=False, x_len=1.0):
+    from goma_b200.mesh import box_mesh
+    from goma_b200.problem import Dirichlet, Problem
+
+    m = box_mesh("HEX27", (n, n, n), lo=(0, 0, 0), hi=(x_len, 1.0, 1.0))
+    bcs = [Dirichlet(v, s, 0.0) for s in (1, 2, 3, 4, 5) for v in "UVW"]
+    bcs += [Dirichlet("U", 6, 1.0), Dirichlet("V", 6, 0.0), Dirichlet("W", 6, 0.0), Dirichlet("P", 7, 0.0)]
+    kw = {}
+    if energy:
+        bcs += [Dirichlet("T", 1, 1.0), Dirichlet("T", 2, 0.0)]
+        kw = dict(energy=True, k=0.0141, Cp=1.0, beta=1.0, Tref=0.0, gravity=(0.0, 0.0, -1.0), ns_source="BOUSSINESQ")
+    return Problem(m, rho=1.0, mu=0.01, bcs=bcs, **kw)
+
+
+def synthetic_state(problem, seed):
+    from tests.cases import make_state
+
+    return make_state(problem, seed=seed)["x"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def reference_sample(cores, sample_n, nrep, energy=False):
+    """The reference's own matrix_fill_full (oracle/_ref) on `cores` independent single-rank processes,
+    one `sample_n`^3 hex27 sub-domain each.  Returns (elements/s, mean seconds/step)."""
+    from oracle import ref_driver
+
+    p = cavity_problem(sample_n, energy)
+    x = synthetic_state(p, 1)
+    n = len(x)
+    tmp = tempfile.mkdtemp(prefix="goma_ref_bench_")
+    dirs = []
+    for c in range(cores):
+        wd = os.path.join(tmp, f"p{c}")
+        ref_driver.write_workdir(p, wd)
+        with open(os.path.join(wd, "state.bin"), "wb") as f:
+            f.write(np.array([n, 1, 1, 0], np.int32).tobytes())
+            f.write(np.array([0.0, 0.0, 0.0, -1.0, -1.0], np.float64).tobytes())
+            f.write(x.tobytes())
+            f.write(np.zeros(4 * n).tobytes())
+        dirs.append(wd)
+    procs = [subprocess.Popen([ref_driver.REF_EXE, wd, "fill", str(nrep)], stdout=subprocess.PIPE,
+                              stderr=subprocess.DEVNULL, text=True) for wd in dirs]
+    means = []
+    for pr in procs:
+        out = pr.communicate()[0]
+        if pr.returncode != 0:
+            raise RuntimeError("goma_ref_fill failed in the CPU baseline")
+        line = [l for l in out.splitlines() if l.startswith("fill[0]")][-1]
+        means.append(float(line.split("mean_s=")[1].split()[0]))
+    subprocess.call(["rm", "-rf", tmp])
+    step_s = max(means)
+    return cores * p.mesh.num_elems / step_s, step_s, p.mesh.num_elems
+
+
+def port_sample(sample_n, nrep, energy=False):
+    from goma_b200 import capi
+    from oracle import port
+
+    p = cavity_problem(sample_n, energy)
+    st = {"x": synthetic_state(p, 1)}
+    ija = capi.pattern_msr(p)
+    t = []
+    for _ in range(nrep):
+        t0 = time.perf_counter()
+        port.port_fill(p, ija, st)
+        t.append(time.perf_counter() - t0)
+    return p.mesh.num_elems / min(t), min(t), p.mesh.num_elems
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(budget_cores=None, nrep=2, energy=False):
+    from oracle import ref_driver
+
+    cores = budget_cores or host_cores()
+    if ref_driver.ref_available():
+        v, step_s, ne = reference_sample(cores, 6, nrep, energy)
+        return {"value": v, "unit": "elements/s", "cores": cores, "kind": "reference",
+                "sample": f"{cores} single-rank processes of the reference's matrix_fill_full, one 6^3 hex27 "
+                          f"sub-domain ({ne} elements) each, {nrep} fills, mean {step_s:.3f} s/fill"}
+    v, step_s, ne = port_sample(6, nrep, energy)
+    return {"value": v, "unit": "elements/s", "cores": 1, "kind": "port",
+            "sample": f"oracle/fill_port.c, one 6^3 hex27 mesh ({ne} elements), best of {nrep}"}
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference CPU path on all host cores, same config/metric/unit."""
+    if rank != 0:
+        return
+    from oracle import ref_driver
+
+    cores = host_cores()
+    nrep = args.warmup + args.steps
+    if ref_driver.ref_available():
+        v, step_s, ne = reference_sample(cores, 6, nrep, args.energy)
+        kind = "reference"
+        sample = (f"{cores} single-rank reference processes x one 6^3 hex27 sub-domain ({ne} elements) each; "
+                  f"{nrep} fills per process, mean s/fill of the slowest process")
+    else:
+        v, step_s, ne = port_sample(6, nrep, args.energy)
+        cores, kind = 1, "port"
+        sample = f"oracle/fill_port.c on one 6^3 hex27 mesh ({ne} elements)"
+    line = {"impl": "reference", "metric": "jacobian_residual_elements_per_s", "value": v, "unit": "elements/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "elements_per_step": cores * ne},
+            "cpu_baseline": {"value": v, "unit": "elements/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    phys = "NS+energy (Boussinesq)" if args.energy else "Navier-Stokes"
+    return f"3D lid-driven cavity {phys}, Q2/P1 hex27, {args.n}^3 elements per GPU (BASELINE.json configs[1])"
+
+
+def fp64_peak_tflops(device):
+    """DFMA micro-benchmark through torch (fp64 matmul runs on the FP64 pipe): measured peak for the roofline."""
+    import torch
+
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.float64, device=device)
+    b = torch.randn(n, n, dtype=torch.float64, device=device)
+    torch.matmul(a, b)
+    torch.cuda.synchronize(device)
+    best = 0.0
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize(device)
+        best = max(best, 2 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    del a, b
+    torch.cuda.empty_cache()
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=100, help="elements per direction per GPU (100 -> 1M hex27 elements)")
+    ap.add_argument("--energy", action="store_true", help="config C3 physics (NS + energy) instead of C2")
+    ap.add_argument("--scatter", type=int, default=0, help="0 fp64 atomics, 1 coloured plain stores")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+    from goma_b200.matrix_fill import MatrixFill
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the GPU fill has no CPU fallback")
+    ge.build(quiet=True)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    t_setup = time.perf_counter()
+    problem = cavity_problem(args.n, args.energy)  # every rank: its own n^3 slab (weak scaling)
+    x = synthetic_state(problem, 20261017 + rank)
+    mf = MatrixFill(problem, device=local_rank)
+    mf.set_option("scatter", args.scatter)
+    ne = problem.mesh.num_elems
+    n_unk, nnz = mf.num_unknowns, mf.nnz_plus
+    t_setup = time.perf_counter() - t_setup
+
+    # state into HBM once (one residual-only host call), then the device-resident steps
+    mf.matrix_fill_full(x, assemble_jacobian=False)
+    for _ in range(args.warmup):
+        mf.fill_device()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    kernel_ms, launches = 0.0, 0
+    for _ in range(args.steps):
+        mf.fill_device()
+        ms, nl = mf.last_stats()
+        kernel_ms += ms
+        launches += nl
+    barrier()
+    step_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    clocks = sampler.stop()
+    dev_ms = max_over_ranks(kernel_ms / args.steps)  # CUDA events on the library's stream: memsets + kernel(s)
+    total_elems = sum_over_ranks(float(ne))
+    value = total_elems / step_s
+
+    # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        try:
+            hx = torch.empty(n_unk, dtype=torch.float64).pin_memory()
+            ha = torch.empty(nnz + 1, dtype=torch.float64).pin_memory()
+            hr = torch.empty(n_unk, dtype=torch.float64).pin_memory()
+            pinned = True
+        except RuntimeError:
+            hx, ha, hr = (torch.empty(k, dtype=torch.float64) for k in (n_unk, nnz + 1, n_unk))
+            pinned = False
+        hx.numpy()[:] = x
+        ptrs = (hx.data_ptr(), 0, 0, 0, 0, ha.data_ptr(), hr.data_ptr())
+        mf.fill_raw(ptrs)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            mf.fill_raw(ptrs)
+        barrier()
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+        e2e = {"value": total_elems / e2e_s, "unit": "elements/s", "h2d_bytes_per_step": 8 * n_unk,
+               "d2h_bytes_per_step": 8 * (nnz + 1) + 8 * n_unk, "ms_per_step": e2e_s * 1e3,
+               "host_buffers": "pinned" if pinned else "pageable", "steps": args.e2e_steps,
+               "resid_checksum": float(hr.numpy().sum())}
+        del hx, ha, hr
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        key = "c3_hex27_ns_energy" if args.energy else "c2_hex27_ns"
+        flops = ALG_FLOPS_PER_ELEM[key]
+        bytes_per_elem = 8.0 * (nnz + n_unk) / ne + 27 * 4 + 8.0 * (3 * problem.mesh.num_nodes + n_unk) / ne
+        kern_s = dev_ms * 1e-3
+        fp64_meas = fp64_peak_tflops(dev)
+        fp64_peak = max(fp64_meas, 1e-9)
+        ach_tf = flops * ne / kern_s / 1e12
+        ach_gbs = bytes_per_elem * ne / kern_s / 1e9
+        line = {
+            "metric": "jacobian_residual_elements_per_s", "value": value, "unit": "elements/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "elements_per_gpu": ne, "unknowns_per_gpu": n_unk,
+                       "nnz_per_gpu": nnz, "scatter": "fp64 atomics" if args.scatter == 0 else "coloured stores",
+                       "l2": "inputs larger than L2 (MSR values %.1f GB per GPU rewritten every step)" % (8e-9 * nnz),
+                       "setup_s": round(t_setup, 1)},
+            "clocks": clocks, "gpu_launches": launches, "device_ms_per_step": dev_ms,
+            "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": ach_tf / fp64_peak, "traffic": None,
+                         "peak_source": "fp64 matmul micro-benchmark in this run (nominal %.0f)" % FP64_PEAK_NOMINAL_TFLOPS,
+                         "flops_per_element": flops,
+                         "note": "binding roof of the hex27 fill is the FP64 pipe (AI ~27 flop/B, SURVEY.md §8d)"},
+            "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                             "bytes_per_element": bytes_per_elem},
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(energy=args.energy)
+            except Exception as ex:  # the baseline must never take the GPU number down with it
+                line["cpu_baseline"] = {"value": None, "unit": "elements/s", "cores": 0, "kind": "reference",
+                                        "sample": f"failed: {ex}"}
+        print(json.dumps(line))
+    mf.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
