@@ -65,13 +65,22 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        """One resident nvidia-smi in loop mode, started before the warm-up so that its start-up
+        (which holds driver locks) stays outside the timed region; mark() opens the window."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 10:
+                time.sleep(0.05)
         except OSError:
             self.proc = None
+        self.first = 0
+
+    def mark(self):
+        self.first = len(self.rows)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -80,6 +89,7 @@ class ClockSampler:
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        self.rows = self.rows[max(self.first - 1, 0):]  # samples taken during the timed window
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -276,11 +286,12 @@ def main():
     t_setup = time.perf_counter() - t_setup
 
     # state into HBM once (one residual-only host call), then the device-resident steps
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     mf.matrix_fill_full(x, assemble_jacobian=False)
     for _ in range(args.warmup):
         mf.fill_device()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     barrier()
     t0 = time.perf_counter()
     kernel_ms, launches = 0.0, 0

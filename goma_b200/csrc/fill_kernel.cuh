@@ -58,9 +58,9 @@ struct FillParams {
   double lame_mu, lame_lambda;
 };
 
-template <int DIM_, int NN_, int NGP_, bool P1_, bool ENERGY_, int NSPEC_, bool ALE_, int TPE_>
+template <int DIM_, int NN_, int NGP_, bool P1_, bool ENERGY_, int NSPEC_, bool ALE_, int TPE_, int TI_>
 struct Cfg {
-  static constexpr int DIM = DIM_, NN = NN_, NGP = NGP_, TPE = TPE_, NSPEC = NSPEC_;
+  static constexpr int DIM = DIM_, NN = NN_, NGP = NGP_, TPE = TPE_, NSPEC = NSPEC_, TI = TI_;
   static constexpr bool P1 = P1_, ENERGY = ENERGY_, ALE = ALE_;
   static constexpr int F_V = 0;
   static constexpr int F_T = DIM;
@@ -70,9 +70,20 @@ struct Cfg {
   static constexpr int NF = F_P + (P1 ? 0 : 1);
   static constexpr int NP = P1 ? DIM + 1 : 0;
   static constexpr int CEN = NN == 9 ? 8 : (NN == 27 ? 20 : 0);
+  static constexpr int NTILE = (NN / TI) * NN;  // register tiles (TI rows x 1 column of node pairs) per element
+  static_assert(NN % TI == 0, "row tile must divide the node count");
   static constexpr int TBL = NGP + NGP * NN + NGP * NN * DIM + NGP * (DIM + 1);
   static constexpr int TBL_PAD = (TBL + 1) & ~1;  // 16-byte multiple for the bulk copy
   static constexpr int T_WT = 0, T_PHI = NGP, T_DPHI = T_PHI + NGP * NN, T_PSI = T_DPHI + NGP * NN * DIM;
+  // per-Gauss-point derived data (doubles): see phase 4b
+  static constexpr int G_GV = 0;                                   // c_adv d_b v_a            [a][b]
+  static constexpr int G_GT = G_GV + DIM * DIM;                    // ce_adv d_b T             [b]
+  static constexpr int G_RQ = G_GT + (ENERGY ? DIM : 0);           // momentum residual, multiplies w phi_i   [a]
+  static constexpr int G_RP = G_RQ + DIM;                          // -e3 Pi[a][p], multiplies w grad_phi_i[p]
+  static constexpr int G_RE = G_RP + DIM * DIM;                    // energy residual scalar
+  static constexpr int G_RF = G_RE + (ENERGY ? 1 : 0);             // e3 q[p]
+  static constexpr int G_DIV = G_RF + (ENERGY ? DIM : 0);          // ec0 div v
+  static constexpr int GPD = (G_DIV + 1 + 1) & ~1;
   __host__ __device__ static constexpr int slot(int f) {
     return f < DIM                       ? GOMA_SLOT_U + f
            : (ENERGY && f == F_T)        ? GOMA_SLOT_T
@@ -85,14 +96,17 @@ struct Cfg {
 template <class C>
 struct alignas(16) Smem {
   double tbl[C::TBL_PAD];
+  double SI[C::NGP][C::NN][4];  // (w phi_i, w grad_phi_i[p])   test-function side
+  double SJ[C::NGP][C::NN][4];  // (phi_j, grad_phi_j[p])       trial-function side
+  double VG[C::NGP][C::NN];     // v . grad_phi_j
+  double GP[C::NGP][C::GPD];    // per-Gauss-point derived quantities
+  double F[C::NGP][C::NF][C::DIM + 2];  // value, grad[DIM], time derivative
   double X[C::DIM][C::NN];
   double U[C::NF][C::NN];
   double Udot[C::NF][C::NN];
   double Pd[C::NP > 0 ? C::NP : 1];
-  double G[C::NGP][C::NN][C::DIM];
   double w[C::NGP];
   double B[C::NGP][C::DIM * C::DIM];
-  double F[C::NGP][C::NF][C::DIM + 2];  // value, grad[DIM], time derivative
   double Pgp[C::NGP];
   long long rs[C::NF][C::NN];  // MSR row start of (field,node); -1 = not written here (ghost/Dirichlet)
   long long rsP[C::NP > 0 ? C::NP : 1];
@@ -153,10 +167,10 @@ __device__ __forceinline__ void mat_add(const FillParams &P, const Smem<C> &s, l
     P.a[pos] += val;
 }
 
+// momentum_source_term (mm_fill_momentum.c:3738) CONSTANT branch and bouss_momentum_source
+// (mm_std_models.c:125-360), temperature piece
 template <class C>
 __device__ __forceinline__ void momentum_source(const FillParams &P, double T, double f[3], double dfdT[3]) {
-  // momentum_source_term (mm_fill_momentum.c:3738) CONSTANT branch and
-  // bouss_momentum_source (mm_std_models.c:125-360), temperature piece only
 #pragma unroll
   for (int a = 0; a < 3; a++) {
     f[a] = 0.0;
@@ -177,7 +191,7 @@ __device__ __forceinline__ void momentum_source(const FillParams &P, double T, d
 
 template <class C>
 __global__ void __launch_bounds__(C::TPE) fill_kernel(const __grid_constant__ FillParams P) {
-  constexpr int DIM = C::DIM, NN = C::NN, NGP = C::NGP, NF = C::NF, NP = C::NP, TPE = C::TPE;
+  constexpr int DIM = C::DIM, NN = C::NN, NGP = C::NGP, NF = C::NF, NP = C::NP, TPE = C::TPE, TI = C::TI;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<C> &s = *reinterpret_cast<Smem<C> *>(smem_raw);
   const int tid = threadIdx.x;
@@ -198,7 +212,12 @@ __global__ void __launch_bounds__(C::TPE) fill_kernel(const __grid_constant__ Fi
   const double *t_dphi = s.tbl + C::T_DPHI;  // [gp][NN][DIM]
   const double *t_psi = s.tbl + C::T_PSI;    // [gp][DIM+1]
 
+  // constants of the closed forms; a zero etm switches the term off
   const double tfac = P.transient ? (1.0 + 2.0 * P.theta) / P.delta_t : 0.0;
+  const double rcp = P.rho * P.Cp;
+  const double c_adv = -P.etm_mom[1] * P.rho, c_diff = -P.etm_mom[3] * P.mu, c_mass = -P.etm_mom[0] * P.rho * tfac;
+  const double ce_adv = -P.etm_energy[1] * rcp, ce_diff = -P.etm_energy[3] * P.k,
+               ce_mass = -P.etm_energy[0] * rcp * tfac;
 
   for (int ee = P.elem_begin + blockIdx.x; ee < P.elem_end; ee += gridDim.x) {
     const int elem = P.elem_list ? P.elem_list[ee] : ee;
@@ -228,8 +247,6 @@ __global__ void __launch_bounds__(C::TPE) fill_kernel(const __grid_constant__ Fi
       bool owned = s.node[C::CEN] < P.num_owned_nodes;
       s.rsP[tid] = (owned && P.dbc_flag[gun] == 0) ? P.rowstart[gun] : -1;
     }
-    __syncthreads();
-
     // ---- phase 1: J[a][b] = sum_k x_b,k dphi_k/dxi_a   (beer_belly, mm_fill_util.c:258-276)
     for (int idx = tid; idx < NGP * DIM * DIM; idx += TPE) {
       int gp = idx / (DIM * DIM), ab = idx - gp * DIM * DIM;
@@ -247,23 +264,25 @@ __global__ void __launch_bounds__(C::TPE) fill_kernel(const __grid_constant__ Fi
       if (DIM == 2) {
         double j00 = J[0], j01 = J[1], j10 = J[2], j11 = J[3];
         det = j00 * j11 - j01 * j10;
-        J[0] = j11 / det;
-        J[1] = -j01 / det;
-        J[2] = -j10 / det;
-        J[3] = j00 / det;
+        double rd = 1.0 / det;
+        J[0] = j11 * rd;
+        J[1] = -j01 * rd;
+        J[2] = -j10 * rd;
+        J[3] = j00 * rd;
       } else {
         double j00 = J[0], j01 = J[1], j02 = J[2], j10 = J[3], j11 = J[4], j12 = J[5], j20 = J[6], j21 = J[7],
                j22 = J[8];
         det = j00 * (j11 * j22 - j12 * j21) - j01 * (j10 * j22 - j20 * j12) + j02 * (j10 * j21 - j20 * j11);
-        J[0] = (j11 * j22 - j21 * j12) / det;
-        J[1] = -(j01 * j22 - j21 * j02) / det;
-        J[2] = (j01 * j12 - j11 * j02) / det;
-        J[3] = -(j10 * j22 - j20 * j12) / det;
-        J[4] = (j00 * j22 - j20 * j02) / det;
-        J[5] = -(j00 * j12 - j10 * j02) / det;
-        J[6] = (j10 * j21 - j11 * j20) / det;
-        J[7] = -(j00 * j21 - j20 * j01) / det;
-        J[8] = (j00 * j11 - j10 * j01) / det;
+        double rd = 1.0 / det;
+        J[0] = (j11 * j22 - j21 * j12) * rd;
+        J[1] = -(j01 * j22 - j21 * j02) * rd;
+        J[2] = (j01 * j12 - j11 * j02) * rd;
+        J[3] = -(j10 * j22 - j20 * j12) * rd;
+        J[4] = (j00 * j22 - j20 * j02) * rd;
+        J[5] = -(j00 * j12 - j10 * j02) * rd;
+        J[6] = (j10 * j21 - j11 * j20) * rd;
+        J[7] = -(j00 * j21 - j20 * j01) * rd;
+        J[8] = (j00 * j11 - j10 * j01) * rd;
       }
       s.w[tid] = det * t_wt[tid];  // d_area = detJ * wt * h3, h3 = 1 (Cartesian)
     }
@@ -273,32 +292,29 @@ __global__ void __launch_bounds__(C::TPE) fill_kernel(const __grid_constant__ Fi
       int gp = idx / NN, i = idx - gp * NN;
       const double *B = s.B[gp];
       const double *dp = &t_dphi[(gp * NN + i) * DIM];
+      const double w = s.w[gp], ph = t_phi[gp * NN + i];
+      double g[3] = {0.0, 0.0, 0.0};
 #pragma unroll
       for (int p = 0; p < DIM; p++) {
-        double acc = 0.0;
 #pragma unroll
-        for (int q = 0; q < DIM; q++) acc += B[p * DIM + q] * dp[q];
-        s.G[gp][i][p] = acc;
+        for (int q = 0; q < DIM; q++) g[p] += B[p * DIM + q] * dp[q];
       }
+      *reinterpret_cast<double2 *>(&s.SJ[gp][i][0]) = make_double2(ph, g[0]);
+      *reinterpret_cast<double2 *>(&s.SJ[gp][i][2]) = make_double2(g[1], g[2]);
+      *reinterpret_cast<double2 *>(&s.SI[gp][i][0]) = make_double2(w * ph, w * g[0]);
+      *reinterpret_cast<double2 *>(&s.SI[gp][i][2]) = make_double2(w * g[1], w * g[2]);
     }
     __syncthreads();
-    // ---- phase 4: field values, gradients, time derivatives at the Gauss points
-    for (int idx = tid; idx < NGP * NF; idx += TPE) {
-      int gp = idx / NF, f = idx - gp * NF;
-      double val = 0.0, dot = 0.0, gr[DIM];
-#pragma unroll
-      for (int p = 0; p < DIM; p++) gr[p] = 0.0;
-      for (int k = 0; k < NN; k++) {
-        double u = s.U[f][k];
-        val += u * t_phi[gp * NN + k];
-        dot += s.Udot[f][k] * t_phi[gp * NN + k];
-#pragma unroll
-        for (int p = 0; p < DIM; p++) gr[p] += u * s.G[gp][k][p];
-      }
-      s.F[gp][f][0] = val;
-#pragma unroll
-      for (int p = 0; p < DIM; p++) s.F[gp][f][1 + p] = gr[p];
-      s.F[gp][f][1 + DIM] = dot;
+    // ---- phase 4: field values, gradients, time derivatives at the Gauss points (load_fv, load_fv_grads)
+    for (int idx = tid; idx < NGP * NF * (DIM + 2); idx += TPE) {
+      int gp = idx / (NF * (DIM + 2)), r = idx - gp * NF * (DIM + 2);
+      int f = r / (DIM + 2), c = r - f * (DIM + 2);
+      const double *u = (c == DIM + 1) ? s.Udot[f] : s.U[f];
+      const int cc = (c == DIM + 1) ? 0 : c;
+      double acc = 0.0;
+#pragma unroll 9
+      for (int k = 0; k < NN; k++) acc += u[k] * s.SJ[gp][k][cc];
+      s.F[gp][f][c] = acc;
     }
     if (C::P1) {
       for (int gp = tid; gp < NGP; gp += TPE) {
@@ -307,6 +323,60 @@ __global__ void __launch_bounds__(C::TPE) fill_kernel(const __grid_constant__ Fi
         for (int p = 0; p < NP; p++) v += s.Pd[p] * t_psi[gp * (DIM + 1) + p];
         s.Pgp[gp] = v;
       }
+    }
+    __syncthreads();
+    // ---- phase 4b: per-Gauss-point terms shared by every row/column of the element
+    for (int gp = tid; gp < NGP; gp += TPE) {
+      double *G = s.GP[gp];
+      double v[DIM], vdot[DIM], gv[DIM][DIM];  // gv[a][b] = d_b v_a
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        v[a] = s.F[gp][C::F_V + a][0];
+        vdot[a] = s.F[gp][C::F_V + a][1 + DIM];
+#pragma unroll
+        for (int b = 0; b < DIM; b++) gv[a][b] = s.F[gp][C::F_V + a][1 + b];
+      }
+      const double T = C::ENERGY ? s.F[gp][C::F_T][0] : 0.0;
+      const double Pr = C::P1 ? s.Pgp[gp] : s.F[gp][C::F_P][0];
+      double fs[3], dfdT[3];
+      momentum_source<C>(P, T, fs, dfdT);
+      double div = 0.0;
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        div += gv[a][a];
+        double adv = 0.0;
+#pragma unroll
+        for (int p = 0; p < DIM; p++) adv += v[p] * gv[a][p];
+        // residual, momentum a (mm_fill_momentum.c:534-662): mass + advection + source multiply phi_i
+        G[C::G_RQ + a] = -P.etm_mom[0] * P.rho * vdot[a] - P.etm_mom[1] * P.rho * adv + P.etm_mom[4] * fs[a];
+#pragma unroll
+        for (int p = 0; p < DIM; p++) {
+          // Pi[a][p] = -P delta + mu (d_a v_p + d_p v_a)  (fluid_stress, mm_fill_momentum.c:3268-3271)
+          double Pi = P.mu * (gv[p][a] + gv[a][p]) - (p == a ? Pr : 0.0);
+          G[C::G_RP + a * DIM + p] = -P.etm_mom[3] * Pi;
+          G[C::G_GV + a * DIM + p] = c_adv * gv[a][p];
+        }
+      }
+      G[C::G_DIV] = P.etm_cont[0] * div;
+      if (C::ENERGY) {
+        double adv = 0.0;
+#pragma unroll
+        for (int p = 0; p < DIM; p++) {
+          double gT = s.F[gp][C::F_T][1 + p];
+          adv += v[p] * gT;
+          G[C::G_GT + p] = ce_adv * gT;
+          G[C::G_RF + p] = P.etm_energy[3] * (-P.k * gT);  // + grad_phi_i . q, q = -k grad T
+        }
+        G[C::G_RE] = -P.etm_energy[0] * rcp * s.F[gp][C::F_T][1 + DIM] - P.etm_energy[1] * rcp * adv +
+                     P.etm_energy[4] * P.heat_source;
+      }
+    }
+    for (int idx = tid; idx < NGP * NN; idx += TPE) {
+      int gp = idx / NN, j = idx - gp * NN;
+      double acc = 0.0;
+#pragma unroll
+      for (int p = 0; p < DIM; p++) acc += s.F[gp][C::F_V + p][0] * s.SJ[gp][j][1 + p];
+      s.VG[gp][j] = acc;
     }
     __syncthreads();
 
@@ -330,109 +400,119 @@ __global__ void __launch_bounds__(C::TPE) fill_kernel(const __grid_constant__ Fi
       }
       if (!P.assemble_residual) continue;
       double R = 0.0;
-      for (int gp = 0; gp < NGP; gp++) {
-        const double w = s.w[gp];
-        double v[DIM], gT[DIM];
+      if (prow) {
+        const int p = idx - NF * NN;
+        for (int gp = 0; gp < NGP; gp++) R += s.w[gp] * t_psi[gp * (DIM + 1) + p] * s.GP[gp][C::G_DIV];
+      } else if (f < DIM) {
+        for (int gp = 0; gp < NGP; gp++) {
+          const double *si = s.SI[gp][i], *G = s.GP[gp];
+          double r = si[0] * G[C::G_RQ + f];
 #pragma unroll
-        for (int p = 0; p < DIM; p++) v[p] = s.F[gp][C::F_V + p][0];
-        if (prow) {
-          double div = 0.0;
-#pragma unroll
-          for (int p = 0; p < DIM; p++) div += s.F[gp][C::F_V + p][1 + p];
-          R += P.etm_cont[0] * w * t_psi[gp * (DIM + 1) + (idx - NF * NN)] * div;
-          continue;
+          for (int p = 0; p < DIM; p++) r += si[1 + p] * G[C::G_RP + f * DIM + p];
+          R += r;
         }
-        const double phi_i = t_phi[gp * NN + i];
-        const double *gi = s.G[gp][i];
-        const double T = C::ENERGY ? s.F[gp][C::F_T][0] : 0.0;
-        if (f < DIM) {
-          const int a = f;
-          double adv = 0.0, diff = 0.0;
+      } else if (C::ENERGY && f == C::F_T) {
+        for (int gp = 0; gp < NGP; gp++) {
+          const double *si = s.SI[gp][i], *G = s.GP[gp];
+          double r = si[0] * G[C::G_RE];
 #pragma unroll
-          for (int p = 0; p < DIM; p++) adv += v[p] * s.F[gp][C::F_V + a][1 + p];
-          const double Pr = C::P1 ? s.Pgp[gp] : s.F[gp][C::F_P][0];
-#pragma unroll
-          for (int p = 0; p < DIM; p++) {
-            double Pi = P.mu * (s.F[gp][C::F_V + p][1 + a] + s.F[gp][C::F_V + a][1 + p]) - (p == a ? Pr : 0.0);
-            diff += gi[p] * Pi;
-          }
-          double fs[3], dfdT[3];
-          momentum_source<C>(P, T, fs, dfdT);
-          R += w * (-P.etm_mom[0] * P.rho * phi_i * s.F[gp][C::F_V + a][1 + DIM] - P.etm_mom[1] * P.rho * phi_i * adv -
-                    P.etm_mom[3] * diff + P.etm_mom[4] * phi_i * fs[a]);
-        } else if (C::ENERGY && f == C::F_T) {
-          double adv = 0.0, diff = 0.0;
-#pragma unroll
-          for (int p = 0; p < DIM; p++) {
-            gT[p] = s.F[gp][C::F_T][1 + p];
-            adv += v[p] * gT[p];
-            diff += gi[p] * (-P.k * gT[p]);
-          }
-          const double rcp = P.rho * P.Cp;
-          R += w * (-P.etm_energy[0] * rcp * phi_i * s.F[gp][C::F_T][1 + DIM] - P.etm_energy[1] * rcp * phi_i * adv +
-                    P.etm_energy[3] * diff + P.etm_energy[4] * phi_i * P.heat_source);
+          for (int p = 0; p < DIM; p++) r += si[1 + p] * G[C::G_RF + p];
+          R += r;
         }
       }
       if (P.use_atomics) atomicAdd(&P.resid[gun], R); else P.resid[gun] += R;
     }
 
     if (P.assemble_jacobian) {
-      // ---- phase 6: node-pair blocks, accumulated in registers over the Gauss points
-      const double rcp = P.rho * P.Cp;
-      for (int pr = tid; pr < NN * NN; pr += TPE) {
-        const int i = pr / NN, j = pr - i * NN;
-        double acc[NF][NF];
+      // ---- phase 6: node-pair blocks.  Thread = (row tile of TI nodes, one column node j); the
+      //      TI x 1 tile of DIMxDIM (+energy) blocks is accumulated in registers over the Gauss points.
+      for (int t = tid; t < C::NTILE; t += TPE) {
+        const int it = t / NN, j = t - it * NN, i0 = it * TI;
+        double A[TI][DIM][DIM], S1[TI], S2[TI], S3[TI], ET[TI][DIM];
 #pragma unroll
-        for (int r = 0; r < NF; r++)
-#pragma unroll
-          for (int c = 0; c < NF; c++) acc[r][c] = 0.0;
-        for (int gp = 0; gp < NGP; gp++) {
-          const double w = s.w[gp];
-          const double phi_i = t_phi[gp * NN + i], phi_j = t_phi[gp * NN + j];
-          const double *gi = s.G[gp][i], *gj = s.G[gp][j];
-          double gij = 0.0, vgj = 0.0;
-#pragma unroll
-          for (int p = 0; p < DIM; p++) {
-            gij += gi[p] * gj[p];
-            vgj += s.F[gp][C::F_V + p][0] * gj[p];
-          }
-          const double wphi_i = w * phi_i, pp = wphi_i * phi_j;
-          // J_m_v
-          const double base = -P.etm_mom[1] * P.rho * wphi_i * vgj - P.etm_mom[3] * P.mu * w * gij -
-                              P.etm_mom[0] * P.rho * tfac * pp;
+        for (int ii = 0; ii < TI; ii++) {
+          S1[ii] = S2[ii] = S3[ii] = 0.0;
 #pragma unroll
           for (int a = 0; a < DIM; a++) {
+            ET[ii][a] = 0.0;
 #pragma unroll
-            for (int b = 0; b < DIM; b++) {
-              double t = -P.etm_mom[1] * P.rho * pp * s.F[gp][C::F_V + a][1 + b] -
-                         P.etm_mom[3] * P.mu * w * gi[b] * gj[a];
-              acc[a][b] += (a == b) ? t + base : t;
-            }
-          }
-          if (C::ENERGY) {
-            double fs[3], dfdT[3];
-            momentum_source<C>(P, s.F[gp][C::F_T][0], fs, dfdT);
-#pragma unroll
-            for (int a = 0; a < DIM; a++) {
-              acc[a][C::F_T] += P.etm_mom[4] * pp * dfdT[a];                               // J_m_T
-              acc[C::F_T][a] += -P.etm_energy[1] * rcp * pp * s.F[gp][C::F_T][1 + a];      // J_e_v
-            }
-            acc[C::F_T][C::F_T] += -P.etm_energy[1] * rcp * wphi_i * vgj - P.etm_energy[3] * P.k * w * gij -
-                                   P.etm_energy[0] * rcp * tfac * pp;                      // J_e_T
+            for (int b = 0; b < DIM; b++) A[ii][a][b] = 0.0;
           }
         }
-        // scatter the block through the slot map
+#pragma unroll 1
+        for (int gp = 0; gp < NGP; gp++) {
+          const double2 j01 = *reinterpret_cast<const double2 *>(&s.SJ[gp][j][0]);
+          const double2 j23 = *reinterpret_cast<const double2 *>(&s.SJ[gp][j][2]);
+          const double phi_j = j01.x;
+          const double gj[3] = {j01.y, j23.x, j23.y};
+          const double vgj = s.VG[gp][j];
+          double gjs[DIM], GV[DIM][DIM], GT[DIM];
+          const double *G = s.GP[gp];
 #pragma unroll
-        for (int r = 0; r < NF; r++) {
-          const long long rstart = s.rs[r][i];
-          if (rstart < 0) continue;
-          const int row = s.gun[r][i];
-          const bool rowT = C::ENERGY && r == C::F_T;
+          for (int a = 0; a < DIM; a++) {
+            gjs[a] = c_diff * gj[a];
+            if (C::ENERGY) GT[a] = G[C::G_GT + a];
 #pragma unroll
-          for (int c = 0; c < NF; c++) {
-            if (rowT && !C::P1 && c == C::F_P) continue;  // Inter_Mask: energy rows carry no pressure columns
-            int col_off = P.kind_slot[s.kind[j]][C::slot(c)];
-            mat_add<C>(P, s, rstart, row, elem, i, j, col_off, rowT, acc[r][c]);
+            for (int b = 0; b < DIM; b++) GV[a][b] = G[C::G_GV + a * DIM + b];
+          }
+#pragma unroll
+          for (int ii = 0; ii < TI; ii++) {
+            const double2 i01 = *reinterpret_cast<const double2 *>(&s.SI[gp][i0 + ii][0]);
+            const double2 i23 = *reinterpret_cast<const double2 *>(&s.SI[gp][i0 + ii][2]);
+            const double wphi = i01.x;
+            const double wg[3] = {i01.y, i23.x, i23.y};
+            const double pp = wphi * phi_j;
+            S1[ii] += wphi * vgj;
+            S3[ii] += pp;
+#pragma unroll
+            for (int p = 0; p < DIM; p++) S2[ii] += wg[p] * gj[p];
+#pragma unroll
+            for (int a = 0; a < DIM; a++) {
+#pragma unroll
+              for (int b = 0; b < DIM; b++) {
+                // J_m_v (mm_fill_momentum.c:1629-1712, d_Pi->v :3458-3469):
+                //   -rho phi_i phi_j d_b v_a  - mu grad_phi_i[b] grad_phi_j[a]   (+ delta_ab terms below)
+                A[ii][a][b] += pp * GV[a][b];
+                A[ii][a][b] += wg[b] * gjs[a];
+              }
+              if (C::ENERGY) ET[ii][a] += pp * GT[a];  // J_e_v (mm_fill_energy.c:640)
+            }
+          }
+        }
+        // scatter the tile through the slot map
+        double dfdT[3] = {0.0, 0.0, 0.0};
+        if (C::ENERGY && P.source_model != 0 && P.etm_mom[4] != 0.0) {
+#pragma unroll
+          for (int a = 0; a < DIM; a++) dfdT[a] = -P.g[a] * P.rho * P.beta * P.etm_mom[4];
+        }
+        const int kj = s.kind[j];
+#pragma unroll
+        for (int ii = 0; ii < TI; ii++) {
+          const int i = i0 + ii;
+          const double dm = c_adv * S1[ii] + c_diff * S2[ii] + c_mass * S3[ii];
+#pragma unroll
+          for (int a = 0; a < DIM; a++) {
+            const long long rstart = s.rs[a][i];
+            if (rstart < 0) continue;
+            const int row = s.gun[a][i];
+#pragma unroll
+            for (int b = 0; b < DIM; b++)
+              mat_add<C>(P, s, rstart, row, elem, i, j, P.kind_slot[kj][GOMA_SLOT_U + b], false,
+                         A[ii][a][b] + (a == b ? dm : 0.0));
+            if (C::ENERGY)  // J_m_T (mm_std_models.c:337): phi_i df_a/dT phi_j
+              mat_add<C>(P, s, rstart, row, elem, i, j, P.kind_slot[kj][GOMA_SLOT_T], false, dfdT[a] * S3[ii]);
+          }
+          if (C::ENERGY) {
+            const long long rstart = s.rs[C::F_T][i];
+            if (rstart >= 0) {
+              const int row = s.gun[C::F_T][i];
+#pragma unroll
+              for (int b = 0; b < DIM; b++)
+                mat_add<C>(P, s, rstart, row, elem, i, j, P.kind_slot[kj][GOMA_SLOT_U + b], true, ET[ii][b]);
+              // J_e_T (mm_fill_energy.c:425-487)
+              mat_add<C>(P, s, rstart, row, elem, i, j, P.kind_slot[kj][GOMA_SLOT_T], true,
+                         ce_adv * S1[ii] + ce_diff * S2[ii] + ce_mass * S3[ii]);
+            }
           }
         }
       }
@@ -444,7 +524,7 @@ __global__ void __launch_bounds__(C::TPE) fill_kernel(const __grid_constant__ Fi
           int i = idx / (DIM * NP), r = idx - i * DIM * NP;
           int a = r / NP, p = r - a * NP;
           double S = 0.0;
-          for (int gp = 0; gp < NGP; gp++) S += s.w[gp] * s.G[gp][i][a] * t_psi[gp * (DIM + 1) + p];
+          for (int gp = 0; gp < NGP; gp++) S += s.SI[gp][i][1 + a] * t_psi[gp * (DIM + 1) + p];
           if (s.rs[a][i] >= 0)
             mat_add<C>(P, s, s.rs[a][i], s.gun[a][i], elem, i, C::CEN, poff + p, false, P.etm_mom[3] * S);
           if (s.rsP[p] >= 0)

@@ -49,6 +49,7 @@ struct goma_gpu_ctx {
   int *d_flags = nullptr;
   int *d_elem_list = nullptr;      // colour-ordered element list
   std::vector<int> colour_begin;   // [ncolours+1]
+  int num_sms = 0, blocks_per_sm = 0;  // cached launch geometry (cudaGetDeviceProperties is slow)
   int scatter_mode = 0;            // 0 atomics, 1 coloured
   int grid_limit = 0;
   double last_ms = 0.0;
@@ -95,12 +96,13 @@ int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
   if (p.pspg || !p1) return fail(-2, "equal-order PSPG path not built yet");
   if (p.num_species) return fail(-2, "species path not built yet");
   if (p.elem_type == GOMA_GPU_QUAD9) {
-    k = p.energy ? entry<Cfg<2, 9, 9, true, true, 0, false, 96>>() : entry<Cfg<2, 9, 9, true, false, 0, false, 96>>();
+    k = p.energy ? entry<Cfg<2, 9, 9, true, true, 0, false, 32, 3>>()
+                 : entry<Cfg<2, 9, 9, true, false, 0, false, 32, 3>>();
     return 0;
   }
   if (p.elem_type == GOMA_GPU_HEX27) {
-    k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256>>()
-                 : entry<Cfg<3, 27, 27, true, false, 0, false, 256>>();
+    k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3>>()
+                 : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3>>();
     return 0;
   }
   return fail(-2, "element type / interpolation combination not supported by the GPU fill");
@@ -381,12 +383,12 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
   P.lame_lambda = p.lame_lambda;
   if (p.transient && !(delta_t > 0.0)) return fail(-2, "transient fill needs delta_t > 0");
 
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, c->device));
-  int per_sm = 1;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)ke.fn, ke.tpe, ke.smem));
-  if (per_sm < 1) return fail(-3, "fill kernel does not fit on an SM");
-  int max_grid = prop.multiProcessorCount * per_sm;
+  if (c->num_sms == 0) {
+    CU(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->blocks_per_sm, (const void *)ke.fn, ke.tpe, ke.smem));
+    if (c->blocks_per_sm < 1) return fail(-3, "fill kernel does not fit on an SM");
+  }
+  int max_grid = c->num_sms * c->blocks_per_sm;
   if (c->grid_limit > 0) max_grid = std::min(max_grid, c->grid_limit);
 
   c->last_launches = 0;
