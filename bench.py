@@ -229,6 +229,7 @@ def main():
     ap.add_argument("--n", type=int, default=100, help="elements per direction per GPU (100 -> 1M hex27 elements)")
     ap.add_argument("--energy", action="store_true", help="config C3 physics (NS + energy) instead of C2")
     ap.add_argument("--scatter", type=int, default=0, help="0 fp64 atomics, 1 coloured plain stores")
+    ap.add_argument("--variant", type=int, default=0, help="kernel variant: 0 role-less CTAs, 1 warp-specialised")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -281,6 +282,7 @@ def main():
     x = synthetic_state(problem, 20261017 + rank)
     mf = MatrixFill(problem, device=local_rank)
     mf.set_option("scatter", args.scatter)
+    mf.set_option("kernel_variant", args.variant)
     ne = problem.mesh.num_elems
     n_unk, nnz = mf.num_unknowns, mf.nnz_plus
     t_setup = time.perf_counter() - t_setup

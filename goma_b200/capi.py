@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgoma_gpu_fill.so")
+LIB_PATH = os.environ.get("GOMA_GPU_LIB") or os.path.join(_HERE, "libgoma_gpu_fill.so")
 
 NSLOT = 12
 MAX_KINDS = 4

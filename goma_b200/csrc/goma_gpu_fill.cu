@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -47,11 +48,13 @@ struct goma_gpu_ctx {
   double *d_x = nullptr, *d_x_old = nullptr, *d_x_older = nullptr, *d_xdot = nullptr, *d_xdot_old = nullptr;
   double *d_a = nullptr, *d_resid = nullptr;
   int *d_flags = nullptr;
+  long long *d_prof = nullptr;     // phase cycle counters (GOMA_GPU_PROFILE=1)
   int *d_elem_list = nullptr;      // colour-ordered element list
   std::vector<int> colour_begin;   // [ncolours+1]
   int num_sms = 0, blocks_per_sm = 0;  // cached launch geometry (cudaGetDeviceProperties is slow)
   int scatter_mode = 0;            // 0 atomics, 1 coloured
   int grid_limit = 0;
+  int kernel_variant = 0;          // 0 role-less CTAs, 1 warp-specialised producer/consumer
   double last_ms = 0.0;
   int last_launches = 0;
   size_t device_bytes = 0;
@@ -90,19 +93,23 @@ KernelEntry entry() {
 }
 
 // the instantiated physics/element combinations
-int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
+int pick_kernel(const goma_gpu_problem &p, KernelEntry &k, int variant = 0) {
   const bool p1 = p.pressure_interp == GOMA_PRESSURE_P1;
   if (p.ale) return fail(-2, "ALE (mesh equations) path not built yet");
   if (p.pspg || !p1) return fail(-2, "equal-order PSPG path not built yet");
   if (p.num_species) return fail(-2, "species path not built yet");
   if (p.elem_type == GOMA_GPU_QUAD9) {
-    k = p.energy ? entry<Cfg<2, 9, 9, true, true, 0, false, 32, 3>>()
-                 : entry<Cfg<2, 9, 9, true, false, 0, false, 32, 3>>();
+    k = p.energy ? entry<Cfg<2, 9, 9, true, true, 0, false, 32, 32, 3, false>>()
+                 : entry<Cfg<2, 9, 9, true, false, 0, false, 32, 32, 3, false>>();
     return 0;
   }
   if (p.elem_type == GOMA_GPU_HEX27) {
-    k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3>>()
-                 : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3>>();
+    if (variant == 1)
+      k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 128, 3, true>>()
+                   : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 256, 3, true>>();
+    else
+      k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 256, 3, false>>()
+                   : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 256, 3, false>>();
     return 0;
   }
   return fail(-2, "element type / interpolation combination not supported by the GPU fill");
@@ -237,6 +244,7 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
     return -3;
   }
 
+  if (getenv("GOMA_GPU_PROFILE")) rc |= dalloc(&c->d_prof, 8 * 4096, c);
   std::vector<int> order;
   colour_elements(p, order, c->colour_begin);
   if (upload(&c->d_elem_list, order.data(), order.size(), c)) {
@@ -309,6 +317,16 @@ extern "C" int goma_gpu_fill_set_option(goma_gpu_ctx *c, const char *name, int v
     c->grid_limit = value;
     return 0;
   }
+  if (!strcmp(name, "kernel_variant")) {
+    if (value != 0 && value != 1) return fail(-2, "kernel_variant must be 0 or 1");
+    c->kernel_variant = value;
+    c->num_sms = 0;  // re-derive the launch geometry
+    KernelEntry ke;
+    if (int rc = pick_kernel(c->prob, ke, value)) return rc;
+    if (ke.smem > 48 * 1024)
+      CU(cudaFuncSetAttribute((const void *)ke.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ke.smem));
+    return 0;
+  }
   return fail(-2, std::string("unknown option ") + name);
 }
 
@@ -330,7 +348,7 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
                        double U_norm, int assemble_residual, int assemble_jacobian) {
   const goma_gpu_problem &p = c->prob;
   KernelEntry ke;
-  if (int rc = pick_kernel(p, ke)) return rc;
+  if (int rc = pick_kernel(p, ke, c->kernel_variant)) return rc;
   FillParams P;
   memset(&P, 0, sizeof(P));
   P.conn = c->d_conn;
@@ -381,6 +399,8 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
   P.U_norm = U_norm;
   P.lame_mu = p.lame_mu;
   P.lame_lambda = p.lame_lambda;
+  P.prof = c->d_prof;
+  P.debug = getenv("GOMA_GPU_DEBUG") ? atoi(getenv("GOMA_GPU_DEBUG")) : 0;
   if (p.transient && !(delta_t > 0.0)) return fail(-2, "transient fill needs delta_t > 0");
 
   if (c->num_sms == 0) {
@@ -426,6 +446,20 @@ static int finish_fill(goma_gpu_ctx *c, int flags_out[3]) {
   int h_flags[4] = {0, 0, 0, 0};
   CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  if (c->d_prof) {
+    std::vector<long long> h(8 * 4096);
+    CU(cudaMemcpy(h.data(), c->d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    double s[8] = {0};
+    int nb = 0;
+    for (int b = 0; b < 4096; b++)
+      if (h[b * 8 + 6] > 0) {
+        nb++;
+        for (int k = 0; k < 6; k++) s[k] += (double)h[b * 8 + k] / (double)h[b * 8 + 6];
+      }
+    if (nb)
+      fprintf(stderr, "[goma_gpu profile] cycles/element (mean over %d CTAs): producer wait %.0f build %.0f rows %.0f | "
+                      "consumer wait %.0f work %.0f\n", nb, s[0] / nb, s[1] / nb, s[2] / nb, s[3] / nb, s[4] / nb);
+  }
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->last_ms = ms;
