@@ -228,8 +228,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=100, help="elements per direction per GPU (100 -> 1M hex27 elements)")
     ap.add_argument("--energy", action="store_true", help="config C3 physics (NS + energy) instead of C2")
-    ap.add_argument("--scatter", type=int, default=0, help="0 fp64 atomics, 1 coloured plain stores")
-    ap.add_argument("--variant", type=int, default=0, help="kernel variant: 0 role-less CTAs, 1 warp-specialised")
+    ap.add_argument("--scatter", type=int, default=2,
+                    help="0 fp64 atomics, 1 coloured load+add+store, 2 coloured first-touch stores (default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -282,7 +282,6 @@ def main():
     x = synthetic_state(problem, 20261017 + rank)
     mf = MatrixFill(problem, device=local_rank)
     mf.set_option("scatter", args.scatter)
-    mf.set_option("kernel_variant", args.variant)
     ne = problem.mesh.num_elems
     n_unk, nnz = mf.num_unknowns, mf.nnz_plus
     t_setup = time.perf_counter() - t_setup
@@ -357,7 +356,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "elements_per_gpu": ne, "unknowns_per_gpu": n_unk,
-                       "nnz_per_gpu": nnz, "scatter": "fp64 atomics" if args.scatter == 0 else "coloured stores",
+                       "nnz_per_gpu": nnz, "scatter": ["fp64 atomics", "coloured load+add+store", "coloured first-touch stores"][args.scatter],
                        "l2": "inputs larger than L2 (MSR values %.1f GB per GPU rewritten every step)" % (8e-9 * nnz),
                        "setup_s": round(t_setup, 1)},
             "clocks": clocks, "gpu_launches": launches, "device_ms_per_step": dev_ms,

@@ -1,7 +1,7 @@
-// Element assembly kernel for sm_100a: persistent, warp-specialised CTAs.  Producer warps build the
-// per-element operand tables (geometry, basis gradients, field values, residual) for element n+1
-// into one half of a double-buffered shared-memory arena while consumer warps accumulate and scatter
-// the Jacobian blocks of element n from the other half.
+// Element assembly kernel for sm_100a: persistent CTAs, one element at a time per CTA, several CTAs
+// per SM.  Per element: operand tables (geometry, basis gradients, field values) are built in shared
+// memory, the node-pair Jacobian blocks are accumulated in registers over the Gauss points, staged
+// through shared memory and written out row by row so that a warp covers contiguous matrix slots.
 //
 // What it replaces in the reference, per element (src/mm_fill.c:317 matrix_fill):
 //   BLOCK 1   load_elem_dofptr / load_ei          -> phase 0 gather through prebuilt tables
@@ -38,6 +38,8 @@ struct FillParams {
   const long long *rowstart;
   const unsigned short *pair_full;
   const unsigned short *pair_p;
+  const unsigned *pair_first;  // first-touch masks (write-once scatter)
+  const unsigned *node_first;
   const unsigned char *dbc_flag;
   const double *dbc_value;
   const int *elem_list;  // optional indirection (colour classes); nullptr = identity
@@ -50,7 +52,8 @@ struct FillParams {
   int *flags;
   const double *tables;
   // switches
-  int assemble_residual, assemble_jacobian, transient, use_atomics;
+  int assemble_residual, assemble_jacobian, transient;
+  int scatter_mode;  // 0 fp64 atomics (any order), 1 coloured load+add+store, 2 coloured first-touch stores
   // constants
   double etm_mom[6], etm_cont[2], etm_energy[5], etm_species[5], etm_mesh[5];
   double rho, mu, k, Cp, beta, Tref, heat_source;
@@ -59,23 +62,13 @@ struct FillParams {
   double diffusivity[4];
   double delta_t, theta, time_value, h_elem_avg, U_norm;
   double lame_mu, lame_lambda;
-  long long *prof;  // optional per-CTA phase cycle counters (debug/profiling), 8 per CTA
+  long long *prof;  // optional per-CTA phase cycle counters (profiling build), 8 per CTA
   int debug;        // experiments only: bit0 = drop the matrix stores, bit1 = skip the Gauss loop
 };
 
-template <int DIM_, int NN_, int NGP_, bool P1_, bool ENERGY_, int NSPEC_, bool ALE_, int NCT_, int NPT_, int TI_,
-          bool SPEC_ = true>
+template <int DIM_, int NN_, int NGP_, bool P1_, bool ENERGY_, int NSPEC_, bool ALE_, int TPE_, int TI_, int MINB_>
 struct Cfg {
-  static constexpr int DIM = DIM_, NN = NN_, NGP = NGP_, NSPEC = NSPEC_, TI = TI_;
-  // SPEC: warp-specialised (NPT producer + NCT consumer threads, double-buffered element data);
-  // !SPEC: every thread plays both roles in turn (NCT == NPT == CTA size), several CTAs per SM
-  static constexpr bool SPEC = SPEC_;
-  static constexpr int NCT = NCT_;        // consumer threads (Jacobian tiles + scatter)
-  static constexpr int NPT = NPT_;        // producer threads (everything else)
-  static constexpr int TPE = SPEC ? NCT + NPT : NCT;   // CTA size
-  static constexpr int NBUF = SPEC ? 2 : 1;
-  static constexpr int MINB = SPEC ? 1 : 2;
-  static_assert(SPEC || NCT == NPT, "role-less variant: all threads do everything");
+  static constexpr int DIM = DIM_, NN = NN_, NGP = NGP_, NSPEC = NSPEC_, TI = TI_, TPE = TPE_, MINB = MINB_;
   static constexpr bool P1 = P1_, ENERGY = ENERGY_, ALE = ALE_;
   static constexpr int F_V = 0;
   static constexpr int F_T = DIM;
@@ -87,7 +80,8 @@ struct Cfg {
   static constexpr int CEN = NN == 9 ? 8 : (NN == 27 ? 20 : 0);
   static constexpr int NTILE = (NN / TI) * NN;  // register tiles (TI rows x 1 column of node pairs) per element
   static_assert(NN % TI == 0, "row tile must divide the node count");
-  static_assert(NCT % 32 == 0 && NPT % 32 == 0, "warp-granular roles");
+  static_assert(TPE % 32 == 0, "whole warps");
+  static constexpr int NWARP = TPE / 32;
   static constexpr int TBL = NGP + NGP * NN + NGP * NN * DIM + NGP * (DIM + 1);
   static constexpr int TBL_PAD = (TBL + 1) & ~1;  // 16-byte multiple for the bulk copy
   static constexpr int T_WT = 0, T_PHI = NGP, T_DPHI = T_PHI + NGP * NN, T_PSI = T_DPHI + NGP * NN * DIM;
@@ -100,6 +94,13 @@ struct Cfg {
   static constexpr int G_RF = G_RE + (ENERGY ? 1 : 0);             // e3 q[p]
   static constexpr int G_DIV = G_RF + (ENERGY ? DIM : 0);          // ec0 div v
   static constexpr int GPD = (G_DIV + 1 + 1) & ~1;
+  // staged write-out of the element block: rows (node i, field) x columns (node j in global order, field)
+  static constexpr int NROW = NF * NN, NCOL = NF * NN;
+  static constexpr int CAP = NGP * NN * 9;  // doubles in the operand arena (SI + SJa + SJb + VG), reused as stage
+  static constexpr int TROWS = TI * NF;     // rows owned by one register tile
+  static constexpr int ROWS_PER_PASS = ((CAP / NCOL) / TROWS) * TROWS < NROW ? ((CAP / NCOL) / TROWS) * TROWS : NROW;
+  static_assert(ROWS_PER_PASS >= TROWS, "stage too small for one row tile");
+  static constexpr int NPASS = (NROW + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
   __host__ __device__ static constexpr int slot(int f) {
     return f < DIM                       ? GOMA_SLOT_U + f
            : (ENERGY && f == F_T)        ? GOMA_SLOT_T
@@ -109,31 +110,24 @@ struct Cfg {
   }
 };
 
-// Everything the consumers need about one element; double-buffered.
 template <class C>
-struct alignas(16) ElemBuf {
+struct Operands {
   double SI[C::NGP][C::NN][4];  // (w phi_i, w grad_phi_i[p])   test-function side (read as broadcast)
   // trial-function side (phi_j, grad_phi_j[p]), split in two 16-byte-stride arrays so that the
-  // consumers' per-lane LDS.128 are bank-conflict free
-  double2 SJa[C::NGP][C::NN];   // (phi_j, g_j[0])
-  double2 SJb[C::NGP][C::NN];   // (g_j[1], g_j[2])
-  double VG[C::NGP][C::NN];     // v . grad_phi_j
-  double GP[C::NGP][C::GPD];    // per-Gauss-point derived quantities
-  long long rs[C::NF][C::NN];   // MSR row start of (field,node); -1 = not written here (ghost/Dirichlet)
-  long long rsP[C::NP > 0 ? C::NP : 1];
-  int node[C::NN];
-  int fu[C::NN];
-  int kind[C::NN];
-  int gun[C::NF][C::NN];
-  int elem;
-  int pad_;
+  // per-lane LDS.128 of the Gauss loop are bank-conflict free
+  double2 SJa[C::NGP][C::NN];  // (phi_j, g_j[0])
+  double2 SJb[C::NGP][C::NN];  // (g_j[1], g_j[2])
+  double VG[C::NGP][C::NN];    // v . grad_phi_j
 };
 
 template <class C>
 struct alignas(16) Smem {
   double tbl[C::TBL_PAD];
-  ElemBuf<C> eb[C::NBUF];
-  // producer scratch
+  union {
+    Operands<C> op;
+    double stage[C::CAP];  // element block rows, after the Gauss loop
+  };
+  double GP[C::NGP][C::GPD];            // per-Gauss-point derived quantities
   double F[C::NGP][C::NF][C::DIM + 2];  // value, grad[DIM], time derivative
   double X[C::DIM][C::NN];
   double U[C::NF][C::NN];
@@ -142,8 +136,29 @@ struct alignas(16) Smem {
   double w[C::NGP];
   double B[C::NGP][C::DIM * C::DIM];
   double Pgp[C::NGP];
+  long long rs[C::NF][C::NN];  // MSR row start of (field,node); -1 = not written here (ghost/Dirichlet)
+  long long rsP[C::NP > 0 ? C::NP : 1];
+  int node[C::NN];
+  int fu[C::NN];
+  int kind[C::NN];
+  int gun[C::NF][C::NN];
+  unsigned first[C::NN];  // first-touch mask of row node i over column nodes j
+  unsigned node_first;
+  unsigned short po[C::NN][C::NN];  // slot-map column offsets of the node pairs
+  unsigned short pp[C::ENERGY ? C::NN : 1][C::ENERGY ? C::NN : 1];
+  unsigned char perm[C::NN];           // local nodes in increasing global id
+  unsigned char rank[C::NN];           // inverse of perm
+  unsigned char cs[C::NN][C::NF + 1];  // column offset of field f inside node j (kind_slot lookup)
+  // write-out tables, columns c = (rank of node j in global order, field): slot-map offset of column c
+  // in a row of node i, the pressure-column correction for energy rows, and the first-touch mask
+  // re-ordered to column order
+  unsigned short colbase[C::NN][C::NCOL];
+  unsigned short ppS[C::ENERGY ? C::NN : 1][C::ENERGY ? C::NN : 1];
+  unsigned firstS[C::NN];
   unsigned long long mbar;
 };
+
+static_assert(sizeof(double2) == 16, "double2 layout");
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
   unsigned a = (unsigned)__cvta_generic_to_shared(bar);
@@ -175,38 +190,29 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigne
                "l"(src), "r"(bytes), "r"(b)
                : "memory");
 }
-// named barriers (ids 1..15; 0 is __syncthreads)
-__device__ __forceinline__ void bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void bar_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-// per-role cycle counters: compiled in only with -DGOMA_PROFILE_PHASES (they cost registers)
+
 #ifdef GOMA_PROFILE_PHASES
 #define GOMA_CLOCK() clock64()
 #else
 #define GOMA_CLOCK() 0LL
 #endif
-enum { BAR_FULL0 = 1, BAR_FULL1 = 2, BAR_EMPTY0 = 3, BAR_EMPTY1 = 4, BAR_PROD = 5 };
 
-__device__ __forceinline__ void acc_add(const FillParams &P, double *addr, double val) {
+// One contribution to a matrix / residual slot.  `first` = this element is the first (lowest colour)
+// writer of the slot in this fill: a plain store then replaces zeroing + accumulation.
+__device__ __forceinline__ void slot_add(const FillParams &P, double *addr, double val, bool first) {
   if (P.debug & 1) return;
-  if (P.use_atomics)
-    atomicAdd(addr, val);  // result unused -> RED.E.ADD.F64
-  else
+  if (P.scatter_mode == 2) {
+    // colour-ordered launches: no concurrent writer of this slot exists, so both forms are race-free;
+    // both are fire-and-forget (no load round trip in the issuing warp)
+    if (first)
+      *addr = val;
+    else
+      atomicAdd(addr, val);
+  } else if (P.scatter_mode == 0) {
+    atomicAdd(addr, val);  // result unused -> no-return reduction
+  } else {
     *addr += val;
-}
-
-// One matrix entry through the slot map: row (MSR row start `rowstart`, global id `row`) of local node
-// li, column `col_off` inside local node lj.  `po` = column offset of node lj's first unknown in a row
-// of node li (already net of masked-out pressure columns for energy rows).
-template <class C>
-__device__ __forceinline__ void mat_add(const FillParams &P, const ElemBuf<C> &e, long long rowstart, int row, int lj,
-                                        int po, int col_off, double val) {
-  const int col = e.fu[lj] + col_off;
-  const long long pos = (row == col) ? (long long)row : rowstart + po + col_off - (col > row ? 1 : 0);
-  acc_add(P, &P.a[pos], val);
+  }
 }
 
 // momentum_source_term (mm_fill_momentum.c:3738) CONSTANT branch and bouss_momentum_source
@@ -232,7 +238,7 @@ __device__ __forceinline__ void momentum_source(const FillParams &P, double T, d
 }
 
 // length-N dot product with three independent accumulation chains (hides DFMA latency in the
-// low-parallelism producer phases)
+// low-parallelism set-up phases)
 template <int N>
 __device__ __forceinline__ double dot3(const double *__restrict__ a, int sa, const double *__restrict__ b, int sb) {
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -249,11 +255,21 @@ __device__ __forceinline__ double dot3(const double *__restrict__ a, int sa, con
 }
 
 // =====================================================================================
-// producer: phases 0-5 and 7 for one element, into buffer `e`
+// phases 0-4: gather + operand tables for one element
 // =====================================================================================
+#ifdef GOMA_PROFILE_PHASES
+#define GOMA_STAMP(k) do { long long t_ = clock64(); if (stamps) stamps[k] += t_ - last_; last_ = t_; } while (0)
+#else
+#define GOMA_STAMP(k) do { } while (0)
+#endif
+
 template <class C>
-__device__ __forceinline__ void produce_element(const FillParams &P, Smem<C> &s, ElemBuf<C> &e, int elem, int tid) {
-  constexpr int DIM = C::DIM, NN = C::NN, NGP = C::NGP, NF = C::NF, NP = C::NP, NPT = C::NPT;
+__device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, int elem, int tid, long long *stamps) {
+#ifdef GOMA_PROFILE_PHASES
+  long long last_ = clock64();
+#endif
+  (void)stamps;
+  constexpr int DIM = C::DIM, NN = C::NN, NGP = C::NGP, NF = C::NF, NP = C::NP, NT = C::TPE;
   const double *t_wt = s.tbl + C::T_WT;
   const double *t_phi = s.tbl + C::T_PHI;    // [gp][NN]
   const double *t_dphi = s.tbl + C::T_DPHI;  // [gp][NN][DIM]
@@ -261,40 +277,74 @@ __device__ __forceinline__ void produce_element(const FillParams &P, Smem<C> &s,
   const double rcp = P.rho * P.Cp;
   const double c_adv = -P.etm_mom[1] * P.rho;
   const double ce_adv = -P.etm_energy[1] * rcp;
+  Operands<C> &op = s.op;
 
   // ---- phase 0: connectivity, coordinates, unknown indices, nodal values (load_elem_dofptr)
-  if (tid == 0) e.elem = elem;
-  for (int k = tid; k < NN; k += NPT) {
+  for (int k = tid; k < NN; k += NT) {
     int nd = P.conn[(size_t)elem * NN + k];
-    e.node[k] = nd;
-    e.fu[k] = P.first_unknown[nd];
-    e.kind[k] = P.node_kind[nd];
+    s.node[k] = nd;
+    s.fu[k] = P.first_unknown[nd];
+    s.kind[k] = P.node_kind[nd];
+    s.first[k] = P.pair_first ? P.pair_first[(size_t)elem * NN + k] : 0u;
 #pragma unroll
     for (int d = 0; d < DIM; d++) s.X[d][k] = P.coord[d][nd];
   }
-  bar_sync(BAR_PROD, NPT);
-  for (int idx = tid; idx < NF * NN; idx += NPT) {
+  if (tid == 0) s.node_first = P.node_first ? P.node_first[elem] : 0u;
+  for (int idx = tid; idx < NN * NN; idx += NT) {
+    (&s.po[0][0])[idx] = P.pair_full[(size_t)elem * NN * NN + idx];
+    if (C::ENERGY) (&s.pp[0][0])[idx] = P.pair_p[(size_t)elem * NN * NN + idx];
+  }
+  __syncthreads();
+  GOMA_STAMP(0);
+  for (int idx = tid; idx < NF * NN; idx += NT) {
     int f = idx / NN, k = idx - f * NN;
-    int gun = e.fu[k] + P.kind_slot[e.kind[k]][C::slot(f)];
-    e.gun[f][k] = gun;
+    int cs = P.kind_slot[s.kind[k]][C::slot(f)];
+    s.cs[k][f] = (unsigned char)cs;
+    int gun = s.fu[k] + cs;
+    s.gun[f][k] = gun;
     s.U[f][k] = P.x[gun];
     s.Udot[f][k] = P.transient ? P.xdot[gun] : 0.0;
-    bool owned = e.node[k] < P.num_owned_nodes;
-    e.rs[f][k] = (owned && P.dbc_flag[gun] == 0) ? P.rowstart[gun] : -1;
+    bool owned = s.node[k] < P.num_owned_nodes;
+    s.rs[f][k] = (owned && P.dbc_flag[gun] == 0) ? P.rowstart[gun] : -1;
   }
   if (C::P1 && tid < NP) {
-    int gun = e.fu[C::CEN] + P.kind_slot[e.kind[C::CEN]][GOMA_SLOT_P] + tid;
+    int gun = s.fu[C::CEN] + P.kind_slot[s.kind[C::CEN]][GOMA_SLOT_P] + tid;
     s.Pd[tid] = P.x[gun];
-    bool owned = e.node[C::CEN] < P.num_owned_nodes;
-    e.rsP[tid] = (owned && P.dbc_flag[gun] == 0) ? P.rowstart[gun] : -1;
+    bool owned = s.node[C::CEN] < P.num_owned_nodes;
+    s.rsP[tid] = (owned && P.dbc_flag[gun] == 0) ? P.rowstart[gun] : -1;
+  }
+  if (tid < NN) {  // order of the local nodes by global id = order of their columns inside a matrix row
+    const int me = s.node[tid];
+    int r = 0;
+#pragma unroll
+    for (int k = 0; k < NN; k++) r += s.node[k] < me ? 1 : 0;
+    s.rank[tid] = (unsigned char)r;
+    s.perm[r] = (unsigned char)tid;
   }
   // ---- phase 1: J[a][b] = sum_k x_b,k dphi_k/dxi_a   (beer_belly, mm_fill_util.c:258-276)
-  for (int idx = tid; idx < NGP * DIM * DIM; idx += NPT) {
+  for (int idx = tid; idx < NGP * DIM * DIM; idx += NT) {
     int gp = idx / (DIM * DIM), ab = idx - gp * DIM * DIM;
     int a = ab / DIM, b = ab - a * DIM;
     s.B[gp][ab] = dot3<NN>(s.X[b], 1, &t_dphi[gp * NN * DIM + a], DIM);
   }
-  bar_sync(BAR_PROD, NPT);
+  __syncthreads();
+  GOMA_STAMP(1);
+  // ---- write-out tables in column (global node) order
+  for (int idx = tid; idx < NN * C::NCOL; idx += NT) {
+    const int i = idx / C::NCOL, c = idx - i * C::NCOL;
+    const int js = c / NF, fc = c - js * NF, j = s.perm[js];
+    s.colbase[i][c] = (unsigned short)(s.po[i][j] + s.cs[j][fc]);
+  }
+  for (int idx = tid; idx < NN * NN; idx += NT) {
+    const int i = idx / NN, js = idx - i * NN;
+    if (C::ENERGY) s.ppS[i][js] = s.pp[i][s.perm[js]];
+  }
+  if (tid < NN) {
+    unsigned f = s.first[tid], fs = 0u;
+#pragma unroll
+    for (int js = 0; js < NN; js++) fs |= ((f >> s.perm[js]) & 1u) << js;
+    s.firstS[tid] = fs;
+  }
   // ---- phase 2: detJ, B = J^-1 by cofactors (mm_fill_util.c:386-391, :450-480)
   if (tid < NGP) {
     double *J = s.B[tid];
@@ -324,9 +374,10 @@ __device__ __forceinline__ void produce_element(const FillParams &P, Smem<C> &s,
     }
     s.w[tid] = det * t_wt[tid];  // d_area = detJ * wt * h3, h3 = 1 (Cartesian)
   }
-  bar_sync(BAR_PROD, NPT);
+  __syncthreads();
+  GOMA_STAMP(2);
   // ---- phase 3: grad_phi[i][p] = sum_q B[p][q] dphi_i/dxi_q  (load_bf_grad, mm_fill_util.c:1765-1776)
-  for (int idx = tid; idx < NGP * NN; idx += NPT) {
+  for (int idx = tid; idx < NGP * NN; idx += NT) {
     int gp = idx / NN, i = idx - gp * NN;
     const double *B = s.B[gp];
     const double *dp = &t_dphi[(gp * NN + i) * DIM];
@@ -337,15 +388,16 @@ __device__ __forceinline__ void produce_element(const FillParams &P, Smem<C> &s,
 #pragma unroll
       for (int q = 0; q < DIM; q++) g[p] += B[p * DIM + q] * dp[q];
     }
-    e.SJa[gp][i] = make_double2(ph, g[0]);
-    e.SJb[gp][i] = make_double2(g[1], g[2]);
-    *reinterpret_cast<double2 *>(&e.SI[gp][i][0]) = make_double2(w * ph, w * g[0]);
-    *reinterpret_cast<double2 *>(&e.SI[gp][i][2]) = make_double2(w * g[1], w * g[2]);
+    op.SJa[gp][i] = make_double2(ph, g[0]);
+    op.SJb[gp][i] = make_double2(g[1], g[2]);
+    *reinterpret_cast<double2 *>(&op.SI[gp][i][0]) = make_double2(w * ph, w * g[0]);
+    *reinterpret_cast<double2 *>(&op.SI[gp][i][2]) = make_double2(w * g[1], w * g[2]);
   }
-  bar_sync(BAR_PROD, NPT);
+  __syncthreads();
+  GOMA_STAMP(3);
   // ---- phase 4: field values, gradients, time derivatives at the Gauss points (load_fv, load_fv_grads)
   //      one thread per (Gauss point, field): 2 vector loads + 2 scalar loads feed DIM+2 FMAs per node
-  for (int idx = tid; idx < NGP * NF; idx += NPT) {
+  for (int idx = tid; idx < NGP * NF; idx += NT) {
     int gp = idx / NF, f = idx - gp * NF;
     double val[3] = {0.0, 0.0, 0.0}, dot[3] = {0.0, 0.0, 0.0}, gr[3][3] = {{0.0}};
     constexpr int M = NN / 3;
@@ -354,7 +406,7 @@ __device__ __forceinline__ void produce_element(const FillParams &P, Smem<C> &s,
 #pragma unroll
       for (int c = 0; c < 3; c++) {  // three independent chains
         const int kk = k + c * M;
-        const double2 a = e.SJa[gp][kk], b = e.SJb[gp][kk];
+        const double2 a = op.SJa[gp][kk], b = op.SJb[gp][kk];
         const double u = s.U[f][kk];
         val[c] += u * a.x;
         gr[c][0] += u * a.y;
@@ -365,7 +417,7 @@ __device__ __forceinline__ void produce_element(const FillParams &P, Smem<C> &s,
     }
 #pragma unroll
     for (int kk = 3 * M; kk < NN; kk++) {
-      const double2 a = e.SJa[gp][kk], b = e.SJb[gp][kk];
+      const double2 a = op.SJa[gp][kk], b = op.SJb[gp][kk];
       const double u = s.U[f][kk];
       val[0] += u * a.x;
       gr[0][0] += u * a.y;
@@ -379,17 +431,18 @@ __device__ __forceinline__ void produce_element(const FillParams &P, Smem<C> &s,
     s.F[gp][f][1 + DIM] = (dot[0] + dot[1]) + dot[2];
   }
   if (C::P1) {
-    for (int gp = tid; gp < NGP; gp += NPT) {
+    for (int gp = tid; gp < NGP; gp += NT) {
       double v = 0.0;
 #pragma unroll
       for (int p = 0; p < NP; p++) v += s.Pd[p] * t_psi[gp * (DIM + 1) + p];
       s.Pgp[gp] = v;
     }
   }
-  bar_sync(BAR_PROD, NPT);
+  __syncthreads();
+  GOMA_STAMP(4);
   // ---- phase 4b: per-Gauss-point terms shared by every row/column of the element
-  for (int gp = tid; gp < NGP; gp += NPT) {
-    double *G = e.GP[gp];
+  for (int gp = tid; gp < NGP; gp += NT) {
+    double *G = s.GP[gp];
     double v[DIM], vdot[DIM], gv[DIM][DIM];  // gv[a][b] = d_b v_a
 #pragma unroll
     for (int a = 0; a < DIM; a++) {
@@ -433,37 +486,38 @@ __device__ __forceinline__ void produce_element(const FillParams &P, Smem<C> &s,
                    P.etm_energy[4] * P.heat_source;
     }
   }
-  for (int idx = tid; idx < NGP * NN; idx += NPT) {
+  for (int idx = tid; idx < NGP * NN; idx += NT) {
     int gp = idx / NN, j = idx - gp * NN;
-    const double2 ja = e.SJa[gp][j], jb = e.SJb[gp][j];
+    const double2 ja = op.SJa[gp][j], jb = op.SJb[gp][j];
     const double gj[3] = {ja.y, jb.x, jb.y};
     double acc = 0.0;
 #pragma unroll
     for (int p = 0; p < DIM; p++) acc += s.F[gp][C::F_V + p][0] * gj[p];
-    e.VG[gp][j] = acc;
+    op.VG[gp][j] = acc;
   }
-  // the consumers may start on this buffer now: everything they read is written above
-  __threadfence_block();
-  bar_sync(BAR_PROD, NPT);
+  __syncthreads();
+  GOMA_STAMP(5);
 }
 
-// residual rows + Dirichlet rows (bc_dirich.c:130-140) and the P1 pressure coupling; producer side,
-// runs after the buffer has been handed to the consumers (reads it only)
+// =====================================================================================
+// phases 5 and 7: residual rows + Dirichlet rows (bc_dirich.c:130-140), P1 pressure coupling
+// =====================================================================================
 template <class C>
-__device__ __forceinline__ void produce_rows(const FillParams &P, Smem<C> &s, const ElemBuf<C> &e, int tid) {
-  constexpr int DIM = C::DIM, NN = C::NN, NGP = C::NGP, NF = C::NF, NP = C::NP, NPT = C::NPT;
+__device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, int elem, int tid) {
+  constexpr int DIM = C::DIM, NN = C::NN, NGP = C::NGP, NF = C::NF, NP = C::NP, NT = C::TPE;
   const double *t_psi = s.tbl + C::T_PSI;
-  // ---- phase 5
-  for (int idx = tid; idx < NF * NN + NP; idx += NPT) {
+  const Operands<C> &op = s.op;
+  for (int idx = tid; idx < NF * NN + NP; idx += NT) {
     const bool prow = idx >= NF * NN;  // P1 continuity row
     const int f = prow ? 0 : idx / NN;
     const int i = prow ? C::CEN : idx - f * NN;
-    const int gun = prow ? e.fu[C::CEN] + P.kind_slot[e.kind[C::CEN]][GOMA_SLOT_P] + (idx - NF * NN) : e.gun[f][i];
-    if (e.node[i] >= P.num_owned_nodes) continue;
+    const int gun = prow ? s.fu[C::CEN] + P.kind_slot[s.kind[C::CEN]][GOMA_SLOT_P] + (idx - NF * NN) : s.gun[f][i];
+    if (s.node[i] >= P.num_owned_nodes) continue;
+    const bool first = (s.node_first >> i) & 1u;
     const int dbc = P.dbc_flag[gun];
     if (dbc) {
-      if (P.assemble_residual) acc_add(P, &P.resid[gun], dbc == 1 ? P.x[gun] - P.dbc_value[gun] : 0.0);
-      if (P.assemble_jacobian) acc_add(P, &P.a[gun], 1.0);
+      if (P.assemble_residual) slot_add(P, &P.resid[gun], dbc == 1 ? P.x[gun] - P.dbc_value[gun] : 0.0, first);
+      if (P.assemble_jacobian) slot_add(P, &P.a[gun], 1.0, first);
       continue;
     }
     if (!P.assemble_residual) continue;
@@ -473,11 +527,11 @@ __device__ __forceinline__ void produce_rows(const FillParams &P, Smem<C> &s, co
       double r0 = 0.0, r1 = 0.0, r2 = 0.0;
 #pragma unroll
       for (int gp = 0; gp + 2 < NGP; gp += 3) {
-        r0 += s.w[gp] * t_psi[gp * (DIM + 1) + p] * e.GP[gp][C::G_DIV];
-        r1 += s.w[gp + 1] * t_psi[(gp + 1) * (DIM + 1) + p] * e.GP[gp + 1][C::G_DIV];
-        r2 += s.w[gp + 2] * t_psi[(gp + 2) * (DIM + 1) + p] * e.GP[gp + 2][C::G_DIV];
+        r0 += s.w[gp] * t_psi[gp * (DIM + 1) + p] * s.GP[gp][C::G_DIV];
+        r1 += s.w[gp + 1] * t_psi[(gp + 1) * (DIM + 1) + p] * s.GP[gp + 1][C::G_DIV];
+        r2 += s.w[gp + 2] * t_psi[(gp + 2) * (DIM + 1) + p] * s.GP[gp + 2][C::G_DIV];
       }
-      for (int gp = NGP - NGP % 3; gp < NGP; gp++) r0 += s.w[gp] * t_psi[gp * (DIM + 1) + p] * e.GP[gp][C::G_DIV];
+      for (int gp = NGP - NGP % 3; gp < NGP; gp++) r0 += s.w[gp] * t_psi[gp * (DIM + 1) + p] * s.GP[gp][C::G_DIV];
       R = (r0 + r1) + r2;
     } else {
       const bool isT = C::ENERGY && f == C::F_T;
@@ -486,179 +540,175 @@ __device__ __forceinline__ void produce_rows(const FillParams &P, Smem<C> &s, co
       double r[3] = {0.0, 0.0, 0.0};
 #pragma unroll 3
       for (int gp = 0; gp < NGP; gp++) {
-        const double *si = e.SI[gp][i], *G = e.GP[gp];
-        double t = si[0] * G[q0];
+        const double2 s01 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][0]);
+        const double2 s23 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][2]);
+        const double sg[3] = {s01.y, s23.x, s23.y};
+        const double *G = s.GP[gp];
+        double t = s01.x * G[q0];
 #pragma unroll
-        for (int p = 0; p < DIM; p++) t += si[1 + p] * G[q1 + p];
+        for (int p = 0; p < DIM; p++) t += sg[p] * G[q1 + p];
         r[gp % 3] += t;
       }
       R = (r[0] + r[1]) + r[2];
     }
-    acc_add(P, &P.resid[gun], R);
+    slot_add(P, &P.resid[gun], R, first);
   }
   // ---- phase 7: P1 pressure coupling, S[i][a][p] = sum_gp w grad_phi_i[a] psi_p
-  //      J_m_P (mm_fill_momentum.c:2091-2104) and J_c_v (mm_fill_continuity.c:686-716) share it
+  //      J_m_P (mm_fill_momentum.c:2091-2104) and J_c_v (mm_fill_continuity.c:686-716) share it.
+  //      The centroid node belongs to this element only: these slots have a single writer.
   if (C::P1 && P.assemble_jacobian) {
-    const int elem = e.elem;
-    const int poff = P.kind_slot[e.kind[C::CEN]][GOMA_SLOT_P];
-    for (int idx = tid; idx < NN * DIM * NP; idx += NPT) {
+    const int poff = P.kind_slot[s.kind[C::CEN]][GOMA_SLOT_P];
+    const int ncen = s.node[C::CEN];
+    for (int idx = tid; idx < NN * DIM * NP; idx += NT) {
       int i = idx / (DIM * NP), r = idx - i * DIM * NP;
       int a = r / NP, p = r - a * NP;
-      const double S = dot3<NGP>(&e.SI[0][i][1 + a], NN * 4, &t_psi[p], DIM + 1);
-      if (e.rs[a][i] >= 0) {
-        size_t pq = ((size_t)elem * NN + i) * NN + C::CEN;
-        mat_add<C>(P, e, e.rs[a][i], e.gun[a][i], C::CEN, (int)P.pair_full[pq], poff + p, P.etm_mom[3] * S);
+      const double S = dot3<NGP>(&op.SI[0][i][1 + a], NN * 4, &t_psi[p], DIM + 1);
+      // (row velocity a of node i, column pressure p of the centroid node)
+      if (s.rs[a][i] >= 0) {
+        const int row = s.gun[a][i], col = s.fu[C::CEN] + poff + p;
+        const long long pos = s.rs[a][i] + s.po[i][C::CEN] + poff + p - (col > row ? 1 : 0);
+        slot_add(P, &P.a[pos], P.etm_mom[3] * S, true);
       }
-      if (e.rsP[p] >= 0) {
-        size_t pq = ((size_t)elem * NN + C::CEN) * NN + i;
-        mat_add<C>(P, e, e.rsP[p], e.fu[C::CEN] + poff + p, i, (int)P.pair_full[pq],
-                   P.kind_slot[e.kind[i]][GOMA_SLOT_U + a], P.etm_cont[0] * S);
+      // (row pressure p of the centroid node, column velocity a of node i)
+      if (s.rsP[p] >= 0) {
+        const int row = s.fu[C::CEN] + poff + p, col = s.gun[a][i];
+        const long long pos = s.rsP[p] + s.po[C::CEN][i] + s.cs[i][a] - (col > row ? 1 : 0);
+        slot_add(P, &P.a[pos], P.etm_cont[0] * S, true);
       }
     }
+    (void)ncen;
   }
 }
 
 // =====================================================================================
-// consumer: phase 6, node-pair blocks.  Thread = (row tile of TI nodes, one column node j); the
-// TI x 1 tile of DIMxDIM (+energy) blocks is accumulated in registers over the Gauss points.
+// phase 6: node-pair blocks.  Thread = (row tile of TI nodes, one column node j); the TI x 1 tile of
+// NF x NF blocks is accumulated in registers over the Gauss points, then staged for the write-out.
 // =====================================================================================
 template <class C>
-__device__ __forceinline__ void consume_element(const FillParams &P, const ElemBuf<C> &e, int tid) {
-  constexpr int DIM = C::DIM, NN = C::NN, NGP = C::NGP, TI = C::TI, NCT = C::NCT;
+struct Tile {
+  double V[C::TI][C::NF][C::NF];
+};
+
+template <class C>
+__device__ __forceinline__ void gauss_loop(const FillParams &P, const Smem<C> &s, int i0, int j, Tile<C> &out) {
+  constexpr int DIM = C::DIM, NGP = C::NGP, TI = C::TI;
+  const Operands<C> &op = s.op;
   const double tfac = P.transient ? (1.0 + 2.0 * P.theta) / P.delta_t : 0.0;
   const double rcp = P.rho * P.Cp;
   const double c_adv = -P.etm_mom[1] * P.rho, c_diff = -P.etm_mom[3] * P.mu, c_mass = -P.etm_mom[0] * P.rho * tfac;
   const double ce_adv = -P.etm_energy[1] * rcp, ce_diff = -P.etm_energy[3] * P.k,
                ce_mass = -P.etm_energy[0] * rcp * tfac;
-  const int elem = e.elem;
-  for (int t = tid; t < C::NTILE; t += NCT) {
-    const int it = t / NN, j = t - it * NN, i0 = it * TI;
-    // slot-map offsets of the TI pairs, fetched before the Gauss loop so their latency is hidden
-    int po[TI], pp_[TI];
+  double A[TI][DIM][DIM], S1[TI], S2[TI], S3[TI], ET[TI][DIM];
 #pragma unroll
-    for (int ii = 0; ii < TI; ii++) {
-      size_t pq = ((size_t)elem * NN + i0 + ii) * NN + j;
-      po[ii] = (int)P.pair_full[pq];
-      pp_[ii] = C::ENERGY ? (int)P.pair_p[pq] : 0;
+  for (int ii = 0; ii < TI; ii++) {
+    S1[ii] = S2[ii] = S3[ii] = 0.0;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+      ET[ii][a] = 0.0;
+#pragma unroll
+      for (int b = 0; b < DIM; b++) A[ii][a][b] = 0.0;
     }
-    double A[TI][DIM][DIM], S1[TI], S2[TI], S3[TI], ET[TI][DIM];
-#pragma unroll
-    for (int ii = 0; ii < TI; ii++) {
-      S1[ii] = S2[ii] = S3[ii] = 0.0;
-#pragma unroll
-      for (int a = 0; a < DIM; a++) {
-        ET[ii][a] = 0.0;
-#pragma unroll
-        for (int b = 0; b < DIM; b++) A[ii][a][b] = 0.0;
-      }
-    }
-    const int ngp_run = (P.debug & 2) ? 1 : NGP;
+  }
+  const int ngp_run = (P.debug & 2) ? 1 : NGP;
 #pragma unroll 1
-    for (int gp = 0; gp < ngp_run; gp++) {
-      const double2 j01 = e.SJa[gp][j];
-      const double2 j23 = e.SJb[gp][j];
-      const double phi_j = j01.x;
-      const double gj[3] = {j01.y, j23.x, j23.y};
-      const double vgj = e.VG[gp][j];
-      double gjs[DIM], GV[DIM][DIM], GT[DIM];
-      const double *G = e.GP[gp];
+  for (int gp = 0; gp < ngp_run; gp++) {
+    const double2 j01 = op.SJa[gp][j];
+    const double2 j23 = op.SJb[gp][j];
+    const double phi_j = j01.x;
+    const double gj[3] = {j01.y, j23.x, j23.y};
+    const double vgj = op.VG[gp][j];
+    double gjs[DIM], GV[DIM][DIM], GT[DIM];
+    const double *G = s.GP[gp];
 #pragma unroll
-      for (int a = 0; a < DIM; a++) {
-        gjs[a] = c_diff * gj[a];
-        if (C::ENERGY) GT[a] = G[C::G_GT + a];
+    for (int a = 0; a < DIM; a++) {
+      gjs[a] = c_diff * gj[a];
+      if (C::ENERGY) GT[a] = G[C::G_GT + a];
 #pragma unroll
-        for (int b = 0; b < DIM; b++) GV[a][b] = G[C::G_GV + a * DIM + b];
-      }
-#pragma unroll
-      for (int ii = 0; ii < TI; ii++) {
-        const double2 i01 = *reinterpret_cast<const double2 *>(&e.SI[gp][i0 + ii][0]);
-        const double2 i23 = *reinterpret_cast<const double2 *>(&e.SI[gp][i0 + ii][2]);
-        const double wphi = i01.x;
-        const double wg[3] = {i01.y, i23.x, i23.y};
-        const double pp = wphi * phi_j;
-        S1[ii] += wphi * vgj;
-        S3[ii] += pp;
-#pragma unroll
-        for (int p = 0; p < DIM; p++) S2[ii] += wg[p] * gj[p];
-#pragma unroll
-        for (int a = 0; a < DIM; a++) {
-#pragma unroll
-          for (int b = 0; b < DIM; b++) {
-            // J_m_v (mm_fill_momentum.c:1629-1712, d_Pi->v :3458-3469):
-            //   -rho phi_i phi_j d_b v_a  - mu grad_phi_i[b] grad_phi_j[a]   (+ delta_ab terms below)
-            A[ii][a][b] += pp * GV[a][b];
-            A[ii][a][b] += wg[b] * gjs[a];
-          }
-          if (C::ENERGY) ET[ii][a] += pp * GT[a];  // J_e_v (mm_fill_energy.c:640)
-        }
-      }
+      for (int b = 0; b < DIM; b++) GV[a][b] = G[C::G_GV + a * DIM + b];
     }
-    // ---- scatter the tile through the slot map (load_lec, MSR branch)
-    double dfdT[3] = {0.0, 0.0, 0.0};
-    if (C::ENERGY && P.source_model != 0 && P.etm_mom[4] != 0.0) {
-#pragma unroll
-      for (int a = 0; a < DIM; a++) dfdT[a] = -P.g[a] * P.rho * P.beta * P.etm_mom[4];
-    }
-    const int kj = e.kind[j];
-    const int colU = P.kind_slot[kj][GOMA_SLOT_U];  // velocity components are contiguous in a node
-    const int colT = C::ENERGY ? P.kind_slot[kj][GOMA_SLOT_T] : 0;
 #pragma unroll
     for (int ii = 0; ii < TI; ii++) {
-      const int i = i0 + ii;
-      const double dm = c_adv * S1[ii] + c_diff * S2[ii] + c_mass * S3[ii];
-      if (i != j) {
-        // distinct nodes: no diagonal inside the block, one shift for the whole block
-        const int sh = e.node[j] > e.node[i] ? 1 : 0;
+      const double2 i01 = *reinterpret_cast<const double2 *>(&op.SI[gp][i0 + ii][0]);
+      const double2 i23 = *reinterpret_cast<const double2 *>(&op.SI[gp][i0 + ii][2]);
+      const double wphi = i01.x;
+      const double wg[3] = {i01.y, i23.x, i23.y};
+      const double pp = wphi * phi_j;
+      S1[ii] += wphi * vgj;
+      S3[ii] += pp;
 #pragma unroll
-        for (int a = 0; a < DIM; a++) {
-          const long long rstart = e.rs[a][i];
-          if (rstart < 0) continue;
-          double *base = &P.a[rstart + po[ii] - sh];
+      for (int p = 0; p < DIM; p++) S2[ii] += wg[p] * gj[p];
 #pragma unroll
-          for (int b = 0; b < DIM; b++) acc_add(P, base + colU + b, A[ii][a][b] + (a == b ? dm : 0.0));
-          if (C::ENERGY) acc_add(P, base + colT, dfdT[a] * S3[ii]);  // J_m_T (mm_std_models.c:337)
+      for (int a = 0; a < DIM; a++) {
+#pragma unroll
+        for (int b = 0; b < DIM; b++) {
+          // J_m_v (mm_fill_momentum.c:1629-1712, d_Pi->v :3458-3469):
+          //   -rho phi_i phi_j d_b v_a  - mu grad_phi_i[b] grad_phi_j[a]   (+ delta_ab terms below)
+          A[ii][a][b] += pp * GV[a][b];
+          A[ii][a][b] += wg[b] * gjs[a];
         }
-        if (C::ENERGY) {
-          const long long rstart = e.rs[C::F_T][i];
-          if (rstart >= 0) {
-            double *base = &P.a[rstart + po[ii] - pp_[ii] - sh];
-#pragma unroll
-            for (int b = 0; b < DIM; b++) acc_add(P, base + colU + b, ET[ii][b]);
-            acc_add(P, base + colT, ce_adv * S1[ii] + ce_diff * S2[ii] + ce_mass * S3[ii]);  // J_e_T
-          }
-        }
-      } else {
-#pragma unroll
-        for (int a = 0; a < DIM; a++) {
-          const long long rstart = e.rs[a][i];
-          if (rstart < 0) continue;
-          const int row = e.gun[a][i];
-#pragma unroll
-          for (int b = 0; b < DIM; b++)
-            mat_add<C>(P, e, rstart, row, j, po[ii], colU + b, A[ii][a][b] + (a == b ? dm : 0.0));
-          if (C::ENERGY) mat_add<C>(P, e, rstart, row, j, po[ii], colT, dfdT[a] * S3[ii]);
-        }
-        if (C::ENERGY) {
-          const long long rstart = e.rs[C::F_T][i];
-          if (rstart >= 0) {
-            const int row = e.gun[C::F_T][i];
-#pragma unroll
-            for (int b = 0; b < DIM; b++) mat_add<C>(P, e, rstart, row, j, po[ii] - pp_[ii], colU + b, ET[ii][b]);
-            mat_add<C>(P, e, rstart, row, j, po[ii] - pp_[ii], colT,
-                       ce_adv * S1[ii] + ce_diff * S2[ii] + ce_mass * S3[ii]);
-          }
-        }
+        if (C::ENERGY) ET[ii][a] += pp * GT[a];  // J_e_v (mm_fill_energy.c:640)
       }
+    }
+  }
+  double dfdT[3] = {0.0, 0.0, 0.0};
+  if (C::ENERGY && P.source_model != 0 && P.etm_mom[4] != 0.0) {
+#pragma unroll
+    for (int a = 0; a < DIM; a++) dfdT[a] = -P.g[a] * P.rho * P.beta * P.etm_mom[4];
+  }
+#pragma unroll
+  for (int ii = 0; ii < TI; ii++) {
+    const double dm = c_adv * S1[ii] + c_diff * S2[ii] + c_mass * S3[ii];
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+#pragma unroll
+      for (int b = 0; b < DIM; b++) out.V[ii][a][b] = A[ii][a][b] + (a == b ? dm : 0.0);
+      if (C::ENERGY) {
+        out.V[ii][a][C::F_T] = dfdT[a] * S3[ii];  // J_m_T (mm_std_models.c:337)
+        out.V[ii][C::F_T][a] = ET[ii][a];
+      }
+    }
+    if (C::ENERGY) out.V[ii][C::F_T][C::F_T] = ce_adv * S1[ii] + ce_diff * S2[ii] + ce_mass * S3[ii];  // J_e_T
+  }
+}
+
+// write-out of staged rows [r0, r1): a warp walks one row, lanes along the columns in matrix order
+template <class C>
+__device__ __forceinline__ void write_rows(const FillParams &P, const Smem<C> &s, int r0, int r1, int tid) {
+  constexpr int NF = C::NF, NCOL = C::NCOL;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int r = r0 + warp; r < r1; r += C::NWARP) {
+    const int i = r / NF, fr = r - i * NF;
+    const long long rstart = s.rs[fr][i];
+    if (rstart < 0) continue;  // Dirichlet or ghost row: nothing is loaded (load_lec, mm_fill.c:5374)
+    const int row = s.gun[fr][i], rank_i = s.rank[i];
+    const unsigned first = s.firstS[i];
+    const bool rowT = C::ENERGY && fr == C::F_T;
+    const double *src = &s.stage[(r - r0) * NCOL];
+    double *arow = P.a + rstart;
+#pragma unroll
+    for (int c0 = 0; c0 < NCOL; c0 += 32) {
+      const int c = c0 + lane;
+      if (c >= NCOL) break;
+      const int js = c / NF, fc = c - js * NF;
+      if (rowT && !C::P1 && fc == C::F_P) continue;  // Inter_Mask: energy rows carry no pressure columns
+      int off = s.colbase[i][c];
+      if (C::ENERGY && rowT) off -= s.ppS[i][js];
+      double *dst;
+      if (js != rank_i)
+        dst = arow + off - (js > rank_i ? 1 : 0);  // columns are sorted by node: one shift past the diagonal node
+      else
+        dst = (fc == fr) ? P.a + row : arow + off - (fc > fr ? 1 : 0);
+      slot_add(P, dst, src[c], (first >> js) & 1u);
     }
   }
 }
 
 template <class C>
 __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_constant__ FillParams P) {
+  constexpr int NN = C::NN, NF = C::NF, TI = C::TI, NCOL = C::NCOL, NT = C::TPE;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<C> &s = *reinterpret_cast<Smem<C> *>(smem_raw);
   const int tid = threadIdx.x;
-  constexpr int NT = C::TPE;
 
   // ---- stage the quadrature/basis tables once per CTA with a TMA bulk copy
   if (tid == 0) {
@@ -672,71 +722,58 @@ __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_cons
   }
   mbar_wait(&s.mbar, 0);
 
-  // elements of this CTA: ee = elem_begin + blockIdx.x + n * gridDim.x
-  const int first = P.elem_begin + blockIdx.x;
-  const int count = first < P.elem_end ? (P.elem_end - first + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-
-  if (!C::SPEC) {
-    // ---- role-less variant: the CTA walks producer and consumer work in turn
-    long long t_elem = 0, t_cons = 0, t_rows = 0;
-    for (int n = 0; n < count; n++) {
-      const int ee = first + n * (int)gridDim.x;
-      const int elem = P.elem_list ? P.elem_list[ee] : ee;
-      long long c0 = GOMA_CLOCK();
-      produce_element<C>(P, s, s.eb[0], elem, tid);
-      long long c1 = GOMA_CLOCK();
-      if (P.assemble_jacobian) consume_element<C>(P, s.eb[0], tid);
-      long long c2 = GOMA_CLOCK();
-      produce_rows<C>(P, s, s.eb[0], tid);
-      bar_sync(BAR_PROD, NT);
+  long long t_build = 0, t_rows = 0, t_loop = 0, t_write = 0;
+  long long stamps_[6] = {0, 0, 0, 0, 0, 0};
+  long long *stamps = (P.prof && tid == 0) ? stamps_ : nullptr;
+  int count = 0;
+  for (int ee = P.elem_begin + blockIdx.x; ee < P.elem_end; ee += gridDim.x, count++) {
+    const int elem = P.elem_list ? P.elem_list[ee] : ee;
+    long long c0 = GOMA_CLOCK();
+    build_element<C>(P, s, elem, tid, stamps);
+    long long c1 = GOMA_CLOCK();
+    element_rows<C>(P, s, elem, tid);
+    long long c2 = GOMA_CLOCK();
+    if (P.assemble_jacobian) {
+      // one register tile per thread (NTILE <= TPE for every instantiated configuration)
+      Tile<C> tile;
+      const bool active = tid < C::NTILE;
+      const int it = active ? tid / NN : 0, j = active ? tid - it * NN : 0, i0 = it * TI;
+      if (active) gauss_loop<C>(P, s, i0, j, tile);
       long long c3 = GOMA_CLOCK();
-      t_elem += c1 - c0; t_cons += c2 - c1; t_rows += c3 - c2;
+      t_loop += c3 - c2;
+      __syncthreads();  // every thread is done reading the operand arena: it becomes the stage
+#pragma unroll 1
+      for (int pass = 0; pass < C::NPASS; pass++) {
+        const int r0 = pass * C::ROWS_PER_PASS;
+        const int r1 = r0 + C::ROWS_PER_PASS < C::NROW ? r0 + C::ROWS_PER_PASS : C::NROW;
+        if (active && i0 * NF >= r0 && i0 * NF < r1) {
+          const int cj = s.rank[j] * NF;
+#pragma unroll
+          for (int ii = 0; ii < TI; ii++)
+#pragma unroll
+            for (int fr = 0; fr < NF; fr++)
+#pragma unroll
+              for (int fc = 0; fc < NF; fc++)
+                s.stage[((i0 + ii) * NF + fr - r0) * NCOL + cj + fc] = tile.V[ii][fr][fc];
+        }
+        __syncthreads();
+        write_rows<C>(P, s, r0, r1, tid);
+        __syncthreads();
+      }
+      t_write += GOMA_CLOCK() - c3;
+    } else {
+      __syncthreads();
     }
-    if (P.prof && tid == 0) {
-      P.prof[blockIdx.x * 8 + 1] = t_elem; P.prof[blockIdx.x * 8 + 2] = t_rows; P.prof[blockIdx.x * 8 + 4] = t_cons;
-      P.prof[blockIdx.x * 8 + 0] = 0; P.prof[blockIdx.x * 8 + 3] = 0; P.prof[blockIdx.x * 8 + 6] = count;
-    }
-    return;
+    t_build += c1 - c0;
+    t_rows += c2 - c1;
   }
-
-  if (tid >= C::NCT) {
-    // ================= producer warps =================
-    const int ptid = tid - C::NCT;
-    long long t_wait = 0, t_elem = 0, t_rows = 0;
-    for (int n = 0; n < count; n++) {
-      const int b = n & 1;
-      const int ee = first + n * (int)gridDim.x;
-      const int elem = P.elem_list ? P.elem_list[ee] : ee;
-      long long c0 = GOMA_CLOCK();
-      if (n >= 2) bar_sync(BAR_EMPTY0 + b, NT);  // consumers are done with what was in this buffer
-      long long c1 = GOMA_CLOCK();
-      produce_element<C>(P, s, s.eb[b & (C::NBUF - 1)], elem, ptid);
-      bar_arrive(BAR_FULL0 + b, NT);
-      long long c2 = GOMA_CLOCK();
-      produce_rows<C>(P, s, s.eb[b & (C::NBUF - 1)], ptid);
-      bar_sync(BAR_PROD, C::NPT);  // scratch (w, F, ...) is reused by the next element
-      long long c3 = GOMA_CLOCK();
-      t_wait += c1 - c0; t_elem += c2 - c1; t_rows += c3 - c2;
-    }
-    if (P.prof && ptid == 0) {
-      P.prof[blockIdx.x * 8 + 0] = t_wait; P.prof[blockIdx.x * 8 + 1] = t_elem; P.prof[blockIdx.x * 8 + 2] = t_rows;
-      P.prof[blockIdx.x * 8 + 6] = count;
-    }
-  } else {
-    // ================= consumer warps =================
-    long long t_wait = 0, t_work = 0;
-    for (int n = 0; n < count; n++) {
-      const int b = n & 1;
-      long long c0 = GOMA_CLOCK();
-      bar_sync(BAR_FULL0 + b, NT);
-      long long c1 = GOMA_CLOCK();
-      if (P.assemble_jacobian) consume_element<C>(P, s.eb[b & (C::NBUF - 1)], tid);
-      if (n + 2 < count) bar_arrive(BAR_EMPTY0 + b, NT);
-      long long c2 = GOMA_CLOCK();
-      t_wait += c1 - c0; t_work += c2 - c1;
-    }
-    if (P.prof && tid == 0) { P.prof[blockIdx.x * 8 + 3] = t_wait; P.prof[blockIdx.x * 8 + 4] = t_work; }
+  if (P.prof && tid == 0 && count) {
+    long long *o = P.prof + blockIdx.x * 8;
+    o[0] = t_build; o[1] = t_rows; o[2] = t_loop; o[3] = t_write; o[6] = count;
+    long long *o2 = P.prof + (4096 + blockIdx.x) * 8;
+    for (int k = 0; k < 6; k++) o2[k] = stamps_[k];
   }
+  (void)NT;
 }
 
 }  // namespace goma_b200

@@ -44,6 +44,7 @@ struct goma_gpu_ctx {
   double *d_dbc_value = nullptr;
   long long *d_rowstart = nullptr;
   unsigned short *d_pair_full = nullptr, *d_pair_p = nullptr;
+  unsigned *d_pair_first = nullptr, *d_node_first = nullptr;
   double *d_tables = nullptr;
   double *d_x = nullptr, *d_x_old = nullptr, *d_x_older = nullptr, *d_xdot = nullptr, *d_xdot_old = nullptr;
   double *d_a = nullptr, *d_resid = nullptr;
@@ -52,9 +53,8 @@ struct goma_gpu_ctx {
   int *d_elem_list = nullptr;      // colour-ordered element list
   std::vector<int> colour_begin;   // [ncolours+1]
   int num_sms = 0, blocks_per_sm = 0;  // cached launch geometry (cudaGetDeviceProperties is slow)
-  int scatter_mode = 0;            // 0 atomics, 1 coloured
+  int scatter_mode = 2;            // 0 fp64 atomics, 1 coloured load+add+store, 2 coloured first-touch stores
   int grid_limit = 0;
-  int kernel_variant = 0;          // 0 role-less CTAs, 1 warp-specialised producer/consumer
   double last_ms = 0.0;
   int last_launches = 0;
   size_t device_bytes = 0;
@@ -93,23 +93,20 @@ KernelEntry entry() {
 }
 
 // the instantiated physics/element combinations
-int pick_kernel(const goma_gpu_problem &p, KernelEntry &k, int variant = 0) {
+//                      DIM NN NGP  P1    ENERGY NSPEC ALE  TPE TI MINB
+int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
   const bool p1 = p.pressure_interp == GOMA_PRESSURE_P1;
   if (p.ale) return fail(-2, "ALE (mesh equations) path not built yet");
   if (p.pspg || !p1) return fail(-2, "equal-order PSPG path not built yet");
   if (p.num_species) return fail(-2, "species path not built yet");
   if (p.elem_type == GOMA_GPU_QUAD9) {
-    k = p.energy ? entry<Cfg<2, 9, 9, true, true, 0, false, 32, 32, 3, false>>()
-                 : entry<Cfg<2, 9, 9, true, false, 0, false, 32, 32, 3, false>>();
+    k = p.energy ? entry<Cfg<2, 9, 9, true, true, 0, false, 32, 3, 8>>()
+                 : entry<Cfg<2, 9, 9, true, false, 0, false, 32, 3, 8>>();
     return 0;
   }
   if (p.elem_type == GOMA_GPU_HEX27) {
-    if (variant == 1)
-      k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 128, 3, true>>()
-                   : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 256, 3, true>>();
-    else
-      k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 256, 3, false>>()
-                   : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 256, 3, false>>();
+    k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 1>>()
+                 : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2>>();
     return 0;
   }
   return fail(-2, "element type / interpolation combination not supported by the GPU fill");
@@ -134,29 +131,6 @@ static int validate(const goma_gpu_problem &p) {
     return fail(-2, "P1 pressure needs a centroid node (QUAD9/HEX27)");
   if (p.num_owned_nodes < 0 || p.num_owned_nodes > p.num_nodes) return fail(-2, "num_owned_nodes out of range");
   return 0;
-}
-
-// greedy element colouring: no two elements of a colour share a node (conflict-free plain stores)
-static void colour_elements(const goma_gpu_problem &p, std::vector<int> &order, std::vector<int> &begin) {
-  const int ne = p.num_elems, npe = p.elem_type;
-  std::vector<unsigned long long> node_mask(p.num_nodes, 0ull);
-  std::vector<int> colour(ne);
-  int ncol = 0;
-  for (int e = 0; e < ne; e++) {
-    unsigned long long used = 0;
-    for (int k = 0; k < npe; k++) used |= node_mask[p.elem_connect[(size_t)e * npe + k]];
-    int c = 0;
-    while (c < 63 && (used >> c) & 1ull) c++;
-    colour[e] = c;
-    ncol = std::max(ncol, c + 1);
-    for (int k = 0; k < npe; k++) node_mask[p.elem_connect[(size_t)e * npe + k]] |= 1ull << c;
-  }
-  begin.assign(ncol + 1, 0);
-  for (int e = 0; e < ne; e++) begin[colour[e] + 1]++;
-  for (int c = 0; c < ncol; c++) begin[c + 1] += begin[c];
-  order.resize(ne);
-  std::vector<int> fill(begin.begin(), begin.end() - 1);
-  for (int e = 0; e < ne; e++) order[fill[colour[e]]++] = e;
 }
 
 extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, goma_gpu_ctx **out) {
@@ -213,6 +187,10 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
   rc |= upload(&c->d_rowstart, (const long long *)c->pat.rowstart.data(), (size_t)N + 1, c);
   rc |= upload(&c->d_pair_full, (const unsigned short *)c->pat.pair_full.data(), c->pat.pair_full.size(), c);
   rc |= upload(&c->d_pair_p, (const unsigned short *)c->pat.pair_p.data(), c->pat.pair_p.size(), c);
+  rc |= upload(&c->d_pair_first, (const unsigned *)c->pat.pair_first.data(), c->pat.pair_first.size(), c);
+  rc |= upload(&c->d_node_first, (const unsigned *)c->pat.node_first.data(), c->pat.node_first.size(), c);
+  rc |= upload(&c->d_elem_list, c->pat.colour_order.data(), c->pat.colour_order.size(), c);
+  c->colour_begin = c->pat.colour_begin;
   if (rc) {
     goma_gpu_fill_destroy(c);
     return -3;
@@ -220,6 +198,9 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
   // pair tables live on the device from here on
   std::vector<uint16_t>().swap(c->pat.pair_full);
   std::vector<uint16_t>().swap(c->pat.pair_p);
+  std::vector<uint32_t>().swap(c->pat.pair_first);
+  std::vector<uint32_t>().swap(c->pat.node_first);
+  std::vector<int>().swap(c->pat.colour_order);
 
   // quadrature / basis tables, packed in the order Smem<C>::tbl expects
   ElemTables t = make_tables(p.elem_type);
@@ -244,13 +225,7 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
     return -3;
   }
 
-  if (getenv("GOMA_GPU_PROFILE")) rc |= dalloc(&c->d_prof, 8 * 4096, c);
-  std::vector<int> order;
-  colour_elements(p, order, c->colour_begin);
-  if (upload(&c->d_elem_list, order.data(), order.size(), c)) {
-    goma_gpu_fill_destroy(c);
-    return -3;
-  }
+  if (getenv("GOMA_GPU_PROFILE")) rc |= dalloc(&c->d_prof, 2 * 8 * 4096, c);
   if (ke.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute((const void *)ke.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ke.smem);
     if (e != cudaSuccess) {
@@ -266,7 +241,7 @@ extern "C" void goma_gpu_fill_destroy(goma_gpu_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   void *ptrs[] = {c->d_conn, c->d_first, c->d_coord[0], c->d_coord[1], c->d_coord[2], c->d_kind, c->d_dbc_flag,
-                  c->d_dbc_value, c->d_rowstart, c->d_pair_full, c->d_pair_p, c->d_tables, c->d_x, c->d_x_old,
+                  c->d_dbc_value, c->d_rowstart, c->d_pair_full, c->d_pair_p, c->d_pair_first, c->d_node_first, c->d_prof, c->d_tables, c->d_x, c->d_x_old,
                   c->d_x_older, c->d_xdot, c->d_xdot_old, c->d_a, c->d_resid, c->d_flags, c->d_elem_list};
   for (void *q : ptrs)
     if (q) cudaFree(q);
@@ -309,22 +284,12 @@ extern "C" int goma_gpu_pattern_msr(const goma_gpu_problem *p, long long *nnz_pl
 extern "C" int goma_gpu_fill_set_option(goma_gpu_ctx *c, const char *name, int value) {
   if (!c || !name) return fail(-2, "null argument");
   if (!strcmp(name, "scatter")) {
-    if (value != 0 && value != 1) return fail(-2, "scatter must be 0 (atomic) or 1 (coloured)");
+    if (value < 0 || value > 2) return fail(-2, "scatter must be 0 (atomic), 1 (coloured) or 2 (first-touch)");
     c->scatter_mode = value;
     return 0;
   }
   if (!strcmp(name, "grid_limit")) {
     c->grid_limit = value;
-    return 0;
-  }
-  if (!strcmp(name, "kernel_variant")) {
-    if (value != 0 && value != 1) return fail(-2, "kernel_variant must be 0 or 1");
-    c->kernel_variant = value;
-    c->num_sms = 0;  // re-derive the launch geometry
-    KernelEntry ke;
-    if (int rc = pick_kernel(c->prob, ke, value)) return rc;
-    if (ke.smem > 48 * 1024)
-      CU(cudaFuncSetAttribute((const void *)ke.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ke.smem));
     return 0;
   }
   return fail(-2, std::string("unknown option ") + name);
@@ -348,7 +313,7 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
                        double U_norm, int assemble_residual, int assemble_jacobian) {
   const goma_gpu_problem &p = c->prob;
   KernelEntry ke;
-  if (int rc = pick_kernel(p, ke, c->kernel_variant)) return rc;
+  if (int rc = pick_kernel(p, ke)) return rc;
   FillParams P;
   memset(&P, 0, sizeof(P));
   P.conn = c->d_conn;
@@ -359,6 +324,8 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
   P.rowstart = c->d_rowstart;
   P.pair_full = c->d_pair_full;
   P.pair_p = c->d_pair_p;
+  P.pair_first = c->d_pair_first;
+  P.node_first = c->d_node_first;
   P.dbc_flag = c->d_dbc_flag;
   P.dbc_value = c->d_dbc_value;
   P.num_owned_nodes = p.num_owned_nodes;
@@ -414,10 +381,14 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
   c->last_launches = 0;
   CU(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int), c->stream));
   CU(cudaEventRecord(c->ev0, c->stream));
-  if (assemble_residual) CU(cudaMemsetAsync(c->d_resid, 0, (size_t)p.num_unknowns * sizeof(double), c->stream));
-  if (assemble_jacobian) CU(cudaMemsetAsync(c->d_a, 0, ((size_t)c->pat.nnz_plus + 1) * sizeof(double), c->stream));
+  P.scatter_mode = c->scatter_mode;
+  if (c->scatter_mode != 2) {
+    // accumulate-into semantics need zeroed storage; the first-touch mode overwrites every slot the
+    // elements touch and never writes the others (zeroed once at init), so it needs no memset
+    if (assemble_residual) CU(cudaMemsetAsync(c->d_resid, 0, (size_t)p.num_unknowns * sizeof(double), c->stream));
+    if (assemble_jacobian) CU(cudaMemsetAsync(c->d_a, 0, ((size_t)c->pat.nnz_plus + 1) * sizeof(double), c->stream));
+  }
   if (c->scatter_mode == 0) {
-    P.use_atomics = 1;
     P.elem_list = nullptr;
     P.elem_begin = 0;
     P.elem_end = p.num_elems;
@@ -425,7 +396,7 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
     ke.fn<<<grid, ke.tpe, ke.smem, c->stream>>>(P);
     c->last_launches++;
   } else {
-    P.use_atomics = 0;
+    // colour classes in increasing order, one launch each: stream order is the inter-colour barrier
     P.elem_list = c->d_elem_list;
     for (size_t col = 0; col + 1 < c->colour_begin.size(); col++) {
       P.elem_begin = c->colour_begin[col];
@@ -447,18 +418,22 @@ static int finish_fill(goma_gpu_ctx *c, int flags_out[3]) {
   CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (c->d_prof) {
-    std::vector<long long> h(8 * 4096);
+    std::vector<long long> h(2 * 8 * 4096);
     CU(cudaMemcpy(h.data(), c->d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    double s[8] = {0};
+    double s[8] = {0}, s2[8] = {0};
     int nb = 0;
     for (int b = 0; b < 4096; b++)
       if (h[b * 8 + 6] > 0) {
         nb++;
         for (int k = 0; k < 6; k++) s[k] += (double)h[b * 8 + k] / (double)h[b * 8 + 6];
+        for (int k = 0; k < 6; k++) s2[k] += (double)h[(4096 + b) * 8 + k] / (double)h[b * 8 + 6];
       }
     if (nb)
-      fprintf(stderr, "[goma_gpu profile] cycles/element (mean over %d CTAs): producer wait %.0f build %.0f rows %.0f | "
-                      "consumer wait %.0f work %.0f\n", nb, s[0] / nb, s[1] / nb, s[2] / nb, s[3] / nb, s[4] / nb);
+      fprintf(stderr, "[goma_gpu profile] build split: gather0 %.0f gather1+J %.0f tables+inv %.0f grads %.0f fields %.0f gp+vg %.0f\n",
+              s2[0] / nb, s2[1] / nb, s2[2] / nb, s2[3] / nb, s2[4] / nb, s2[5] / nb);
+    if (nb)
+      fprintf(stderr, "[goma_gpu profile] cycles/element/CTA (mean over %d CTAs of the last launch): build %.0f rows %.0f "
+                      "gauss loop %.0f stage+write %.0f\n", nb, s[0] / nb, s[1] / nb, s[2] / nb, s[3] / nb);
   }
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));

@@ -193,6 +193,59 @@ std::string build_pattern(const goma_gpu_problem &p, Pattern &out, int num_threa
     }
   });
   if (missing) return "Could not find vbl in sparse matrix";  // mm_fill.c:5462 wording
+
+  // ---- greedy colouring in element order (structured hex meshes: 8 colours, quads: 4)
+  std::vector<int> colour(ne);
+  {
+    std::vector<unsigned long long> node_mask(nn, 0ull);
+    int ncol = 0;
+    for (int e = 0; e < ne; e++) {
+      unsigned long long used = 0;
+      for (int k = 0; k < npe; k++) used |= node_mask[conn[(int64_t)e * npe + k]];
+      int c = 0;
+      while (c < 63 && ((used >> c) & 1ull)) c++;
+      if (c >= 63) return "element colouring needs more than 63 colours";
+      colour[e] = c;
+      ncol = std::max(ncol, c + 1);
+      for (int k = 0; k < npe; k++) node_mask[conn[(int64_t)e * npe + k]] |= 1ull << c;
+    }
+    out.colour_begin.assign(ncol + 1, 0);
+    for (int e = 0; e < ne; e++) out.colour_begin[colour[e] + 1]++;
+    for (int c = 0; c < ncol; c++) out.colour_begin[c + 1] += out.colour_begin[c];
+    out.colour_order.resize(ne);
+    std::vector<int> fill(out.colour_begin.begin(), out.colour_begin.end() - 1);
+    for (int e = 0; e < ne; e++) out.colour_order[fill[colour[e]]++] = e;
+  }
+  // ---- first-touch masks: pair (i,j) of e is NOT first iff an element of lower colour holds both nodes
+  if (npe > 32) return "first-touch masks need <= 32 nodes per element";
+  out.pair_first.assign((size_t)ne * npe, 0u);
+  out.node_first.assign(ne, 0u);
+  parallel_chunks(ne, T, [&](int, int64_t lo, int64_t hi) {
+    std::vector<int> nb;
+    for (int64_t e = lo; e < hi; e++) {
+      const int *c = conn + e * npe;
+      nb.clear();
+      for (int i = 0; i < npe; i++)
+        for (int64_t q = ne_ptr[c[i]]; q < ne_ptr[c[i] + 1]; q++)
+          if (colour[ne_list[q]] < colour[e]) nb.push_back(ne_list[q]);
+      std::sort(nb.begin(), nb.end());
+      nb.erase(std::unique(nb.begin(), nb.end()), nb.end());
+      uint32_t notfirst[32] = {0};
+      uint32_t node_nf = 0;
+      for (int e2 : nb) {
+        uint32_t shared = 0;  // local nodes of e that e2 also holds
+        for (int i = 0; i < npe; i++)
+          for (int64_t q = ne_ptr[c[i]]; q < ne_ptr[c[i] + 1]; q++)
+            if (ne_list[q] == e2) shared |= 1u << i;
+        node_nf |= shared;
+        for (int i = 0; i < npe; i++)
+          if ((shared >> i) & 1u) notfirst[i] |= shared;
+      }
+      const uint32_t all = npe == 32 ? 0xffffffffu : ((1u << npe) - 1u);
+      for (int i = 0; i < npe; i++) out.pair_first[e * npe + i] = all & ~notfirst[i];
+      out.node_first[e] = all & ~node_nf;
+    }
+  });
   return "";
 }
 

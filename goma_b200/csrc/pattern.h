@@ -27,6 +27,13 @@ struct Pattern {
   // unknown inside a row of node i, and the number of pressure unknowns before it
   std::vector<uint16_t> pair_full, pair_p;  // [num_elems*npe*npe]
   bool need_pair_p = false;
+  // Element colouring (no two elements of a colour share a node) and first-touch masks for the
+  // write-once scatter: colours are processed in increasing order, so the element of lowest colour
+  // among those sharing a node pair writes the slot with a plain store and the later ones add to it.
+  std::vector<int> colour_order;      // elements sorted by colour
+  std::vector<int> colour_begin;      // [ncolours+1] into colour_order
+  std::vector<uint32_t> pair_first;   // [num_elems*npe] bit j of word (e,i): e is the first writer of pair (i,j)
+  std::vector<uint32_t> node_first;   // [num_elems]     bit i: e is the first element touching node i's rows
 };
 
 // returns "" on success, else an error message

@@ -33,7 +33,7 @@ def assert_close(got, ref, what):
     assert e < TOL, f"{what}: max rel err {e:.3e}"
 
 
-@pytest.mark.parametrize("scatter", [0, 1], ids=["atomic", "coloured"])
+@pytest.mark.parametrize("scatter", [0, 1, 2], ids=["atomic", "coloured", "first_touch"])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_gpu_matches_reference_fixture(built, name, scatter):
     """CUDA assembly == the reference's own matrix_fill_full output (committed fixture)."""
@@ -74,7 +74,7 @@ def test_gpu_matches_port_oracle_seeded(built, et, n, energy):
     rc, a_ref, r_ref = port.port_fill(p, ija, st)
     assert rc == 0
     mf = MatrixFill(p)
-    for scatter in (0, 1):
+    for scatter in (0, 1, 2, 2):
         mf.set_option("scatter", scatter)
         err, a, r = mf.matrix_fill_full(st["x"])
         assert err == 0
