@@ -49,6 +49,19 @@ def cavity_problem(n, energy=False, x_len=1.0):
     return Problem(m, rho=1.0, mu=0.01, bcs=bcs, **kw)
 
 
+def cavity_problem_on(mesh, energy=False):
+    """Same cards as cavity_problem on a given (sub-domain) mesh: empty node sets simply match nothing."""
+    from goma_b200.problem import Dirichlet, Problem
+
+    bcs = [Dirichlet(v, s, 0.0) for s in (1, 2, 3, 4, 5) for v in "UVW"]
+    bcs += [Dirichlet("U", 6, 1.0), Dirichlet("V", 6, 0.0), Dirichlet("W", 6, 0.0), Dirichlet("P", 7, 0.0)]
+    kw = {}
+    if energy:
+        bcs += [Dirichlet("T", 1, 1.0), Dirichlet("T", 2, 0.0)]
+        kw = dict(energy=True, k=0.0141, Cp=1.0, beta=1.0, Tref=0.0, gravity=(0.0, 0.0, -1.0), ns_source="BOUSSINESQ")
+    return Problem(mesh, rho=1.0, mu=0.01, bcs=bcs, **kw)
+
+
 def synthetic_state(problem, seed):
     from tests.cases import make_state
 
@@ -278,26 +291,49 @@ def main():
         return float(t.item())
 
     t_setup = time.perf_counter()
-    problem = cavity_problem(args.n, args.energy)  # every rank: its own n^3 slab (weak scaling)
+    sub = None
+    if world == 1:
+        problem = cavity_problem(args.n, args.energy)
+        num_owned_nodes = None
+        ne_owned = problem.mesh.num_elems
+    else:
+        # weak scaling: rank r owns the r-th n^3 slab of a (world*n) x n x n cavity, plus its ghost column
+        from goma_b200.dp_comm import exchange_dof, slab_subdomain
+
+        sub = slab_subdomain(lambda mesh: cavity_problem_on(mesh, args.energy), args.n, rank, world)
+        problem = sub.problem
+        num_owned_nodes = sub.num_owned_nodes
+        ne_owned = int(sub.elem_owned.sum())
     x = synthetic_state(problem, 20261017 + rank)
-    mf = MatrixFill(problem, device=local_rank)
+    mf = MatrixFill(problem, device=local_rank, num_owned_nodes=num_owned_nodes)
     mf.set_option("scatter", args.scatter)
-    ne = problem.mesh.num_elems
+    ne = problem.mesh.num_elems  # assembled per step on this rank (owned + ghost elements)
     n_unk, nnz = mf.num_unknowns, mf.nnz_plus
     t_setup = time.perf_counter() - t_setup
+
+    from goma_b200.matrix_fill import device_view
+
+    bufs = mf.device_buffers()
+    d_x = device_view(bufs.d_x, n_unk, dev)
+
+    def step():
+        if sub is not None:
+            exchange_dof(d_x, sub)  # ghost refresh before the fill (mm_sol_nonlinear.c:1273), NCCL send/recv
+            torch.cuda.current_stream(dev).synchronize()
+        mf.fill_device()
 
     # state into HBM once (one residual-only host call), then the device-resident steps
     sampler = ClockSampler(local_rank)
     sampler.start()
     mf.matrix_fill_full(x, assemble_jacobian=False)
     for _ in range(args.warmup):
-        mf.fill_device()
+        step()
     sampler.mark()
     barrier()
     t0 = time.perf_counter()
     kernel_ms, launches = 0.0, 0
     for _ in range(args.steps):
-        mf.fill_device()
+        step()
         ms, nl = mf.last_stats()
         kernel_ms += ms
         launches += nl
@@ -305,7 +341,7 @@ def main():
     step_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     clocks = sampler.stop()
     dev_ms = max_over_ranks(kernel_ms / args.steps)  # CUDA events on the library's stream: memsets + kernel(s)
-    total_elems = sum_over_ranks(float(ne))
+    total_elems = sum_over_ranks(float(ne_owned))  # ghost elements are assembled twice but counted once
     value = total_elems / step_s
 
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
@@ -355,7 +391,9 @@ def main():
             "metric": "jacobian_residual_elements_per_s", "value": value, "unit": "elements/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "elements_per_gpu": ne, "unknowns_per_gpu": n_unk,
+            "config": {"workload": workload_name(args), "elements_per_gpu": ne_owned,
+                       "elements_assembled_per_gpu": ne, "unknowns_per_gpu": n_unk,
+                       "halo": None if sub is None else "exchange_dof over NCCL send/recv before every fill",
                        "nnz_per_gpu": nnz, "scatter": ["fp64 atomics", "coloured load+add+store", "coloured first-touch stores"][args.scatter],
                        "l2": "inputs larger than L2 (MSR values %.1f GB per GPU rewritten every step)" % (8e-9 * nnz),
                        "setup_s": round(t_setup, 1)},

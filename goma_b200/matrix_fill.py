@@ -110,6 +110,20 @@ class MatrixFill:
             pass
 
 
+class _CudaArray:
+    """Minimal __cuda_array_interface__ holder so torch can view a buffer owned by the C library."""
+
+    def __init__(self, ptr, n, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_view(ptr, n, device, typestr="<f8"):
+    """torch tensor aliasing ``n`` elements at device address ``ptr`` (no copy, no ownership)."""
+    import torch
+
+    return torch.as_tensor(_CudaArray(ptr, n, typestr), device=device)
+
+
 def msr_to_csr(ija, a, n):
     """MSR (diagonal first, reference ``mm_fill_util.c:2865-3031``) -> scipy CSR, for the host Newton loop."""
     import scipy.sparse as sp

@@ -26,7 +26,12 @@ def main(rep, out, title):
             lines.append(f"{h} [{u}] = {v}")
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
-    hdr, data = rows[1], rows[2:]
+    hdr = rows[1]
+    data = []
+    for r in rows[2:]:  # several launches are concatenated: keep the first table
+        if len(r) != len(hdr):
+            break
+        data.append(r)
     iS, iSrc, iEx = hdr.index("# Samples"), hdr.index("Source"), hdr.index("Instructions Executed")
     tot = sum(int(r[iS] or 0) for r in data)
     lines.append(f"# SASS sample distribution ({tot} samples, {len(data)} instructions), blocks of 100 instructions")
