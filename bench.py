@@ -239,7 +239,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=100, help="elements per direction per GPU (100 -> 1M hex27 elements)")
+    ap.add_argument("--edge", dest="n", type=int, default=100, help="elements per direction per GPU (100 -> 1M hex27 elements)")
     ap.add_argument("--energy", action="store_true", help="config C3 physics (NS + energy) instead of C2")
     ap.add_argument("--scatter", type=int, default=2,
                     help="0 fp64 atomics, 1 coloured load+add+store, 2 coloured first-touch stores (default)")
