@@ -227,7 +227,10 @@ def exchange_dof(x, sub: Subdomain, group=None, pack=None):
 
     if not sub.neighbors:
         return x
-    idx = torch.as_tensor(sub.list_dof_send, dtype=torch.long, device=x.device)
+    cache = sub.__dict__.setdefault("_idx_cache", {})
+    idx = cache.get(x.device)
+    if idx is None:  # the send list is static: upload it once per device
+        idx = cache[x.device] = torch.as_tensor(sub.list_dof_send, dtype=torch.long, device=x.device)
     send = pack(x, idx) if pack is not None else x.index_select(0, idx)
     ops = []
     tail = sub.num_owned_dofs
