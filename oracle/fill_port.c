@@ -20,6 +20,12 @@
  *                                              :3458-3469, :3704; sources :3738, src/mm_std_models.c:125
  *   continuity         assemble_continuity     src/mm_fill_continuity.c:435-444 (R), :665-761 (J_c_v)
  *   energy             assemble_energy         src/mm_fill_energy.c:322-381 (R), :425-487 (J_e_T), :628-692 (J_e_v)
+ *   species            assemble_mass_transport src/mm_fill_species.c:194- (Fickian, constant D; concentration
+ *                                              form: coeff_rho = 1), get_continuous_species_terms :9739
+ *   PSPG               calc_pspg               src/mm_fill_stabilization.c:852-1591 (tau :1030-1096, momentum
+ *                                              residual :1281-1319, d_pspg :1321-1524); continuity terms
+ *                                              src/mm_fill_continuity.c:604-613,746-756,~870,~1200;
+ *                                              h_elem_siz src/mm_fill_aux.c:844, element_velocity :759
  *   Dirichlet          put_dirichlet_in_matrix src/bc_dirich.c:44-151
  *   scatter            load_lec (MSR)          src/mm_fill.c:5241-5483 (in_list search :5461)
  * Cartesian coordinates only (h3 = 1, grad_phi_e[i][a][p][q] = delta_aq grad_phi[i][p],
@@ -99,7 +105,7 @@ static long msr_pos(const int *ija, int ie, int je) {
 int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const double *x, const double *x_old,
                    const double *xdot, double delta_t, double theta, double time_value, double h_elem_avg,
                    double U_norm, int assemble_residual, int assemble_jacobian, double *a, double *resid) {
-  (void)x_old; (void)time_value; (void)h_elem_avg; (void)U_norm;
+  (void)x_old; (void)time_value;
   const int dim = p->dim, et = p->elem_type, nn = et;
   const int n1 = (et == 4 || et == 8) ? 2 : 3;
   const int ngp = dim == 2 ? n1 * n1 : n1 * n1 * n1;
@@ -107,19 +113,21 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
   const int cen = et == 9 ? 8 : et == 27 ? 20 : 0;
   const int np = p1 ? dim + 1 : 0;
   /* fields interpolated with phi, in nodal order */
-  int fslot[MAXF], nf = 0, fT = -1, fP = -1;
+  int fslot[MAXF], nf = 0, fT = -1, fP = -1, fY = -1;
   for (int d = 0; d < dim; d++) fslot[nf++] = GOMA_SLOT_U + d;
   if (p->energy) { fT = nf; fslot[nf++] = GOMA_SLOT_T; }
+  if (p->num_species) fY = nf;
   for (int w = 0; w < p->num_species; w++) fslot[nf++] = GOMA_SLOT_Y0 + w;
   if (p->ale) for (int d = 0; d < dim; d++) fslot[nf++] = GOMA_SLOT_DX + d;
   if (!p1) { fP = nf; fslot[nf++] = GOMA_SLOT_P; }
-  (void)fP;
+  const int ns = p->num_species;
   const int ndof = nf * nn + np; /* element block size; P1 dofs last */
   const int transient = p->transient;
-  double em[6], ee[5];
+  double em[6], ee[5], es[5];
   memcpy(em, p->etm_momentum, sizeof(em));
   memcpy(ee, p->etm_energy, sizeof(ee));
-  if (!transient) em[0] = ee[0] = 0.0;
+  memcpy(es, p->etm_species, sizeof(es));
+  if (!transient) em[0] = ee[0] = es[0] = 0.0;
   const double ec0 = p->etm_continuity[0];
   const double tfac = transient ? (1.0 + 2.0 * theta) / delta_t : 0.0;
   const double rho = p->rho, mu = p->mu, rcp = p->rho * p->heat_capacity, kc = p->conductivity;
@@ -153,6 +161,47 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
     }
     memset(R, 0, sizeof(double) * ndof);
     memset(J, 0, sizeof(double) * ndof * ndof);
+
+    /* BLOCK 1.5 (mm_fill.c:754-787): element-level PSPG data */
+    double tau = 0.0, tau1 = 0.0, hh_siz = 0.0, v_avg[3] = {0, 0, 0}, dtau_dv[3] = {0, 0, 0};
+    if (p->pspg) {
+      const double mu_avg = mu, rho_avg = rho;
+      if (p->pspg == 1) { /* global: Re from the global norms, no Jacobian dependence */
+        double Re = rho * U_norm * h_elem_avg / (2.0 * mu_avg);
+        tau = Re <= 3.0 ? p->ps_scaling * h_elem_avg * h_elem_avg / (12.0 * mu_avg)
+                        : p->ps_scaling * h_elem_avg / (2.0 * rho * U_norm);
+      } else { /* local: h_elem_siz (face-centroid differences) and element_velocity */
+        double hsq[3] = {0, 0, 0};
+        if (dim == 2) {
+          for (int a_ = 0; a_ < 2; a_++) {
+            double h0 = 0.5 * (X[a_][1] + X[a_][2]) - 0.5 * (X[a_][0] + X[a_][3]);
+            double h1 = 0.5 * (X[a_][0] + X[a_][1]) - 0.5 * (X[a_][2] + X[a_][3]);
+            hsq[0] += h0 * h0; hsq[1] += h1 * h1;
+          }
+        } else {
+          for (int a_ = 0; a_ < 3; a_++) {
+            const double *xx = X[a_];
+            double p1 = 0.25 * (xx[0] + xx[1] + xx[2] + xx[3]), p2 = 0.25 * (xx[1] + xx[2] + xx[5] + xx[6]);
+            double p3 = 0.25 * (xx[2] + xx[3] + xx[6] + xx[7]), p4 = 0.25 * (xx[0] + xx[1] + xx[4] + xx[5]);
+            double p5 = 0.25 * (xx[0] + xx[3] + xx[4] + xx[7]), p6 = 0.25 * (xx[4] + xx[5] + xx[6] + xx[7]);
+            hsq[0] += (p2 - p5) * (p2 - p5); hsq[1] += (p3 - p4) * (p3 - p4); hsq[2] += (p1 - p6) * (p1 - p6);
+          }
+        }
+        for (int a_ = 0; a_ < dim; a_++) hh_siz += hsq[a_];
+        hh_siz /= (double)dim;
+        double vv = 0.0;
+        const int q2 = (et == 9 || et == 27);
+        for (int a_ = 0; a_ < dim; a_++) {
+          if (q2) v_avg[a_] = U[a_][nn - 1]; /* I_Q2: "centroid_node = dofs - 1" (mm_fill_aux.c:809-817) */
+          else for (int k = 0; k < nn; k++) v_avg[a_] += U[a_][k] / (double)nn;
+          vv += v_avg[a_] * v_avg[a_];
+        }
+        tau1 = rho_avg * rho_avg * vv / hh_siz + 9.0 * mu_avg * mu_avg / (hh_siz * hh_siz);
+        if (transient) tau1 += 4.0 / (delta_t * delta_t);
+        tau = p->ps_scaling / sqrt(tau1);
+        for (int b = 0; b < dim; b++) dtau_dv[b] = -tau / tau1 * rho_avg * rho_avg / hh_siz * v_avg[b];
+      }
+    }
 
     for (int ip = 0; ip < ngp; ip++) {
       double xi[3], wt, phi[MAXN], dphi[MAXN][3], g[MAXN][3], psi[4];
@@ -201,6 +250,7 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
       }
       double Pr = 0.0;
       if (p1) for (int q = 0; q < np; q++) Pr += Pd[q] * psi[q];
+      else Pr = val[fP];
       const double T = p->energy ? val[fT] : 0.0;
       /* momentum_source_term */
       double fs[3] = {0, 0, 0}, dfdT[3] = {0, 0, 0};
@@ -246,6 +296,69 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
               if (p->energy) J[row * ndof + fT * nn + j] += em[4] * phi_i * dfdT[a_] * phi[j] * d_area;
             }
             for (int q = 0; q < np; q++) J[row * ndof + nf * nn + q] += em[3] * g[i][a_] * psi[q] * d_area;
+            if (!p1) for (int j = 0; j < nn; j++) J[row * ndof + fP * nn + j] += em[3] * g[i][a_] * phi[j] * d_area;
+          }
+        }
+        /* ---- species rows (Fickian, constant D, concentration form) */
+        for (int w = 0; w < ns; w++) {
+          const int fw = fY + w, row = fw * nn + i;
+          const double D = p->diffusivity[w];
+          if (assemble_residual) {
+            double adv = 0.0, diff = 0.0;
+            for (int q = 0; q < dim; q++) { adv += val[q] * grad[fw][q]; diff += g[i][q] * (-D * grad[fw][q]); }
+            R[row] += -es[0] * phi_i * dot[fw] * d_area - es[1] * phi_i * adv * d_area + es[3] * diff * d_area;
+          }
+          if (assemble_jacobian) {
+            for (int j = 0; j < nn; j++) {
+              double gij = 0.0, vgj = 0.0;
+              for (int q = 0; q < dim; q++) { gij += g[i][q] * g[j][q]; vgj += val[q] * g[j][q]; }
+              J[row * ndof + fw * nn + j] += (-es[0] * phi_i * phi[j] * tfac - es[1] * phi_i * vgj - es[3] * D * gij) * d_area;
+              for (int b = 0; b < dim; b++) J[row * ndof + b * nn + j] += -es[1] * phi_i * phi[j] * grad[fw][b] * d_area;
+            }
+          }
+        }
+        /* ---- continuity rows, equal-order pressure (+ PSPG) */
+        if (!p1) {
+          const int row = fP * nn + i;
+          double mom[3] = {0, 0, 0}, pspg[3] = {0, 0, 0};
+          if (p->pspg) {
+            for (int a_ = 0; a_ < dim; a_++) {
+              double adv = 0.0;
+              for (int q = 0; q < dim; q++) adv += val[q] * grad[a_][q];
+              mom[a_] = em[0] * rho * dot[a_] + em[1] * rho * adv + em[3] * grad[fP][a_] - em[4] * fs[a_];
+              pspg[a_] = tau * mom[a_];
+            }
+          }
+          if (assemble_residual) {
+            double ps = 0.0;
+            for (int a_ = 0; a_ < dim; a_++) ps += g[i][a_] * pspg[a_];
+            R[row] += ec0 * phi_i * div_v * d_area + ps * d_area;
+          }
+          if (assemble_jacobian) {
+            for (int j = 0; j < nn; j++) {
+              double vgj = 0.0;
+              for (int q = 0; q < dim; q++) vgj += val[q] * g[j][q];
+              for (int b = 0; b < dim; b++) {
+                double ps = 0.0;
+                if (p->pspg)
+                  for (int a_ = 0; a_ < dim; a_++) {
+                    double d = tau * (em[0] * rho * tfac * phi[j] * (a_ == b) +
+                                      em[1] * rho * (phi[j] * grad[a_][b] + (a_ == b ? vgj : 0.0))) +
+                               dtau_dv[b] * (et == 9 || et == 27 ? (j == nn - 1 ? 1.0 : 0.0) : 1.0 / nn) * mom[a_];
+                    ps += g[i][a_] * d;
+                  }
+                J[row * ndof + b * nn + j] += ec0 * phi_i * g[j][b] * d_area + ps * d_area;
+              }
+              if (p->pspg) {
+                double psP = 0.0, psT = 0.0;
+                for (int a_ = 0; a_ < dim; a_++) {
+                  psP += g[i][a_] * tau * em[3] * g[j][a_];
+                  psT += g[i][a_] * tau * (-em[4] * dfdT[a_] * phi[j]);
+                }
+                J[row * ndof + fP * nn + j] += psP * d_area;
+                if (p->energy) J[row * ndof + fT * nn + j] += psT * d_area;
+              }
+            }
           }
         }
         /* ---- energy row */
