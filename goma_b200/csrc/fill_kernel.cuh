@@ -62,6 +62,8 @@ struct FillParams {
   double diffusivity[4];
   double delta_t, theta, time_value, h_elem_avg, U_norm;
   double lame_mu, lame_lambda;
+  int pspg;  // 0 off, 1 global, 2 local (calc_pspg)
+  double ps_scaling;
   long long *prof;  // optional per-CTA phase cycle counters (profiling build), 8 per CTA
   int debug;        // experiments only: bit0 = drop the matrix stores, bit1 = skip the Gauss loop
 };
@@ -93,7 +95,14 @@ struct Cfg {
   static constexpr int G_RE = G_RP + DIM * DIM;                    // energy residual scalar
   static constexpr int G_RF = G_RE + (ENERGY ? 1 : 0);             // e3 q[p]
   static constexpr int G_DIV = G_RF + (ENERGY ? DIM : 0);          // ec0 div v
-  static constexpr int GPD = (G_DIV + 1 + 1) & ~1;
+  static constexpr int G_GY = G_DIV + 1;                           // cs_adv d_b Y_w           [w][b]
+  static constexpr int G_RY = G_GY + NSPEC * DIM;                  // species residual scalar  [w]
+  static constexpr int G_RFY = G_RY + NSPEC;                       // e3 j_w[p]                [w][p]
+  static constexpr int G_HB = G_RFY + NSPEC * DIM;                 // PSPG: tau e1 rho d_b v_a [a][b]
+  static constexpr int G_MOM = G_HB + (P1 ? 0 : DIM * DIM);        // PSPG: momentum residual  [a]
+  static constexpr int G_PS = G_MOM + (P1 ? 0 : DIM);              // PSPG: tau * momentum     [a]
+  static constexpr int GPD = (G_PS + (P1 ? 0 : DIM) + 1) & ~1;
+  static constexpr bool GENERAL = !P1 || NSPEC > 0;  // generic block accumulation instead of the NS(+T) fast path
   // staged write-out of the element block: rows (node i, field) x columns (node j in global order, field)
   static constexpr int NROW = NF * NN, NCOL = NF * NN;
   static constexpr int CAP = NGP * NN * 9;  // doubles in the operand arena (SI + SJa + SJb + VG), reused as stage
@@ -142,6 +151,7 @@ struct alignas(16) Smem {
   int fu[C::NN];
   int kind[C::NN];
   int gun[C::NF][C::NN];
+  double tau, dtau[3];    // PSPG tau and d tau / d v_avg[b] (element level)
   unsigned first[C::NN];  // first-touch mask of row node i over column nodes j
   unsigned node_first;
   unsigned short po[C::NN][C::NN];  // slot-map column offsets of the node pairs
@@ -374,6 +384,46 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
     }
     s.w[tid] = det * t_wt[tid];  // d_area = detJ * wt * h3, h3 = 1 (Cartesian)
   }
+  if (!C::P1 && tid == NT - 1) {
+    // BLOCK 1.5 of matrix_fill (mm_fill.c:754-787) + the tau of calc_pspg (mm_fill_stabilization.c:1030-1096)
+    double tau = 0.0, dtau[3] = {0.0, 0.0, 0.0};
+    if (P.pspg == 1) {  // global: element Reynolds number from the global norms, no Jacobian dependence
+      const double Re = P.rho * P.U_norm * P.h_elem_avg / (2.0 * P.mu);
+      tau = Re <= 3.0 ? P.ps_scaling * P.h_elem_avg * P.h_elem_avg / (12.0 * P.mu)
+                      : P.ps_scaling * P.h_elem_avg / (2.0 * P.rho * P.U_norm);
+    } else if (P.pspg == 2) {  // local: h_elem_siz (mm_fill_aux.c:844) and element_velocity (:759)
+      double hh = 0.0;
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        const double *xx = s.X[a];
+        if (DIM == 2) {
+          const double h0 = 0.5 * (xx[1] + xx[2]) - 0.5 * (xx[0] + xx[3]);
+          const double h1 = 0.5 * (xx[0] + xx[1]) - 0.5 * (xx[2] + xx[3]);
+          hh += h0 * h0 + h1 * h1;
+        } else {
+          const double p1 = 0.25 * (xx[0] + xx[1] + xx[2] + xx[3]), p2 = 0.25 * (xx[1] + xx[2] + xx[5] + xx[6]);
+          const double p3 = 0.25 * (xx[2] + xx[3] + xx[6] + xx[7]), p4 = 0.25 * (xx[0] + xx[1] + xx[4] + xx[5]);
+          const double p5 = 0.25 * (xx[0] + xx[3] + xx[4] + xx[7]), p6 = 0.25 * (xx[4] + xx[5] + xx[6] + xx[7]);
+          hh += (p2 - p5) * (p2 - p5) + (p3 - p4) * (p3 - p4) + (p1 - p6) * (p1 - p6);
+        }
+      }
+      hh /= (double)DIM;
+      double vavg[3] = {0.0, 0.0, 0.0}, vv = 0.0;
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        for (int k = 0; k < NN; k++) vavg[a] += s.U[C::F_V + a][k] / (double)NN;  // I_Q1: mean of the nodes
+        vv += vavg[a] * vavg[a];
+      }
+      double tau1 = P.rho * P.rho * vv / hh + 9.0 * P.mu * P.mu / (hh * hh);
+      if (P.transient) tau1 += 4.0 / (P.delta_t * P.delta_t);
+      tau = P.ps_scaling / sqrt(tau1);
+#pragma unroll
+      for (int b = 0; b < DIM; b++) dtau[b] = -tau / tau1 * P.rho * P.rho / hh * vavg[b] / (double)NN;
+    }
+    s.tau = tau;
+#pragma unroll
+    for (int b = 0; b < 3; b++) s.dtau[b] = dtau[b];
+  }
   __syncthreads();
   GOMA_STAMP(2);
   // ---- phase 3: grad_phi[i][p] = sum_q B[p][q] dphi_i/dxi_q  (load_bf_grad, mm_fill_util.c:1765-1776)
@@ -473,6 +523,36 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
       }
     }
     G[C::G_DIV] = P.etm_cont[0] * div;
+#pragma unroll
+    for (int w = 0; w < C::NSPEC; w++) {
+      // assemble_mass_transport, Fickian constant-D, concentration form (mm_fill_species.c:527-640)
+      double adv = 0.0;
+#pragma unroll
+      for (int p = 0; p < DIM; p++) {
+        const double gY = s.F[gp][C::F_Y + w][1 + p];
+        adv += v[p] * gY;
+        G[C::G_GY + w * DIM + p] = -P.etm_species[1] * gY;
+        G[C::G_RFY + w * DIM + p] = P.etm_species[3] * (-P.diffusivity[w] * gY);
+      }
+      G[C::G_RY + w] = -P.etm_species[0] * s.F[gp][C::F_Y + w][1 + DIM] - P.etm_species[1] * adv;
+    }
+    if (!C::P1) {
+      // calc_pspg (mm_fill_stabilization.c:1281-1319): momentum residual without the viscous term
+      const double tau = s.tau;
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        double adv = 0.0;
+#pragma unroll
+        for (int p = 0; p < DIM; p++) {
+          adv += v[p] * gv[a][p];
+          G[C::G_HB + a * DIM + p] = tau * P.etm_mom[1] * P.rho * gv[a][p];
+        }
+        const double mom = P.etm_mom[0] * P.rho * vdot[a] + P.etm_mom[1] * P.rho * adv +
+                           P.etm_mom[3] * s.F[gp][C::F_P][1 + a] - P.etm_mom[4] * fs[a];
+        G[C::G_MOM + a] = mom;
+        G[C::G_PS + a] = tau * mom;
+      }
+    }
     if (C::ENERGY) {
       double adv = 0.0;
 #pragma unroll
@@ -535,8 +615,12 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
       R = (r0 + r1) + r2;
     } else {
       const bool isT = C::ENERGY && f == C::F_T;
-      if (f >= DIM && !isT) continue;
-      const int q0 = isT ? C::G_RE : C::G_RQ + f, q1 = isT ? C::G_RF : C::G_RP + f * DIM;
+      const bool isY = f >= C::F_Y && f < C::F_Y + C::NSPEC;
+      const bool isP = !C::P1 && f == C::F_P;
+      if (f >= DIM && !isT && !isY && !isP) continue;
+      // row = sum_gp  w phi_i * G[q0]  +  w grad_phi_i[p] * G[q1 + p]
+      const int q0 = isT ? C::G_RE : isY ? C::G_RY + (f - C::F_Y) : isP ? C::G_DIV : C::G_RQ + f;
+      const int q1 = isT ? C::G_RF : isY ? C::G_RFY + (f - C::F_Y) * DIM : isP ? C::G_PS : C::G_RP + f * DIM;
       double r[3] = {0.0, 0.0, 0.0};
 #pragma unroll 3
       for (int gp = 0; gp < NGP; gp++) {
@@ -671,6 +755,92 @@ __device__ __forceinline__ void gauss_loop(const FillParams &P, const Smem<C> &s
   }
 }
 
+// Generic block accumulation: every active field pair, straight into the NF x NF tile.  Used for the
+// equal-order (PSPG) and species configurations; the NS(+T) P1 configurations use gauss_loop above.
+template <class C>
+__device__ __forceinline__ void gauss_loop_general(const FillParams &P, const Smem<C> &s, int i0, int j, Tile<C> &out) {
+  constexpr int DIM = C::DIM, NGP = C::NGP, TI = C::TI, NF = C::NF, NN = C::NN;
+  const Operands<C> &op = s.op;
+  const double tfac = P.transient ? (1.0 + 2.0 * P.theta) / P.delta_t : 0.0;
+  const double rcp = P.rho * P.Cp;
+  const double c_adv = -P.etm_mom[1] * P.rho, c_diff = -P.etm_mom[3] * P.mu, c_mass = -P.etm_mom[0] * P.rho * tfac;
+  const double ce_adv = -P.etm_energy[1] * rcp, ce_diff = -P.etm_energy[3] * P.k,
+               ce_mass = -P.etm_energy[0] * rcp * tfac;
+  const double cs_adv = -P.etm_species[1], cs_mass = -P.etm_species[0] * tfac;
+  const double tau = C::P1 ? 0.0 : s.tau;
+  double dfdT[3] = {0.0, 0.0, 0.0};
+  if (C::ENERGY && P.source_model != 0 && P.etm_mom[4] != 0.0) {
+#pragma unroll
+    for (int a = 0; a < DIM; a++) dfdT[a] = -P.g[a] * P.rho * P.beta;
+  }
+#pragma unroll
+  for (int ii = 0; ii < TI; ii++)
+#pragma unroll
+    for (int r = 0; r < NF; r++)
+#pragma unroll
+      for (int c = 0; c < NF; c++) out.V[ii][r][c] = 0.0;
+  const int ngp_run = (P.debug & 2) ? 1 : NGP;
+#pragma unroll 1
+  for (int gp = 0; gp < ngp_run; gp++) {
+    const double2 j01 = op.SJa[gp][j], j23 = op.SJb[gp][j];
+    const double phi_j = j01.x;
+    const double gj[3] = {j01.y, j23.x, j23.y};
+    const double vgj = op.VG[gp][j];
+    const double *G = s.GP[gp];
+#pragma unroll
+    for (int ii = 0; ii < TI; ii++) {
+      const double2 i01 = *reinterpret_cast<const double2 *>(&op.SI[gp][i0 + ii][0]);
+      const double2 i23 = *reinterpret_cast<const double2 *>(&op.SI[gp][i0 + ii][2]);
+      const double wphi = i01.x;
+      const double wg[3] = {i01.y, i23.x, i23.y};
+      const double pp = wphi * phi_j;
+      double gij = 0.0;
+#pragma unroll
+      for (int p = 0; p < DIM; p++) gij += wg[p] * gj[p];
+      const double s1 = wphi * vgj;
+      double (&V)[NF][NF] = out.V[ii];
+      const double dm = c_adv * s1 + c_diff * gij + c_mass * pp;
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+#pragma unroll
+        for (int b = 0; b < DIM; b++) V[a][b] += pp * G[C::G_GV + a * DIM + b] + c_diff * wg[b] * gj[a];
+        V[a][a] += dm;
+        if (C::ENERGY) {
+          V[a][C::F_T] += P.etm_mom[4] * dfdT[a] * pp;              // J_m_T
+          V[C::F_T][a] += pp * G[C::G_GT + a];                      // J_e_v
+        }
+#pragma unroll
+        for (int w = 0; w < C::NSPEC; w++) V[C::F_Y + w][a] += pp * G[C::G_GY + w * DIM + a];  // J_s_v
+        if (!C::P1) V[a][C::F_P] += P.etm_mom[3] * wg[a] * phi_j;  // J_m_P (mm_fill_momentum.c:2091-2104)
+      }
+      if (C::ENERGY) V[C::F_T][C::F_T] += ce_adv * s1 + ce_diff * gij + ce_mass * pp;  // J_e_T
+#pragma unroll
+      for (int w = 0; w < C::NSPEC; w++)
+        V[C::F_Y + w][C::F_Y + w] += cs_adv * s1 - P.etm_species[3] * P.diffusivity[w] * gij + cs_mass * pp;
+      if (!C::P1) {
+        // continuity row of node i: div term + PSPG (mm_fill_continuity.c:686-756, d_pspg mm_fill_stabilization.c:1321-)
+        double rmom = 0.0, rdf = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+          rmom += wg[a] * G[C::G_MOM + a];
+          rdf += wg[a] * dfdT[a];
+        }
+        const double t1 = tau * P.rho * (P.etm_mom[0] * tfac * phi_j + P.etm_mom[1] * vgj);
+#pragma unroll
+        for (int b = 0; b < DIM; b++) {
+          double q = 0.0;
+#pragma unroll
+          for (int a = 0; a < DIM; a++) q += wg[a] * G[C::G_HB + a * DIM + b];
+          V[C::F_P][b] += P.etm_cont[0] * wphi * gj[b] + phi_j * q + wg[b] * t1 + s.dtau[b] * rmom;
+        }
+        V[C::F_P][C::F_P] += tau * P.etm_mom[3] * gij;
+        if (C::ENERGY) V[C::F_P][C::F_T] += -tau * P.etm_mom[4] * phi_j * rdf;
+      }
+    }
+  }
+  (void)NN;
+}
+
 // write-out of staged rows [r0, r1): a warp walks one row, lanes along the columns in matrix order
 template <class C>
 __device__ __forceinline__ void write_rows(const FillParams &P, const Smem<C> &s, int r0, int r1, int tid) {
@@ -738,7 +908,12 @@ __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_cons
       Tile<C> tile;
       const bool active = tid < C::NTILE;
       const int it = active ? tid / NN : 0, j = active ? tid - it * NN : 0, i0 = it * TI;
-      if (active) gauss_loop<C>(P, s, i0, j, tile);
+      if (active) {
+        if (C::GENERAL)
+          gauss_loop_general<C>(P, s, i0, j, tile);
+        else
+          gauss_loop<C>(P, s, i0, j, tile);
+      }
       long long c3 = GOMA_CLOCK();
       t_loop += c3 - c2;
       __syncthreads();  // every thread is done reading the operand arena: it becomes the stage

@@ -97,17 +97,29 @@ KernelEntry entry() {
 int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
   const bool p1 = p.pressure_interp == GOMA_PRESSURE_P1;
   if (p.ale) return fail(-2, "ALE (mesh equations) path not built yet");
-  if (p.pspg || !p1) return fail(-2, "equal-order PSPG path not built yet");
-  if (p.num_species) return fail(-2, "species path not built yet");
-  if (p.elem_type == GOMA_GPU_QUAD9) {
+  if (p.pspg && p1) return fail(-2, "PSPG with P1 pressure is not supported by the GPU fill");
+  if (!p1 && !p.pspg) return fail(-2, "equal-order velocity/pressure needs Pressure Stabilization (PSPG)");
+  if (p1 && p.num_species) return fail(-2, "species with Q2/P1 not instantiated yet");
+  if (p1 && p.elem_type == GOMA_GPU_QUAD9) {
     k = p.energy ? entry<Cfg<2, 9, 9, true, true, 0, false, 32, 3, 8>>()
                  : entry<Cfg<2, 9, 9, true, false, 0, false, 32, 3, 8>>();
     return 0;
   }
-  if (p.elem_type == GOMA_GPU_HEX27) {
+  if (p1 && p.elem_type == GOMA_GPU_HEX27) {
     k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 1>>()
                  : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2>>();
     return 0;
+  }
+  if (!p1 && p.elem_type == GOMA_GPU_HEX8) {  // Q1/Q1 PSPG (config C5 and its sub-cases)
+    if (p.energy && p.num_species == 2) { k = entry<Cfg<3, 8, 8, false, true, 2, false, 64, 1, 4>>(); return 0; }
+    if (p.energy && p.num_species == 0) { k = entry<Cfg<3, 8, 8, false, true, 0, false, 64, 1, 4>>(); return 0; }
+    if (!p.energy && p.num_species == 0) { k = entry<Cfg<3, 8, 8, false, false, 0, false, 64, 1, 4>>(); return 0; }
+    return fail(-2, "hex8 Q1/Q1: instantiated field sets are NS, NS+T, NS+T+2 species");
+  }
+  if (!p1 && p.elem_type == GOMA_GPU_QUAD4) {
+    if (p.energy && p.num_species == 2) { k = entry<Cfg<2, 4, 4, false, true, 2, false, 32, 1, 8>>(); return 0; }
+    if (!p.energy && p.num_species == 0) { k = entry<Cfg<2, 4, 4, false, false, 0, false, 32, 1, 8>>(); return 0; }
+    return fail(-2, "quad4 Q1/Q1: instantiated field sets are NS, NS+T+2 species");
   }
   return fail(-2, "element type / interpolation combination not supported by the GPU fill");
 }
@@ -366,6 +378,8 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
   P.U_norm = U_norm;
   P.lame_mu = p.lame_mu;
   P.lame_lambda = p.lame_lambda;
+  P.pspg = p.pspg;
+  P.ps_scaling = p.ps_scaling;
   P.prof = c->d_prof;
   P.debug = getenv("GOMA_GPU_DEBUG") ? atoi(getenv("GOMA_GPU_DEBUG")) : 0;
   if (p.transient && !(delta_t > 0.0)) return fail(-2, "transient fill needs delta_t > 0");

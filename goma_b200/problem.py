@@ -186,6 +186,42 @@ class Problem:
                         xdot[idx] = 0.0
         return x
 
+    # ------------------------------------------------- PSPG global norms (host side)
+    def global_h_elem_siz(self, elem_owned=None) -> float:
+        """global_h_elem_siz (``mm_fill_aux.c:1128-1207``): mean over the (owned) elements of
+        sqrt(sum_p hsquared[p] / dim), hsquared from face-centroid differences (h_elem_siz, ``:844``).
+        In a distributed run this is the local sum; the host all-reduces (SUM) and divides by the
+        global element count."""
+        m = self.mesh
+        X = m.coords[:, m.conn]  # [dim, ne, npe]
+        if m.dim == 2:
+            h0 = 0.5 * (X[:, :, 1] + X[:, :, 2]) - 0.5 * (X[:, :, 0] + X[:, :, 3])
+            h1 = 0.5 * (X[:, :, 0] + X[:, :, 1]) - 0.5 * (X[:, :, 2] + X[:, :, 3])
+            hsq = (h0 ** 2).sum(0) + (h1 ** 2).sum(0)
+        else:
+            f = lambda a, b, c, d: 0.25 * (X[:, :, a] + X[:, :, b] + X[:, :, c] + X[:, :, d])
+            p1, p2, p3 = f(0, 1, 2, 3), f(1, 2, 5, 6), f(2, 3, 6, 7)
+            p4, p5, p6 = f(0, 1, 4, 5), f(0, 3, 4, 7), f(4, 5, 6, 7)
+            hsq = ((p2 - p5) ** 2).sum(0) + ((p3 - p4) ** 2).sum(0) + ((p1 - p6) ** 2).sum(0)
+        h = np.sqrt(hsq / m.dim)
+        if elem_owned is not None:
+            h = h[elem_owned]
+        return float(h.sum() / m.num_elems) if elem_owned is None else float(h.sum())
+
+    def global_velocity_norm(self, x, num_owned_nodes=None) -> float:
+        """global_velocity_norm (``mm_fill_aux.c:612-680``): mean of the squared velocity unknowns over
+        the owned nodes (note: no square root in the reference)."""
+        first, node_kind, kinds = self.unknown_map()
+        nown = self.mesh.num_nodes if num_owned_nodes is None else num_owned_nodes
+        tot, cnt = 0.0, 0
+        for kind_id, slots in enumerate(kinds):
+            nodes = np.nonzero(node_kind[:nown] == kind_id)[0]
+            for name in ("U", "V", "W")[: self.dim]:
+                v = x[first[nodes] + slots.index(name)]
+                tot += float((v * v).sum())
+                cnt += len(v)
+        return tot / cnt
+
     # ------------------------------------------------------------------- decks
     def deck(self) -> str:
         """Goma problem-description file for this problem (cards per SURVEY.md App. C)."""

@@ -98,11 +98,32 @@ def build_case(name):
                     etm_momentum=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0), etm_energy=(1.0, 1.0, 1.0, 1.0, 1.0),
                     bcs=_bcs(2, True))
         return p, {"delta_t": 0.02, "theta": 0.0, "time": 0.1}
+    if name.startswith("c5_"):
+        bcs = [Dirichlet("U", 1, 1.0), Dirichlet("V", 1, 0.0), Dirichlet("U", 4, 0.0, relax=1.0), Dirichlet("T", 1, 1.0),
+               Dirichlet("T", 2, 0.0, relax=1.0), Dirichlet("Y", 3, 0.7, species=1), Dirichlet("Y", 4, 0.2, relax=1.0),
+               Dirichlet("P", 7, 0.0)]
+        common = dict(interp="Q1Q1", energy=True, n_species=2, rho=1.2, mu=0.3, k=0.2, Cp=1.5, beta=0.4, Tref=0.2,
+                      diffusivity=(0.05, 0.11, 1.0, 1.0), gravity=(0.1, -0.2, -1.0), ns_source="BOUSSINESQ",
+                      heat_source=0.3, ps_scaling=0.1)
+        if name == "c5_hex8_pspg_local_transient":
+            m = box_mesh("HEX8", (3, 2, 2), perturb=0.15, seed=3)
+            p = Problem(m, pspg="local", transient=True, etm_momentum=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0),
+                        etm_energy=(1.0,) * 5, etm_species=(1.0,) * 5, bcs=bcs + [Dirichlet("W", 5, 0.0)], **common)
+            return p, {"delta_t": 0.05, "theta": 0.0, "time": 0.3}
+        if name == "c5_hex8_pspg_global":
+            m = box_mesh("HEX8", (3, 3, 2), perturb=0.15, seed=6)
+            p = Problem(m, pspg="global", bcs=bcs + [Dirichlet("W", 5, 0.0)], **common)
+            return p, {}
+        if name == "c5_quad4_pspg_local":
+            m = box_mesh("QUAD4", (5, 4), perturb=0.15, seed=8)
+            p = Problem(m, pspg="local", bcs=bcs, **common)
+            return p, {}
     raise KeyError(name)
 
 
 GOLDEN_CASES = ["c1_quad9_ns", "c1_quad9_ns_transient", "c2_hex27_ns", "c3_hex27_boussinesq",
-                "c3_quad9_bouss_transient"]
+                "c3_quad9_bouss_transient", "c5_hex8_pspg_local_transient", "c5_hex8_pspg_global",
+                "c5_quad4_pspg_local"]
 
 
 def case_state(name):

@@ -43,16 +43,17 @@ def test_gpu_matches_reference_fixture(built, name, scatter):
     mf.set_option("scatter", scatter)
     assert mf.nnz_plus == len(g["ija"])
     np.testing.assert_array_equal(mf.export_msr(), g["ija"])
+    h, U = (p.global_h_elem_siz(), p.global_velocity_norm(st["x"])) if p.pspg else (0.0, 0.0)
     err, a, r = mf.matrix_fill_full(st["x"], st.get("x_old"), st.get("x_older"), st.get("xdot"), st.get("xdot_old"),
                                     delta_t=kw.get("delta_t", 0.0), theta=kw.get("theta", 0.0),
-                                    time_value=kw.get("time", 0.0))
+                                    time_value=kw.get("time", 0.0), h_elem_avg=h, U_norm=U)
     assert err == 0 and not mf.flags.any()
     assert_close(a, g["a"], "Jacobian")
     assert_close(r, g["resid"], "residual")
     # residual-only call (modified Newton, mm_sol_nonlinear.c:1226-1231) leaves the same residual
     err, _, r2 = mf.matrix_fill_full(st["x"], st.get("x_old"), st.get("x_older"), st.get("xdot"), st.get("xdot_old"),
                                      delta_t=kw.get("delta_t", 0.0), theta=kw.get("theta", 0.0),
-                                     assemble_jacobian=False)
+                                     h_elem_avg=h, U_norm=U, assemble_jacobian=False)
     assert_close(r2, g["resid"], "residual-only")
     mf.close()
 
@@ -136,6 +137,33 @@ def test_gpu_stokes_residual_is_affine(built):
     lhs = r - r0
     rhs = A @ st["x"]
     assert np.abs(lhs - rhs).max() / np.abs(rhs).max() < 1e-11
+    mf.close()
+
+
+@pytest.mark.parametrize("pspg,transient", [("local", False), ("global", True)])
+def test_gpu_c5_hex8_matches_port_oracle(built, pspg, transient):
+    """Config C5 physics (hex8 Q1/Q1 PSPG + energy + 2 species) on a seeded mesh larger than the fixtures."""
+    m = box_mesh("HEX8", (7, 6, 5), perturb=0.12, seed=31)
+    bcs = [Dirichlet("U", 1, 1.0), Dirichlet("V", 1, 0.0), Dirichlet("W", 5, 0.0), Dirichlet("T", 1, 1.0),
+           Dirichlet("T", 2, 0.0, relax=1.0), Dirichlet("Y", 3, 0.7, species=1), Dirichlet("P", 7, 0.0)]
+    p = Problem(m, interp="Q1Q1", energy=True, n_species=2, rho=0.9, mu=0.02, k=0.1, Cp=1.2, beta=0.6, Tref=0.1,
+                diffusivity=(0.03, 0.2, 1.0, 1.0), gravity=(0.0, 0.3, -1.0), ns_source="BOUSSINESQ", heat_source=0.2,
+                pspg=pspg, ps_scaling=0.1, transient=transient, etm_momentum=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0),
+                etm_energy=(1.0,) * 5, etm_species=(1.0,) * 5, bcs=bcs)
+    st = make_state(p, seed=17, transient=transient, delta_t=0.02, theta=0.5)
+    kw = dict(delta_t=0.02, theta=0.5) if transient else {}
+    h, U = p.global_h_elem_siz(), p.global_velocity_norm(st["x"])
+    ija = capi.pattern_msr(p)
+    rc, a_ref, r_ref = port.port_fill(p, ija, st, h_elem_avg=h, U_norm=U, **kw)
+    assert rc == 0
+    mf = MatrixFill(p)
+    for scatter in (0, 2):
+        mf.set_option("scatter", scatter)
+        err, a, r = mf.matrix_fill_full(st["x"], st.get("x_old"), st.get("x_older"), st.get("xdot"), st.get("xdot_old"),
+                                        h_elem_avg=h, U_norm=U, **kw)
+        assert err == 0
+        assert_close(a, a_ref, f"Jacobian scatter={scatter}")
+        assert_close(r, r_ref, f"residual scatter={scatter}")
     mf.close()
 
 

@@ -30,7 +30,11 @@ def test_port_oracle_matches_reference_fixture(built, name):
     p, kw, st = case_state(name)
     g = golden(name)
     np.testing.assert_array_equal(g["state_x"], st["x"])  # the fixture was made from this very state
-    rc, a, r = port.port_fill(p, g["ija"], st, delta_t=kw.get("delta_t", 0.0), theta=kw.get("theta", 0.0))
+    h, U = (p.global_h_elem_siz(), p.global_velocity_norm(st["x"])) if p.pspg else (0.0, 0.0)
+    if p.pspg:  # host restatement of global_h_elem_siz / global_velocity_norm vs the reference's values
+        assert abs(h - float(g["h_elem_avg"])) < 1e-14 and abs(U - float(g["U_norm"])) < 1e-14
+    rc, a, r = port.port_fill(p, g["ija"], st, delta_t=kw.get("delta_t", 0.0), theta=kw.get("theta", 0.0),
+                              h_elem_avg=h, U_norm=U)
     assert rc == 0
     assert rel_err(a, g["a"]) < TOL
     assert rel_err(r, g["resid"]) < TOL
@@ -51,7 +55,7 @@ def test_unknown_map_and_sparsity_bit_exact(built, name):
     xm = p.preset_dirichlet(np.full(len(st["x"]), -7.77e77))
     np.testing.assert_array_equal(xm, g["x_dirichlet"])
     # Inter_Mask rows restated in Problem.inter_mask
-    ids = [0, 1, 2, 3, 9]
+    ids = [0, 1, 2, 3, 4, 9]
     for r in ids:
         for c in ids:
             if g["inter_mask"][r, r] and g["inter_mask"][c, c]:
