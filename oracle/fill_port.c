@@ -26,6 +26,13 @@
  *                                              residual :1281-1319, d_pspg :1321-1524); continuity terms
  *                                              src/mm_fill_continuity.c:604-613,746-756,~870,~1200;
  *                                              h_elem_siz src/mm_fill_aux.c:844, element_velocity :759
+ *   mesh (ALE)         assemble_mesh           src/mm_fill_terms.c:421-428 (R, ARBITRARY), :529-576 (J_d_d);
+ *                                              belly_flop src/mm_fill_solid.c:77-1120 (grad_d, Eulerian strain,
+ *                                              volume change, neg_elem_volume :659-815); mesh_stress_tensor :3208-3287;
+ *                                              mesh sensitivities J_m_d src/mm_fill_momentum.c:2200-2442,
+ *                                              J_c_d src/mm_fill_continuity.c:1004-1148, in the closed forms
+ *                                              d(grad_phi_i[p])/d(d_bj) = -grad_phi_j[p] grad_phi_i[b],
+ *                                              d(detJ)/d(d_bj) = detJ grad_phi_j[b]  
  *   Dirichlet          put_dirichlet_in_matrix src/bc_dirich.c:44-151
  *   scatter            load_lec (MSR)          src/mm_fill.c:5241-5483 (in_list search :5461)
  * Cartesian coordinates only (h3 = 1, grad_phi_e[i][a][p][q] = delta_aq grad_phi[i][p],
@@ -113,12 +120,12 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
   const int cen = et == 9 ? 8 : et == 27 ? 20 : 0;
   const int np = p1 ? dim + 1 : 0;
   /* fields interpolated with phi, in nodal order */
-  int fslot[MAXF], nf = 0, fT = -1, fP = -1, fY = -1;
+  int fslot[MAXF], nf = 0, fT = -1, fP = -1, fY = -1, fD = -1;
   for (int d = 0; d < dim; d++) fslot[nf++] = GOMA_SLOT_U + d;
   if (p->energy) { fT = nf; fslot[nf++] = GOMA_SLOT_T; }
   if (p->num_species) fY = nf;
   for (int w = 0; w < p->num_species; w++) fslot[nf++] = GOMA_SLOT_Y0 + w;
-  if (p->ale) for (int d = 0; d < dim; d++) fslot[nf++] = GOMA_SLOT_DX + d;
+  if (p->ale) { fD = nf; for (int d = 0; d < dim; d++) fslot[nf++] = GOMA_SLOT_DX + d; }
   if (!p1) { fP = nf; fslot[nf++] = GOMA_SLOT_P; }
   const int ns = p->num_species;
   const int ndof = nf * nn + np; /* element block size; P1 dofs last */
@@ -128,6 +135,9 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
   memcpy(ee, p->etm_energy, sizeof(ee));
   memcpy(es, p->etm_species, sizeof(es));
   if (!transient) em[0] = ee[0] = es[0] = 0.0;
+  const double ed3 = p->etm_mesh[3];
+  const double lam = p->lame_lambda, mus = p->lame_mu;
+  const int nonlinear_mesh = 1; /* Solid Constitutive Equation = NONLINEAR (the deck this repo writes) */
   const double ec0 = p->etm_continuity[0];
   const double tfac = transient ? (1.0 + 2.0 * theta) / delta_t : 0.0;
   const double rho = p->rho, mu = p->mu, rcp = p->rho * p->heat_capacity, kc = p->conductivity;
@@ -161,6 +171,9 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
     }
     memset(R, 0, sizeof(double) * ndof);
     memset(J, 0, sizeof(double) * ndof * ndof);
+    if (p->ale) /* the map uses the displaced coordinates x = X + d (beer_belly, mm_fill_util.c:258-276) */
+      for (int d = 0; d < dim; d++)
+        for (int i = 0; i < nn; i++) X[d][i] += U[fD + d][i];
 
     /* BLOCK 1.5 (mm_fill.c:754-787): element-level PSPG data */
     double tau = 0.0, tau1 = 0.0, hh_siz = 0.0, v_avg[3] = {0, 0, 0}, dtau_dv[3] = {0, 0, 0};
@@ -267,6 +280,10 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
       }
       double div_v = 0.0;
       for (int q = 0; q < dim; q++) div_v += grad[q][q];
+      /* convection velocity v - xdot_mesh (get_convection_velocity, mm_fill_species.c:9479-9492;
+       * assemble_momentum's x_dot, mm_fill_momentum.c:414-416) */
+      double vcv[3] = {0, 0, 0};
+      for (int q = 0; q < dim; q++) vcv[q] = val[q] - (p->ale && transient ? dot[fD + q] : 0.0);
 
       for (int i = 0; i < nn; i++) {
         const double phi_i = phi[i];
@@ -275,7 +292,7 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
           const int row = a_ * nn + i;
           if (assemble_residual) {
             double adv = 0.0, diff = 0.0;
-            for (int q = 0; q < dim; q++) adv += val[q] * grad[a_][q]; /* v_q d_q v_a */
+            for (int q = 0; q < dim; q++) adv += vcv[q] * grad[a_][q]; /* (v - xdot)_q d_q v_a */
             for (int q = 0; q < dim; q++) {
               double Pi = mu * (grad[q][a_] + grad[a_][q]) - (q == a_ ? Pr : 0.0);
               diff += g[i][q] * Pi;
@@ -286,7 +303,7 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
           if (assemble_jacobian) {
             for (int j = 0; j < nn; j++) {
               double gij = 0.0, vgj = 0.0;
-              for (int q = 0; q < dim; q++) { gij += g[i][q] * g[j][q]; vgj += val[q] * g[j][q]; }
+              for (int q = 0; q < dim; q++) { gij += g[i][q] * g[j][q]; vgj += vcv[q] * g[j][q]; }
               for (int b = 0; b < dim; b++) {
                 double mass = (a_ == b) ? -em[0] * rho * phi_i * phi[j] * tfac * d_area : 0.0;
                 double adv = -em[1] * rho * phi_i * (phi[j] * grad[a_][b] + (a_ == b ? vgj : 0.0)) * d_area;
@@ -305,13 +322,13 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
           const double D = p->diffusivity[w];
           if (assemble_residual) {
             double adv = 0.0, diff = 0.0;
-            for (int q = 0; q < dim; q++) { adv += val[q] * grad[fw][q]; diff += g[i][q] * (-D * grad[fw][q]); }
+            for (int q = 0; q < dim; q++) { adv += vcv[q] * grad[fw][q]; diff += g[i][q] * (-D * grad[fw][q]); }
             R[row] += -es[0] * phi_i * dot[fw] * d_area - es[1] * phi_i * adv * d_area + es[3] * diff * d_area;
           }
           if (assemble_jacobian) {
             for (int j = 0; j < nn; j++) {
               double gij = 0.0, vgj = 0.0;
-              for (int q = 0; q < dim; q++) { gij += g[i][q] * g[j][q]; vgj += val[q] * g[j][q]; }
+              for (int q = 0; q < dim; q++) { gij += g[i][q] * g[j][q]; vgj += vcv[q] * g[j][q]; }
               J[row * ndof + fw * nn + j] += (-es[0] * phi_i * phi[j] * tfac - es[1] * phi_i * vgj - es[3] * D * gij) * d_area;
               for (int b = 0; b < dim; b++) J[row * ndof + b * nn + j] += -es[1] * phi_i * phi[j] * grad[fw][b] * d_area;
             }
@@ -366,18 +383,132 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
           const int row = fT * nn + i;
           if (assemble_residual) {
             double adv = 0.0, diff = 0.0;
-            for (int q = 0; q < dim; q++) { adv += val[q] * grad[fT][q]; diff += g[i][q] * (-kc * grad[fT][q]); }
+            for (int q = 0; q < dim; q++) { adv += vcv[q] * grad[fT][q]; diff += g[i][q] * (-kc * grad[fT][q]); }
             R[row] += -ee[0] * rcp * phi_i * dot[fT] * d_area - ee[1] * rcp * phi_i * adv * d_area +
                       ee[3] * diff * d_area + ee[4] * phi_i * p->heat_source * d_area;
           }
           if (assemble_jacobian) {
             for (int j = 0; j < nn; j++) {
               double gij = 0.0, vgj = 0.0;
-              for (int q = 0; q < dim; q++) { gij += g[i][q] * g[j][q]; vgj += val[q] * g[j][q]; }
+              for (int q = 0; q < dim; q++) { gij += g[i][q] * g[j][q]; vgj += vcv[q] * g[j][q]; }
               J[row * ndof + fT * nn + j] += (-ee[0] * rcp * phi_i * phi[j] * tfac - ee[1] * rcp * phi_i * vgj -
                                               ee[3] * kc * gij) * d_area;
               for (int b = 0; b < dim; b++)
                 J[row * ndof + b * nn + j] += -ee[1] * rcp * phi_i * phi[j] * grad[fT][b] * d_area;
+            }
+          }
+        }
+      }
+      /* ---- pseudo-solid mesh equations and the mesh sensitivities of the fluid equations */
+      if (p->ale) {
+        double G[3][3] = {{0}}, E[3][3], F[3][3], TT[3][3], vc, vs;
+        for (int pp_ = 0; pp_ < dim; pp_++)
+          for (int q = 0; q < dim; q++) G[pp_][q] = grad[fD + q][pp_]; /* grad_d[p][q] = d_p d_q */
+        for (int pp_ = 0; pp_ < dim; pp_++)
+          for (int q = 0; q < dim; q++) {
+            E[pp_][q] = 0.5 * (G[pp_][q] + G[q][pp_]);
+            if (nonlinear_mesh)
+              for (int a_ = 0; a_ < dim; a_++) E[pp_][q] -= 0.5 * G[pp_][a_] * G[q][a_];
+            F[pp_][q] = (pp_ == q ? 1.0 : 0.0) - G[pp_][q];
+          }
+        double cof[3][3] = {{0}}; /* d(det F)/dF[p][q] */
+        double detF;
+        if (dim == 2) {
+          detF = F[0][0] * F[1][1] - F[0][1] * F[1][0];
+          cof[0][0] = F[1][1]; cof[0][1] = -F[1][0]; cof[1][0] = -F[0][1]; cof[1][1] = F[0][0];
+        } else {
+          cof[0][0] = F[1][1] * F[2][2] - F[1][2] * F[2][1]; cof[0][1] = F[1][2] * F[2][0] - F[1][0] * F[2][2];
+          cof[0][2] = F[1][0] * F[2][1] - F[1][1] * F[2][0]; cof[1][0] = F[0][2] * F[2][1] - F[0][1] * F[2][2];
+          cof[1][1] = F[0][0] * F[2][2] - F[0][2] * F[2][0]; cof[1][2] = F[0][1] * F[2][0] - F[0][0] * F[2][1];
+          cof[2][0] = F[0][1] * F[1][2] - F[0][2] * F[1][1]; cof[2][1] = F[0][2] * F[1][0] - F[0][0] * F[1][2];
+          cof[2][2] = F[0][0] * F[1][1] - F[0][1] * F[1][0];
+          detF = F[0][0] * cof[0][0] + F[0][1] * cof[0][1] + F[0][2] * cof[0][2];
+        }
+        if (detF <= 0.0) { rc = -1; goto done; } /* neg_elem_volume (mm_fill_solid.c:659-663, :811-815) */
+        vc = 1.0 / detF;
+        vs = 3.0 * (pow(vc, 1.0 / 3.0) - 1.0);
+        for (int pp_ = 0; pp_ < dim; pp_++)
+          for (int q = 0; q < dim; q++) TT[pp_][q] = lam * vs * (pp_ == q) + 2.0 * mus * E[pp_][q];
+        /* fluid stress at this point, for J_m_d */
+        double Pi[3][3], advv[3];
+        for (int a_ = 0; a_ < dim; a_++) {
+          advv[a_] = 0.0;
+          for (int q = 0; q < dim; q++) {
+            advv[a_] += vcv[q] * grad[a_][q];
+            Pi[a_][q] = mu * (grad[q][a_] + grad[a_][q]) - (q == a_ ? Pr : 0.0);
+          }
+        }
+        for (int i = 0; i < nn; i++) {
+          double giTT[3], giPi[3];
+          for (int a_ = 0; a_ < dim; a_++) {
+            giTT[a_] = giPi[a_] = 0.0;
+            for (int q = 0; q < dim; q++) { giTT[a_] += g[i][q] * TT[a_][q]; giPi[a_] += g[i][q] * Pi[a_][q]; }
+            if (assemble_residual) R[(fD + a_) * nn + i] += -ed3 * giTT[a_] * d_area;
+          }
+          if (!assemble_jacobian) continue;
+          for (int j = 0; j < nn; j++) {
+            double vgj = 0.0;
+            for (int q = 0; q < dim; q++) vgj += vcv[q] * g[j][q];
+            for (int b = 0; b < dim; b++) {
+              /* d grad_d[p][q] / d d_bj = grad_phi_j[p] (delta_qb - grad_d[b][q]) */
+              double dG[3][3], dE[3][3], ddet = 0.0;
+              for (int pp_ = 0; pp_ < dim; pp_++)
+                for (int q = 0; q < dim; q++) dG[pp_][q] = g[j][pp_] * ((q == b ? 1.0 : 0.0) - G[b][q]);
+              for (int pp_ = 0; pp_ < dim; pp_++)
+                for (int q = 0; q < dim; q++) {
+                  dE[pp_][q] = 0.5 * (dG[pp_][q] + dG[q][pp_]);
+                  if (nonlinear_mesh)
+                    for (int a_ = 0; a_ < dim; a_++) dE[pp_][q] -= 0.5 * (dG[pp_][a_] * G[q][a_] + G[pp_][a_] * dG[q][a_]);
+                  ddet += cof[pp_][q] * (-dG[pp_][q]); /* d det(F), F = I - grad_d */
+                }
+              const double dvc = -ddet * vc * vc, dvs = dvc * pow(vc, -2.0 / 3.0);
+              for (int a_ = 0; a_ < dim; a_++) {
+                /* J_d_d = diff_a + diff_b + diff_c (mm_fill_terms.c:529-576) */
+                double gjTT = 0.0, gidTT = 0.0;
+                for (int q = 0; q < dim; q++) {
+                  gjTT += g[j][q] * TT[a_][q];
+                  gidTT += g[i][q] * (lam * dvs * (a_ == q) + 2.0 * mus * dE[a_][q]);
+                }
+                J[((fD + a_) * nn + i) * ndof + (fD + b) * nn + j] +=
+                    ed3 * (g[i][b] * gjTT - gidTT - g[j][b] * giTT[a_]) * d_area;
+                /* J_m_d (mm_fill_momentum.c:2200-2442), steady */
+                double gjPi = 0.0, gidPi = 0.0;
+                for (int q = 0; q < dim; q++) {
+                  gjPi += g[j][q] * Pi[a_][q];
+                  gidPi += g[i][q] * mu * (-g[j][a_] * grad[q][b] - g[j][q] * grad[a_][b]);
+                }
+                J[(a_ * nn + i) * ndof + (fD + b) * nn + j] +=
+                    (em[1] * rho * phi[i] * (vgj * grad[a_][b] - advv[a_] * g[j][b]) +
+                     em[3] * (g[i][b] * gjPi - gidPi - g[j][b] * giPi[a_]) + em[4] * phi[i] * fs[a_] * g[j][b]) * d_area;
+                /* transient: mass x d|J| (:2213-2220) and advection_c = d(v - xdot)/d d_bj . grad v, which the
+                 * reference adds only when the mass term is on (:2300-2318) */
+                if (em[0] != 0.0)
+                  J[(a_ * nn + i) * ndof + (fD + b) * nn + j] +=
+                      (-em[0] * rho * phi[i] * dot[a_] * g[j][b] + em[1] * rho * phi[i] * tfac * phi[j] * grad[a_][b]) * d_area;
+              }
+              /* J_e_d (mm_fill_energy.c:758-925) and J_s_d (mm_fill_species.c:1103-1330): same three-part pattern */
+              for (int s_ = 0; s_ < (p->energy ? 1 : 0) + ns; s_++) {
+                const int fs_ = (p->energy && s_ == 0) ? fT : fY + s_ - (p->energy ? 1 : 0);
+                const int isT = (fs_ == fT);
+                const double cm = isT ? ee[0] * rcp : es[0], ca = isT ? ee[1] * rcp : es[1];
+                const double cd = isT ? ee[3] * kc : es[3] * p->diffusivity[fs_ - fY];
+                const double src = isT ? ee[4] * p->heat_source : 0.0;
+                double vgs = 0.0, gjgs = 0.0, gigs = 0.0, gij = 0.0;
+                for (int q = 0; q < dim; q++) {
+                  vgs += vcv[q] * grad[fs_][q]; gjgs += g[j][q] * grad[fs_][q];
+                  gigs += g[i][q] * grad[fs_][q]; gij += g[i][q] * g[j][q];
+                }
+                double v = ca * phi[i] * (vgj * grad[fs_][b] - vgs * g[j][b]) +
+                           cd * (gjgs * g[i][b] + gij * grad[fs_][b] - gigs * g[j][b]) + src * phi[i] * g[j][b];
+                if (cm != 0.0) v += -cm * phi[i] * dot[fs_] * g[j][b] + ca * phi[i] * tfac * phi[j] * grad[fs_][b];
+                J[(fs_ * nn + i) * ndof + (fD + b) * nn + j] += v * d_area;
+              }
+              /* J_c_d (mm_fill_continuity.c:1004-1148): d(div v) + div v d|J| */
+              double ddiv = 0.0;
+              for (int q = 0; q < dim; q++) ddiv -= g[j][q] * grad[q][b];
+              if (i == 0)
+                for (int q = 0; q < np; q++)
+                  J[(nf * nn + q) * ndof + (fD + b) * nn + j] += ec0 * psi[q] * (ddiv + div_v * g[j][b]) * d_area;
             }
           }
         }
@@ -416,6 +547,7 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
       }
     }
   }
+done:
   free(R); free(J); free(gun); free(lnode);
   return rc;
 }

@@ -118,12 +118,31 @@ def build_case(name):
             m = box_mesh("QUAD4", (5, 4), perturb=0.15, seed=8)
             p = Problem(m, pspg="local", bcs=bcs, **common)
             return p, {}
+    if name.startswith("c4_"):
+        # ALE pseudo-solid mesh (ARBITRARY / NONLINEAR), volumetric assembly only: every mesh-sensitivity block
+        bcs2 = [Dirichlet("U", 1, 1.0), Dirichlet("V", 1, 0.0), Dirichlet("DX", 1, 0.0), Dirichlet("DY", 1, 0.0),
+                Dirichlet("DX", 3, 0.01, relax=1.0), Dirichlet("DY", 3, 0.0), Dirichlet("U", 4, 0.0),
+                Dirichlet("V", 4, 0.0, relax=1.0)]
+        mat = dict(ale=True, rho=1.3, mu=0.7, gravity=(0.3, -0.2, 0.1), lame_mu=0.9, lame_lambda=1.7)
+        if name == "c4_quad9_ale":
+            m = box_mesh("QUAD9", (6, 3), lo=(0, 0), hi=(2, 1), perturb=0.1, seed=11)
+            return Problem(m, bcs=bcs2, **mat), {}
+        if name == "c4_hex27_ale":
+            m = box_mesh("HEX27", (2, 2, 1), perturb=0.1, seed=12)
+            bcs3 = bcs2 + [Dirichlet("DZ", 5, 0.0), Dirichlet("W", 6, 0.5, relax=1.0), Dirichlet("DZ", 6, 0.02, relax=1.0)]
+            return Problem(m, bcs=bcs3, **mat), {}
+        if name == "c4_quad9_ale_energy_transient":
+            m = box_mesh("QUAD9", (4, 3), lo=(0, 0), hi=(2, 1), perturb=0.1, seed=13)
+            p = Problem(m, transient=True, energy=True, k=0.07, Cp=1.4, beta=0.8, Tref=0.3, ns_source="BOUSSINESQ",
+                        heat_source=0.6, etm_momentum=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0), etm_energy=(1.0,) * 5,
+                        etm_mesh=(1.0, 1.0, 1.0, 1.0, 1.0), bcs=bcs2 + [Dirichlet("T", 1, 1.0)], **mat)
+            return p, {"delta_t": 0.02, "theta": 0.5, "time": 0.1}
     raise KeyError(name)
 
 
 GOLDEN_CASES = ["c1_quad9_ns", "c1_quad9_ns_transient", "c2_hex27_ns", "c3_hex27_boussinesq",
                 "c3_quad9_bouss_transient", "c5_hex8_pspg_local_transient", "c5_hex8_pspg_global",
-                "c5_quad4_pspg_local"]
+                "c5_quad4_pspg_local", "c4_quad9_ale", "c4_hex27_ale", "c4_quad9_ale_energy_transient"]
 
 
 def case_state(name):
