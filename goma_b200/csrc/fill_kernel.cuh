@@ -101,8 +101,15 @@ struct Cfg {
   static constexpr int G_HB = G_RFY + NSPEC * DIM;                 // PSPG: tau e1 rho d_b v_a [a][b]
   static constexpr int G_MOM = G_HB + (P1 ? 0 : DIM * DIM);        // PSPG: momentum residual  [a]
   static constexpr int G_PS = G_MOM + (P1 ? 0 : DIM);              // PSPG: tau * momentum     [a]
-  static constexpr int GPD = (G_PS + (P1 ? 0 : DIM) + 1) & ~1;
-  static constexpr bool GENERAL = !P1 || NSPEC > 0;  // generic block accumulation instead of the NS(+T) fast path
+  // ALE (pseudo-solid mesh): mesh residual operand and the per-Gauss-point pieces of J_d_d
+  static constexpr int G_ZERO = G_PS + (P1 ? 0 : DIM);             // 0.0 (rows without a phi_i term)
+  static constexpr int G_RD = G_ZERO + (ALE ? 1 : 0);              // -ed3 TT[a][p], multiplies w grad_phi_i[p]
+  static constexpr int G_GM = G_RD + (ALE ? DIM * DIM : 0);        // sum_c grad_d[a][c] M[b][c],  M = I - grad_d^T
+  static constexpr int G_CM = G_GM + (ALE ? DIM * DIM : 0);        // sum_q cof(F)[p][q] M[b][q]   [p][b]
+  static constexpr int G_C1 = G_CM + (ALE ? DIM * DIM : 0);        // ed3 lambda vc^2 vc^(-2/3)
+  static constexpr int GPD = (G_C1 + (ALE ? 1 : 0) + 1) & ~1;
+  static constexpr bool GENERAL = !P1 || NSPEC > 0 || ALE;  // generic block accumulation instead of the NS(+T) fast path
+  static constexpr bool DIRECT = ALE;  // tiles go from registers straight to their matrix slots (no staging)
   // staged write-out of the element block: rows (node i, field) x columns (node j in global order, field)
   static constexpr int NROW = NF * NN, NCOL = NF * NN;
   static constexpr int CAP = NGP * NN * 9;  // doubles in the operand arena (SI + SJa + SJb + VG), reused as stage
@@ -297,7 +304,12 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
     s.kind[k] = P.node_kind[nd];
     s.first[k] = P.pair_first ? P.pair_first[(size_t)elem * NN + k] : 0u;
 #pragma unroll
-    for (int d = 0; d < DIM; d++) s.X[d][k] = P.coord[d][nd];
+    for (int d = 0; d < DIM; d++) {
+      double xc = P.coord[d][nd];
+      // ALE: the map is built on the displaced coordinates x = X + d (beer_belly, mm_fill_util.c:258-276)
+      if (C::ALE) xc += P.x[s.fu[k] + P.kind_slot[s.kind[k]][GOMA_SLOT_DX + d]];
+      s.X[d][k] = xc;
+    }
   }
   if (tid == 0) s.node_first = P.node_first ? P.node_first[elem] : 0u;
   for (int idx = tid; idx < NN * NN; idx += NT) {
@@ -382,6 +394,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
       J[7] = -(j00 * j21 - j20 * j01) * rd;
       J[8] = (j00 * j11 - j10 * j01) * rd;
     }
+    if (fabs(det) < 1.e-10) P.flags[2] = 1;  // zero_detJ (mm_fill_util.c:335-343)
     s.w[tid] = det * t_wt[tid];  // d_area = detJ * wt * h3, h3 = 1 (Cartesian)
   }
   if (!C::P1 && tid == NT - 1) {
@@ -501,6 +514,11 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
 #pragma unroll
       for (int b = 0; b < DIM; b++) gv[a][b] = s.F[gp][C::F_V + a][1 + b];
     }
+    // convection velocity v - xdot_mesh (get_convection_velocity, mm_fill_species.c:9479-9492;
+    // x_dot of assemble_momentum, mm_fill_momentum.c:414-416); Udot is zero in steady runs
+    double vc[DIM];
+#pragma unroll
+    for (int a = 0; a < DIM; a++) vc[a] = v[a] - (C::ALE ? s.F[gp][C::F_D + a][1 + DIM] : 0.0);
     const double T = C::ENERGY ? s.F[gp][C::F_T][0] : 0.0;
     const double Pr = C::P1 ? s.Pgp[gp] : s.F[gp][C::F_P][0];
     double fs[3], dfdT[3];
@@ -511,7 +529,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
       div += gv[a][a];
       double adv = 0.0;
 #pragma unroll
-      for (int p = 0; p < DIM; p++) adv += v[p] * gv[a][p];
+      for (int p = 0; p < DIM; p++) adv += vc[p] * gv[a][p];
       // residual, momentum a (mm_fill_momentum.c:534-662): mass + advection + source multiply phi_i
       G[C::G_RQ + a] = -P.etm_mom[0] * P.rho * vdot[a] - P.etm_mom[1] * P.rho * adv + P.etm_mom[4] * fs[a];
 #pragma unroll
@@ -530,7 +548,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
 #pragma unroll
       for (int p = 0; p < DIM; p++) {
         const double gY = s.F[gp][C::F_Y + w][1 + p];
-        adv += v[p] * gY;
+        adv += vc[p] * gY;
         G[C::G_GY + w * DIM + p] = -P.etm_species[1] * gY;
         G[C::G_RFY + w * DIM + p] = P.etm_species[3] * (-P.diffusivity[w] * gY);
       }
@@ -558,12 +576,59 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
 #pragma unroll
       for (int p = 0; p < DIM; p++) {
         double gT = s.F[gp][C::F_T][1 + p];
-        adv += v[p] * gT;
+        adv += vc[p] * gT;
         G[C::G_GT + p] = ce_adv * gT;
         G[C::G_RF + p] = P.etm_energy[3] * (-P.k * gT);  // + grad_phi_i . q, q = -k grad T
       }
       G[C::G_RE] = -P.etm_energy[0] * rcp * s.F[gp][C::F_T][1 + DIM] - P.etm_energy[1] * rcp * adv +
                    P.etm_energy[4] * P.heat_source;
+    }
+    if (C::ALE) {
+      // belly_flop (mm_fill_solid.c:77-1120): grad_d, Eulerian strain of the NONLINEAR model, volume change;
+      // mesh_stress_tensor (:3208-3287): TT = lambda vs I + 2 mu E,  vs = 3 (vc^(1/3) - 1)
+      double Gd[DIM][DIM], M[DIM][DIM], Fm[3][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 0.0, 1.0}}, cof[3][3];
+#pragma unroll
+      for (int p = 0; p < DIM; p++)
+#pragma unroll
+        for (int q = 0; q < DIM; q++) {
+          Gd[p][q] = s.F[gp][C::F_D + q][1 + p];  // grad_d[p][q] = d_p d_q
+          Fm[p][q] = (p == q ? 1.0 : 0.0) - Gd[p][q];
+        }
+#pragma unroll
+      for (int b = 0; b < DIM; b++)
+#pragma unroll
+        for (int q = 0; q < DIM; q++) M[b][q] = (q == b ? 1.0 : 0.0) - Gd[b][q];
+      cof[0][0] = Fm[1][1] * Fm[2][2] - Fm[1][2] * Fm[2][1];
+      cof[0][1] = Fm[1][2] * Fm[2][0] - Fm[1][0] * Fm[2][2];
+      cof[0][2] = Fm[1][0] * Fm[2][1] - Fm[1][1] * Fm[2][0];
+      cof[1][0] = Fm[0][2] * Fm[2][1] - Fm[0][1] * Fm[2][2];
+      cof[1][1] = Fm[0][0] * Fm[2][2] - Fm[0][2] * Fm[2][0];
+      cof[1][2] = Fm[0][1] * Fm[2][0] - Fm[0][0] * Fm[2][1];
+      cof[2][0] = Fm[0][1] * Fm[1][2] - Fm[0][2] * Fm[1][1];
+      cof[2][1] = Fm[0][2] * Fm[1][0] - Fm[0][0] * Fm[1][2];
+      cof[2][2] = Fm[0][0] * Fm[1][1] - Fm[0][1] * Fm[1][0];
+      const double detF = Fm[0][0] * cof[0][0] + Fm[0][1] * cof[0][1] + Fm[0][2] * cof[0][2];
+      if (detF <= 0.0) P.flags[0] = 1;  // neg_elem_volume (mm_fill_solid.c:659-663, :811-815)
+      const double vch = 1.0 / detF, cb = cbrt(vch);
+      const double vs = 3.0 * (cb - 1.0);
+      const double ed3 = P.etm_mesh[3];
+      G[C::G_ZERO] = 0.0;
+      G[C::G_C1] = ed3 * P.lame_lambda * vch * vch / (cb * cb);
+#pragma unroll
+      for (int a = 0; a < DIM; a++)
+#pragma unroll
+        for (int b = 0; b < DIM; b++) {
+          double E = 0.5 * (Gd[a][b] + Gd[b][a]), gm = 0.0, cm = 0.0;
+#pragma unroll
+          for (int c = 0; c < DIM; c++) {
+            E -= 0.5 * Gd[a][c] * Gd[b][c];
+            gm += Gd[a][c] * M[b][c];
+            cm += cof[a][c] * M[b][c];
+          }
+          G[C::G_RD + a * DIM + b] = -ed3 * (P.lame_lambda * vs * (a == b ? 1.0 : 0.0) + 2.0 * P.lame_mu * E);
+          G[C::G_GM + a * DIM + b] = gm;
+          G[C::G_CM + a * DIM + b] = cm;
+        }
     }
   }
   for (int idx = tid; idx < NGP * NN; idx += NT) {
@@ -572,7 +637,8 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
     const double gj[3] = {ja.y, jb.x, jb.y};
     double acc = 0.0;
 #pragma unroll
-    for (int p = 0; p < DIM; p++) acc += s.F[gp][C::F_V + p][0] * gj[p];
+    for (int p = 0; p < DIM; p++)
+      acc += (s.F[gp][C::F_V + p][0] - (C::ALE ? s.F[gp][C::F_D + p][1 + DIM] : 0.0)) * gj[p];
     op.VG[gp][j] = acc;
   }
   __syncthreads();
@@ -617,10 +683,15 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
       const bool isT = C::ENERGY && f == C::F_T;
       const bool isY = f >= C::F_Y && f < C::F_Y + C::NSPEC;
       const bool isP = !C::P1 && f == C::F_P;
-      if (f >= DIM && !isT && !isY && !isP) continue;
+      const bool isD = C::ALE && f >= C::F_D && f < C::F_D + DIM;  // assemble_mesh residual (mm_fill_terms.c:421-428)
+      if (f >= DIM && !isT && !isY && !isP && !isD) continue;
       // row = sum_gp  w phi_i * G[q0]  +  w grad_phi_i[p] * G[q1 + p]
-      const int q0 = isT ? C::G_RE : isY ? C::G_RY + (f - C::F_Y) : isP ? C::G_DIV : C::G_RQ + f;
-      const int q1 = isT ? C::G_RF : isY ? C::G_RFY + (f - C::F_Y) * DIM : isP ? C::G_PS : C::G_RP + f * DIM;
+      const int q0 = isT ? C::G_RE : isY ? C::G_RY + (f - C::F_Y) : isP ? C::G_DIV : isD ? C::G_ZERO : C::G_RQ + f;
+      const int q1 = isT   ? C::G_RF
+                     : isY ? C::G_RFY + (f - C::F_Y) * DIM
+                     : isP ? C::G_PS
+                     : isD ? C::G_RD + (f - C::F_D) * DIM
+                           : C::G_RP + f * DIM;
       double r[3] = {0.0, 0.0, 0.0};
 #pragma unroll 3
       for (int gp = 0; gp < NGP; gp++) {
@@ -640,7 +711,7 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
   // ---- phase 7: P1 pressure coupling, S[i][a][p] = sum_gp w grad_phi_i[a] psi_p
   //      J_m_P (mm_fill_momentum.c:2091-2104) and J_c_v (mm_fill_continuity.c:686-716) share it.
   //      The centroid node belongs to this element only: these slots have a single writer.
-  if (C::P1 && P.assemble_jacobian) {
+  if constexpr (C::P1) if (P.assemble_jacobian) {
     const int poff = P.kind_slot[s.kind[C::CEN]][GOMA_SLOT_P];
     const int ncen = s.node[C::CEN];
     for (int idx = tid; idx < NN * DIM * NP; idx += NT) {
@@ -661,6 +732,27 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
       }
     }
     (void)ncen;
+    if constexpr (C::ALE) {
+      // J_c_d (mm_fill_continuity.c:1004-1148): d(div v)/d d_bj + div v d|J|/d d_bj, with
+      // d(grad_phi_k[q])/d d_bj = -grad_phi_j[q] grad_phi_k[b] and d|J|/d d_bj = |J| grad_phi_j[b]
+      for (int idx = tid; idx < NN * DIM * NP; idx += NT) {
+        const int j = idx / (DIM * NP), r = idx - j * DIM * NP;
+        const int b = r / NP, p = r - b * NP;
+        if (s.rsP[p] < 0) continue;
+        double acc = 0.0;
+        for (int gp = 0; gp < NGP; gp++) {
+          const double2 ja = op.SJa[gp][j], jb = op.SJb[gp][j];
+          const double gj[3] = {ja.y, jb.x, jb.y};
+          double ddiv = 0.0;
+#pragma unroll
+          for (int q = 0; q < DIM; q++) ddiv -= gj[q] * s.F[gp][C::F_V + q][1 + b];
+          acc += s.w[gp] * t_psi[gp * (DIM + 1) + p] * (P.etm_cont[0] * ddiv + s.GP[gp][C::G_DIV] * gj[b]);
+        }
+        const int row = s.fu[C::CEN] + poff + p, col = s.gun[C::F_D + b][j];
+        const long long pos = s.rsP[p] + s.po[C::CEN][j] + s.cs[j][C::F_D + b] - (col > row ? 1 : 0);
+        slot_add(P, &P.a[pos], acc, true);
+      }
+    }
   }
 }
 
@@ -836,9 +928,134 @@ __device__ __forceinline__ void gauss_loop_general(const FillParams &P, const Sm
         V[C::F_P][C::F_P] += tau * P.etm_mom[3] * gij;
         if (C::ENERGY) V[C::F_P][C::F_T] += -tau * P.etm_mom[4] * phi_j * rdf;
       }
+      if (C::ALE) {
+        // Mesh-sensitivity blocks.  Every term of a residual integrand  phi_i q0 + grad_phi_i . q1  depends on
+        // d_bj through (i) |J| -> integrand x grad_phi_j[b], (ii) grad_phi_i -> -grad_phi_i[b] (grad_phi_j . q1),
+        // (iii) the gradients inside q0/q1 -> -grad_phi_j[.] (d_b field), (iv) in transient runs the mesh
+        // velocity in v - xdot (which the reference differentiates only when the mass term is on).
+        // J_m_d mm_fill_momentum.c:2200-2442, J_e_d mm_fill_energy.c:758-925, J_s_d mm_fill_species.c:1103-1330,
+        // J_d_d mm_fill_terms.c:529-576 with d(TT)/d d_bj from mesh_stress_tensor (mm_fill_solid.c:3288-3430).
+        const double ed3 = P.etm_mesh[3];
+        double Gd[DIM][DIM], gvu[DIM][DIM];  // grad_d[p][q] = d_p d_q ; gvu[a][b] = d_b v_a
+#pragma unroll
+        for (int p = 0; p < DIM; p++)
+#pragma unroll
+          for (int q = 0; q < DIM; q++) {
+            Gd[p][q] = s.F[gp][C::F_D + q][1 + p];
+            gvu[p][q] = s.F[gp][C::F_V + p][1 + q];
+          }
+        double iM[DIM], iG[DIM], MiG[DIM], igv[DIM], CMj[DIM];
+#pragma unroll
+        for (int c = 0; c < DIM; c++) {
+          iG[c] = 0.0;
+          igv[c] = 0.0;
+#pragma unroll
+          for (int q = 0; q < DIM; q++) {
+            iG[c] += wg[q] * Gd[q][c];
+            igv[c] += wg[q] * gvu[q][c];
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < DIM; b++) {
+          iM[b] = wg[b];
+          CMj[b] = 0.0;
+#pragma unroll
+          for (int q = 0; q < DIM; q++) {
+            iM[b] -= wg[q] * Gd[b][q];
+            CMj[b] += gj[q] * G[C::G_CM + q * DIM + b];
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < DIM; b++) {
+          MiG[b] = iG[b];
+#pragma unroll
+          for (int c = 0; c < DIM; c++) MiG[b] -= Gd[b][c] * iG[c];
+        }
+        const double mass_on_m = P.etm_mom[0] != 0.0 ? tfac : 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+          // momentum a and mesh a integrands, and grad_phi_j . q1
+          double Rm = wphi * G[C::G_RQ + a], Rd = 0.0, jm = 0.0, jd = 0.0;
+#pragma unroll
+          for (int q = 0; q < DIM; q++) {
+            Rm += wg[q] * G[C::G_RP + a * DIM + q];
+            Rd += wg[q] * G[C::G_RD + a * DIM + q];
+            jm += gj[q] * G[C::G_RP + a * DIM + q];
+            jd += gj[q] * G[C::G_RD + a * DIM + q];
+          }
+#pragma unroll
+          for (int b = 0; b < DIM; b++) {
+            const double GVab = G[C::G_GV + a * DIM + b];
+            V[a][C::F_D + b] += gj[b] * Rm - wg[b] * jm - wphi * vgj * GVab - c_diff * (gj[a] * igv[b] + gij * gvu[a][b]) -
+                                mass_on_m * pp * GVab;
+            // sum_q grad_phi_i[q] dE[a][q] of the NONLINEAR (Eulerian) strain
+            const double idE = 0.5 * (gj[a] * iM[b] + gij * ((a == b ? 1.0 : 0.0) - Gd[b][a])) -
+                               0.5 * (gj[a] * MiG[b] + gij * G[C::G_GM + a * DIM + b]);
+            V[C::F_D + a][C::F_D + b] +=
+                gj[b] * Rd - wg[b] * jd - (G[C::G_C1] * CMj[b] * wg[a] + ed3 * 2.0 * P.lame_mu * idE);
+          }
+        }
+        if (C::ENERGY) {
+          double Re = wphi * G[C::G_RE], je = 0.0;
+#pragma unroll
+          for (int q = 0; q < DIM; q++) {
+            Re += wg[q] * G[C::G_RF + q];
+            je += gj[q] * G[C::G_RF + q];
+          }
+          const double mass_on = P.etm_energy[0] != 0.0 ? tfac : 0.0;
+#pragma unroll
+          for (int b = 0; b < DIM; b++)
+            V[C::F_T][C::F_D + b] += gj[b] * Re - wg[b] * je - gij * G[C::G_RF + b] -
+                                     (wphi * vgj + mass_on * pp) * G[C::G_GT + b];
+        }
+#pragma unroll
+        for (int w = 0; w < C::NSPEC; w++) {
+          double Ry = wphi * G[C::G_RY + w], jy = 0.0;
+#pragma unroll
+          for (int q = 0; q < DIM; q++) {
+            Ry += wg[q] * G[C::G_RFY + w * DIM + q];
+            jy += gj[q] * G[C::G_RFY + w * DIM + q];
+          }
+          const double mass_on = P.etm_species[0] != 0.0 ? tfac : 0.0;
+#pragma unroll
+          for (int b = 0; b < DIM; b++)
+            V[C::F_Y + w][C::F_D + b] += gj[b] * Ry - wg[b] * jy - gij * G[C::G_RFY + w * DIM + b] -
+                                         (wphi * vgj + mass_on * pp) * G[C::G_GY + w * DIM + b];
+        }
+      }
     }
   }
   (void)NN;
+}
+
+// write-out of one node-pair tile straight from registers (ALE configurations): same slot arithmetic
+// as write_rows, one thread per (i, j)
+template <class C>
+__device__ __forceinline__ void write_tile_direct(const FillParams &P, const Smem<C> &s, int i, int j, const Tile<C> &t) {
+  constexpr int NF = C::NF;
+  static_assert(C::TI == 1, "direct write-out uses 1 x 1 node-pair tiles");
+  const bool first = (s.first[i] >> j) & 1u;
+  const int ri = s.rank[i], rj = s.rank[j];
+#pragma unroll
+  for (int fr = 0; fr < NF; fr++) {
+    const long long rstart = s.rs[fr][i];
+    if (rstart < 0) continue;
+    const bool rowT = C::ENERGY && fr == C::F_T;
+    const int row = s.gun[fr][i];
+    double *arow = P.a + rstart;
+#pragma unroll
+    for (int fc = 0; fc < NF; fc++) {
+      if (rowT && !C::P1 && fc == C::F_P) continue;
+      int off = s.po[i][j] + s.cs[j][fc];
+      if (C::ENERGY && rowT) off -= s.pp[i][j];
+      double *dst;
+      if (rj != ri)
+        dst = arow + off - (rj > ri ? 1 : 0);
+      else
+        dst = (fc == fr) ? P.a + row : arow + off - (fc > fr ? 1 : 0);
+      slot_add(P, dst, t.V[0][fr][fc], first);
+    }
+  }
 }
 
 // write-out of staged rows [r0, r1): a warp walks one row, lanes along the columns in matrix order
@@ -903,7 +1120,18 @@ __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_cons
     long long c1 = GOMA_CLOCK();
     element_rows<C>(P, s, elem, tid);
     long long c2 = GOMA_CLOCK();
-    if (P.assemble_jacobian) {
+    if constexpr (C::DIRECT) {
+      if (P.assemble_jacobian) {
+#pragma unroll 1
+        for (int t = tid; t < NN * NN; t += NT) {
+          Tile<C> tile;
+          const int i = t / NN, j = t - i * NN;
+          gauss_loop_general<C>(P, s, i, j, tile);
+          write_tile_direct<C>(P, s, i, j, tile);
+        }
+      }
+      __syncthreads();
+    } else if (P.assemble_jacobian) {
       // one register tile per thread (NTILE <= TPE for every instantiated configuration)
       Tile<C> tile;
       const bool active = tid < C::NTILE;

@@ -96,7 +96,20 @@ KernelEntry entry() {
 //                      DIM NN NGP  P1    ENERGY NSPEC ALE  TPE TI MINB
 int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
   const bool p1 = p.pressure_interp == GOMA_PRESSURE_P1;
-  if (p.ale) return fail(-2, "ALE (mesh equations) path not built yet");
+  if (p.ale) {  // pseudo-solid ARBITRARY mesh motion (config C4): Q2/P1, NS (+ energy)
+    if (!p1 || p.pspg) return fail(-2, "ALE is instantiated for Q2/P1 (QUAD9/HEX27) without PSPG only");
+    if (p.num_species) return fail(-2, "ALE with species is not instantiated");
+    if (p.elem_type == GOMA_GPU_QUAD9) {
+      k = p.energy ? entry<Cfg<2, 9, 9, true, true, 0, true, 96, 1, 4>>() : entry<Cfg<2, 9, 9, true, false, 0, true, 96, 1, 4>>();
+      return 0;
+    }
+    if (p.elem_type == GOMA_GPU_HEX27) {
+      k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, true, 256, 1, 1>>()
+                   : entry<Cfg<3, 27, 27, true, false, 0, true, 256, 1, 1>>();
+      return 0;
+    }
+    return fail(-2, "ALE needs QUAD9 or HEX27 elements");
+  }
   if (p.pspg && p1) return fail(-2, "PSPG with P1 pressure is not supported by the GPU fill");
   if (!p1 && !p.pspg) return fail(-2, "equal-order velocity/pressure needs Pressure Stabilization (PSPG)");
   if (p1 && p.num_species) return fail(-2, "species with Q2/P1 not instantiated yet");

@@ -183,3 +183,80 @@ def test_gpu_matches_reference_live(built):
     assert_close(a, ref["a"], "Jacobian vs live reference")
     assert_close(r, ref["resid"], "residual vs live reference")
     mf.close()
+
+
+def _ale_problem(et, n, energy=False, transient=False, seed=41):
+    m = box_mesh(et, n, perturb=0.08, seed=seed)
+    bcs = [Dirichlet("U", 1, 1.0), Dirichlet("V", 1, 0.0), Dirichlet("DX", 1, 0.0), Dirichlet("DY", 1, 0.0),
+           Dirichlet("DX", 3, 0.01, relax=1.0), Dirichlet("U", 4, 0.0), Dirichlet("DY", 4, 0.0)]
+    if m.dim == 3:
+        bcs += [Dirichlet("DZ", 5, 0.0), Dirichlet("W", 6, 0.5, relax=1.0)]
+    if energy:
+        bcs += [Dirichlet("T", 1, 1.0), Dirichlet("T", 2, 0.0, relax=1.0)]
+    kw = dict(etm_momentum=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0), etm_energy=(1.0,) * 5, etm_mesh=(1.0,) * 5) if transient else {}
+    return Problem(m, ale=True, energy=energy, transient=transient, rho=1.1, mu=0.4, k=0.06, Cp=1.3, beta=0.7, Tref=0.2,
+                   gravity=(0.2, -0.3, 0.1), ns_source="BOUSSINESQ" if energy else "CONSTANT", heat_source=0.4,
+                   lame_mu=0.8, lame_lambda=1.9, bcs=bcs, **kw)
+
+
+@pytest.mark.parametrize("et,n,energy,transient", [("QUAD9", (20, 8), False, False), ("QUAD9", (9, 7), True, True),
+                                                   ("HEX27", (4, 3, 3), False, False), ("HEX27", (3, 3, 2), True, True)])
+def test_gpu_c4_ale_matches_port_oracle(built, et, n, energy, transient):
+    """Config C4 (ALE pseudo-solid mesh): all mesh-sensitivity blocks J_d_d, J_m_d, J_c_d, J_e_d on seeded
+    meshes larger than the fixtures, against the CPU restatement (itself pinned to the reference)."""
+    p = _ale_problem(et, n, energy, transient)
+    st = make_state(p, seed=23, transient=transient, delta_t=0.02, theta=0.5)
+    kw = dict(delta_t=0.02, theta=0.5) if transient else {}
+    ija = capi.pattern_msr(p)
+    rc, a_ref, r_ref = port.port_fill(p, ija, st, **kw)
+    assert rc == 0
+    mf = MatrixFill(p)
+    for scatter in (0, 1, 2, 2):
+        mf.set_option("scatter", scatter)
+        err, a, r = mf.matrix_fill_full(st["x"], st.get("x_old"), st.get("x_older"), st.get("xdot"), st.get("xdot_old"), **kw)
+        assert err == 0 and not mf.flags.any()
+        assert_close(a, a_ref, f"Jacobian scatter={scatter}")
+        assert_close(r, r_ref, f"residual scatter={scatter}")
+    mf.close()
+
+
+def test_gpu_c4_ale_jacobian_is_derivative_of_residual(built):
+    """numerical_jacobian-style check (mm_numjac.c:716) of the full ALE block structure at a size the CPU
+    oracle would need minutes for: J d == (R(x + eps d) - R(x - eps d)) / (2 eps)."""
+    p = _ale_problem("HEX27", (8, 8, 8), energy=True)
+    st = make_state(p, seed=4)
+    mf = MatrixFill(p)
+    n = mf.num_unknowns
+    err, a, _ = mf.matrix_fill_full(st["x"])
+    assert err == 0
+    A = msr_to_csr(mf.export_msr(), a, n)
+    d = np.random.default_rng(0).normal(size=n)
+    first, node_kind, kinds = p.unknown_map()
+    eps = 1e-7
+    _, _, rp = mf.matrix_fill_full(st["x"] + eps * d, assemble_jacobian=False)
+    rp = rp.copy()
+    _, _, rm = mf.matrix_fill_full(st["x"] - eps * d, assemble_jacobian=False)
+    fd, jd = (rp - rm) / (2 * eps), A @ d
+    is_dbc, _, hard = p.dirichlet_table()
+    keep = ~((is_dbc == 1) & (hard == 1))  # hard-set rows: residual 0, diagonal 1 (bc_dirich.c:134-135)
+    assert np.abs(fd - jd)[keep].max() / np.abs(jd).max() < 1e-6
+    mf.close()
+
+
+def test_gpu_c4_ale_inverted_element_is_a_domain_failure(built):
+    """A displacement field that folds an element makes belly_flop raise neg_elem_volume and matrix_fill_full
+    return -1 (mm_fill_solid.c:659-663,811-815; mm_fill.c:285-311); the GPU entry reports the same."""
+    p = _ale_problem("QUAD9", (6, 4))
+    st = make_state(p, seed=3)
+    first, node_kind, kinds = p.unknown_map()
+    x = st["x"].copy()
+    nd = p.mesh.conn[7, 2]  # drag one corner node across its element
+    off = kinds[node_kind[nd]].index("DX")
+    x[first[nd] + off] -= 1.2 * (2.0 / 6)
+    x[first[nd] + off + 1] -= 1.2 * (1.0 / 4)
+    rc, _, _ = port.port_fill(p, capi.pattern_msr(p), {"x": x})
+    assert rc == -1
+    mf = MatrixFill(p)
+    err, _, _ = mf.matrix_fill_full(x)
+    assert err == -1 and mf.flags[0] == 1
+    mf.close()
