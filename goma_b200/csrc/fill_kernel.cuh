@@ -109,7 +109,11 @@ struct Cfg {
   static constexpr int G_C1 = G_CM + (ALE ? DIM * DIM : 0);        // ed3 lambda vc^2 vc^(-2/3)
   static constexpr int GPD = (G_C1 + (ALE ? 1 : 0) + 1) & ~1;
   static constexpr bool GENERAL = !P1 || NSPEC > 0 || ALE;  // generic block accumulation instead of the NS(+T) fast path
+#ifdef GOMA_DIRECT_ALL
+  static constexpr bool DIRECT = true;
+#else
   static constexpr bool DIRECT = ALE;  // tiles go from registers straight to their matrix slots (no staging)
+#endif
   // staged write-out of the element block: rows (node i, field) x columns (node j in global order, field)
   static constexpr int NROW = NF * NN, NCOL = NF * NN;
   static constexpr int CAP = NGP * NN * 9;  // doubles in the operand arena (SI + SJa + SJb + VG), reused as stage
@@ -1033,9 +1037,11 @@ __device__ __forceinline__ void gauss_loop_general(const FillParams &P, const Sm
 template <class C>
 __device__ __forceinline__ void write_tile_direct(const FillParams &P, const Smem<C> &s, int i, int j, const Tile<C> &t) {
   constexpr int NF = C::NF;
-  static_assert(C::TI == 1, "direct write-out uses 1 x 1 node-pair tiles");
+  const int rj = s.rank[j];
+#pragma unroll
+  for (int ii = 0; ii < C::TI; ii++, i++) {
   const bool first = (s.first[i] >> j) & 1u;
-  const int ri = s.rank[i], rj = s.rank[j];
+  const int ri = s.rank[i];
 #pragma unroll
   for (int fr = 0; fr < NF; fr++) {
     const long long rstart = s.rs[fr][i];
@@ -1053,8 +1059,9 @@ __device__ __forceinline__ void write_tile_direct(const FillParams &P, const Sme
         dst = arow + off - (rj > ri ? 1 : 0);
       else
         dst = (fc == fr) ? P.a + row : arow + off - (fc > fr ? 1 : 0);
-      slot_add(P, dst, t.V[0][fr][fc], first);
+      slot_add(P, dst, t.V[ii][fr][fc], first);
     }
+  }
   }
 }
 
@@ -1123,10 +1130,13 @@ __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_cons
     if constexpr (C::DIRECT) {
       if (P.assemble_jacobian) {
 #pragma unroll 1
-        for (int t = tid; t < NN * NN; t += NT) {
+        for (int t = tid; t < C::NTILE; t += NT) {
           Tile<C> tile;
-          const int i = t / NN, j = t - i * NN;
-          gauss_loop_general<C>(P, s, i, j, tile);
+          const int it = t / NN, j = t - it * NN, i = it * TI;
+          if (C::GENERAL)
+            gauss_loop_general<C>(P, s, i, j, tile);
+          else
+            gauss_loop<C>(P, s, i, j, tile);
           write_tile_direct<C>(P, s, i, j, tile);
         }
       }
