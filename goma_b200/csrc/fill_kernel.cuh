@@ -42,6 +42,7 @@ struct FillParams {
   const unsigned *node_first;
   const unsigned char *dbc_flag;
   const double *dbc_value;
+  const unsigned char *erec;  // per-element gather records (ElemRec<C>), built once by build_records_kernel
   const int *elem_list;  // optional indirection (colour classes); nullptr = identity
   int elem_begin, elem_end;
   int num_owned_nodes;
@@ -108,19 +109,9 @@ struct Cfg {
   static constexpr int G_CM = G_GM + (ALE ? DIM * DIM : 0);        // sum_q cof(F)[p][q] M[b][q]   [p][b]
   static constexpr int G_C1 = G_CM + (ALE ? DIM * DIM : 0);        // ed3 lambda vc^2 vc^(-2/3)
   static constexpr int GPD = (G_C1 + (ALE ? 1 : 0) + 1) & ~1;
+  static constexpr int NROWS = NF * NN + NP;  // rows of the element block
+  static constexpr int NPART = NGP >= 3 ? 3 : 1;  // Gauss-point thirds of the row sums
   static constexpr bool GENERAL = !P1 || NSPEC > 0 || ALE;  // generic block accumulation instead of the NS(+T) fast path
-#ifdef GOMA_DIRECT_ALL
-  static constexpr bool DIRECT = true;
-#else
-  static constexpr bool DIRECT = ALE;  // tiles go from registers straight to their matrix slots (no staging)
-#endif
-  // staged write-out of the element block: rows (node i, field) x columns (node j in global order, field)
-  static constexpr int NROW = NF * NN, NCOL = NF * NN;
-  static constexpr int CAP = NGP * NN * 9;  // doubles in the operand arena (SI + SJa + SJb + VG), reused as stage
-  static constexpr int TROWS = TI * NF;     // rows owned by one register tile
-  static constexpr int ROWS_PER_PASS = ((CAP / NCOL) / TROWS) * TROWS < NROW ? ((CAP / NCOL) / TROWS) * TROWS : NROW;
-  static_assert(ROWS_PER_PASS >= TROWS, "stage too small for one row tile");
-  static constexpr int NPASS = (NROW + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
   __host__ __device__ static constexpr int slot(int f) {
     return f < DIM                       ? GOMA_SLOT_U + f
            : (ENERGY && f == F_T)        ? GOMA_SLOT_T
@@ -140,43 +131,46 @@ struct Operands {
   double VG[C::NGP][C::NN];    // v . grad_phi_j
 };
 
+// Everything about one element that does not depend on the state vector, gathered once at init
+// (what load_ei / load_elem_dofptr, mm_fill_ptrs.c:170,1136, recompute per element and per Newton
+// iteration) and laid out so that ONE TMA bulk copy brings it into shared memory.
+template <class C>
+struct alignas(16) ElemRec {
+  double X[C::DIM][C::NN];               // nodal coordinates (undeformed)
+  long long rs[C::NF][C::NN];            // MSR row start of (field, node); -1 = not written here (ghost / Dirichlet)
+  long long rsP[C::NP > 0 ? C::NP : 1];  // ... of the P1 pressure rows on the centroid node
+  int gun[C::NF][C::NN];                 // global unknown number (gun_list)
+  int gunP;                              // first P1 pressure unknown of the centroid node
+  unsigned node_first;                   // bit i: this element is the first writer of node i's residual / diagonal
+  unsigned first[C::NN];                 // bit j of word i: first writer of the node pair (i, j)
+  unsigned short po[C::NN][C::NN];       // slot map: column offset of node j's first unknown in a row of node i
+  unsigned short pp[C::ENERGY ? C::NN : 1][C::ENERGY ? C::NN : 1];  // pressure columns before j (energy rows skip them)
+  unsigned char rank[C::NN];             // position of the local node in increasing global id (= column order)
+  unsigned char cs[C::NN][C::NF + 1];    // offset of field f inside node j
+  unsigned char flag[C::NF][C::NN];      // bits 0-1: Dirichlet flag of the unknown, bit 2: row is owned by this rank
+  unsigned char flagP[4];
+  unsigned char poffP;                   // offset of the first P1 unknown inside the centroid node
+};
+
 template <class C>
 struct alignas(16) Smem {
   double tbl[C::TBL_PAD];
-  union {
-    Operands<C> op;
-    double stage[C::CAP];  // element block rows, after the Gauss loop
-  };
+  ElemRec<C> rec[2];  // double buffer: the record of the next element lands while this one is assembled
+  Operands<C> op;
   double GP[C::NGP][C::GPD];            // per-Gauss-point derived quantities
   double F[C::NGP][C::NF][C::DIM + 2];  // value, grad[DIM], time derivative
-  double X[C::DIM][C::NN];
-  double U[C::NF][C::NN];
-  double Udot[C::NF][C::NN];
-  double Pd[C::NP > 0 ? C::NP : 1];
+  double X[C::ALE ? C::DIM : 1][C::ALE ? C::NN : 1];  // ALE: displaced coordinates x = X + d
+  double U[2][C::NF][C::NN];            // nodal unknowns, double-buffered like rec (cp.async gather)
+  double Udot[2][C::NF][C::NN];
+  double Pd[2][C::NP > 0 ? C::NP : 2];
   double w[C::NGP];
   double B[C::NGP][C::DIM * C::DIM];
   double Pgp[C::NGP];
-  long long rs[C::NF][C::NN];  // MSR row start of (field,node); -1 = not written here (ghost/Dirichlet)
-  long long rsP[C::NP > 0 ? C::NP : 1];
-  int node[C::NN];
-  int fu[C::NN];
-  int kind[C::NN];
-  int gun[C::NF][C::NN];
-  double tau, dtau[3];    // PSPG tau and d tau / d v_avg[b] (element level)
-  unsigned first[C::NN];  // first-touch mask of row node i over column nodes j
-  unsigned node_first;
-  unsigned short po[C::NN][C::NN];  // slot-map column offsets of the node pairs
-  unsigned short pp[C::ENERGY ? C::NN : 1][C::ENERGY ? C::NN : 1];
-  unsigned char perm[C::NN];           // local nodes in increasing global id
-  unsigned char rank[C::NN];           // inverse of perm
-  unsigned char cs[C::NN][C::NF + 1];  // column offset of field f inside node j (kind_slot lookup)
-  // write-out tables, columns c = (rank of node j in global order, field): slot-map offset of column c
-  // in a row of node i, the pressure-column correction for energy rows, and the first-touch mask
-  // re-ordered to column order
-  unsigned short colbase[C::NN][C::NCOL];
-  unsigned short ppS[C::ENERGY ? C::NN : 1][C::ENERGY ? C::NN : 1];
-  unsigned firstS[C::NN];
+  double tau, dtau[3];  // PSPG tau and d tau / d v_avg[b] (element level)
+  double redR[C::NPART][C::NROWS];  // partial row sums (element_rows)
+  double redS[C::NPART][C::P1 ? C::DIM * C::NN : 1][C::NP > 0 ? C::NP : 1];
   unsigned long long mbar;
+  unsigned long long mbar_rec[2];
 };
 
 static_assert(sizeof(double2) == 16, "double2 layout");
@@ -211,6 +205,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigne
                "l"(src), "r"(bytes), "r"(b)
                : "memory");
 }
+
+// per-thread asynchronous 8-byte global -> shared copy (SASS: LDGSTS), the indirect gather of x[gun]
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 #ifdef GOMA_PROFILE_PHASES
 #define GOMA_CLOCK() clock64()
@@ -284,8 +286,79 @@ __device__ __forceinline__ double dot3(const double *__restrict__ a, int sa, con
 #define GOMA_STAMP(k) do { } while (0)
 #endif
 
+// One-off (init): fill the gather record of every element.  Restates load_ei / load_elem_dofptr
+// (mm_fill_ptrs.c:170-1050,1136-1530) for the in-scope variables plus the Dirichlet / ownership
+// tests of load_lec (mm_fill.c:5374) and put_dirichlet_in_matrix (bc_dirich.c:86-140).
 template <class C>
-__device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, int elem, int tid, long long *stamps) {
+__global__ void build_records_kernel(const FillParams P, int num_elems) {
+  constexpr int DIM = C::DIM, NN = C::NN, NF = C::NF, NP = C::NP;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= num_elems) return;
+  ElemRec<C> &r = reinterpret_cast<ElemRec<C> *>(const_cast<unsigned char *>(P.erec))[e];
+  int node[NN], fu[NN], kind[NN];
+  for (int k = 0; k < NN; k++) {
+    const int nd = P.conn[(size_t)e * NN + k];
+    node[k] = nd;
+    fu[k] = P.first_unknown[nd];
+    kind[k] = P.node_kind[nd];
+    r.first[k] = P.pair_first ? P.pair_first[(size_t)e * NN + k] : 0u;
+    for (int d = 0; d < DIM; d++) r.X[d][k] = P.coord[d][nd];
+  }
+  r.node_first = P.node_first ? P.node_first[e] : 0u;
+  for (int idx = 0; idx < NN * NN; idx++) {
+    (&r.po[0][0])[idx] = P.pair_full[(size_t)e * NN * NN + idx];
+    if (C::ENERGY) (&r.pp[0][0])[idx] = P.pair_p[(size_t)e * NN * NN + idx];
+  }
+  for (int k = 0; k < NN; k++) {
+    int rk = 0;
+    for (int m = 0; m < NN; m++) rk += node[m] < node[k] ? 1 : 0;
+    r.rank[k] = (unsigned char)rk;
+    const bool owned = node[k] < P.num_owned_nodes;
+    for (int f = 0; f < NF; f++) {
+      const int cs = P.kind_slot[kind[k]][C::slot(f)];
+      const int gun = fu[k] + cs;
+      const int dbc = P.dbc_flag[gun];
+      r.cs[k][f] = (unsigned char)cs;
+      r.gun[f][k] = gun;
+      r.flag[f][k] = (unsigned char)(dbc | (owned ? 4 : 0));
+      r.rs[f][k] = (owned && dbc == 0) ? P.rowstart[gun] : -1;
+    }
+    r.cs[k][NF] = 0;
+  }
+  r.gunP = 0;
+  r.poffP = 0;
+  for (int p = 0; p < 4; p++) r.flagP[p] = 0;
+  r.rsP[0] = -1;
+  if (C::P1) {
+    const int poff = P.kind_slot[kind[C::CEN]][GOMA_SLOT_P];
+    const bool owned = node[C::CEN] < P.num_owned_nodes;
+    r.poffP = (unsigned char)poff;
+    r.gunP = fu[C::CEN] + poff;
+    for (int p = 0; p < NP; p++) {
+      const int gun = r.gunP + p;
+      const int dbc = P.dbc_flag[gun];
+      r.flagP[p] = (unsigned char)(dbc | (owned ? 4 : 0));
+      r.rsP[p] = (owned && dbc == 0) ? P.rowstart[gun] : -1;
+    }
+  }
+}
+
+// indirect gather of the state for one element: x[gun] (and xdot[gun]) -> shared memory, asynchronously
+template <class C>
+__device__ __forceinline__ void gather_state(const FillParams &P, Smem<C> &s, int buf, int tid) {
+  constexpr int NN = C::NN, NF = C::NF, NT = C::TPE;
+  const ElemRec<C> &r = s.rec[buf];
+  for (int idx = tid; idx < NF * NN; idx += NT) {
+    const int gun = (&r.gun[0][0])[idx];
+    cp_async8(&(&s.U[buf][0][0])[idx], &P.x[gun]);
+    if (P.transient) cp_async8(&(&s.Udot[buf][0][0])[idx], &P.xdot[gun]);
+  }
+  if (C::P1 && tid < C::NP) cp_async8(&s.Pd[buf][tid], &P.x[r.gunP + tid]);
+  cp_async_commit();
+}
+
+template <class C>
+__device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, int buf, int tid, long long *stamps) {
 #ifdef GOMA_PROFILE_PHASES
   long long last_ = clock64();
 #endif
@@ -299,78 +372,28 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
   const double c_adv = -P.etm_mom[1] * P.rho;
   const double ce_adv = -P.etm_energy[1] * rcp;
   Operands<C> &op = s.op;
+  const ElemRec<C> &rec = s.rec[buf];
+  const double (*U)[NN] = s.U[buf];
+  const double (*Udot)[NN] = s.Udot[buf];
 
-  // ---- phase 0: connectivity, coordinates, unknown indices, nodal values (load_elem_dofptr)
-  for (int k = tid; k < NN; k += NT) {
-    int nd = P.conn[(size_t)elem * NN + k];
-    s.node[k] = nd;
-    s.fu[k] = P.first_unknown[nd];
-    s.kind[k] = P.node_kind[nd];
-    s.first[k] = P.pair_first ? P.pair_first[(size_t)elem * NN + k] : 0u;
-#pragma unroll
-    for (int d = 0; d < DIM; d++) {
-      double xc = P.coord[d][nd];
-      // ALE: the map is built on the displaced coordinates x = X + d (beer_belly, mm_fill_util.c:258-276)
-      if (C::ALE) xc += P.x[s.fu[k] + P.kind_slot[s.kind[k]][GOMA_SLOT_DX + d]];
-      s.X[d][k] = xc;
+  // ---- ALE: the map is built on the displaced coordinates x = X + d (beer_belly, mm_fill_util.c:258-276)
+  if (C::ALE) {
+    for (int idx = tid; idx < DIM * NN; idx += NT) {
+      const int d = idx / NN, k = idx - d * NN;
+      s.X[d][k] = rec.X[d][k] + U[C::F_D + d][k];
     }
+    __syncthreads();
   }
-  if (tid == 0) s.node_first = P.node_first ? P.node_first[elem] : 0u;
-  for (int idx = tid; idx < NN * NN; idx += NT) {
-    (&s.po[0][0])[idx] = P.pair_full[(size_t)elem * NN * NN + idx];
-    if (C::ENERGY) (&s.pp[0][0])[idx] = P.pair_p[(size_t)elem * NN * NN + idx];
-  }
-  __syncthreads();
   GOMA_STAMP(0);
-  for (int idx = tid; idx < NF * NN; idx += NT) {
-    int f = idx / NN, k = idx - f * NN;
-    int cs = P.kind_slot[s.kind[k]][C::slot(f)];
-    s.cs[k][f] = (unsigned char)cs;
-    int gun = s.fu[k] + cs;
-    s.gun[f][k] = gun;
-    s.U[f][k] = P.x[gun];
-    s.Udot[f][k] = P.transient ? P.xdot[gun] : 0.0;
-    bool owned = s.node[k] < P.num_owned_nodes;
-    s.rs[f][k] = (owned && P.dbc_flag[gun] == 0) ? P.rowstart[gun] : -1;
-  }
-  if (C::P1 && tid < NP) {
-    int gun = s.fu[C::CEN] + P.kind_slot[s.kind[C::CEN]][GOMA_SLOT_P] + tid;
-    s.Pd[tid] = P.x[gun];
-    bool owned = s.node[C::CEN] < P.num_owned_nodes;
-    s.rsP[tid] = (owned && P.dbc_flag[gun] == 0) ? P.rowstart[gun] : -1;
-  }
-  if (tid < NN) {  // order of the local nodes by global id = order of their columns inside a matrix row
-    const int me = s.node[tid];
-    int r = 0;
-#pragma unroll
-    for (int k = 0; k < NN; k++) r += s.node[k] < me ? 1 : 0;
-    s.rank[tid] = (unsigned char)r;
-    s.perm[r] = (unsigned char)tid;
-  }
   // ---- phase 1: J[a][b] = sum_k x_b,k dphi_k/dxi_a   (beer_belly, mm_fill_util.c:258-276)
   for (int idx = tid; idx < NGP * DIM * DIM; idx += NT) {
     int gp = idx / (DIM * DIM), ab = idx - gp * DIM * DIM;
     int a = ab / DIM, b = ab - a * DIM;
-    s.B[gp][ab] = dot3<NN>(s.X[b], 1, &t_dphi[gp * NN * DIM + a], DIM);
+    const double *Xb = C::ALE ? s.X[b] : rec.X[b];
+    s.B[gp][ab] = dot3<NN>(Xb, 1, &t_dphi[gp * NN * DIM + a], DIM);
   }
   __syncthreads();
   GOMA_STAMP(1);
-  // ---- write-out tables in column (global node) order
-  for (int idx = tid; idx < NN * C::NCOL; idx += NT) {
-    const int i = idx / C::NCOL, c = idx - i * C::NCOL;
-    const int js = c / NF, fc = c - js * NF, j = s.perm[js];
-    s.colbase[i][c] = (unsigned short)(s.po[i][j] + s.cs[j][fc]);
-  }
-  for (int idx = tid; idx < NN * NN; idx += NT) {
-    const int i = idx / NN, js = idx - i * NN;
-    if (C::ENERGY) s.ppS[i][js] = s.pp[i][s.perm[js]];
-  }
-  if (tid < NN) {
-    unsigned f = s.first[tid], fs = 0u;
-#pragma unroll
-    for (int js = 0; js < NN; js++) fs |= ((f >> s.perm[js]) & 1u) << js;
-    s.firstS[tid] = fs;
-  }
   // ---- phase 2: detJ, B = J^-1 by cofactors (mm_fill_util.c:386-391, :450-480)
   if (tid < NGP) {
     double *J = s.B[tid];
@@ -412,7 +435,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
       double hh = 0.0;
 #pragma unroll
       for (int a = 0; a < DIM; a++) {
-        const double *xx = s.X[a];
+        const double *xx = C::ALE ? s.X[a] : rec.X[a];
         if (DIM == 2) {
           const double h0 = 0.5 * (xx[1] + xx[2]) - 0.5 * (xx[0] + xx[3]);
           const double h1 = 0.5 * (xx[0] + xx[1]) - 0.5 * (xx[2] + xx[3]);
@@ -428,7 +451,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
       double vavg[3] = {0.0, 0.0, 0.0}, vv = 0.0;
 #pragma unroll
       for (int a = 0; a < DIM; a++) {
-        for (int k = 0; k < NN; k++) vavg[a] += s.U[C::F_V + a][k] / (double)NN;  // I_Q1: mean of the nodes
+        for (int k = 0; k < NN; k++) vavg[a] += U[C::F_V + a][k] / (double)NN;  // I_Q1: mean of the nodes
         vv += vavg[a] * vavg[a];
       }
       double tau1 = P.rho * P.rho * vv / hh + 9.0 * P.mu * P.mu / (hh * hh);
@@ -463,52 +486,64 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
   __syncthreads();
   GOMA_STAMP(3);
   // ---- phase 4: field values, gradients, time derivatives at the Gauss points (load_fv, load_fv_grads)
-  //      one thread per (Gauss point, field): 2 vector loads + 2 scalar loads feed DIM+2 FMAs per node
-  for (int idx = tid; idx < NGP * NF; idx += NT) {
-    int gp = idx / NF, f = idx - gp * NF;
-    double val[3] = {0.0, 0.0, 0.0}, dot[3] = {0.0, 0.0, 0.0}, gr[3][3] = {{0.0}};
-    constexpr int M = NN / 3;
+  //      four lanes per (Gauss point, field), each over a quarter of the nodes, combined by shuffles
+  {
+    constexpr int NITEM = NGP * NF, Q = (NN + 3) / 4;
+    constexpr int NROUND = (NITEM * 4 + NT - 1) / NT;
+#pragma unroll 1
+    for (int rnd = 0; rnd < NROUND; rnd++) {
+      const int idx = rnd * NT + tid;
+      const int item = idx >> 2, c = idx & 3;
+      const bool live = item < NITEM;
+      const int gp = live ? item / NF : 0, f = live ? item - gp * NF : 0;
+      double val = 0.0, dot = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
+      const int k0 = c * Q, k1 = (k0 + Q < NN) ? k0 + Q : NN;
+      if (live) {
+#pragma unroll 4
+        for (int kk = k0; kk < k1; kk++) {
+          const double2 a = op.SJa[gp][kk], b = op.SJb[gp][kk];
+          const double u = U[f][kk];
+          val += u * a.x;
+          g0 += u * a.y;
+          g1 += u * b.x;
+          g2 += u * b.y;
+          if (P.transient) dot += Udot[f][kk] * a.x;
+        }
+      }
 #pragma unroll
-    for (int k = 0; k < M; k++) {
-#pragma unroll
-      for (int c = 0; c < 3; c++) {  // three independent chains
-        const int kk = k + c * M;
-        const double2 a = op.SJa[gp][kk], b = op.SJb[gp][kk];
-        const double u = s.U[f][kk];
-        val[c] += u * a.x;
-        gr[c][0] += u * a.y;
-        gr[c][1] += u * b.x;
-        gr[c][2] += u * b.y;
-        dot[c] += s.Udot[f][kk] * a.x;
+      for (int o = 1; o <= 2; o <<= 1) {
+        val += __shfl_xor_sync(0xffffffffu, val, o);
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        g0 += __shfl_xor_sync(0xffffffffu, g0, o);
+        g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+        if (DIM == 3) g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+      }
+      if (live && c == 0) {
+        double *Fo = s.F[gp][f];
+        Fo[0] = val;
+        Fo[1] = g0;
+        Fo[2] = g1;
+        if (DIM == 3) Fo[3] = g2;
+        Fo[1 + DIM] = dot;
       }
     }
-#pragma unroll
-    for (int kk = 3 * M; kk < NN; kk++) {
-      const double2 a = op.SJa[gp][kk], b = op.SJb[gp][kk];
-      const double u = s.U[f][kk];
-      val[0] += u * a.x;
-      gr[0][0] += u * a.y;
-      gr[0][1] += u * b.x;
-      gr[0][2] += u * b.y;
-      dot[0] += s.Udot[f][kk] * a.x;
-    }
-    s.F[gp][f][0] = (val[0] + val[1]) + val[2];
-#pragma unroll
-    for (int p = 0; p < DIM; p++) s.F[gp][f][1 + p] = (gr[0][p] + gr[1][p]) + gr[2][p];
-    s.F[gp][f][1 + DIM] = (dot[0] + dot[1]) + dot[2];
   }
   if (C::P1) {
     for (int gp = tid; gp < NGP; gp += NT) {
       double v = 0.0;
 #pragma unroll
-      for (int p = 0; p < NP; p++) v += s.Pd[p] * t_psi[gp * (DIM + 1) + p];
+      for (int p = 0; p < NP; p++) v += s.Pd[buf][p] * t_psi[gp * (DIM + 1) + p];
       s.Pgp[gp] = v;
     }
   }
   __syncthreads();
   GOMA_STAMP(4);
   // ---- phase 4b: per-Gauss-point terms shared by every row/column of the element
-  for (int gp = tid; gp < NGP; gp += NT) {
+  //      one thread per (Gauss point, job): momentum component a | energy | species | PSPG | ALE
+  constexpr int J_EN = DIM, J_SP = J_EN + (C::ENERGY ? 1 : 0), J_PS = J_SP + (C::NSPEC > 0 ? 1 : 0),
+                J_AL = J_PS + (C::P1 ? 0 : 1), NJOB = J_AL + (C::ALE ? 1 : 0);
+  for (int idx = tid; idx < NGP * NJOB; idx += NT) {
+    const int gp = idx / NJOB, job = idx - gp * NJOB;
     double *G = s.GP[gp];
     double v[DIM], vdot[DIM], gv[DIM][DIM];  // gv[a][b] = d_b v_a
 #pragma unroll
@@ -529,8 +564,11 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
     momentum_source<C>(P, T, fs, dfdT);
     double div = 0.0;
 #pragma unroll
+    for (int a = 0; a < DIM; a++) div += gv[a][a];
+    if (job == 0) G[C::G_DIV] = P.etm_cont[0] * div;
+#pragma unroll
     for (int a = 0; a < DIM; a++) {
-      div += gv[a][a];
+      if (job != a) continue;
       double adv = 0.0;
 #pragma unroll
       for (int p = 0; p < DIM; p++) adv += vc[p] * gv[a][p];
@@ -544,7 +582,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
         G[C::G_GV + a * DIM + p] = c_adv * gv[a][p];
       }
     }
-    G[C::G_DIV] = P.etm_cont[0] * div;
+    if (C::NSPEC > 0 && job == J_SP) {
 #pragma unroll
     for (int w = 0; w < C::NSPEC; w++) {
       // assemble_mass_transport, Fickian constant-D, concentration form (mm_fill_species.c:527-640)
@@ -558,7 +596,8 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
       }
       G[C::G_RY + w] = -P.etm_species[0] * s.F[gp][C::F_Y + w][1 + DIM] - P.etm_species[1] * adv;
     }
-    if (!C::P1) {
+    }
+    if (!C::P1 && job == J_PS) {
       // calc_pspg (mm_fill_stabilization.c:1281-1319): momentum residual without the viscous term
       const double tau = s.tau;
 #pragma unroll
@@ -575,7 +614,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
         G[C::G_PS + a] = tau * mom;
       }
     }
-    if (C::ENERGY) {
+    if (C::ENERGY && job == J_EN) {
       double adv = 0.0;
 #pragma unroll
       for (int p = 0; p < DIM; p++) {
@@ -587,7 +626,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
       G[C::G_RE] = -P.etm_energy[0] * rcp * s.F[gp][C::F_T][1 + DIM] - P.etm_energy[1] * rcp * adv +
                    P.etm_energy[4] * P.heat_source;
     }
-    if (C::ALE) {
+    if (C::ALE && job == J_AL) {
       // belly_flop (mm_fill_solid.c:77-1120): grad_d, Eulerian strain of the NONLINEAR model, volume change;
       // mesh_stress_tensor (:3208-3287): TT = lambda vs I + 2 mu E,  vs = 3 (vc^(1/3) - 1)
       double Gd[DIM][DIM], M[DIM][DIM], Fm[3][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 0.0, 1.0}}, cof[3][3];
@@ -653,42 +692,33 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
 // phases 5 and 7: residual rows + Dirichlet rows (bc_dirich.c:130-140), P1 pressure coupling
 // =====================================================================================
 template <class C>
-__device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, int elem, int tid) {
+__device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, int buf, int tid) {
   constexpr int DIM = C::DIM, NN = C::NN, NGP = C::NGP, NF = C::NF, NP = C::NP, NT = C::TPE;
+  constexpr int NROW = C::NROWS, NPART = C::NPART;
   const double *t_psi = s.tbl + C::T_PSI;
   const Operands<C> &op = s.op;
-  for (int idx = tid; idx < NF * NN + NP; idx += NT) {
-    const bool prow = idx >= NF * NN;  // P1 continuity row
-    const int f = prow ? 0 : idx / NN;
-    const int i = prow ? C::CEN : idx - f * NN;
-    const int gun = prow ? s.fu[C::CEN] + P.kind_slot[s.kind[C::CEN]][GOMA_SLOT_P] + (idx - NF * NN) : s.gun[f][i];
-    if (s.node[i] >= P.num_owned_nodes) continue;
-    const bool first = (s.node_first >> i) & 1u;
-    const int dbc = P.dbc_flag[gun];
-    if (dbc) {
-      if (P.assemble_residual) slot_add(P, &P.resid[gun], dbc == 1 ? P.x[gun] - P.dbc_value[gun] : 0.0, first);
-      if (P.assemble_jacobian) slot_add(P, &P.a[gun], 1.0, first);
-      continue;
-    }
-    if (!P.assemble_residual) continue;
-    double R = 0.0;
-    if (prow) {
-      const int p = idx - NF * NN;
-      double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+  const ElemRec<C> &rec = s.rec[buf];
+  // ---- part A: every row (field f of node i | P1 continuity row p) is summed over a third of the Gauss
+  //      points by one thread; the velocity rows accumulate the P1 pressure coupling on the way:
+  //      S[i][a][p] = sum_gp w grad_phi_i[a] psi_p, shared by J_m_P (mm_fill_momentum.c:2091-2104) and
+  //      J_c_v (mm_fill_continuity.c:686-716)
+  for (int idx = tid; idx < NROW * NPART; idx += NT) {
+    const int c = idx / NROW, r = idx - c * NROW;
+    const int gp0 = c * NGP / NPART, gp1 = (c + 1) * NGP / NPART;
+    const bool prow = r >= NF * NN;  // P1 continuity row
+    const int f = prow ? 0 : r / NN;
+    const int i = prow ? C::CEN : r - f * NN;
+    double R = 0.0, S[NP > 0 ? NP : 1];
 #pragma unroll
-      for (int gp = 0; gp + 2 < NGP; gp += 3) {
-        r0 += s.w[gp] * t_psi[gp * (DIM + 1) + p] * s.GP[gp][C::G_DIV];
-        r1 += s.w[gp + 1] * t_psi[(gp + 1) * (DIM + 1) + p] * s.GP[gp + 1][C::G_DIV];
-        r2 += s.w[gp + 2] * t_psi[(gp + 2) * (DIM + 1) + p] * s.GP[gp + 2][C::G_DIV];
-      }
-      for (int gp = NGP - NGP % 3; gp < NGP; gp++) r0 += s.w[gp] * t_psi[gp * (DIM + 1) + p] * s.GP[gp][C::G_DIV];
-      R = (r0 + r1) + r2;
+    for (int p = 0; p < NP; p++) S[p] = 0.0;
+    if (prow) {
+      const int p = r - NF * NN;
+      for (int gp = gp0; gp < gp1; gp++) R += s.w[gp] * t_psi[gp * (DIM + 1) + p] * s.GP[gp][C::G_DIV];
     } else {
       const bool isT = C::ENERGY && f == C::F_T;
       const bool isY = f >= C::F_Y && f < C::F_Y + C::NSPEC;
       const bool isP = !C::P1 && f == C::F_P;
       const bool isD = C::ALE && f >= C::F_D && f < C::F_D + DIM;  // assemble_mesh residual (mm_fill_terms.c:421-428)
-      if (f >= DIM && !isT && !isY && !isP && !isD) continue;
       // row = sum_gp  w phi_i * G[q0]  +  w grad_phi_i[p] * G[q1 + p]
       const int q0 = isT ? C::G_RE : isY ? C::G_RY + (f - C::F_Y) : isP ? C::G_DIV : isD ? C::G_ZERO : C::G_RQ + f;
       const int q1 = isT   ? C::G_RF
@@ -696,9 +726,8 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
                      : isP ? C::G_PS
                      : isD ? C::G_RD + (f - C::F_D) * DIM
                            : C::G_RP + f * DIM;
-      double r[3] = {0.0, 0.0, 0.0};
-#pragma unroll 3
-      for (int gp = 0; gp < NGP; gp++) {
+      const bool vel = f < DIM;
+      for (int gp = gp0; gp < gp1; gp++) {
         const double2 s01 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][0]);
         const double2 s23 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][2]);
         const double sg[3] = {s01.y, s23.x, s23.y};
@@ -706,43 +735,77 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
         double t = s01.x * G[q0];
 #pragma unroll
         for (int p = 0; p < DIM; p++) t += sg[p] * G[q1 + p];
-        r[gp % 3] += t;
+        R += t;
+        if (C::P1 && vel) {
+          const double sgf = f == 0 ? sg[0] : (f == 1 ? sg[1] : sg[2]);
+#pragma unroll
+          for (int p = 0; p < NP; p++) S[p] += sgf * t_psi[gp * (DIM + 1) + p];
+        }
       }
-      R = (r[0] + r[1]) + r[2];
+      if (C::P1 && vel) {
+#pragma unroll
+        for (int p = 0; p < NP; p++) s.redS[c][r][p] = S[p];
+      }
     }
+    s.redR[c][r] = R;
+  }
+  __syncthreads();
+  // ---- part B: residual rows and Dirichlet rows (put_dirichlet_in_matrix, bc_dirich.c:86-140)
+  for (int r = tid; r < NROW; r += NT) {
+    const bool prow = r >= NF * NN;
+    const int f = prow ? 0 : r / NN;
+    const int i = prow ? C::CEN : r - f * NN;
+    const int gun = prow ? rec.gunP + (r - NF * NN) : rec.gun[f][i];
+    const int flag = prow ? rec.flagP[r - NF * NN] : rec.flag[f][i];
+    if (!(flag & 4)) continue;  // row of an external node (load_lec, mm_fill.c:5374)
+    const bool first = (rec.node_first >> i) & 1u;
+    const int dbc = flag & 3;
+    if (dbc) {
+      if (P.assemble_residual) slot_add(P, &P.resid[gun], dbc == 1 ? P.x[gun] - P.dbc_value[gun] : 0.0, first);
+      if (P.assemble_jacobian) slot_add(P, &P.a[gun], 1.0, first);
+      continue;
+    }
+    if (!P.assemble_residual) continue;
+    if (!prow) {
+      const bool known = f < DIM || (C::ENERGY && f == C::F_T) || (f >= C::F_Y && f < C::F_Y + C::NSPEC) ||
+                         (!C::P1 && f == C::F_P) || (C::ALE && f >= C::F_D && f < C::F_D + DIM);
+      if (!known) continue;
+    }
+    double R = s.redR[0][r];
+#pragma unroll
+    for (int c = 1; c < NPART; c++) R += s.redR[c][r];
     slot_add(P, &P.resid[gun], R, first);
   }
-  // ---- phase 7: P1 pressure coupling, S[i][a][p] = sum_gp w grad_phi_i[a] psi_p
-  //      J_m_P (mm_fill_momentum.c:2091-2104) and J_c_v (mm_fill_continuity.c:686-716) share it.
-  //      The centroid node belongs to this element only: these slots have a single writer.
+  // ---- part C (phase 7): P1 pressure coupling.  The centroid node belongs to this element only: these
+  //      slots have a single writer.
   if constexpr (C::P1) if (P.assemble_jacobian) {
-    const int poff = P.kind_slot[s.kind[C::CEN]][GOMA_SLOT_P];
-    const int ncen = s.node[C::CEN];
+    const int poff = rec.poffP;
     for (int idx = tid; idx < NN * DIM * NP; idx += NT) {
       int i = idx / (DIM * NP), r = idx - i * DIM * NP;
       int a = r / NP, p = r - a * NP;
-      const double S = dot3<NGP>(&op.SI[0][i][1 + a], NN * 4, &t_psi[p], DIM + 1);
+      double S = s.redS[0][a * NN + i][p];
+#pragma unroll
+      for (int c = 1; c < NPART; c++) S += s.redS[c][a * NN + i][p];
       // (row velocity a of node i, column pressure p of the centroid node)
-      if (s.rs[a][i] >= 0) {
-        const int row = s.gun[a][i], col = s.fu[C::CEN] + poff + p;
-        const long long pos = s.rs[a][i] + s.po[i][C::CEN] + poff + p - (col > row ? 1 : 0);
+      if (rec.rs[a][i] >= 0) {
+        const int row = rec.gun[a][i], col = rec.gunP + p;
+        const long long pos = rec.rs[a][i] + rec.po[i][C::CEN] + poff + p - (col > row ? 1 : 0);
         slot_add(P, &P.a[pos], P.etm_mom[3] * S, true);
       }
       // (row pressure p of the centroid node, column velocity a of node i)
-      if (s.rsP[p] >= 0) {
-        const int row = s.fu[C::CEN] + poff + p, col = s.gun[a][i];
-        const long long pos = s.rsP[p] + s.po[C::CEN][i] + s.cs[i][a] - (col > row ? 1 : 0);
+      if (rec.rsP[p] >= 0) {
+        const int row = rec.gunP + p, col = rec.gun[a][i];
+        const long long pos = rec.rsP[p] + rec.po[C::CEN][i] + rec.cs[i][a] - (col > row ? 1 : 0);
         slot_add(P, &P.a[pos], P.etm_cont[0] * S, true);
       }
     }
-    (void)ncen;
     if constexpr (C::ALE) {
       // J_c_d (mm_fill_continuity.c:1004-1148): d(div v)/d d_bj + div v d|J|/d d_bj, with
       // d(grad_phi_k[q])/d d_bj = -grad_phi_j[q] grad_phi_k[b] and d|J|/d d_bj = |J| grad_phi_j[b]
       for (int idx = tid; idx < NN * DIM * NP; idx += NT) {
         const int j = idx / (DIM * NP), r = idx - j * DIM * NP;
         const int b = r / NP, p = r - b * NP;
-        if (s.rsP[p] < 0) continue;
+        if (rec.rsP[p] < 0) continue;
         double acc = 0.0;
         for (int gp = 0; gp < NGP; gp++) {
           const double2 ja = op.SJa[gp][j], jb = op.SJb[gp][j];
@@ -752,8 +815,8 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
           for (int q = 0; q < DIM; q++) ddiv -= gj[q] * s.F[gp][C::F_V + q][1 + b];
           acc += s.w[gp] * t_psi[gp * (DIM + 1) + p] * (P.etm_cont[0] * ddiv + s.GP[gp][C::G_DIV] * gj[b]);
         }
-        const int row = s.fu[C::CEN] + poff + p, col = s.gun[C::F_D + b][j];
-        const long long pos = s.rsP[p] + s.po[C::CEN][j] + s.cs[j][C::F_D + b] - (col > row ? 1 : 0);
+        const int row = rec.gunP + p, col = rec.gun[C::F_D + b][j];
+        const long long pos = rec.rsP[p] + rec.po[C::CEN][j] + rec.cs[j][C::F_D + b] - (col > row ? 1 : 0);
         slot_add(P, &P.a[pos], acc, true);
       }
     }
@@ -1035,7 +1098,7 @@ __device__ __forceinline__ void gauss_loop_general(const FillParams &P, const Sm
 // write-out of one node-pair tile straight from registers (ALE configurations): same slot arithmetic
 // as write_rows, one thread per (i, j)
 template <class C>
-__device__ __forceinline__ void write_tile_direct(const FillParams &P, const Smem<C> &s, int i, int j, const Tile<C> &t) {
+__device__ __forceinline__ void write_tile_direct(const FillParams &P, const ElemRec<C> &s, int i, int j, const Tile<C> &t) {
   constexpr int NF = C::NF;
   const int rj = s.rank[j];
 #pragma unroll
@@ -1065,128 +1128,90 @@ __device__ __forceinline__ void write_tile_direct(const FillParams &P, const Sme
   }
 }
 
-// write-out of staged rows [r0, r1): a warp walks one row, lanes along the columns in matrix order
-template <class C>
-__device__ __forceinline__ void write_rows(const FillParams &P, const Smem<C> &s, int r0, int r1, int tid) {
-  constexpr int NF = C::NF, NCOL = C::NCOL;
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int r = r0 + warp; r < r1; r += C::NWARP) {
-    const int i = r / NF, fr = r - i * NF;
-    const long long rstart = s.rs[fr][i];
-    if (rstart < 0) continue;  // Dirichlet or ghost row: nothing is loaded (load_lec, mm_fill.c:5374)
-    const int row = s.gun[fr][i], rank_i = s.rank[i];
-    const unsigned first = s.firstS[i];
-    const bool rowT = C::ENERGY && fr == C::F_T;
-    const double *src = &s.stage[(r - r0) * NCOL];
-    double *arow = P.a + rstart;
-#pragma unroll
-    for (int c0 = 0; c0 < NCOL; c0 += 32) {
-      const int c = c0 + lane;
-      if (c >= NCOL) break;
-      const int js = c / NF, fc = c - js * NF;
-      if (rowT && !C::P1 && fc == C::F_P) continue;  // Inter_Mask: energy rows carry no pressure columns
-      int off = s.colbase[i][c];
-      if (C::ENERGY && rowT) off -= s.ppS[i][js];
-      double *dst;
-      if (js != rank_i)
-        dst = arow + off - (js > rank_i ? 1 : 0);  // columns are sorted by node: one shift past the diagonal node
-      else
-        dst = (fc == fr) ? P.a + row : arow + off - (fc > fr ? 1 : 0);
-      slot_add(P, dst, src[c], (first >> js) & 1u);
-    }
-  }
-}
-
 template <class C>
 __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_constant__ FillParams P) {
-  constexpr int NN = C::NN, NF = C::NF, TI = C::TI, NCOL = C::NCOL, NT = C::TPE;
+  constexpr int NN = C::NN, NF = C::NF, TI = C::TI, NT = C::TPE;
+  constexpr unsigned REC_BYTES = (unsigned)sizeof(ElemRec<C>);
+  static_assert(REC_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<C> &s = *reinterpret_cast<Smem<C> *>(smem_raw);
   const int tid = threadIdx.x;
+  int ee = P.elem_begin + blockIdx.x;
 
-  // ---- stage the quadrature/basis tables once per CTA with a TMA bulk copy
+  // ---- prologue: quadrature/basis tables and the record of the first element, one TMA bulk copy each
   if (tid == 0) {
     mbar_init(&s.mbar, 1);
+    mbar_init(&s.mbar_rec[0], 1);
+    mbar_init(&s.mbar_rec[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (!P.transient)
+    for (int idx = tid; idx < 2 * NF * NN; idx += NT) (&s.Udot[0][0][0])[idx] = 0.0;
   __syncthreads();
+  if (ee >= P.elem_end) return;
   if (tid == 0) {
     mbar_expect_tx(&s.mbar, C::TBL_PAD * 8);
     tma_bulk_g2s(s.tbl, P.tables, C::TBL_PAD * 8, &s.mbar);
+    const int elem = P.elem_list ? P.elem_list[ee] : ee;
+    mbar_expect_tx(&s.mbar_rec[0], REC_BYTES);
+    tma_bulk_g2s(&s.rec[0], P.erec + (size_t)elem * REC_BYTES, REC_BYTES, &s.mbar_rec[0]);
   }
+  mbar_wait(&s.mbar_rec[0], 0);
+  gather_state<C>(P, s, 0, tid);
+  cp_async_wait_all();
   mbar_wait(&s.mbar, 0);
+  __syncthreads();
 
-  long long t_build = 0, t_rows = 0, t_loop = 0, t_write = 0;
+  long long t_build = 0, t_rows = 0, t_loop = 0;
   long long stamps_[6] = {0, 0, 0, 0, 0, 0};
   long long *stamps = (P.prof && tid == 0) ? stamps_ : nullptr;
   int count = 0;
-  for (int ee = P.elem_begin + blockIdx.x; ee < P.elem_end; ee += gridDim.x, count++) {
-    const int elem = P.elem_list ? P.elem_list[ee] : ee;
-    long long c0 = GOMA_CLOCK();
-    build_element<C>(P, s, elem, tid, stamps);
-    long long c1 = GOMA_CLOCK();
-    element_rows<C>(P, s, elem, tid);
-    long long c2 = GOMA_CLOCK();
-    if constexpr (C::DIRECT) {
-      if (P.assemble_jacobian) {
 #pragma unroll 1
-        for (int t = tid; t < C::NTILE; t += NT) {
-          Tile<C> tile;
-          const int it = t / NN, j = t - it * NN, i = it * TI;
-          if (C::GENERAL)
-            gauss_loop_general<C>(P, s, i, j, tile);
-          else
-            gauss_loop<C>(P, s, i, j, tile);
-          write_tile_direct<C>(P, s, i, j, tile);
-        }
-      }
-      __syncthreads();
-    } else if (P.assemble_jacobian) {
-      // one register tile per thread (NTILE <= TPE for every instantiated configuration)
-      Tile<C> tile;
-      const bool active = tid < C::NTILE;
-      const int it = active ? tid / NN : 0, j = active ? tid - it * NN : 0, i0 = it * TI;
-      if (active) {
-        if (C::GENERAL)
-          gauss_loop_general<C>(P, s, i0, j, tile);
-        else
-          gauss_loop<C>(P, s, i0, j, tile);
-      }
-      long long c3 = GOMA_CLOCK();
-      t_loop += c3 - c2;
-      __syncthreads();  // every thread is done reading the operand arena: it becomes the stage
-#pragma unroll 1
-      for (int pass = 0; pass < C::NPASS; pass++) {
-        const int r0 = pass * C::ROWS_PER_PASS;
-        const int r1 = r0 + C::ROWS_PER_PASS < C::NROW ? r0 + C::ROWS_PER_PASS : C::NROW;
-        if (active && i0 * NF >= r0 && i0 * NF < r1) {
-          const int cj = s.rank[j] * NF;
-#pragma unroll
-          for (int ii = 0; ii < TI; ii++)
-#pragma unroll
-            for (int fr = 0; fr < NF; fr++)
-#pragma unroll
-              for (int fc = 0; fc < NF; fc++)
-                s.stage[((i0 + ii) * NF + fr - r0) * NCOL + cj + fc] = tile.V[ii][fr][fc];
-        }
-        __syncthreads();
-        write_rows<C>(P, s, r0, r1, tid);
-        __syncthreads();
-      }
-      t_write += GOMA_CLOCK() - c3;
-    } else {
-      __syncthreads();
+  for (; ee < P.elem_end; ee += gridDim.x, count++) {
+    const int buf = count & 1;
+    const bool has_next = ee + (int)gridDim.x < P.elem_end;
+    // the record of the next element starts its way into the other buffer (free since the barrier that
+    // closed the previous iteration)
+    if (has_next && tid == 0) {
+      const int nxt = P.elem_list ? P.elem_list[ee + gridDim.x] : ee + (int)gridDim.x;
+      mbar_expect_tx(&s.mbar_rec[buf ^ 1], REC_BYTES);
+      tma_bulk_g2s(&s.rec[buf ^ 1], P.erec + (size_t)nxt * REC_BYTES, REC_BYTES, &s.mbar_rec[buf ^ 1]);
     }
+    long long c0 = GOMA_CLOCK();
+    build_element<C>(P, s, buf, tid, stamps);
+    long long c1 = GOMA_CLOCK();
+    element_rows<C>(P, s, buf, tid);
+    long long c2 = GOMA_CLOCK();
+    // ... and, once it has landed, the gather of the next element's unknowns runs under the Gauss loop
+    if (has_next) {
+      mbar_wait(&s.mbar_rec[buf ^ 1], ((count + 1) >> 1) & 1);
+      gather_state<C>(P, s, buf ^ 1, tid);
+    }
+    if (P.assemble_jacobian) {
+      const ElemRec<C> &rec = s.rec[buf];
+#pragma unroll 1
+      for (int t = tid; t < C::NTILE; t += NT) {
+        Tile<C> tile;
+        const int it = t / NN, j = t - it * NN, i = it * TI;
+        if (C::GENERAL)
+          gauss_loop_general<C>(P, s, i, j, tile);
+        else
+          gauss_loop<C>(P, s, i, j, tile);
+        write_tile_direct<C>(P, rec, i, j, tile);
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    t_loop += GOMA_CLOCK() - c2;
     t_build += c1 - c0;
     t_rows += c2 - c1;
   }
   if (P.prof && tid == 0 && count) {
     long long *o = P.prof + blockIdx.x * 8;
-    o[0] = t_build; o[1] = t_rows; o[2] = t_loop; o[3] = t_write; o[6] = count;
+    o[0] = t_build; o[1] = t_rows; o[2] = t_loop; o[3] = 0; o[6] = count;
     long long *o2 = P.prof + (4096 + blockIdx.x) * 8;
     for (int k = 0; k < 6; k++) o2[k] = stamps_[k];
   }
-  (void)NT;
 }
 
 }  // namespace goma_b200
