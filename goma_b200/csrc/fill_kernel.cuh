@@ -345,8 +345,8 @@ __global__ void build_records_kernel(const FillParams P, int num_elems) {
 
 // indirect gather of the state for one element: x[gun] (and xdot[gun]) -> shared memory, asynchronously
 template <class C>
-__device__ __forceinline__ void gather_state(const FillParams &P, Smem<C> &s, int buf, int tid) {
-  constexpr int NN = C::NN, NF = C::NF, NT = C::TPE;
+__device__ __forceinline__ void gather_state(const FillParams &P, Smem<C> &s, int buf, int tid, int NT = C::TPE) {
+  constexpr int NN = C::NN, NF = C::NF;
   const ElemRec<C> &r = s.rec[buf];
   for (int idx = tid; idx < NF * NN; idx += NT) {
     const int gun = (&r.gun[0][0])[idx];
@@ -386,11 +386,36 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
   }
   GOMA_STAMP(0);
   // ---- phase 1: J[a][b] = sum_k x_b,k dphi_k/dxi_a   (beer_belly, mm_fill_util.c:258-276)
-  for (int idx = tid; idx < NGP * DIM * DIM; idx += NT) {
-    int gp = idx / (DIM * DIM), ab = idx - gp * DIM * DIM;
-    int a = ab / DIM, b = ab - a * DIM;
-    const double *Xb = C::ALE ? s.X[b] : rec.X[b];
-    s.B[gp][ab] = dot3<NN>(Xb, 1, &t_dphi[gp * NN * DIM + a], DIM);
+  //      one thread per (Gauss point, a, third of the nodes): each dphi load feeds DIM FMAs
+  {
+    constexpr int NITEM = NGP * DIM, Q = (NN + 3) / 4;
+    constexpr int NROUND = (NITEM * 4 + NT - 1) / NT;
+#pragma unroll 1
+    for (int rnd = 0; rnd < NROUND; rnd++) {
+      const int idx = rnd * NT + tid;
+      const int item = idx >> 2, c = idx & 3;
+      const bool live = item < NITEM;
+      const int gp = live ? item / DIM : 0, a = live ? item - gp * DIM : 0;
+      const int k0 = c * Q, k1 = (k0 + Q < NN) ? k0 + Q : NN;
+      double acc[3] = {0.0, 0.0, 0.0};
+      if (live) {
+        const double *dp = &t_dphi[gp * NN * DIM + a];
+#pragma unroll 4
+        for (int k = k0; k < k1; k++) {
+          const double d = dp[k * DIM];
+#pragma unroll
+          for (int b = 0; b < DIM; b++) acc[b] += (C::ALE ? s.X[b][k] : rec.X[b][k]) * d;
+        }
+      }
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1)
+#pragma unroll
+        for (int b = 0; b < DIM; b++) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+      if (live && c == 0) {
+#pragma unroll
+        for (int b = 0; b < DIM; b++) s.B[gp][a * DIM + b] = acc[b];
+      }
+    }
   }
   __syncthreads();
   GOMA_STAMP(1);
@@ -702,15 +727,50 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
   //      points by one thread; the velocity rows accumulate the P1 pressure coupling on the way:
   //      S[i][a][p] = sum_gp w grad_phi_i[a] psi_p, shared by J_m_P (mm_fill_momentum.c:2091-2104) and
   //      J_c_v (mm_fill_continuity.c:686-716)
-  for (int idx = tid; idx < NROW * NPART; idx += NT) {
-    const int c = idx / NROW, r = idx - c * NROW;
+  //      velocity rows: one thread per (node i, third) does all DIM components off one load of the test functions
+  for (int idx = tid; idx < NN * NPART; idx += NT) {
+    const int c = idx / NN, i = idx - c * NN;
+    const int gp0 = c * NGP / NPART, gp1 = (c + 1) * NGP / NPART;
+    double R[DIM], S[DIM][NP > 0 ? NP : 1];
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+      R[a] = 0.0;
+#pragma unroll
+      for (int p = 0; p < NP; p++) S[a][p] = 0.0;
+    }
+    for (int gp = gp0; gp < gp1; gp++) {
+      const double2 s01 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][0]);
+      const double2 s23 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][2]);
+      const double sg[3] = {s01.y, s23.x, s23.y};
+      const double *G = s.GP[gp];
+      double ps[NP > 0 ? NP : 1];
+#pragma unroll
+      for (int p = 0; p < NP; p++) ps[p] = t_psi[gp * (DIM + 1) + p];
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        double t = s01.x * G[C::G_RQ + a];
+#pragma unroll
+        for (int p = 0; p < DIM; p++) t += sg[p] * G[C::G_RP + a * DIM + p];
+        R[a] += t;
+#pragma unroll
+        for (int p = 0; p < NP; p++) S[a][p] += sg[a] * ps[p];
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+      s.redR[c][a * NN + i] = R[a];
+#pragma unroll
+      for (int p = 0; p < NP; p++) s.redS[c][a * NN + i][p] = S[a][p];
+    }
+  }
+  //      the other rows: one thread per (row, third)
+  for (int idx = tid; idx < (NROW - DIM * NN) * NPART; idx += NT) {
+    const int c = idx / (NROW - DIM * NN), r = DIM * NN + idx - c * (NROW - DIM * NN);
     const int gp0 = c * NGP / NPART, gp1 = (c + 1) * NGP / NPART;
     const bool prow = r >= NF * NN;  // P1 continuity row
     const int f = prow ? 0 : r / NN;
     const int i = prow ? C::CEN : r - f * NN;
-    double R = 0.0, S[NP > 0 ? NP : 1];
-#pragma unroll
-    for (int p = 0; p < NP; p++) S[p] = 0.0;
+    double R = 0.0;
     if (prow) {
       const int p = r - NF * NN;
       for (int gp = gp0; gp < gp1; gp++) R += s.w[gp] * t_psi[gp * (DIM + 1) + p] * s.GP[gp][C::G_DIV];
@@ -718,15 +778,10 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
       const bool isT = C::ENERGY && f == C::F_T;
       const bool isY = f >= C::F_Y && f < C::F_Y + C::NSPEC;
       const bool isP = !C::P1 && f == C::F_P;
-      const bool isD = C::ALE && f >= C::F_D && f < C::F_D + DIM;  // assemble_mesh residual (mm_fill_terms.c:421-428)
-      // row = sum_gp  w phi_i * G[q0]  +  w grad_phi_i[p] * G[q1 + p]
-      const int q0 = isT ? C::G_RE : isY ? C::G_RY + (f - C::F_Y) : isP ? C::G_DIV : isD ? C::G_ZERO : C::G_RQ + f;
-      const int q1 = isT   ? C::G_RF
-                     : isY ? C::G_RFY + (f - C::F_Y) * DIM
-                     : isP ? C::G_PS
-                     : isD ? C::G_RD + (f - C::F_D) * DIM
-                           : C::G_RP + f * DIM;
-      const bool vel = f < DIM;
+      // row = sum_gp  w phi_i * G[q0]  +  w grad_phi_i[p] * G[q1 + p]; the last case is the mesh rows
+      // (assemble_mesh residual, mm_fill_terms.c:421-428)
+      const int q0 = isT ? C::G_RE : isY ? C::G_RY + (f - C::F_Y) : isP ? C::G_DIV : C::G_ZERO;
+      const int q1 = isT ? C::G_RF : isY ? C::G_RFY + (f - C::F_Y) * DIM : isP ? C::G_PS : C::G_RD + (f - C::F_D) * DIM;
       for (int gp = gp0; gp < gp1; gp++) {
         const double2 s01 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][0]);
         const double2 s23 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][2]);
@@ -736,15 +791,6 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
 #pragma unroll
         for (int p = 0; p < DIM; p++) t += sg[p] * G[q1 + p];
         R += t;
-        if (C::P1 && vel) {
-          const double sgf = f == 0 ? sg[0] : (f == 1 ? sg[1] : sg[2]);
-#pragma unroll
-          for (int p = 0; p < NP; p++) S[p] += sgf * t_psi[gp * (DIM + 1) + p];
-        }
-      }
-      if (C::P1 && vel) {
-#pragma unroll
-        for (int p = 0; p < NP; p++) s.redS[c][r][p] = S[p];
       }
     }
     s.redR[c][r] = R;
@@ -841,10 +887,12 @@ __device__ __forceinline__ void gauss_loop(const FillParams &P, const Smem<C> &s
   const double c_adv = -P.etm_mom[1] * P.rho, c_diff = -P.etm_mom[3] * P.mu, c_mass = -P.etm_mom[0] * P.rho * tfac;
   const double ce_adv = -P.etm_energy[1] * rcp, ce_diff = -P.etm_energy[3] * P.k,
                ce_mass = -P.etm_energy[0] * rcp * tfac;
-  double A[TI][DIM][DIM], S1[TI], S2[TI], S3[TI], ET[TI][DIM];
+  // D: the delta_ab part of J_m_v, sum_gp w phi_i (c_adv v.grad_phi_j + c_mass phi_j) + c_diff w grad_phi_i.grad_phi_j;
+  // the energy configurations also need the three sums separately (J_e_T has other coefficients, J_m_T wants S3)
+  double A[TI][DIM][DIM], D[TI], S1[TI], S2[TI], S3[TI], ET[TI][DIM];
 #pragma unroll
   for (int ii = 0; ii < TI; ii++) {
-    S1[ii] = S2[ii] = S3[ii] = 0.0;
+    D[ii] = S1[ii] = S2[ii] = S3[ii] = 0.0;
 #pragma unroll
     for (int a = 0; a < DIM; a++) {
       ET[ii][a] = 0.0;
@@ -860,6 +908,7 @@ __device__ __forceinline__ void gauss_loop(const FillParams &P, const Smem<C> &s
     const double phi_j = j01.x;
     const double gj[3] = {j01.y, j23.x, j23.y};
     const double vgj = op.VG[gp][j];
+    const double qj = c_adv * vgj + c_mass * phi_j;
     double gjs[DIM], GV[DIM][DIM], GT[DIM];
     const double *G = s.GP[gp];
 #pragma unroll
@@ -876,10 +925,17 @@ __device__ __forceinline__ void gauss_loop(const FillParams &P, const Smem<C> &s
       const double wphi = i01.x;
       const double wg[3] = {i01.y, i23.x, i23.y};
       const double pp = wphi * phi_j;
-      S1[ii] += wphi * vgj;
-      S3[ii] += pp;
+      if (C::ENERGY) {
+        S1[ii] += wphi * vgj;
+        S3[ii] += pp;
 #pragma unroll
-      for (int p = 0; p < DIM; p++) S2[ii] += wg[p] * gj[p];
+        for (int p = 0; p < DIM; p++) S2[ii] += wg[p] * gj[p];
+      } else {
+        double d = D[ii] + wphi * qj;
+#pragma unroll
+        for (int p = 0; p < DIM; p++) d += wg[p] * gjs[p];
+        D[ii] = d;
+      }
 #pragma unroll
       for (int a = 0; a < DIM; a++) {
 #pragma unroll
@@ -900,7 +956,7 @@ __device__ __forceinline__ void gauss_loop(const FillParams &P, const Smem<C> &s
   }
 #pragma unroll
   for (int ii = 0; ii < TI; ii++) {
-    const double dm = c_adv * S1[ii] + c_diff * S2[ii] + c_mass * S3[ii];
+    const double dm = C::ENERGY ? c_adv * S1[ii] + c_diff * S2[ii] + c_mass * S3[ii] : D[ii];
 #pragma unroll
     for (int a = 0; a < DIM; a++) {
 #pragma unroll
