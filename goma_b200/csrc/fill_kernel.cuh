@@ -237,6 +237,20 @@ __device__ __forceinline__ void slot_add(const FillParams &P, double *addr, doub
     *addr += val;
   }
 }
+// the same with the scatter mode fixed at compile time (the node-pair write-out issues thousands per element)
+template <int MODE>
+__device__ __forceinline__ void slot_add_m(double *addr, double val, bool first) {
+  if (MODE == 2) {
+    if (first)
+      *addr = val;
+    else
+      atomicAdd(addr, val);
+  } else if (MODE == 0) {
+    atomicAdd(addr, val);
+  } else {
+    *addr += val;
+  }
+}
 
 // momentum_source_term (mm_fill_momentum.c:3738) CONSTANT branch and bouss_momentum_source
 // (mm_std_models.c:125-360), temperature piece
@@ -511,45 +525,55 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
   __syncthreads();
   GOMA_STAMP(3);
   // ---- phase 4: field values, gradients, time derivatives at the Gauss points (load_fv, load_fv_grads)
-  //      four lanes per (Gauss point, field), each over a quarter of the nodes, combined by shuffles
+  //      four lanes per Gauss point, each over a quarter of the nodes for ALL fields (one load of the basis
+  //      functions feeds NF x (DIM+2) FMAs), combined by shuffles
   {
-    constexpr int NITEM = NGP * NF, Q = (NN + 3) / 4;
-    constexpr int NROUND = (NITEM * 4 + NT - 1) / NT;
+    constexpr int Q = (NN + 3) / 4;
+    constexpr int NROUND = (NGP * 4 + NT - 1) / NT;
 #pragma unroll 1
     for (int rnd = 0; rnd < NROUND; rnd++) {
       const int idx = rnd * NT + tid;
-      const int item = idx >> 2, c = idx & 3;
-      const bool live = item < NITEM;
-      const int gp = live ? item / NF : 0, f = live ? item - gp * NF : 0;
-      double val = 0.0, dot = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
+      const int gpi = idx >> 2, c = idx & 3;
+      const bool live = gpi < NGP;
+      const int gp = live ? gpi : 0;
+      double acc[NF][DIM + 2];
+#pragma unroll
+      for (int f = 0; f < NF; f++)
+#pragma unroll
+        for (int q = 0; q < DIM + 2; q++) acc[f][q] = 0.0;
       const int k0 = c * Q, k1 = (k0 + Q < NN) ? k0 + Q : NN;
       if (live) {
-#pragma unroll 4
+#pragma unroll 2
         for (int kk = k0; kk < k1; kk++) {
           const double2 a = op.SJa[gp][kk], b = op.SJb[gp][kk];
-          const double u = U[f][kk];
-          val += u * a.x;
-          g0 += u * a.y;
-          g1 += u * b.x;
-          g2 += u * b.y;
-          if (P.transient) dot += Udot[f][kk] * a.x;
+#pragma unroll
+          for (int f = 0; f < NF; f++) {
+            const double u = U[f][kk];
+            acc[f][0] += u * a.x;
+            acc[f][1] += u * a.y;
+            acc[f][2] += u * b.x;
+            if (DIM == 3) acc[f][3] += u * b.y;
+            if (P.transient) acc[f][DIM + 1] += Udot[f][kk] * a.x;
+          }
         }
       }
 #pragma unroll
-      for (int o = 1; o <= 2; o <<= 1) {
-        val += __shfl_xor_sync(0xffffffffu, val, o);
-        dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        g0 += __shfl_xor_sync(0xffffffffu, g0, o);
-        g1 += __shfl_xor_sync(0xffffffffu, g1, o);
-        if (DIM == 3) g2 += __shfl_xor_sync(0xffffffffu, g2, o);
-      }
-      if (live && c == 0) {
-        double *Fo = s.F[gp][f];
-        Fo[0] = val;
-        Fo[1] = g0;
-        Fo[2] = g1;
-        if (DIM == 3) Fo[3] = g2;
-        Fo[1 + DIM] = dot;
+      for (int f = 0; f < NF; f++)
+#pragma unroll
+        for (int q = 0; q < DIM + 2; q++) {
+          double v = acc[f][q];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          acc[f][q] = v;
+        }
+      if (live) {
+        // lane c of the group stores fields c, c+4, ...
+#pragma unroll
+        for (int f = 0; f < NF; f++)
+          if ((f & 3) == c) {
+#pragma unroll
+            for (int q = 0; q < DIM + 2; q++) s.F[gp][f][q] = acc[f][q];
+          }
       }
     }
   }
@@ -1153,7 +1177,7 @@ __device__ __forceinline__ void gauss_loop_general(const FillParams &P, const Sm
 
 // write-out of one node-pair tile straight from registers (ALE configurations): same slot arithmetic
 // as write_rows, one thread per (i, j)
-template <class C>
+template <class C, int MODE>
 __device__ __forceinline__ void write_tile_direct(const FillParams &P, const ElemRec<C> &s, int i, int j, const Tile<C> &t) {
   constexpr int NF = C::NF;
   const int rj = s.rank[j];
@@ -1178,7 +1202,7 @@ __device__ __forceinline__ void write_tile_direct(const FillParams &P, const Ele
         dst = arow + off - (rj > ri ? 1 : 0);
       else
         dst = (fc == fr) ? P.a + row : arow + off - (fc > fr ? 1 : 0);
-      slot_add(P, dst, t.V[ii][fr][fc], first);
+      slot_add_m<MODE>(dst, t.V[ii][fr][fc], first);
     }
   }
   }
@@ -1253,7 +1277,13 @@ __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_cons
           gauss_loop_general<C>(P, s, i, j, tile);
         else
           gauss_loop<C>(P, s, i, j, tile);
-        write_tile_direct<C>(P, rec, i, j, tile);
+        if (P.debug & 1) continue;
+        if (P.scatter_mode == 2)
+          write_tile_direct<C, 2>(P, rec, i, j, tile);
+        else if (P.scatter_mode == 0)
+          write_tile_direct<C, 0>(P, rec, i, j, tile);
+        else
+          write_tile_direct<C, 1>(P, rec, i, j, tile);
       }
     }
     cp_async_wait_all();
