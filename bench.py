@@ -298,7 +298,7 @@ def main():
         ne_owned = problem.mesh.num_elems
     else:
         # weak scaling: rank r owns the r-th n^3 slab of a (world*n) x n x n cavity, plus its ghost column
-        from goma_b200.dp_comm import exchange_dof, slab_subdomain
+        from goma_b200.dp_comm import exchange_dof, setup_peer_exchange, slab_subdomain
 
         sub = slab_subdomain(lambda mesh: cavity_problem_on(mesh, args.energy), args.n, rank, world)
         problem = sub.problem
@@ -316,11 +316,31 @@ def main():
     bufs = mf.device_buffers()
     d_x = device_view(bufs.d_x, n_unk, dev)
 
+    trace = [] if os.environ.get("GOMA_BENCH_TRACE") else None
+    halo = None
+    if sub is not None:
+        # ghost refresh = goma_gpu_exchange_dof: one kernel pulling the ghost values out of the neighbours'
+        # HBM over NVLink.  Checked once against the torch.distributed (NCCL send/recv) restatement.
+        setup_peer_exchange(mf, sub)
+        mf.matrix_fill_full(x, assemble_jacobian=False)  # state into HBM
+        ref = d_x.clone()
+        exchange_dof(ref, sub)
+        torch.cuda.synchronize(dev)
+        mf.exchange_dof(0)
+        torch.cuda.synchronize(dev)
+        same = bool(torch.equal(ref, d_x))
+        if not same:
+            raise SystemExit(f"rank {rank}: peer-memory exchange_dof differs from the NCCL send/recv result")
+        halo = "goma_gpu_exchange_dof (one pull kernel over NVLink peer memory) before every fill; checked == NCCL send/recv"
+
     def step():
+        t0 = time.perf_counter()
         if sub is not None:
-            exchange_dof(d_x, sub)  # ghost refresh before the fill (mm_sol_nonlinear.c:1273), NCCL send/recv
-            torch.cuda.current_stream(dev).synchronize()
+            mf.exchange_dof(0)  # ghost refresh before the fill (mm_sol_nonlinear.c:1273), same stream as the fill
+        t1 = time.perf_counter()
         mf.fill_device()
+        if trace is not None:
+            trace.append((t1 - t0, time.perf_counter() - t1))
 
     # state into HBM once (one residual-only host call), then the device-resident steps
     sampler = ClockSampler(local_rank)
@@ -340,6 +360,9 @@ def main():
     barrier()
     step_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     clocks = sampler.stop()
+    if trace is not None:
+        print(f"[bench trace rank {rank}] (exchange_s, fill_s) per step:", [(round(a * 1e3, 3), round(b * 1e3, 3)) for a, b in trace[-args.steps:]],
+              file=sys.stderr)
     dev_ms = max_over_ranks(kernel_ms / args.steps)  # CUDA events on the library's stream: memsets + kernel(s)
     total_elems = sum_over_ranks(float(ne_owned))  # ghost elements are assembled twice but counted once
     value = total_elems / step_s
@@ -393,7 +416,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "elements_per_gpu": ne_owned,
                        "elements_assembled_per_gpu": ne, "unknowns_per_gpu": n_unk,
-                       "halo": None if sub is None else "exchange_dof over NCCL send/recv before every fill",
+                       "halo": halo,
                        "nnz_per_gpu": nnz, "scatter": ["fp64 atomics", "coloured load+add+store", "coloured first-touch stores"][args.scatter],
                        "l2": "inputs larger than L2 (MSR values %.1f GB per GPU rewritten every step)" % (8e-9 * nnz),
                        "setup_s": round(t_setup, 1)},

@@ -23,7 +23,8 @@ EXPORTED = [
     "goma_gpu_fill_init", "goma_gpu_fill_destroy", "goma_gpu_fill_get_msr", "goma_gpu_fill_export_msr",
     "goma_gpu_fill", "goma_gpu_fill_device_buffers", "goma_gpu_fill_device", "goma_gpu_global_h_U",
     "goma_gpu_pack_dofs", "goma_gpu_unpack_dofs", "goma_gpu_fill_last_stats", "goma_gpu_fill_set_option",
-    "goma_gpu_last_error", "goma_gpu_pattern_msr",
+    "goma_gpu_last_error", "goma_gpu_pattern_msr", "goma_gpu_exchange_export", "goma_gpu_exchange_setup",
+    "goma_gpu_exchange_dof",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -48,6 +49,16 @@ class GomaGpuProblem(C.Structure):
         ("heat_source", C.c_double), ("lame_mu", C.c_double), ("lame_lambda", C.c_double),
         ("dbc_flag", _bp), ("dbc_value", _dp),
     ]
+
+
+IPC_HANDLE_BYTES = 64
+MAX_NEIGHBORS = 32
+
+
+class ExchangeHandles(C.Structure):
+    """``struct goma_gpu_exchange_handles``: CUDA IPC handles of x, xdot, x_old and of the flag block."""
+    _fields_ = [("vec", (C.c_ubyte * IPC_HANDLE_BYTES) * 3), ("flags", C.c_ubyte * IPC_HANDLE_BYTES),
+                ("device", C.c_int)]
 
 
 class DeviceBuffers(C.Structure):
@@ -79,7 +90,10 @@ def load_library():
     lib.goma_gpu_fill_device_buffers.argtypes = [C.c_void_p, C.POINTER(DeviceBuffers)]
     lib.goma_gpu_fill_device.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                          C.c_int, C.c_int, _ip]
-    lib.goma_gpu_global_h_U.argtypes = [C.c_void_p, _dp]
+    lib.goma_gpu_global_h_U.argtypes = [C.c_void_p, _bp, _dp]
+    lib.goma_gpu_exchange_export.argtypes = [C.c_void_p, C.POINTER(ExchangeHandles)]
+    lib.goma_gpu_exchange_setup.argtypes = [C.c_void_p, C.c_int, C.POINTER(ExchangeHandles), _ip, _ip, _ip, C.c_int]
+    lib.goma_gpu_exchange_dof.argtypes = [C.c_void_p, C.c_int]
     lib.goma_gpu_pack_dofs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.goma_gpu_unpack_dofs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.goma_gpu_fill_last_stats.argtypes = [C.c_void_p, _dp, _ip]

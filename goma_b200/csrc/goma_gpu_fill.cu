@@ -52,6 +52,17 @@ struct goma_gpu_ctx {
   int *d_flags = nullptr;
   long long *d_prof = nullptr;     // phase cycle counters (GOMA_GPU_PROFILE=1)
   int *d_elem_list = nullptr;      // colour-ordered element list
+  // peer-memory exchange_dof
+  unsigned long long *d_xflags = nullptr;  // [3][GOMA_GPU_MAX_NEIGHBORS] epochs published by the neighbours
+  int num_neighbors = 0;
+  void *peer_vec[3][GOMA_GPU_MAX_NEIGHBORS] = {};
+  unsigned long long *peer_flags[GOMA_GPU_MAX_NEIGHBORS] = {};
+  int my_slot_at[GOMA_GPU_MAX_NEIGHBORS] = {};
+  int *d_recv_list = nullptr;
+  std::vector<int> recv_ptr;
+  int tail_begin = 0;
+  unsigned long long epoch[3] = {0, 0, 0};
+  double *d_sums = nullptr;  // goma_gpu_global_h_U
   std::vector<int> colour_begin;   // [ncolours+1]
   int num_sms = 0, blocks_per_sm = 0;  // cached launch geometry (cudaGetDeviceProperties is slow)
   int scatter_mode = 2;            // 0 fp64 atomics, 1 coloured load+add+store, 2 coloured first-touch stores
@@ -291,6 +302,14 @@ extern "C" void goma_gpu_fill_destroy(goma_gpu_ctx *c) {
                   c->d_x_older, c->d_xdot, c->d_xdot_old, c->d_a, c->d_resid, c->d_flags, c->d_elem_list};
   for (void *q : ptrs)
     if (q) cudaFree(q);
+  for (int k = 0; k < c->num_neighbors; k++) {
+    for (int v = 0; v < 3; v++)
+      if (c->peer_vec[v][k]) cudaIpcCloseMemHandle(c->peer_vec[v][k]);
+    if (c->peer_flags[k]) cudaIpcCloseMemHandle(c->peer_flags[k]);
+  }
+  if (c->d_xflags) cudaFree(c->d_xflags);
+  if (c->d_recv_list) cudaFree(c->d_recv_list);
+  if (c->d_sums) cudaFree(c->d_sums);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -573,8 +592,184 @@ extern "C" int goma_gpu_unpack_dofs(goma_gpu_ctx *c, double *d_vec, const int *d
   return 0;
 }
 
-extern "C" int goma_gpu_global_h_U(goma_gpu_ctx *c, double sums_out[4]) {
-  (void)sums_out;
+// ------------------------------------------------------------------ PSPG global norms
+// h_elem_siz (mm_fill_aux.c:844-1070): squared distances between opposite face centroids, from the vertex nodes
+__global__ void global_h_U_kernel(const int *__restrict__ conn, int npe, int dim, int num_elems,
+                                  const double *__restrict__ cx, const double *__restrict__ cy,
+                                  const double *__restrict__ cz, const unsigned char *__restrict__ elem_owned,
+                                  const int *__restrict__ first_unknown, const unsigned char *__restrict__ node_kind,
+                                  int slot_u0, int slot_u1, int slot_u2, int k0u, int k1u, int k2u, int k3u,
+                                  int num_owned_nodes, const double *__restrict__ x, double *__restrict__ sums) {
+  double h = 0.0, cnt = 0.0, vv = 0.0, nv = 0.0;
+  const int stride = gridDim.x * blockDim.x;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < num_elems; e += stride) {
+    if (elem_owned && !elem_owned[e]) continue;
+    const int *c = conn + (size_t)e * npe;
+    double hsq = 0.0;
+    for (int a = 0; a < dim; a++) {
+      const double *X = a == 0 ? cx : (a == 1 ? cy : cz);
+      if (dim == 2) {
+        const double x0 = X[c[0]], x1 = X[c[1]], x2 = X[c[2]], x3 = X[c[3]];
+        const double h0 = 0.5 * (x1 + x2) - 0.5 * (x0 + x3), h1 = 0.5 * (x0 + x1) - 0.5 * (x2 + x3);
+        hsq += h0 * h0 + h1 * h1;
+      } else {
+        double v[8];
+        for (int k = 0; k < 8; k++) v[k] = X[c[k]];
+        const double p1 = 0.25 * (v[0] + v[1] + v[2] + v[3]), p2 = 0.25 * (v[1] + v[2] + v[5] + v[6]);
+        const double p3 = 0.25 * (v[2] + v[3] + v[6] + v[7]), p4 = 0.25 * (v[0] + v[1] + v[4] + v[5]);
+        const double p5 = 0.25 * (v[0] + v[3] + v[4] + v[7]), p6 = 0.25 * (v[4] + v[5] + v[6] + v[7]);
+        hsq += (p2 - p5) * (p2 - p5) + (p3 - p4) * (p3 - p4) + (p1 - p6) * (p1 - p6);
+      }
+    }
+    h += sqrt(hsq / (double)dim);
+    cnt += 1.0;
+  }
+  const int ku[4][3] = {{k0u, k0u + 1, k0u + 2}, {k1u, k1u + 1, k1u + 2}, {k2u, k2u + 1, k2u + 2}, {k3u, k3u + 1, k3u + 2}};
+  (void)slot_u0; (void)slot_u1; (void)slot_u2;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < num_owned_nodes; n += stride) {
+    const int kd = node_kind[n];
+    if (ku[kd][0] < 0) continue;
+    const int f = first_unknown[n];
+    for (int a = 0; a < dim; a++) {
+      const double v = x[f + ku[kd][a]];
+      vv += v * v;
+      nv += 1.0;
+    }
+  }
+  double vals[4] = {h, cnt, vv, nv};
+  for (int q = 0; q < 4; q++) {
+    double v = vals[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&sums[q], v);
+  }
+}
+
+extern "C" int goma_gpu_global_h_U(goma_gpu_ctx *c, const unsigned char *elem_owned, double sums_out[4]) {
+  if (!c || !sums_out) return fail(-2, "null argument");
+  CU(cudaSetDevice(c->device));
+  const goma_gpu_problem &p = c->prob;
+  unsigned char *d_owned = nullptr;
+  if (elem_owned) {
+    CU(cudaMalloc((void **)&d_owned, std::max(1, p.num_elems)));
+    CU(cudaMemcpyAsync(d_owned, elem_owned, p.num_elems, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (!c->d_sums) CU(cudaMalloc((void **)&c->d_sums, 4 * sizeof(double)));
+  CU(cudaMemsetAsync(c->d_sums, 0, 4 * sizeof(double), c->stream));
+  int ku[4] = {-1, -1, -1, -1};  // offset of U inside a node of each kind (V, W follow it)
+  for (int k = 0; k < p.num_kinds && k < 4; k++) ku[k] = p.kind_slot[k][GOMA_SLOT_U];
+  const int threads = 256, blocks = std::max(1, std::min(148 * 8, (std::max(p.num_elems, p.num_owned_nodes) + threads - 1) / threads));
+  global_h_U_kernel<<<blocks, threads, 0, c->stream>>>(c->d_conn, p.elem_type, p.dim, p.num_elems, c->d_coord[0],
+                                                       c->d_coord[1], c->d_coord[2], d_owned, c->d_first, c->d_kind, 0, 1, 2,
+                                                       ku[0], ku[1], ku[2], ku[3], p.num_owned_nodes, c->d_x, c->d_sums);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(sums_out, c->d_sums, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (d_owned) cudaFree(d_owned);
+  return 0;
+}
+
+// ------------------------------------------------------------------ exchange_dof over peer memory
+struct ExchangeArgs {
+  int nn;
+  unsigned long long epoch;
+  unsigned long long *peer_ready[GOMA_GPU_MAX_NEIGHBORS];  // the slot of this rank in each neighbour's flag block
+  const unsigned long long *my_ready;                      // this rank's flag block, row of the vector
+  const double *peer_vec[GOMA_GPU_MAX_NEIGHBORS];
+  int recv_ptr[GOMA_GPU_MAX_NEIGHBORS + 1];
+  const int *recv_list;
+  double *tail;
+};
+
+__global__ void exchange_dof_kernel(const __grid_constant__ ExchangeArgs A) {
+  // publish: everything written to this rank's vector before this kernel (stream order) is visible to the
+  // neighbours once they observe the epoch
+  if (blockIdx.x == 0 && threadIdx.x < A.nn) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.peer_ready[threadIdx.x]), "l"(A.epoch) : "memory");
+  }
+  const int total = A.recv_ptr[A.nn];
+  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+    const int k = base + threadIdx.x;
+    int nb = 0;
+    if (k < total) {
+      while (k >= A.recv_ptr[nb + 1]) nb++;
+      unsigned long long seen;
+      do {  // the neighbour's vector of this epoch is complete
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(A.my_ready + nb) : "memory");
+      } while (seen < A.epoch);
+      A.tail[k] = A.peer_vec[nb][A.recv_list[k]];
+    }
+  }
+}
+
+extern "C" int goma_gpu_exchange_export(goma_gpu_ctx *c, goma_gpu_exchange_handles *out) {
+  if (!c || !out) return fail(-2, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (!c->d_xflags) {
+    CU(cudaMalloc((void **)&c->d_xflags, 3 * GOMA_GPU_MAX_NEIGHBORS * sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_xflags, 0, 3 * GOMA_GPU_MAX_NEIGHBORS * sizeof(unsigned long long)));
+    CU(cudaDeviceSynchronize());
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == GOMA_GPU_IPC_HANDLE_BYTES, "IPC handle size");
+  memset(out, 0, sizeof(*out));
+  double *vecs[3] = {c->d_x, c->d_xdot, c->d_x_old};
+  for (int v = 0; v < 3; v++) CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->vec[v], vecs[v]));
+  CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->flags, c->d_xflags));
+  out->device = c->device;
+  return 0;
+}
+
+extern "C" int goma_gpu_exchange_setup(goma_gpu_ctx *c, int num_neighbors, const goma_gpu_exchange_handles *nh,
+                                       const int *my_slot_at_neighbor, const int *recv_ptr, const int *recv_list,
+                                       int tail_begin) {
   if (!c) return fail(-2, "null context");
-  return fail(-2, "global_h_elem_siz / global_velocity_norm: PSPG path not built yet");
+  if (num_neighbors < 0 || num_neighbors > GOMA_GPU_MAX_NEIGHBORS) return fail(-2, "too many neighbours");
+  if (num_neighbors && (!nh || !my_slot_at_neighbor || !recv_ptr || !recv_list)) return fail(-2, "null argument");
+  if (!c->d_xflags) return fail(-2, "call goma_gpu_exchange_export first");
+  CU(cudaSetDevice(c->device));
+  c->num_neighbors = num_neighbors;
+  c->tail_begin = tail_begin;
+  c->recv_ptr.assign(recv_ptr, recv_ptr + num_neighbors + 1);
+  if (tail_begin + c->recv_ptr[num_neighbors] > c->prob.num_unknowns) return fail(-2, "external tail exceeds the vector");
+  for (int k = 0; k < num_neighbors; k++) {
+    if (my_slot_at_neighbor[k] < 0 || my_slot_at_neighbor[k] >= GOMA_GPU_MAX_NEIGHBORS) return fail(-2, "bad neighbour slot");
+    c->my_slot_at[k] = my_slot_at_neighbor[k];
+    for (int v = 0; v < 3; v++)
+      CU(cudaIpcOpenMemHandle(&c->peer_vec[v][k], *(const cudaIpcMemHandle_t *)nh[k].vec[v], cudaIpcMemLazyEnablePeerAccess));
+    void *pf = nullptr;
+    CU(cudaIpcOpenMemHandle(&pf, *(const cudaIpcMemHandle_t *)nh[k].flags, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_flags[k] = (unsigned long long *)pf;
+  }
+  if (c->d_recv_list) cudaFree(c->d_recv_list);
+  c->d_recv_list = nullptr;
+  const int total = c->recv_ptr[num_neighbors];
+  CU(cudaMalloc((void **)&c->d_recv_list, std::max(1, total) * sizeof(int)));
+  if (total) CU(cudaMemcpy(c->d_recv_list, recv_list, (size_t)total * sizeof(int), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int goma_gpu_exchange_dof(goma_gpu_ctx *c, int which) {
+  if (!c) return fail(-2, "null context");
+  if (which < 0 || which > 2) return fail(-2, "which must be 0 (x), 1 (xdot) or 2 (x_old)");
+  if (c->num_neighbors == 0) return 0;
+  CU(cudaSetDevice(c->device));
+  ExchangeArgs A;
+  memset(&A, 0, sizeof(A));
+  A.nn = c->num_neighbors;
+  A.epoch = ++c->epoch[which];
+  double *vecs[3] = {c->d_x, c->d_xdot, c->d_x_old};
+  for (int k = 0; k < A.nn; k++) {
+    A.peer_ready[k] = c->peer_flags[k] + which * GOMA_GPU_MAX_NEIGHBORS + c->my_slot_at[k];
+    A.peer_vec[k] = (const double *)c->peer_vec[which][k];
+    A.recv_ptr[k] = c->recv_ptr[k];
+  }
+  A.recv_ptr[A.nn] = c->recv_ptr[A.nn];
+  A.my_ready = c->d_xflags + which * GOMA_GPU_MAX_NEIGHBORS;
+  A.recv_list = c->d_recv_list;
+  A.tail = vecs[which] + c->tail_begin;
+  const int total = c->recv_ptr[A.nn];
+  const int threads = 256, blocks = std::max(1, std::min(148, (total + threads - 1) / threads));
+  exchange_dof_kernel<<<blocks, threads, 0, c->stream>>>(A);
+  CU(cudaGetLastError());
+  return 0;
 }

@@ -258,3 +258,34 @@ def allreduce_flags(flags, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return t
+
+
+def setup_peer_exchange(mf, sub: Subdomain, group=None):
+    """Wire the ranks' GPU contexts together for ``MatrixFill.exchange_dof`` (``goma_gpu_exchange_*``).
+
+    Host plumbing only, once per problem: every rank publishes the CUDA IPC handles of its state vectors
+    and, per neighbour, its ``list_dof_send`` block (``dp_map_comm_vec.c:224-461``); the receiver hands that
+    block to the library as the list of neighbour-local indices that fill its external tail -- the same
+    pairing the reference's send/receive establishes (``dp_comm.c:77-96``).
+    """
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    mine = {"handles": mf.exchange_export(), "neighbors": [int(p) for p in sub.neighbors],
+            "send": {int(p): np.asarray(sub.list_dof_send[int(sub.ptr_dof_send[k]):int(sub.ptr_dof_send[k + 1])], np.int32)
+                     for k, p in enumerate(sub.neighbors)}}
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    handles, slots, recv_ptr, recv_list = [], [], [0], []
+    for k, p in enumerate(sub.neighbors):
+        other = everyone[int(p)]
+        handles.append(other["handles"])
+        slots.append(other["neighbors"].index(sub.rank))
+        block = other["send"][sub.rank]
+        if len(block) != int(sub.num_dofs_recv[k]):
+            raise RuntimeError(f"rank {sub.rank}: neighbour {p} sends {len(block)} dofs, {int(sub.num_dofs_recv[k])} expected")
+        recv_list.append(block)
+        recv_ptr.append(recv_ptr[-1] + len(block))
+    rl = np.concatenate(recv_list) if recv_list else np.zeros(0, np.int32)
+    mf.exchange_setup(handles, slots, recv_ptr, rl, sub.num_owned_dofs)
+    dist.barrier(group=group)  # every flag block exists and is zero before the first epoch is published

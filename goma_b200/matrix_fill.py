@@ -93,6 +93,38 @@ class MatrixFill:
                                                         int(assemble_jacobian),
                                                         self.flags.ctypes.data_as(capi._ip)), "goma_gpu_fill_device")
 
+    def global_h_U(self, elem_owned=None):
+        """Local sums of global_h_elem_siz / global_velocity_norm from the device-resident ``x``:
+        (sum_h, n_elems, sum_v2, n_velocity_unknowns); the caller all-reduces and divides
+        (``mm_fill_aux.c:1194-1204``)."""
+        out = np.zeros(4)
+        eo = None if elem_owned is None else np.ascontiguousarray(elem_owned, np.uint8)
+        capi.check(self.lib.goma_gpu_global_h_U(self._ctx, capi._ptr(eo, capi._bp), out.ctypes.data_as(capi._dp)),
+                   "goma_gpu_global_h_U")
+        return out
+
+    # -- exchange_dof over NVLink peer memory (dp_comm.setup_peer_exchange wires the ranks together)
+    def exchange_export(self) -> bytes:
+        h = capi.ExchangeHandles()
+        capi.check(self.lib.goma_gpu_exchange_export(self._ctx, C.byref(h)), "goma_gpu_exchange_export")
+        return bytes(h)
+
+    def exchange_setup(self, handles, my_slot_at_neighbor, recv_ptr, recv_list, tail_begin):
+        n = len(handles)
+        arr = (capi.ExchangeHandles * max(n, 1))()
+        for k, b in enumerate(handles):
+            arr[k] = capi.ExchangeHandles.from_buffer_copy(b)
+        slot = np.ascontiguousarray(my_slot_at_neighbor, np.int32)
+        rp = np.ascontiguousarray(recv_ptr, np.int32)
+        rl = np.ascontiguousarray(recv_list, np.int32)
+        ip = lambda v: v.ctypes.data_as(capi._ip)
+        capi.check(self.lib.goma_gpu_exchange_setup(self._ctx, n, arr, ip(slot), ip(rp), ip(rl), int(tail_begin)),
+                   "goma_gpu_exchange_setup")
+
+    def exchange_dof(self, which: int = 0):
+        """Ghost refresh of x (0), xdot (1) or x_old (2): one kernel on the context's stream, no host sync."""
+        capi.check(self.lib.goma_gpu_exchange_dof(self._ctx, int(which)), "goma_gpu_exchange_dof")
+
     def last_stats(self):
         ms, n = C.c_double(), C.c_int()
         capi.check(self.lib.goma_gpu_fill_last_stats(self._ctx, C.byref(ms), C.byref(n)), "last_stats")

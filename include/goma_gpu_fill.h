@@ -24,9 +24,11 @@
  *   goma_gpu_global_h_U     global_h_elem_siz / global_velocity_norm,
  *                           src/mm_fill_aux.c:1128 and :612 (PSPG only,
  *                           src/mm_sol_nonlinear.c:1184-1192).
- *   goma_gpu_pack_dofs /    the gather (src/dp_comm.c:77-80) and the contiguous receive
- *   goma_gpu_ghost_tail     tail (src/dp_comm.c:86-96) of exchange_dof(); the transport
- *                           itself is ncclSend/ncclRecv issued by the host on these buffers.
+ *   goma_gpu_exchange_*     exchange_dof() (src/dp_comm.c:48-102): gather of list_dof_send (:77-80) and
+ *                           the contiguous receive tail (:86-96), as one kernel that pulls the ghost
+ *                           values out of the neighbours' HBM over NVLink (CUDA IPC peer pointers).
+ *   goma_gpu_pack_dofs /    the two halves on their own, for a host that wants to drive the transport
+ *   goma_gpu_unpack_dofs    itself (ncclSend/ncclRecv on the packed buffer).
  *   goma_gpu_fill_destroy   (no counterpart: the reference never frees lec/ei.)
  *
  * Conventions kept from the reference: return 0 on success, -1 on "domain failure"
@@ -152,12 +154,43 @@ int goma_gpu_fill_device(goma_gpu_ctx *ctx, double delta_t, double theta, double
                          double h_elem_avg, double U_norm, int assemble_residual,
                          int assemble_jacobian, int flags_out[3]);
 
-/* global_h_elem_siz / global_velocity_norm local sums (owner-weighted); the host all-reduces. */
-int goma_gpu_global_h_U(goma_gpu_ctx *ctx, double sums_out[4]);
+/* global_h_elem_siz / global_velocity_norm (src/mm_fill_aux.c:1128-1207, :612-680) local sums over the
+ * elements listed as owned and the owned nodes, from the device-resident x:
+ *   sums_out = { sum_e sqrt(sum_p hsquared[p] / dim), number of elements summed,
+ *                sum of squared velocity unknowns on owned nodes, number of those unknowns }.
+ * The host all-reduces (SUM) and divides (mm_fill_aux.c:1194-1204).  elem_owned may be NULL (all). */
+int goma_gpu_global_h_U(goma_gpu_ctx *ctx, const unsigned char *elem_owned, double sums_out[4]);
 
 /* exchange_dof halves: gather x[list[k]] into buf (device), and the ghost tail pointer */
 int goma_gpu_pack_dofs(goma_gpu_ctx *ctx, const double *d_vec, const int *d_list, int n, double *d_buf);
 int goma_gpu_unpack_dofs(goma_gpu_ctx *ctx, double *d_vec, const int *d_list, int n, const double *d_buf);
+
+/* exchange_dof() (src/dp_comm.c:48-102) over NVLink peer memory, one rank per GPU of one node.
+ * Every rank exports CUDA IPC handles of its state vectors and of a small flag block
+ * (goma_gpu_exchange_export); the host passes them round once (any transport) and each rank opens its
+ * neighbours' (goma_gpu_exchange_setup), handing over, per neighbour, the dof indices IN THE NEIGHBOUR'S
+ * numbering whose values fill this rank's contiguous external tail -- i.e. the neighbour's
+ * list_dof_send block for this rank (src/dp_map_comm_vec.c:224-461), in its order.
+ * goma_gpu_exchange_dof then is ONE kernel on the context's stream: it publishes "my vector of this epoch
+ * is complete" in the neighbours' flag blocks, waits for theirs and pulls the ghost values straight out of
+ * the neighbours' HBM.  No host synchronisation, no staging buffer.  The caller must not overwrite a
+ * vector again before every rank has finished the fill that follows the exchange (in Goma the linear
+ * solve, a collective, sits in between).  which: 0 = x, 1 = xdot, 2 = x_old. */
+#define GOMA_GPU_IPC_HANDLE_BYTES 64
+#define GOMA_GPU_MAX_NEIGHBORS 32
+struct goma_gpu_exchange_handles {
+  unsigned char vec[3][GOMA_GPU_IPC_HANDLE_BYTES]; /* x, xdot, x_old */
+  unsigned char flags[GOMA_GPU_IPC_HANDLE_BYTES];
+  int device; /* CUDA device ordinal of the exporting rank */
+};
+int goma_gpu_exchange_export(goma_gpu_ctx *ctx, struct goma_gpu_exchange_handles *out);
+int goma_gpu_exchange_setup(goma_gpu_ctx *ctx, int num_neighbors,
+                            const struct goma_gpu_exchange_handles *neighbor_handles, /* [num_neighbors] */
+                            const int *my_slot_at_neighbor, /* [num_neighbors] my index in that rank's neighbour list */
+                            const int *recv_ptr,  /* [num_neighbors + 1] offsets into recv_list */
+                            const int *recv_list, /* neighbour-local dof indices, tail order */
+                            int tail_begin /* first external unknown = num owned unknowns */);
+int goma_gpu_exchange_dof(goma_gpu_ctx *ctx, int which);
 
 /* timing / accounting of the last goma_gpu_fill*: device ms of the assembly kernel(s)
  * (CUDA events on the context's stream) and number of kernel launches */
