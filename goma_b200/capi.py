@@ -24,7 +24,7 @@ EXPORTED = [
     "goma_gpu_fill", "goma_gpu_fill_device_buffers", "goma_gpu_fill_device", "goma_gpu_global_h_U",
     "goma_gpu_pack_dofs", "goma_gpu_unpack_dofs", "goma_gpu_fill_last_stats", "goma_gpu_fill_set_option",
     "goma_gpu_last_error", "goma_gpu_pattern_msr", "goma_gpu_exchange_export", "goma_gpu_exchange_setup",
-    "goma_gpu_exchange_dof",
+    "goma_gpu_exchange_dof", "goma_gpu_row_sum_scale", "goma_gpu_scale_buffer", "goma_gpu_vector_norms",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -94,6 +94,9 @@ def load_library():
     lib.goma_gpu_exchange_export.argtypes = [C.c_void_p, C.POINTER(ExchangeHandles)]
     lib.goma_gpu_exchange_setup.argtypes = [C.c_void_p, C.c_int, C.POINTER(ExchangeHandles), _ip, _ip, _ip, C.c_int]
     lib.goma_gpu_exchange_dof.argtypes = [C.c_void_p, C.c_int]
+    lib.goma_gpu_row_sum_scale.argtypes = [C.c_void_p, _dp, _ip]
+    lib.goma_gpu_scale_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _ip]
+    lib.goma_gpu_vector_norms.argtypes = [C.c_void_p, C.c_int, _dp]
     lib.goma_gpu_pack_dofs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.goma_gpu_unpack_dofs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.goma_gpu_fill_last_stats.argtypes = [C.c_void_p, _dp, _ip]

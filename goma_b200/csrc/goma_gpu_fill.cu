@@ -63,6 +63,10 @@ struct goma_gpu_ctx {
   int tail_begin = 0;
   unsigned long long epoch[3] = {0, 0, 0};
   double *d_sums = nullptr;  // goma_gpu_global_h_U
+  double *d_scale = nullptr;      // row-sum scale vector
+  double *d_partials = nullptr;   // per-block partial norms
+  int *d_zero_rows = nullptr;
+  int num_owned_unknowns = 0;
   std::vector<int> colour_begin;   // [ncolours+1]
   int num_sms = 0, blocks_per_sm = 0;  // cached launch geometry (cudaGetDeviceProperties is slow)
   int scatter_mode = 2;            // 0 fp64 atomics, 1 coloured load+add+store, 2 coloured first-touch stores
@@ -188,6 +192,7 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
   goma_gpu_ctx *c = new goma_gpu_ctx();
   c->prob = p;
   c->device = device;
+  c->num_owned_unknowns = p.num_owned_nodes < p.num_nodes ? p.first_unknown[p.num_owned_nodes] : p.num_unknowns;
   int nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
   std::string perr = build_pattern(p, c->pat, std::min(nthreads, 32));
   if (!perr.empty()) {
@@ -310,6 +315,9 @@ extern "C" void goma_gpu_fill_destroy(goma_gpu_ctx *c) {
   if (c->d_xflags) cudaFree(c->d_xflags);
   if (c->d_recv_list) cudaFree(c->d_recv_list);
   if (c->d_sums) cudaFree(c->d_sums);
+  if (c->d_scale) cudaFree(c->d_scale);
+  if (c->d_partials) cudaFree(c->d_partials);
+  if (c->d_zero_rows) cudaFree(c->d_zero_rows);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -771,5 +779,110 @@ extern "C" int goma_gpu_exchange_dof(goma_gpu_ctx *c, int which) {
   const int threads = 256, blocks = std::max(1, std::min(148, (total + threads - 1) / threads));
   exchange_dof_kernel<<<blocks, threads, 0, c->stream>>>(A);
   CU(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ after the fill: row-sum scaling, norms
+// One warp per owned row: the off-diagonal run of an MSR row is contiguous, lanes stride over it (coalesced),
+// the second sweep over the row (the division) hits L1/L2.  HBM-bound: reads and writes every value once.
+__global__ void row_sum_scale_kernel(int nrows, const long long *__restrict__ rowstart, double *__restrict__ a,
+                                     double *__restrict__ b, double *__restrict__ scale, int *__restrict__ zero_rows) {
+  const int lane = threadIdx.x & 31;
+  const int nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < nrows; row += nwarp) {
+    const long long k0 = rowstart[row], k1 = rowstart[row + 1];
+    double sum = 0.0;
+    for (long long k = k0 + lane; k < k1; k += 32) sum += fabs(a[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const double diag = a[row];
+    double row_sum = fabs(diag) + sum;
+    if (fabs(diag) > 1.0e-200) row_sum = diag >= 0.0 ? row_sum : -row_sum;  // keep the diagonal positive (:547-549)
+    for (long long k = k0 + lane; k < k1; k += 32) a[k] = a[k] / row_sum;
+    if (lane == 0) {
+      scale[row] = row_sum;
+      if (row_sum == 0.0) atomicAdd(zero_rows, 1);
+      a[row] = diag / row_sum;
+      b[row] = b[row] / row_sum;
+    }
+  }
+}
+
+extern "C" int goma_gpu_row_sum_scale(goma_gpu_ctx *c, double *scale_out, int *zero_rows_out) {
+  if (!c) return fail(-2, "null context");
+  CU(cudaSetDevice(c->device));
+  const int n = c->num_owned_unknowns;
+  if (!c->d_scale) CU(cudaMalloc((void **)&c->d_scale, std::max(1, c->prob.num_unknowns) * sizeof(double)));
+  if (!c->d_zero_rows) CU(cudaMalloc((void **)&c->d_zero_rows, sizeof(int)));
+  CU(cudaMemsetAsync(c->d_zero_rows, 0, sizeof(int), c->stream));
+  if (n > 0) {
+    const int threads = 256, blocks = std::min(148 * 8, (n + 7) / 8);
+    row_sum_scale_kernel<<<blocks, threads, 0, c->stream>>>(n, c->d_rowstart, c->d_a, c->d_resid, c->d_scale, c->d_zero_rows);
+    CU(cudaGetLastError());
+  }
+  int zr = 0;
+  CU(cudaMemcpyAsync(&zr, c->d_zero_rows, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (scale_out && n > 0) CU(cudaMemcpyAsync(scale_out, c->d_scale, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (zero_rows_out) *zero_rows_out = zr;
+  return 0;
+}
+
+extern "C" int goma_gpu_scale_buffer(goma_gpu_ctx *c, double **d_scale, int *num_owned_unknowns) {
+  if (!c) return fail(-2, "null context");
+  if (d_scale) *d_scale = c->d_scale;
+  if (num_owned_unknowns) *num_owned_unknowns = c->num_owned_unknowns;
+  return 0;
+}
+
+constexpr int NORM_BLOCKS = 592, NORM_THREADS = 256;
+__global__ void vector_norms_kernel(const double *__restrict__ v, int n, double *__restrict__ partials) {
+  __shared__ double sh[4][NORM_THREADS / 32];
+  double mx = -1.0, l1 = 0.0, l2 = 0.0, idx = -1.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double t = v[i], w = fabs(t);
+    l1 += w;
+    l2 += t * t;
+    if (w > mx) { mx = w; idx = (double)i; }  // first occurrence of the maximum, as the reference's strict '>'
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    l2 += __shfl_xor_sync(0xffffffffu, l2, o);
+    const double m2 = __shfl_xor_sync(0xffffffffu, mx, o), i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (m2 > mx || (m2 == mx && i2 >= 0.0 && (idx < 0.0 || i2 < idx))) { mx = m2; idx = i2; }
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sh[0][w] = mx; sh[1][w] = l1; sh[2][w] = l2; sh[3][w] = idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < NORM_THREADS / 32; k++) {
+      l1 += sh[1][k];
+      l2 += sh[2][k];
+      if (sh[0][k] > mx || (sh[0][k] == mx && sh[3][k] >= 0.0 && (idx < 0.0 || sh[3][k] < idx))) { mx = sh[0][k]; idx = sh[3][k]; }
+    }
+    double *o = partials + 4 * blockIdx.x;
+    o[0] = mx; o[1] = l1; o[2] = l2; o[3] = idx;
+  }
+}
+
+extern "C" int goma_gpu_vector_norms(goma_gpu_ctx *c, int which, double out[4]) {
+  if (!c || !out) return fail(-2, "null argument");
+  if (which < 0 || which > 2) return fail(-2, "which must be 0 (resid), 1 (x) or 2 (xdot)");
+  CU(cudaSetDevice(c->device));
+  const double *v = which == 0 ? c->d_resid : (which == 1 ? c->d_x : c->d_xdot);
+  if (!c->d_partials) CU(cudaMalloc((void **)&c->d_partials, 4 * NORM_BLOCKS * sizeof(double)));
+  vector_norms_kernel<<<NORM_BLOCKS, NORM_THREADS, 0, c->stream>>>(v, c->num_owned_unknowns, c->d_partials);
+  CU(cudaGetLastError());
+  std::vector<double> h(4 * NORM_BLOCKS);
+  CU(cudaMemcpyAsync(h.data(), c->d_partials, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  double mx = -1.0, l1 = 0.0, l2 = 0.0, idx = -1.0;
+  for (int b = 0; b < NORM_BLOCKS; b++) {  // fixed order: reproducible run to run
+    l1 += h[4 * b + 1];
+    l2 += h[4 * b + 2];
+    if (h[4 * b] > mx || (h[4 * b] == mx && h[4 * b + 3] >= 0.0 && (idx < 0.0 || h[4 * b + 3] < idx))) { mx = h[4 * b]; idx = h[4 * b + 3]; }
+  }
+  out[0] = mx; out[1] = l1; out[2] = l2; out[3] = idx;
   return 0;
 }

@@ -21,6 +21,7 @@ class MatrixFill:
     def __init__(self, problem, device: int = 0, ija=None, num_owned_nodes=None):
         self.lib = capi.load_library()
         self.problem = problem
+        self.device = int(device)
         self._struct, self._keep = capi.make_problem_struct(problem, ija=ija, num_owned_nodes=num_owned_nodes)
         self._ctx = C.c_void_p()
         capi.check(self.lib.goma_gpu_fill_init(C.byref(self._struct), device, C.byref(self._ctx)),
@@ -102,6 +103,36 @@ class MatrixFill:
         capi.check(self.lib.goma_gpu_global_h_U(self._ctx, capi._ptr(eo, capi._bp), out.ctypes.data_as(capi._dp)),
                    "goma_gpu_global_h_U")
         return out
+
+    # -- the passes that follow the fill in the Newton loop, on the device-resident system
+    def row_sum_scale(self, want_scale=True):
+        """row_sum_scaling_scale (``sl_matrix_util.c:441``) of the device-resident matrix and residual, in place.
+        Returns (scale[owned unknowns] or None, number of zero rows)."""
+        n = C.c_int()
+        capi.check(self.lib.goma_gpu_scale_buffer(self._ctx, None, C.byref(n)), "goma_gpu_scale_buffer")
+        scale = np.empty(n.value) if want_scale else None
+        zr = C.c_int()
+        capi.check(self.lib.goma_gpu_row_sum_scale(self._ctx, capi._ptr(scale, capi._dp), C.byref(zr)),
+                   "goma_gpu_row_sum_scale")
+        return scale, int(zr.value)
+
+    def vector_norms(self, which: int = 0):
+        """(Loo, L1, L2, index) of the owned part of resid (0), x (1) or xdot (2) -- local values; a distributed
+        host combines them with MPI_MAXLOC / MPI_SUM before the square root (``mm_sol_nonlinear.c:3177-3375``)."""
+        out = np.zeros(4)
+        capi.check(self.lib.goma_gpu_vector_norms(self._ctx, int(which), out.ctypes.data_as(capi._dp)),
+                   "goma_gpu_vector_norms")
+        return float(out[0]), float(out[1]), float(np.sqrt(out[2])), int(out[3])
+
+    def download_system(self):
+        """D2H of the device-resident MSR values and residual (after row_sum_scale, say)."""
+        import torch
+
+        b = self.device_buffers()
+        dev = torch.device("cuda", self.device)
+        a = device_view(b.d_a, self.nnz_plus + 1, dev).cpu().numpy()
+        r = device_view(b.d_resid, self.num_unknowns, dev).cpu().numpy()
+        return a, r
 
     # -- exchange_dof over NVLink peer memory (dp_comm.setup_peer_exchange wires the ranks together)
     def exchange_export(self) -> bytes:

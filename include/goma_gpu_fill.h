@@ -165,6 +165,21 @@ int goma_gpu_global_h_U(goma_gpu_ctx *ctx, const unsigned char *elem_owned, doub
 int goma_gpu_pack_dofs(goma_gpu_ctx *ctx, const double *d_vec, const int *d_list, int n, double *d_buf);
 int goma_gpu_unpack_dofs(goma_gpu_ctx *ctx, double *d_vec, const int *d_list, int n, const double *d_buf);
 
+/* The two O(nnz) passes that follow matrix_fill_full in solve_nonlinear_problem, on the device-resident
+ * system (so the 45 GB matrix need not cross PCIe to be scaled):
+ *   goma_gpu_row_sum_scale   row_sum_scaling_scale -> row_sum_scale_MSR (src/sl_matrix_util.c:441,507-600,
+ *                            call site src/mm_sol_nonlinear.c:1317): over the owned rows, scale = sum |a_row|
+ *                            with the sign of the diagonal; a_row /= scale, resid /= scale.  scale_out (host,
+ *                            [owned unknowns]) may be NULL; the device copy is at goma_gpu_scale_buffer().
+ *                            zero_rows_out counts rows whose sum is 0 (the reference warns and goes on).
+ *   goma_gpu_vector_norms    Loo_norm / L1_norm / L2_norm (src/mm_sol_nonlinear.c:3320,3275,3177; call sites
+ *                            :1451-1453) of the owned part of a device vector: which 0 = resid, 1 = x,
+ *                            2 = xdot.  out = { max |v|, sum |v|, sum v^2, index of the max }: local values,
+ *                            the host applies MPI_MAXLOC / MPI_SUM and the square root as the reference does. */
+int goma_gpu_row_sum_scale(goma_gpu_ctx *ctx, double *scale_out, int *zero_rows_out);
+int goma_gpu_scale_buffer(goma_gpu_ctx *ctx, double **d_scale, int *num_owned_unknowns);
+int goma_gpu_vector_norms(goma_gpu_ctx *ctx, int which, double out[4]);
+
 /* exchange_dof() (src/dp_comm.c:48-102) over NVLink peer memory, one rank per GPU of one node.
  * Every rank exports CUDA IPC handles of its state vectors and of a small flag block
  * (goma_gpu_exchange_export); the host passes them round once (any transport) and each rank opens its

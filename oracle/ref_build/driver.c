@@ -39,6 +39,8 @@
 #include "mm_input.h"
 #include "mm_mp.h"
 #include "mm_prob_def.h"
+#include "mm_sol_nonlinear.h"
+#include "sl_matrix_util.h"
 #include "mm_unknown_map.h"
 #include "rd_exo.h"
 #include "rd_mesh.h"
@@ -348,6 +350,26 @@ int main(int argc, char **argv) {
     wr(fo, resid, numProcUnknowns, 8);
     printf("fill[%d]: err=%d elems=%d best_s=%.6f mean_s=%.6f elems_per_s=%.1f\n", s, err, exo->num_elems, best,
            total / nrep, exo->num_elems / best);
+    if (argc > 4 && !strcmp(argv[4], "post")) {
+      /* what solve_nonlinear_problem does next: row-sum scaling (mm_sol_nonlinear.c:1317), then the norms of
+       * the scaled residual (:1451-1453) */
+      double *scale = (double *)calloc(numProcUnknowns, sizeof(double));
+      char dofname_r[80];
+      int num_unk_r = -1;
+      row_sum_scaling_scale(ams, resid, scale);
+      double nrm[4];
+      nrm[0] = Loo_norm(resid, NumUnknowns[pg->imtrx], &num_unk_r, dofname_r);
+      nrm[1] = L1_norm(resid, NumUnknowns[pg->imtrx]);
+      nrm[2] = L2_norm(resid, NumUnknowns[pg->imtrx]);
+      nrm[3] = (double)num_unk_r;
+      FILE *fp = fopen("post_out.bin", s == 0 ? "wb" : "ab");
+      wr(fp, nrm, 4, 8);
+      wr(fp, scale, numProcUnknowns, 8);
+      wr(fp, a, nnz_plus + 1, 8);
+      wr(fp, resid, numProcUnknowns, 8);
+      fclose(fp);
+      free(scale);
+    }
   }
   fclose(fo);
   fclose(fs);

@@ -79,7 +79,7 @@ def run_map(problem, workdir=None):
 
 
 def run_fill(problem, states, delta_t=0.0, theta=0.0, time=0.0, assemble_jacobian=True,
-             preset_dirichlet=False, h_elem_avg=-1.0, U_norm=-1.0, nrep=1, workdir=None, timeout=3600):
+             preset_dirichlet=False, h_elem_avg=-1.0, U_norm=-1.0, nrep=1, workdir=None, timeout=3600, post=False):
     """``states``: list of dicts with x and optional x_old, x_older, xdot, xdot_old.
 
     Returns a list of dicts: err, flags, a (MSR values, length nnz_plus+1), resid, x (after the
@@ -96,8 +96,9 @@ def run_fill(problem, states, delta_t=0.0, theta=0.0, time=0.0, assemble_jacobia
             for s in states:
                 for key in ("x", "x_old", "x_older", "xdot", "xdot_old"):
                     f.write(np.ascontiguousarray(s.get(key, z), np.float64).tobytes())
-        stdout = _run(wd, "fill", str(nrep), timeout=timeout)
+        stdout = _run(wd, "fill", str(nrep), *(["post"] if post else []), timeout=timeout)
         b = open(os.path.join(wd, "fill_out.bin"), "rb").read()
+        pb = open(os.path.join(wd, "post_out.bin"), "rb").read() if post else None
     nu, nnzp, ns, N = (int(v) for v in np.frombuffer(b, np.int32, 4))
     o = 16
     res = []
@@ -111,4 +112,12 @@ def run_fill(problem, states, delta_t=0.0, theta=0.0, time=0.0, assemble_jacobia
                     "zero_detJ": int(fl[3]), "best_s": float(tm[0]), "mean_s": float(tm[1]),
                     "h_elem_avg": float(tm[2]), "U_norm": float(tm[3]), "x": x, "a": a, "resid": r, "N": N,
                     "stdout": stdout})
+    if post:  # row_sum_scaling_scale + norms of the scaled residual, by the reference's own functions
+        o = 0
+        for r_ in res:
+            nrm = np.frombuffer(pb, np.float64, 4, o); o += 32
+            r_["post_norms"] = nrm.copy()
+            r_["post_scale"] = np.frombuffer(pb, np.float64, nu, o).copy(); o += 8 * nu
+            r_["post_a"] = np.frombuffer(pb, np.float64, nnzp + 1, o).copy(); o += 8 * (nnzp + 1)
+            r_["post_resid"] = np.frombuffer(pb, np.float64, nu, o).copy(); o += 8 * nu
     return res

@@ -260,3 +260,106 @@ def test_gpu_c4_ale_inverted_element_is_a_domain_failure(built):
     err, _, _ = mf.matrix_fill_full(x)
     assert err == -1 and mf.flags[0] == 1
     mf.close()
+
+
+def test_gpu_c1_newton_iterations_and_solution_match_oracle(built):
+    """BASELINE.json configs[0] (C1): the full Newton solve of the 40x10 quad9 channel, once with the CUDA
+    fill and once with the CPU oracle as the assembly: same iteration count, converged solutions agree to
+    1e-10 (north_star), and at the converged state the assembled systems agree to 1e-12."""
+    from tests.newton_util import channel_problem, newton
+
+    p = channel_problem()
+    ija = capi.pattern_msr(p)
+    n = int(p.unknown_map()[0][-1])
+    x0 = p.preset_dirichlet(np.zeros(n))
+    mf = MatrixFill(p)
+    xg, itg, ng = newton(lambda x: mf.matrix_fill_full(x), ija, x0)
+    xo, ito, no = newton(lambda x: port.port_fill(p, ija, {"x": x}), ija, x0)
+    assert itg == ito and 2 <= itg <= 8, (itg, ito, ng, no)
+    assert np.abs(xg - xo).max() <= 1e-10 * max(1.0, np.abs(xo).max())
+    # the flow developed: parabolic-ish profile with centreline velocity > inflow value at mid-channel
+    first, node_kind, kinds = p.unknown_map()
+    mid = np.nonzero((np.abs(p.mesh.coords[0] - 2.0) < 1e-12) & (np.abs(p.mesh.coords[1] - 0.5) < 1e-12))[0][0]
+    assert xg[first[mid]] > 1.2
+    _, a, r = mf.matrix_fill_full(xg)
+    _, a_ref, r_ref = port.port_fill(p, ija, {"x": xg})
+    assert_close(a, a_ref, "Jacobian at the converged state")
+    assert np.abs(r - r_ref).max() < 1e-12
+    if ref_driver.ref_available():  # the reference's own assembly at the GPU-converged state
+        ref = ref_driver.run_fill(p, [{"x": xg}])[0]
+        assert_close(a, ref["a"], "Jacobian vs live reference at the converged state")
+        assert np.abs(r - ref["resid"]).max() < 1e-12
+    mf.close()
+
+
+def test_gpu_global_h_and_velocity_norm(built):
+    """goma_gpu_global_h_U == the host restatement of global_h_elem_siz / global_velocity_norm
+    (mm_fill_aux.c:1128-1207, :612-680) that the PSPG parity tests feed to both sides."""
+    m = box_mesh("HEX8", (7, 6, 5), perturb=0.12, seed=31)
+    p = Problem(m, interp="Q1Q1", pspg="global", energy=True, ns_source="BOUSSINESQ")
+    st = make_state(p, seed=17)
+    mf = MatrixFill(p)
+    mf.matrix_fill_full(st["x"], h_elem_avg=0.1, U_norm=1.0, assemble_jacobian=False)  # x into HBM
+    sh, ne, sv, nv = mf.global_h_U()
+    assert ne == m.num_elems and nv == 3 * m.num_nodes
+    assert abs(sh / ne - p.global_h_elem_siz()) < 1e-13
+    assert abs(sv / nv - p.global_velocity_norm(st["x"])) < 1e-13 * max(1.0, sv / nv)
+    owned = np.zeros(m.num_elems, np.uint8)
+    owned[::3] = 1
+    sh2, ne2, _, _ = mf.global_h_U(owned)
+    assert ne2 == owned.sum() and abs(sh2 - p.global_h_elem_siz(owned.astype(bool))) < 1e-12
+    m2 = box_mesh("QUAD9", (9, 7), perturb=0.1, seed=3)
+    p2 = Problem(m2)
+    st2 = make_state(p2, seed=2)
+    mf2 = MatrixFill(p2)
+    mf2.matrix_fill_full(st2["x"], assemble_jacobian=False)
+    sh, ne, sv, nv = mf2.global_h_U()
+    assert abs(sh / ne - p2.global_h_elem_siz()) < 1e-13 and abs(sv / nv - p2.global_velocity_norm(st2["x"])) < 1e-13
+    mf.close()
+    mf2.close()
+
+
+def test_gpu_row_sum_scaling_and_norms_match_reference(built):
+    """row_sum_scaling_scale and the residual norms on the device-resident system ==
+    the reference's own row_sum_scale_MSR / Loo_norm / L1_norm / L2_norm output (committed fixture)."""
+    p, kw, st = case_state("c1_quad9_ns")
+    q = golden("post_c1_quad9_ns")
+    mf = MatrixFill(p)
+    err, _, _ = mf.matrix_fill_full(st["x"])
+    assert err == 0
+    scale, zero_rows = mf.row_sum_scale()
+    a, r = mf.download_system()
+    assert zero_rows == 0
+    assert_close(scale, q["scale"], "scale")
+    assert_close(a[:-1], q["a"][:-1], "scaled matrix")
+    assert_close(r, q["resid"], "scaled residual")
+    loo, l1, l2, k = mf.vector_norms(0)
+    assert abs(loo - q["norms"][0]) < 1e-12 and abs(l1 - q["norms"][1]) < 1e-11 and abs(l2 - q["norms"][2]) < 1e-12
+    assert k == int(q["norms"][3])
+    mf.close()
+
+
+def test_gpu_row_sum_scaling_matches_oracle_seeded(built):
+    """Larger seeded hex27 system with ghost rows: only owned rows are scaled; against oracle/post_fill.py."""
+    from oracle import post_fill
+
+    m = box_mesh("HEX27", (3, 3, 2), perturb=0.1, seed=5)
+    p = Problem(m, energy=True, rho=1.2, mu=0.03, k=0.05, Cp=1.3, ns_source="BOUSSINESQ", gravity=(0, 0, -1.0),
+                bcs=[Dirichlet("U", 1, 1.0), Dirichlet("T", 2, 0.0, relax=1.0)])
+    st = make_state(p, seed=6)
+    owned = m.num_nodes - 30
+    n_owned = int(p.unknown_map()[0][owned])
+    mf = MatrixFill(p, num_owned_nodes=owned)
+    ija = mf.export_msr()
+    _, a0, r0 = mf.matrix_fill_full(st["x"])
+    a_ref, r_ref, s_ref = post_fill.row_sum_scale_msr(n_owned, a0, ija, r0)
+    scale, zero_rows = mf.row_sum_scale()
+    a, r = mf.download_system()
+    assert zero_rows == 0 and len(scale) == n_owned
+    assert_close(scale, s_ref[:n_owned], "scale")
+    assert_close(a[:-1], a_ref[:-1], "scaled matrix")
+    assert_close(r, r_ref, "scaled residual")
+    loo, l1, l2, k = mf.vector_norms(0)
+    ref = post_fill.norms(r_ref, n_owned)
+    assert abs(loo - ref[0]) < 1e-12 * ref[0] + 1e-300 and abs(l2 - ref[2]) < 1e-12 * ref[2] and k == ref[3]
+    mf.close()

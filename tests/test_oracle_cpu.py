@@ -149,3 +149,33 @@ def test_reference_live_matches_fixture():
     res = ref_driver.run_fill(p, [st])[0]
     np.testing.assert_array_equal(res["a"], g["a"])
     np.testing.assert_array_equal(res["resid"], g["resid"])
+
+
+def test_c1_newton_converges_with_the_oracle_assembly(built):
+    """BASELINE.json configs[0] (C1) through the CPU oracle: Newton on the 40x10 quad9 channel converges
+    quadratically to a developed (Poiseuille-like) profile -- the reference case the GPU path is compared to."""
+    from tests.newton_util import channel_problem, newton
+
+    p = channel_problem()
+    ija = capi.pattern_msr(p)
+    first, node_kind, kinds = p.unknown_map()
+    x0 = p.preset_dirichlet(np.zeros(int(first[-1])))
+    x, it, norms = newton(lambda v: port.port_fill(p, ija, {"x": v}), ija, x0)
+    assert 2 <= it <= 8 and norms[-1] < 1e-10 and norms[-1] < norms[0] * 1e-9
+    mid = np.nonzero((np.abs(p.mesh.coords[0] - 2.0) < 1e-12) & (np.abs(p.mesh.coords[1] - 0.5) < 1e-12))[0][0]
+    assert 1.4 < x[first[mid]] < 1.6  # fully developed plane Poiseuille flow: 1.5 x mean velocity
+
+
+def test_post_fill_oracle_matches_reference_fixture():
+    """oracle/post_fill.py (row_sum_scale_MSR + Loo/L1/L2 norms) == the reference's own functions, bit for bit,
+    on the system the reference assembled for c1_quad9_ns (tests/golden/make_golden_post.py)."""
+    from oracle import post_fill
+
+    g, q = golden("c1_quad9_ns"), golden("post_c1_quad9_ns")
+    n = len(g["resid"])
+    a, b, scale = post_fill.row_sum_scale_msr(n, g["a"], g["ija"], g["resid"])
+    np.testing.assert_array_equal(scale, q["scale"])
+    np.testing.assert_array_equal(b, q["resid"])
+    np.testing.assert_array_equal(a[: len(q["a"]) - 1], q["a"][:-1])
+    loo, l1, l2, k = post_fill.norms(b, n)
+    assert (loo, l1, l2, float(k)) == tuple(q["norms"])
