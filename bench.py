@@ -367,6 +367,24 @@ def main():
     total_elems = sum_over_ranks(float(ne_owned))  # ghost elements are assembled twice but counted once
     value = total_elems / step_s
 
+    # ---- the pass that follows the fill in the Newton loop, HBM-bound: row-sum scaling of the
+    #      device-resident matrix (reads and writes every value once).  Not part of `value`.
+    post = None
+    if world == 1:
+        mf.fill_device()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st_lib = torch.cuda.ExternalStream(bufs.stream, device=dev)
+        ts = []
+        for _ in range(3):
+            ev0.record(st_lib)
+            mf.row_sum_scale(want_scale=False)
+            ev1.record(st_lib)
+            torch.cuda.synchronize(dev)
+            ts.append(ev0.elapsed_time(ev1))
+        ms = min(ts[1:])
+        post = {"row_sum_scale_ms": ms, "GB/s": 16.0 * nnz / ms / 1e6, "bytes": 16 * nnz,
+                "note": "row_sum_scaling_scale on device: one read + one write of the MSR values"}
+
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -406,6 +424,13 @@ def main():
         flops = ALG_FLOPS_PER_ELEM[key]
         bytes_per_elem = 8.0 * (nnz + n_unk) / ne + 27 * 4 + 8.0 * (3 * problem.mesh.num_nodes + n_unk) / ne
         kern_s = dev_ms * 1e-3
+        traffic = None  # measured DRAM bytes per launch (ncu capture summarised under profiles/)
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+            if key in tj and launches:
+                traffic = tj[key]["bytes_per_element"] * ne * args.steps / launches
+        except OSError:
+            pass
         fp64_meas = fp64_peak_tflops(dev)
         fp64_peak = max(fp64_meas, 1e-9)
         ach_tf = flops * ne / kern_s / 1e12
@@ -422,14 +447,17 @@ def main():
                        "setup_s": round(t_setup, 1)},
             "clocks": clocks, "gpu_launches": launches, "device_ms_per_step": dev_ms,
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": ach_tf / fp64_peak, "traffic": None,
+                         "frac": ach_tf / fp64_peak, "traffic": traffic,
                          "peak_source": "fp64 matmul micro-benchmark in this run (nominal %.0f)" % FP64_PEAK_NOMINAL_TFLOPS,
                          "flops_per_element": flops,
                          "note": "binding roof of the hex27 fill is the FP64 pipe (AI ~27 flop/B, SURVEY.md §8d)"},
             "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                             "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
                              "bytes_per_element": bytes_per_elem},
         }
+        if post:
+            post["hbm_frac"] = post["GB/s"] / hbm_peak
+            line["post_fill"] = post
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

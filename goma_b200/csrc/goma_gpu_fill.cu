@@ -785,20 +785,48 @@ extern "C" int goma_gpu_exchange_dof(goma_gpu_ctx *c, int which) {
 // ------------------------------------------------------------------ after the fill: row-sum scaling, norms
 // One warp per owned row: the off-diagonal run of an MSR row is contiguous, lanes stride over it (coalesced),
 // the second sweep over the row (the division) hits L1/L2.  HBM-bound: reads and writes every value once.
-__global__ void row_sum_scale_kernel(int nrows, const long long *__restrict__ rowstart, double *__restrict__ a,
+__global__ void __launch_bounds__(256, 6) row_sum_scale_kernel(int nrows, const long long *__restrict__ rowstart, double *__restrict__ a,
                                      double *__restrict__ b, double *__restrict__ scale, int *__restrict__ zero_rows) {
   const int lane = threadIdx.x & 31;
   const int nwarp = (gridDim.x * blockDim.x) >> 5;
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < nrows; row += nwarp) {
-    const long long k0 = rowstart[row], k1 = rowstart[row + 1];
-    double sum = 0.0;
-    for (long long k = k0 + lane; k < k1; k += 32) sum += fabs(a[k]);
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  long long k0n = 0, k1n = 0;
+  if (row < nrows) {
+    k0n = rowstart[row];
+    k1n = rowstart[row + 1];
+  }
+  for (; row < nrows; row += nwarp) {
+    const long long k0 = k0n, k1 = k1n;
+    if (row + nwarp < nrows) {  // the next row's extent is on its way while this row streams
+      k0n = rowstart[row + nwarp];
+      k1n = rowstart[row + nwarp + 1];
+    }
+    double sum = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    long long k = k0 + lane;
+    for (; k + 96 < k1; k += 128) {  // four independent 256-byte requests in flight per warp
+      const double v0 = a[k], v1 = a[k + 32], v2 = a[k + 64], v3 = a[k + 96];
+      sum += fabs(v0);
+      s1 += fabs(v1);
+      s2 += fabs(v2);
+      s3 += fabs(v3);
+    }
+    for (; k < k1; k += 32) sum += fabs(a[k]);
+    sum = (sum + s1) + (s2 + s3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const double diag = a[row];
     double row_sum = fabs(diag) + sum;
     if (fabs(diag) > 1.0e-200) row_sum = diag >= 0.0 ? row_sum : -row_sum;  // keep the diagonal positive (:547-549)
-    for (long long k = k0 + lane; k < k1; k += 32) a[k] = a[k] / row_sum;
+    const double inv_guard = row_sum;  // true division, as the reference (a[k] /= row_sum)
+    k = k0 + lane;
+    for (; k + 96 < k1; k += 128) {
+      const double v0 = a[k], v1 = a[k + 32], v2 = a[k + 64], v3 = a[k + 96];
+      a[k] = v0 / inv_guard;
+      a[k + 32] = v1 / inv_guard;
+      a[k + 64] = v2 / inv_guard;
+      a[k + 96] = v3 / inv_guard;
+    }
+    for (; k < k1; k += 32) a[k] = a[k] / inv_guard;
     if (lane == 0) {
       scale[row] = row_sum;
       if (row_sum == 0.0) atomicAdd(zero_rows, 1);
@@ -816,7 +844,12 @@ extern "C" int goma_gpu_row_sum_scale(goma_gpu_ctx *c, double *scale_out, int *z
   if (!c->d_zero_rows) CU(cudaMalloc((void **)&c->d_zero_rows, sizeof(int)));
   CU(cudaMemsetAsync(c->d_zero_rows, 0, sizeof(int), c->stream));
   if (n > 0) {
-    const int threads = 256, blocks = std::min(148 * 8, (n + 7) / 8);
+    const int threads = 256;
+    int per_sm = 0;  // a whole number of resident waves: the rows are handed out grid-stride
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)row_sum_scale_kernel, threads, 0));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    const int blocks = std::max(1, std::min(sms * std::max(per_sm, 1), (n + 7) / 8));
     row_sum_scale_kernel<<<blocks, threads, 0, c->stream>>>(n, c->d_rowstart, c->d_a, c->d_resid, c->d_scale, c->d_zero_rows);
     CU(cudaGetLastError());
   }
