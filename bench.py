@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # SURVEY.md §8(d) / BASELINE.md §3 per-element algorithmic work, fixed per config
-ALG_FLOPS_PER_ELEM = {"c2_hex27_ns": 1.2e6, "c3_hex27_ns_energy": 1.85e6}
+ALG_FLOPS_PER_ELEM = {"c2_hex27_ns": 1.2e6, "c3_hex27_ns_energy": 1.85e6, "c5_hex8_pspg_T_2Y": 0.25e6}
 FP64_PEAK_NOMINAL_TFLOPS = 40.0  # BASELINE.json north_star; replaced by the DFMA micro-benchmark when it runs
 
 
@@ -47,6 +47,18 @@ def cavity_problem(n, energy=False, x_len=1.0):
         bcs += [Dirichlet("T", 1, 1.0), Dirichlet("T", 2, 0.0)]
         kw = dict(energy=True, k=0.0141, Cp=1.0, beta=1.0, Tref=0.0, gravity=(0.0, 0.0, -1.0), ns_source="BOUSSINESQ")
     return Problem(m, rho=1.0, mu=0.01, bcs=bcs, **kw)
+
+
+def c5_problem_on(mesh):
+    """BASELINE.json configs[4] / SURVEY.md §8d C5: hex8 Q1/Q1 PSPG (local) + energy + 2 species."""
+    from goma_b200.problem import Dirichlet, Problem
+
+    bcs = [Dirichlet(v, s, 0.0) for s in (1, 2, 3, 4, 5) for v in "UVW"]
+    bcs += [Dirichlet("U", 6, 1.0), Dirichlet("V", 6, 0.0), Dirichlet("W", 6, 0.0), Dirichlet("P", 7, 0.0),
+            Dirichlet("T", 1, 1.0), Dirichlet("T", 2, 0.0), Dirichlet("Y", 1, 0.7, species=0), Dirichlet("Y", 2, 0.2, species=1)]
+    return Problem(mesh, interp="Q1Q1", pspg="local", ps_scaling=0.1, energy=True, n_species=2, rho=1.0, mu=0.01,
+                   k=0.0141, Cp=1.0, beta=1.0, Tref=0.0, gravity=(0.0, 0.0, -1.0), ns_source="BOUSSINESQ",
+                   diffusivity=(0.01, 0.02, 1.0, 1.0), bcs=bcs)
 
 
 def cavity_problem_on(mesh, energy=False):
@@ -207,6 +219,9 @@ def run_reference_arm(args, rank):
 
 
 def workload_name(args):
+    if getattr(args, "config", "c2") == "c5":
+        return (f"3D NS + energy + 2 species, PSPG Q1/Q1 hex8, {args.n}^3 elements per GPU (BASELINE.json configs[4]; "
+                "not the headline config)")
     phys = "NS+energy (Boussinesq)" if args.energy else "Navier-Stokes"
     return f"3D lid-driven cavity {phys}, Q2/P1 hex27, {args.n}^3 elements per GPU (BASELINE.json configs[1])"
 
@@ -241,6 +256,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--edge", dest="n", type=int, default=100, help="elements per direction per GPU (100 -> 1M hex27 elements)")
     ap.add_argument("--energy", action="store_true", help="config C3 physics (NS + energy) instead of C2")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
+                    help="c2 = headline (default); c3 = --energy; c5 = hex8 PSPG + T + 2 species (kernel number only)")
     ap.add_argument("--scatter", type=int, default=2,
                     help="0 fp64 atomics, 1 coloured load+add+store, 2 coloured first-touch stores (default)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -248,6 +265,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.config == "c3":
+        args.energy = True
+    if args.config == "c5" and args.impl == "reference":
+        raise SystemExit("the reference arm is defined on the headline config (c2) and c3")
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -292,15 +313,21 @@ def main():
 
     t_setup = time.perf_counter()
     sub = None
+    make_on = c5_problem_on if args.config == "c5" else (lambda mesh: cavity_problem_on(mesh, args.energy))
     if world == 1:
-        problem = cavity_problem(args.n, args.energy)
+        if args.config == "c5":
+            from goma_b200.mesh import box_mesh
+
+            problem = c5_problem_on(box_mesh("HEX8", (args.n,) * 3))
+        else:
+            problem = cavity_problem(args.n, args.energy)
         num_owned_nodes = None
         ne_owned = problem.mesh.num_elems
     else:
         # weak scaling: rank r owns the r-th n^3 slab of a (world*n) x n x n cavity, plus its ghost column
         from goma_b200.dp_comm import exchange_dof, setup_peer_exchange, slab_subdomain
 
-        sub = slab_subdomain(lambda mesh: cavity_problem_on(mesh, args.energy), args.n, rank, world)
+        sub = slab_subdomain(make_on, args.n, rank, world, elem_type="HEX8" if args.config == "c5" else "HEX27")
         problem = sub.problem
         num_owned_nodes = sub.num_owned_nodes
         ne_owned = int(sub.elem_owned.sum())
@@ -333,12 +360,21 @@ def main():
             raise SystemExit(f"rank {rank}: peer-memory exchange_dof differs from the NCCL send/recv result")
         halo = "goma_gpu_exchange_dof (one pull kernel over NVLink peer memory) before every fill; checked == NCCL send/recv"
 
+    hU = [0.0, 0.0]
+
     def step():
         t0 = time.perf_counter()
         if sub is not None:
             mf.exchange_dof(0)  # ghost refresh before the fill (mm_sol_nonlinear.c:1273), same stream as the fill
+        if problem.pspg:  # global_h_elem_siz / global_velocity_norm on the device (mm_sol_nonlinear.c:1184-1192)
+            sums = mf.global_h_U(None if sub is None else sub.elem_owned)
+            if world > 1:
+                t = torch.tensor(sums, dtype=torch.float64, device=dev)
+                dist.all_reduce(t)
+                sums = t.cpu().numpy()
+            hU[0], hU[1] = sums[0] / sums[1], sums[2] / sums[3]
         t1 = time.perf_counter()
-        mf.fill_device()
+        mf.fill_device(h_elem_avg=hU[0], U_norm=hU[1])
         if trace is not None:
             trace.append((t1 - t0, time.perf_counter() - t1))
 
@@ -420,9 +456,9 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        key = "c3_hex27_ns_energy" if args.energy else "c2_hex27_ns"
+        key = "c5_hex8_pspg_T_2Y" if args.config == "c5" else ("c3_hex27_ns_energy" if args.energy else "c2_hex27_ns")
         flops = ALG_FLOPS_PER_ELEM[key]
-        bytes_per_elem = 8.0 * (nnz + n_unk) / ne + 27 * 4 + 8.0 * (3 * problem.mesh.num_nodes + n_unk) / ne
+        bytes_per_elem = 8.0 * (nnz + n_unk) / ne + problem.mesh.npe * 4 + 8.0 * (3 * problem.mesh.num_nodes + n_unk) / ne
         kern_s = dev_ms * 1e-3
         traffic = None  # measured DRAM bytes per launch (ncu capture summarised under profiles/)
         try:

@@ -142,7 +142,7 @@ int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
     return 0;
   }
   if (!p1 && p.elem_type == GOMA_GPU_HEX8) {  // Q1/Q1 PSPG (config C5 and its sub-cases)
-    if (p.energy && p.num_species == 2) { k = entry<Cfg<3, 8, 8, false, true, 2, false, 64, 1, 4>>(); return 0; }
+    if (p.energy && p.num_species == 2) { k = entry<Cfg<3, 8, 8, false, true, 2, false, 64, 1, 8>>(); return 0; }
     if (p.energy && p.num_species == 0) { k = entry<Cfg<3, 8, 8, false, true, 0, false, 64, 1, 4>>(); return 0; }
     if (!p.energy && p.num_species == 0) { k = entry<Cfg<3, 8, 8, false, false, 0, false, 64, 1, 4>>(); return 0; }
     return fail(-2, "hex8 Q1/Q1: instantiated field sets are NS, NS+T, NS+T+2 species");
