@@ -137,7 +137,7 @@ int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
     return 0;
   }
   if (p1 && p.elem_type == GOMA_GPU_HEX27) {
-    k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 1>>()
+    k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2>>()
                  : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2>>();
     return 0;
   }
