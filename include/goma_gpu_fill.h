@@ -112,7 +112,7 @@ struct goma_gpu_problem {
   double rho, mu, conductivity, heat_capacity, volume_expansion, reference_temperature;
   double diffusivity[4];
   double momentum_source[3]; /* Navier-Stokes Source vector */
-  int momentum_source_model; /* 0 CONSTANT, 1 BOUSS */
+  int momentum_source_model; /* 0 CONSTANT, 1 BOUSS (hydrostatic part kept), 2 BOUSSINESQ (mm_std_models.c:125-360) */
   double heat_source;
   double lame_mu, lame_lambda;
 
@@ -211,7 +211,8 @@ int goma_gpu_exchange_dof(goma_gpu_ctx *ctx, int which);
  * (CUDA events on the context's stream) and number of kernel launches */
 int goma_gpu_fill_last_stats(goma_gpu_ctx *ctx, double *kernel_ms, int *launches);
 
-/* tuning knob: 0 = fp64 atomic scatter, 1 = coloured plain-store scatter */
+/* options: "scatter" = 0 fp64 atomics into zeroed storage | 1 coloured load+add+store | 2 coloured first-touch
+ * stores (default; no memset of the matrix, bit-reproducible);  "grid_limit" = cap on resident CTAs (tests). */
 int goma_gpu_fill_set_option(goma_gpu_ctx *ctx, const char *name, int value);
 
 const char *goma_gpu_last_error(void);
