@@ -69,7 +69,7 @@ struct FillParams {
   int debug;        // experiments only: bit0 = drop the matrix stores, bit1 = skip the Gauss loop
 };
 
-template <int DIM_, int NN_, int NGP_, bool P1_, bool ENERGY_, int NSPEC_, bool ALE_, int TPE_, int TI_, int MINB_>
+template <int DIM_, int NN_, int NGP_, bool P1_, bool ENERGY_, int NSPEC_, bool ALE_, int TPE_, int TI_, int MINB_, bool WS_ = false>
 struct Cfg {
   static constexpr int DIM = DIM_, NN = NN_, NGP = NGP_, NSPEC = NSPEC_, TI = TI_, TPE = TPE_, MINB = MINB_;
   static constexpr bool P1 = P1_, ENERGY = ENERGY_, ALE = ALE_;
@@ -82,6 +82,12 @@ struct Cfg {
   static constexpr int NP = P1 ? DIM + 1 : 0;
   static constexpr int CEN = NN == 9 ? 8 : (NN == 27 ? 20 : 0);
   static constexpr int NTILE = (NN / TI) * NN;  // register tiles (TI rows x 1 column of node pairs) per element
+  // WS: warp-specialised kernel (fill_kernel_ws): TPE builder threads prepare element e+1 while NMUL multiplier
+  // threads run the Gauss loop of element e; operands double-buffered, records in a ring of four
+  static constexpr bool WS = WS_;
+  static constexpr int NOPB = WS ? 2 : 1, NRECB = WS ? 4 : 2;
+  static constexpr int NMUL = 256, NJP = (NN + 1) / 2, NTILE2 = (NN / TI) * NJP;
+  static_assert(!WS || (NTILE <= NMUL && !ENERGY && NSPEC == 0 && !ALE && P1), "the warp-specialised kernel is the Q2/P1 NS block");
   static_assert(NN % TI == 0, "row tile must divide the node count");
   static_assert(TPE % 32 == 0, "whole warps");
   static constexpr int NWARP = TPE / 32;
@@ -155,14 +161,14 @@ struct alignas(16) ElemRec {
 template <class C>
 struct alignas(16) Smem {
   double tbl[C::TBL_PAD];
-  ElemRec<C> rec[2];  // double buffer: the record of the next element lands while this one is assembled
-  Operands<C> op;
-  double GP[C::NGP][C::GPD];            // per-Gauss-point derived quantities
+  ElemRec<C> rec[C::NRECB];  // ring: the record of the next element lands while this one is assembled
+  Operands<C> op[C::NOPB];
+  double GP[C::NOPB][C::NGP][C::GPD];   // per-Gauss-point derived quantities
   double F[C::NGP][C::NF][C::DIM + 2];  // value, grad[DIM], time derivative
   double X[C::ALE ? C::DIM : 1][C::ALE ? C::NN : 1];  // ALE: displaced coordinates x = X + d
-  double U[2][C::NF][C::NN];            // nodal unknowns, double-buffered like rec (cp.async gather)
-  double Udot[2][C::NF][C::NN];
-  double Pd[2][C::NP > 0 ? C::NP : 2];
+  double U[C::NRECB][C::NF][C::NN];     // nodal unknowns, buffered like rec (cp.async gather)
+  double Udot[C::NRECB][C::NF][C::NN];
+  double Pd[C::NRECB][C::NP > 0 ? C::NP : 2];
   double w[C::NGP];
   double B[C::NGP][C::DIM * C::DIM];
   double Pgp[C::NGP];
@@ -170,7 +176,8 @@ struct alignas(16) Smem {
   double redR[C::NPART][C::NROWS];  // partial row sums (element_rows)
   double redS[C::NPART][C::P1 ? C::DIM * C::NN : 1][C::NP > 0 ? C::NP : 1];
   unsigned long long mbar;
-  unsigned long long mbar_rec[2];
+  unsigned long long mbar_rec[C::NRECB];
+  unsigned long long full[2], empty[2];  // WS: operand buffer hand-off between builders and multipliers
 };
 
 static_assert(sizeof(double2) == 16, "double2 layout");
@@ -213,6 +220,19 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// barrier over the threads that run the set-up phases: the whole CTA, or the builder warps of the WS kernel
+template <class C>
+__device__ __forceinline__ void cta_sync() {
+  if constexpr (C::WS)
+    asm volatile("bar.sync 1, %0;" ::"n"(C::TPE) : "memory");
+  else
+    __syncthreads();
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
 
 #ifdef GOMA_PROFILE_PHASES
 #define GOMA_CLOCK() clock64()
@@ -372,7 +392,7 @@ __device__ __forceinline__ void gather_state(const FillParams &P, Smem<C> &s, in
 }
 
 template <class C>
-__device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, int buf, int tid, long long *stamps) {
+__device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, int buf, int bo, int tid, long long *stamps) {
 #ifdef GOMA_PROFILE_PHASES
   long long last_ = clock64();
 #endif
@@ -385,7 +405,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
   const double rcp = P.rho * P.Cp;
   const double c_adv = -P.etm_mom[1] * P.rho;
   const double ce_adv = -P.etm_energy[1] * rcp;
-  Operands<C> &op = s.op;
+  Operands<C> &op = s.op[bo];
   const ElemRec<C> &rec = s.rec[buf];
   const double (*U)[NN] = s.U[buf];
   const double (*Udot)[NN] = s.Udot[buf];
@@ -396,7 +416,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
       const int d = idx / NN, k = idx - d * NN;
       s.X[d][k] = rec.X[d][k] + U[C::F_D + d][k];
     }
-    __syncthreads();
+    cta_sync<C>();
   }
   GOMA_STAMP(0);
   // ---- phase 1: J[a][b] = sum_k x_b,k dphi_k/dxi_a   (beer_belly, mm_fill_util.c:258-276)
@@ -431,7 +451,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
       }
     }
   }
-  __syncthreads();
+  cta_sync<C>();
   GOMA_STAMP(1);
   // ---- phase 2: detJ, B = J^-1 by cofactors (mm_fill_util.c:386-391, :450-480)
   if (tid < NGP) {
@@ -503,7 +523,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
 #pragma unroll
     for (int b = 0; b < 3; b++) s.dtau[b] = dtau[b];
   }
-  __syncthreads();
+  cta_sync<C>();
   GOMA_STAMP(2);
   // ---- phase 3: grad_phi[i][p] = sum_q B[p][q] dphi_i/dxi_q  (load_bf_grad, mm_fill_util.c:1765-1776)
   for (int idx = tid; idx < NGP * NN; idx += NT) {
@@ -522,7 +542,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
     *reinterpret_cast<double2 *>(&op.SI[gp][i][0]) = make_double2(w * ph, w * g[0]);
     *reinterpret_cast<double2 *>(&op.SI[gp][i][2]) = make_double2(w * g[1], w * g[2]);
   }
-  __syncthreads();
+  cta_sync<C>();
   GOMA_STAMP(3);
   // ---- phase 4: field values, gradients, time derivatives at the Gauss points (load_fv, load_fv_grads)
   //      four lanes per Gauss point, each over a quarter of the nodes for ALL fields (one load of the basis
@@ -585,7 +605,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
       s.Pgp[gp] = v;
     }
   }
-  __syncthreads();
+  cta_sync<C>();
   GOMA_STAMP(4);
   // ---- phase 4b: per-Gauss-point terms shared by every row/column of the element
   //      one thread per (Gauss point, job): momentum component a | energy | species | PSPG | ALE
@@ -593,7 +613,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
                 J_AL = J_PS + (C::P1 ? 0 : 1), NJOB = J_AL + (C::ALE ? 1 : 0);
   for (int idx = tid; idx < NGP * NJOB; idx += NT) {
     const int gp = idx / NJOB, job = idx - gp * NJOB;
-    double *G = s.GP[gp];
+    double *G = s.GP[bo][gp];
     double v[DIM], vdot[DIM], gv[DIM][DIM];  // gv[a][b] = d_b v_a
 #pragma unroll
     for (int a = 0; a < DIM; a++) {
@@ -733,7 +753,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
       acc += (s.F[gp][C::F_V + p][0] - (C::ALE ? s.F[gp][C::F_D + p][1 + DIM] : 0.0)) * gj[p];
     op.VG[gp][j] = acc;
   }
-  __syncthreads();
+  cta_sync<C>();
   GOMA_STAMP(5);
 }
 
@@ -741,11 +761,11 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
 // phases 5 and 7: residual rows + Dirichlet rows (bc_dirich.c:130-140), P1 pressure coupling
 // =====================================================================================
 template <class C>
-__device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, int buf, int tid) {
+__device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, int buf, int bo, int tid) {
   constexpr int DIM = C::DIM, NN = C::NN, NGP = C::NGP, NF = C::NF, NP = C::NP, NT = C::TPE;
   constexpr int NROW = C::NROWS, NPART = C::NPART;
   const double *t_psi = s.tbl + C::T_PSI;
-  const Operands<C> &op = s.op;
+  const Operands<C> &op = s.op[bo];
   const ElemRec<C> &rec = s.rec[buf];
   // ---- part A: every row (field f of node i | P1 continuity row p) is summed over a third of the Gauss
   //      points by one thread; the velocity rows accumulate the P1 pressure coupling on the way:
@@ -766,7 +786,7 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
       const double2 s01 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][0]);
       const double2 s23 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][2]);
       const double sg[3] = {s01.y, s23.x, s23.y};
-      const double *G = s.GP[gp];
+      const double *G = s.GP[bo][gp];
       double ps[NP > 0 ? NP : 1];
 #pragma unroll
       for (int p = 0; p < NP; p++) ps[p] = t_psi[gp * (DIM + 1) + p];
@@ -797,7 +817,7 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
     double R = 0.0;
     if (prow) {
       const int p = r - NF * NN;
-      for (int gp = gp0; gp < gp1; gp++) R += s.w[gp] * t_psi[gp * (DIM + 1) + p] * s.GP[gp][C::G_DIV];
+      for (int gp = gp0; gp < gp1; gp++) R += s.w[gp] * t_psi[gp * (DIM + 1) + p] * s.GP[bo][gp][C::G_DIV];
     } else {
       const bool isT = C::ENERGY && f == C::F_T;
       const bool isY = f >= C::F_Y && f < C::F_Y + C::NSPEC;
@@ -810,7 +830,7 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
         const double2 s01 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][0]);
         const double2 s23 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][2]);
         const double sg[3] = {s01.y, s23.x, s23.y};
-        const double *G = s.GP[gp];
+        const double *G = s.GP[bo][gp];
         double t = s01.x * G[q0];
 #pragma unroll
         for (int p = 0; p < DIM; p++) t += sg[p] * G[q1 + p];
@@ -819,7 +839,7 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
     }
     s.redR[c][r] = R;
   }
-  __syncthreads();
+  cta_sync<C>();
   // ---- part B: residual rows and Dirichlet rows (put_dirichlet_in_matrix, bc_dirich.c:86-140)
   for (int r = tid; r < NROW; r += NT) {
     const bool prow = r >= NF * NN;
@@ -883,7 +903,7 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
           double ddiv = 0.0;
 #pragma unroll
           for (int q = 0; q < DIM; q++) ddiv -= gj[q] * s.F[gp][C::F_V + q][1 + b];
-          acc += s.w[gp] * t_psi[gp * (DIM + 1) + p] * (P.etm_cont[0] * ddiv + s.GP[gp][C::G_DIV] * gj[b]);
+          acc += s.w[gp] * t_psi[gp * (DIM + 1) + p] * (P.etm_cont[0] * ddiv + s.GP[bo][gp][C::G_DIV] * gj[b]);
         }
         const int row = rec.gunP + p, col = rec.gun[C::F_D + b][j];
         const long long pos = rec.rsP[p] + rec.po[C::CEN][j] + rec.cs[j][C::F_D + b] - (col > row ? 1 : 0);
@@ -903,9 +923,9 @@ struct Tile {
 };
 
 template <class C>
-__device__ __forceinline__ void gauss_loop(const FillParams &P, const Smem<C> &s, int i0, int j, Tile<C> &out) {
+__device__ __forceinline__ void gauss_loop(const FillParams &P, const Smem<C> &s, int i0, int j, Tile<C> &out, int bo = 0) {
   constexpr int DIM = C::DIM, NGP = C::NGP, TI = C::TI;
-  const Operands<C> &op = s.op;
+  const Operands<C> &op = s.op[bo];
   const double tfac = P.transient ? (1.0 + 2.0 * P.theta) / P.delta_t : 0.0;
   const double rcp = P.rho * P.Cp;
   const double c_adv = -P.etm_mom[1] * P.rho, c_diff = -P.etm_mom[3] * P.mu, c_mass = -P.etm_mom[0] * P.rho * tfac;
@@ -934,7 +954,7 @@ __device__ __forceinline__ void gauss_loop(const FillParams &P, const Smem<C> &s
     const double vgj = op.VG[gp][j];
     const double qj = c_adv * vgj + c_mass * phi_j;
     double gjs[DIM], GV[DIM][DIM], GT[DIM];
-    const double *G = s.GP[gp];
+    const double *G = s.GP[bo][gp];
 #pragma unroll
     for (int a = 0; a < DIM; a++) {
       gjs[a] = c_diff * gj[a];
@@ -997,9 +1017,9 @@ __device__ __forceinline__ void gauss_loop(const FillParams &P, const Smem<C> &s
 // Generic block accumulation: every active field pair, straight into the NF x NF tile.  Used for the
 // equal-order (PSPG) and species configurations; the NS(+T) P1 configurations use gauss_loop above.
 template <class C>
-__device__ __forceinline__ void gauss_loop_general(const FillParams &P, const Smem<C> &s, int i0, int j, Tile<C> &out) {
+__device__ __forceinline__ void gauss_loop_general(const FillParams &P, const Smem<C> &s, int i0, int j, Tile<C> &out, int bo = 0) {
   constexpr int DIM = C::DIM, NGP = C::NGP, TI = C::TI, NF = C::NF, NN = C::NN;
-  const Operands<C> &op = s.op;
+  const Operands<C> &op = s.op[bo];
   const double tfac = P.transient ? (1.0 + 2.0 * P.theta) / P.delta_t : 0.0;
   const double rcp = P.rho * P.Cp;
   const double c_adv = -P.etm_mom[1] * P.rho, c_diff = -P.etm_mom[3] * P.mu, c_mass = -P.etm_mom[0] * P.rho * tfac;
@@ -1025,7 +1045,7 @@ __device__ __forceinline__ void gauss_loop_general(const FillParams &P, const Sm
     const double phi_j = j01.x;
     const double gj[3] = {j01.y, j23.x, j23.y};
     const double vgj = op.VG[gp][j];
-    const double *G = s.GP[gp];
+    const double *G = s.GP[bo][gp];
 #pragma unroll
     for (int ii = 0; ii < TI; ii++) {
       const double2 i01 = *reinterpret_cast<const double2 *>(&op.SI[gp][i0 + ii][0]);
@@ -1175,36 +1195,52 @@ __device__ __forceinline__ void gauss_loop_general(const FillParams &P, const Sm
   (void)NN;
 }
 
-// write-out of one node-pair tile straight from registers (ALE configurations): same slot arithmetic
-// as write_rows, one thread per (i, j)
+// write-out of one node-pair tile straight from registers: one thread per (row tile, column node j).  In a
+// row (i, fr) the entries of column node j are contiguous; when the tile is the first writer of the pair and
+// the fields of node j sit next to each other, the NF doubles go out as 16-byte + 8-byte stores (fewer LSU
+// sector operations than NF scalar stores -- the LSU data path is the busiest unit of this kernel).
 template <class C, int MODE>
 __device__ __forceinline__ void write_tile_direct(const FillParams &P, const ElemRec<C> &s, int i, int j, const Tile<C> &t) {
   constexpr int NF = C::NF;
   const int rj = s.rank[j];
+  bool packed = true;  // cs[j][f] == cs[j][0] + f: node j's fields occupy consecutive columns
+#pragma unroll
+  for (int f = 1; f < NF; f++) packed = packed && (s.cs[j][f] == s.cs[j][0] + f);
 #pragma unroll
   for (int ii = 0; ii < C::TI; ii++, i++) {
-  const bool first = (s.first[i] >> j) & 1u;
-  const int ri = s.rank[i];
+    const bool first = (s.first[i] >> j) & 1u;
+    const int ri = s.rank[i];
 #pragma unroll
-  for (int fr = 0; fr < NF; fr++) {
-    const long long rstart = s.rs[fr][i];
-    if (rstart < 0) continue;
-    const bool rowT = C::ENERGY && fr == C::F_T;
-    const int row = s.gun[fr][i];
-    double *arow = P.a + rstart;
+    for (int fr = 0; fr < NF; fr++) {
+      const long long rstart = s.rs[fr][i];
+      if (rstart < 0) continue;
+      const bool rowT = C::ENERGY && fr == C::F_T;
+      const int row = s.gun[fr][i];
+      double *arow = P.a + rstart;
+      if (MODE == 2 && NF == 3 && !C::ENERGY && first && packed && rj != ri) {
+        double *dst = arow + s.po[i][j] + s.cs[j][0] - (rj > ri ? 1 : 0);
+        if ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
+          *reinterpret_cast<double2 *>(dst) = make_double2(t.V[ii][fr][0], t.V[ii][fr][1]);
+          dst[2] = t.V[ii][fr][2];
+        } else {
+          dst[0] = t.V[ii][fr][0];
+          *reinterpret_cast<double2 *>(dst + 1) = make_double2(t.V[ii][fr][1], t.V[ii][fr][2]);
+        }
+        continue;
+      }
 #pragma unroll
-    for (int fc = 0; fc < NF; fc++) {
-      if (rowT && !C::P1 && fc == C::F_P) continue;
-      int off = s.po[i][j] + s.cs[j][fc];
-      if (C::ENERGY && rowT) off -= s.pp[i][j];
-      double *dst;
-      if (rj != ri)
-        dst = arow + off - (rj > ri ? 1 : 0);
-      else
-        dst = (fc == fr) ? P.a + row : arow + off - (fc > fr ? 1 : 0);
-      slot_add_m<MODE>(dst, t.V[ii][fr][fc], first);
+      for (int fc = 0; fc < NF; fc++) {
+        if (rowT && !C::P1 && fc == C::F_P) continue;
+        int off = s.po[i][j] + s.cs[j][fc];
+        if (C::ENERGY && rowT) off -= s.pp[i][j];
+        double *dst;
+        if (rj != ri)
+          dst = arow + off - (rj > ri ? 1 : 0);
+        else
+          dst = (fc == fr) ? P.a + row : arow + off - (fc > fr ? 1 : 0);
+        slot_add_m<MODE>(dst, t.V[ii][fr][fc], first);
+      }
     }
-  }
   }
 }
 
@@ -1258,9 +1294,9 @@ __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_cons
       tma_bulk_g2s(&s.rec[buf ^ 1], P.erec + (size_t)nxt * REC_BYTES, REC_BYTES, &s.mbar_rec[buf ^ 1]);
     }
     long long c0 = GOMA_CLOCK();
-    build_element<C>(P, s, buf, tid, stamps);
+    build_element<C>(P, s, buf, 0, tid, stamps);
     long long c1 = GOMA_CLOCK();
-    element_rows<C>(P, s, buf, tid);
+    element_rows<C>(P, s, buf, 0, tid);
     long long c2 = GOMA_CLOCK();
     // ... and, once it has landed, the gather of the next element's unknowns runs under the Gauss loop
     if (has_next) {
@@ -1297,6 +1333,117 @@ __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_cons
     o[0] = t_build; o[1] = t_rows; o[2] = t_loop; o[3] = 0; o[6] = count;
     long long *o2 = P.prof + (4096 + blockIdx.x) * 8;
     for (int k = 0; k < 6; k++) o2[k] = stamps_[k];
+  }
+}
+
+// =====================================================================================
+// Warp-specialised variant for the Q2/P1 Navier-Stokes block: one CTA per SM.  C::TPE "builder" threads run
+// the set-up phases and the residual rows of element k while C::NMUL "multiplier" threads run the Gauss loop
+// (TI x 1 register tiles) and the write-out of element k-1.  Hand-off through mbarriers:
+//   full[b]  : operands of buffer b complete (builders -> multipliers)
+//   empty[b] : multipliers are done with buffer b and with the record of that element (-> builders)
+// Records travel by TMA two elements ahead (ring of four), the state gather by cp.async one element ahead.
+// =====================================================================================
+template <class C>
+__global__ void __launch_bounds__(C::TPE + C::NMUL, 1) fill_kernel_ws(const __grid_constant__ FillParams P) {
+  constexpr int NN = C::NN, NF = C::NF, TI = C::TI, NB = C::TPE, NR = C::NRECB;
+  constexpr unsigned REC_BYTES = (unsigned)sizeof(ElemRec<C>);
+  static_assert(C::WS && NR == 4, "ring of four records");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<C> &s = *reinterpret_cast<Smem<C> *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int ee0 = P.elem_begin + blockIdx.x, stride = gridDim.x;
+  const int nel = ee0 < P.elem_end ? (P.elem_end - ee0 + stride - 1) / stride : 0;
+  if (tid == 0) {
+    mbar_init(&s.mbar, 1);
+    for (int k = 0; k < NR; k++) mbar_init(&s.mbar_rec[k], 1);
+    for (int k = 0; k < 2; k++) {
+      mbar_init(&s.full[k], 1);
+      mbar_init(&s.empty[k], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (!P.transient)
+    for (int idx = tid; idx < NR * NF * NN; idx += NB + C::NMUL) (&s.Udot[0][0][0])[idx] = 0.0;
+  __syncthreads();
+  if (nel == 0) return;
+
+  if (tid < NB) {
+    // ------------------------------------------------------------------ builders
+    auto elem_of = [&](int k) { const int ee = ee0 + k * stride; return P.elem_list ? P.elem_list[ee] : ee; };
+    auto fetch_record = [&](int k) {  // one thread: TMA bulk copy of the record of the CTA's k-th element
+      mbar_expect_tx(&s.mbar_rec[k % NR], REC_BYTES);
+      tma_bulk_g2s(&s.rec[k % NR], P.erec + (size_t)elem_of(k) * REC_BYTES, REC_BYTES, &s.mbar_rec[k % NR]);
+    };
+    if (tid == 0) {
+      mbar_expect_tx(&s.mbar, C::TBL_PAD * 8);
+      tma_bulk_g2s(s.tbl, P.tables, C::TBL_PAD * 8, &s.mbar);
+      fetch_record(0);
+      if (nel > 1) fetch_record(1);
+    }
+    mbar_wait(&s.mbar_rec[0], 0);
+    gather_state<C>(P, s, 0, tid, NB);
+    cp_async_wait_all();
+    mbar_wait(&s.mbar, 0);
+    cta_sync<C>();
+    long long tw = 0, tb = 0, tr = 0, tt = 0;
+#pragma unroll 1
+    for (int k = 0; k < nel; k++) {
+      const int br = k % NR, bo = k & 1;
+      long long c0 = GOMA_CLOCK();
+      // buffer bo and the ring slots of elements <= k-2 are free once the multipliers have finished element k-2
+      if (k >= 2) mbar_wait(&s.empty[bo], ((k - 2) >> 1) & 1);
+      if (k + 2 < nel && tid == 0) fetch_record(k + 2);
+      if (k + 1 < nel) {  // record k+1 was requested one iteration ago: its state gather runs under this build
+        mbar_wait(&s.mbar_rec[(k + 1) % NR], ((k + 1) / NR) & 1);
+        gather_state<C>(P, s, (k + 1) % NR, tid, NB);
+      }
+      long long c1 = GOMA_CLOCK();
+      build_element<C>(P, s, br, bo, tid, nullptr);
+      long long c2 = GOMA_CLOCK();
+      element_rows<C>(P, s, br, bo, tid);
+      long long c3 = GOMA_CLOCK();
+      cp_async_wait_all();
+      cta_sync<C>();  // operands of k and the unknowns of k+1 are in shared memory, written by all builders
+      if (tid == 0) mbar_arrive(&s.full[bo]);
+      tw += c1 - c0; tb += c2 - c1; tr += c3 - c2; tt += GOMA_CLOCK() - c3;
+    }
+    if (P.prof && tid == 0) {
+      long long *o = P.prof + blockIdx.x * 8;
+      o[0] = tw; o[1] = tb; o[2] = tr; o[3] = tt; o[6] = nel;
+    }
+  } else {
+    // ------------------------------------------------------------------ multipliers
+    const int mt = tid - NB;
+    const int it = mt / NN, j = mt - it * NN, i0 = it * TI;
+    long long mw = 0, ml = 0, mo = 0;
+#pragma unroll 1
+    for (int k = 0; k < nel; k++) {
+      const int br = k % NR, bo = k & 1;
+      long long c0 = GOMA_CLOCK();
+      mbar_wait(&s.full[bo], (k >> 1) & 1);
+      long long c1 = GOMA_CLOCK(), c2 = c1;
+      if (P.assemble_jacobian && mt < C::NTILE) {
+        Tile<C> tile;
+        gauss_loop<C>(P, s, i0, j, tile, bo);
+        c2 = GOMA_CLOCK();
+        if (!(P.debug & 1)) {
+          if (P.scatter_mode == 2)
+            write_tile_direct<C, 2>(P, s.rec[br], i0, j, tile);
+          else if (P.scatter_mode == 0)
+            write_tile_direct<C, 0>(P, s.rec[br], i0, j, tile);
+          else
+            write_tile_direct<C, 1>(P, s.rec[br], i0, j, tile);
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(C::NMUL) : "memory");  // every multiplier is done reading buffer bo
+      if (mt == 0) mbar_arrive(&s.empty[bo]);
+      mw += c1 - c0; ml += c2 - c1; mo += GOMA_CLOCK() - c2;
+    }
+    if (P.prof && mt == 0) {
+      long long *o = P.prof + (4096 + blockIdx.x) * 8;
+      o[0] = mw; o[1] = ml; o[2] = mo; o[3] = 0; o[4] = 0; o[5] = 0;
+    }
   }
 }
 

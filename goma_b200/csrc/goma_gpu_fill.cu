@@ -107,7 +107,10 @@ struct KernelEntry {
 
 template <class C>
 KernelEntry entry() {
-  return {fill_kernel<C>, build_records_kernel<C>, C::TPE, sizeof(Smem<C>), C::TBL_PAD, sizeof(ElemRec<C>)};
+  if constexpr (C::WS)
+    return {fill_kernel_ws<C>, build_records_kernel<C>, C::TPE + C::NMUL, sizeof(Smem<C>), C::TBL_PAD, sizeof(ElemRec<C>)};
+  else
+    return {fill_kernel<C>, build_records_kernel<C>, C::TPE, sizeof(Smem<C>), C::TBL_PAD, sizeof(ElemRec<C>)};
 }
 
 // the instantiated physics/element combinations
@@ -137,7 +140,10 @@ int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
     return 0;
   }
   if (p1 && p.elem_type == GOMA_GPU_HEX27) {
+    // config C2 (Q2/P1 Navier-Stokes): warp-specialised kernel, 192 builder + 128 multiplier threads, one CTA per SM
+    static const bool ws = getenv("GOMA_GPU_WS") ? atoi(getenv("GOMA_GPU_WS")) != 0 : false;
     k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2>>()
+        : ws     ? entry<Cfg<3, 27, 27, true, false, 0, false, 192, 3, 1, true>>()
                  : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2>>();
     return 0;
   }
