@@ -129,7 +129,10 @@ struct Cfg {
 
 template <class C>
 struct Operands {
-  double SI[C::NGP][C::NN][4];  // (w phi_i, w grad_phi_i[p])   test-function side (read as broadcast)
+  // test-function side, component-major: SI[gp][0][i] = w phi_i, SI[gp][1+p][i] = w grad_phi_i[p].  A warp of the
+  // Gauss loop spans at most two row tiles: each of these 8-byte loads is one shared-memory wavefront (a broadcast
+  // 16-byte load costs two); the set-up phases read them with the lanes along i (conflict-free)
+  double SI[C::NGP][4][C::NN];
   // trial-function side (phi_j, grad_phi_j[p]), split in two 16-byte-stride arrays so that the
   // per-lane LDS.128 of the Gauss loop are bank-conflict free
   double2 SJa[C::NGP][C::NN];  // (phi_j, g_j[0])
@@ -539,8 +542,10 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
     }
     op.SJa[gp][i] = make_double2(ph, g[0]);
     op.SJb[gp][i] = make_double2(g[1], g[2]);
-    *reinterpret_cast<double2 *>(&op.SI[gp][i][0]) = make_double2(w * ph, w * g[0]);
-    *reinterpret_cast<double2 *>(&op.SI[gp][i][2]) = make_double2(w * g[1], w * g[2]);
+    op.SI[gp][0][i] = w * ph;
+    op.SI[gp][1][i] = w * g[0];
+    op.SI[gp][2][i] = w * g[1];
+    op.SI[gp][3][i] = w * g[2];
   }
   cta_sync<C>();
   GOMA_STAMP(3);
@@ -783,8 +788,8 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
       for (int p = 0; p < NP; p++) S[a][p] = 0.0;
     }
     for (int gp = gp0; gp < gp1; gp++) {
-      const double2 s01 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][0]);
-      const double2 s23 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][2]);
+      const double2 s01 = make_double2(op.SI[gp][0][i], op.SI[gp][1][i]);
+      const double2 s23 = make_double2(op.SI[gp][2][i], op.SI[gp][3][i]);
       const double sg[3] = {s01.y, s23.x, s23.y};
       const double *G = s.GP[bo][gp];
       double ps[NP > 0 ? NP : 1];
@@ -827,8 +832,8 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
       const int q0 = isT ? C::G_RE : isY ? C::G_RY + (f - C::F_Y) : isP ? C::G_DIV : C::G_ZERO;
       const int q1 = isT ? C::G_RF : isY ? C::G_RFY + (f - C::F_Y) * DIM : isP ? C::G_PS : C::G_RD + (f - C::F_D) * DIM;
       for (int gp = gp0; gp < gp1; gp++) {
-        const double2 s01 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][0]);
-        const double2 s23 = *reinterpret_cast<const double2 *>(&op.SI[gp][i][2]);
+        const double2 s01 = make_double2(op.SI[gp][0][i], op.SI[gp][1][i]);
+        const double2 s23 = make_double2(op.SI[gp][2][i], op.SI[gp][3][i]);
         const double sg[3] = {s01.y, s23.x, s23.y};
         const double *G = s.GP[bo][gp];
         double t = s01.x * G[q0];
@@ -964,8 +969,8 @@ __device__ __forceinline__ void gauss_loop(const FillParams &P, const Smem<C> &s
     }
 #pragma unroll
     for (int ii = 0; ii < TI; ii++) {
-      const double2 i01 = *reinterpret_cast<const double2 *>(&op.SI[gp][i0 + ii][0]);
-      const double2 i23 = *reinterpret_cast<const double2 *>(&op.SI[gp][i0 + ii][2]);
+      const double2 i01 = make_double2(op.SI[gp][0][i0 + ii], op.SI[gp][1][i0 + ii]);
+      const double2 i23 = make_double2(op.SI[gp][2][i0 + ii], op.SI[gp][3][i0 + ii]);
       const double wphi = i01.x;
       const double wg[3] = {i01.y, i23.x, i23.y};
       const double pp = wphi * phi_j;
@@ -1048,8 +1053,8 @@ __device__ __forceinline__ void gauss_loop_general(const FillParams &P, const Sm
     const double *G = s.GP[bo][gp];
 #pragma unroll
     for (int ii = 0; ii < TI; ii++) {
-      const double2 i01 = *reinterpret_cast<const double2 *>(&op.SI[gp][i0 + ii][0]);
-      const double2 i23 = *reinterpret_cast<const double2 *>(&op.SI[gp][i0 + ii][2]);
+      const double2 i01 = make_double2(op.SI[gp][0][i0 + ii], op.SI[gp][1][i0 + ii]);
+      const double2 i23 = make_double2(op.SI[gp][2][i0 + ii], op.SI[gp][3][i0 + ii]);
       const double wphi = i01.x;
       const double wg[3] = {i01.y, i23.x, i23.y};
       const double pp = wphi * phi_j;
