@@ -427,3 +427,55 @@ def test_gpu_all_rows_ghost_or_dirichlet(built):
     assert_close(a, a_ref, "Jacobian")
     assert_close(r, r_ref, "residual")
     mf2.close()
+
+
+def test_gpu_full_size_c2_properties(built):
+    """BASELINE.json configs[1] at its full size (100^3 = 1M hex27 elements, 28.4M unknowns, 5.6e9 non-zeros --
+    beyond what the CPU oracle or a 32-bit ija can hold): size-independent properties of the assembled system.
+      * a uniform velocity field with zero pressure solves the unforced Navier-Stokes equations: residual == 0;
+      * with advection off the residual is affine in x: R(x1 + x2) - R(x1) - R(x2) + R(0) == 0;
+      * a uniform shift of the velocity changes no momentum residual of the Stokes problem (only gradients enter);
+      * the device-resident Jacobian of two fills of the same state is bit-identical (first-touch scatter)."""
+    import torch
+
+    from goma_b200.matrix_fill import device_view
+
+    m = box_mesh("HEX27", (100, 100, 100))
+    p = Problem(m, rho=1.0, mu=0.01, gravity=(0.0, 0.0, 0.0))
+    first, node_kind, kinds = p.unknown_map()
+    n = int(first[-1])
+    assert n == 28361803
+    mf = MatrixFill(p)
+    assert mf.nnz_plus > 2 ** 31  # the reference's int ija cannot index this matrix
+    vel = np.zeros(n, bool)
+    for kind_id, slots in enumerate(kinds):
+        nodes = np.nonzero(node_kind == kind_id)[0]
+        for name in "UVW":
+            vel[first[nodes] + slots.index(name)] = True
+    uniform = np.zeros(n)
+    uniform[vel] = 0.7
+    err, _, r = mf.matrix_fill_full(uniform, assemble_jacobian=False)
+    assert err == 0 and np.abs(r).max() < 1e-12
+    mf.close()
+    # Stokes: affine residual
+    p2 = Problem(m, rho=1.0, mu=0.5, etm_momentum=(0.0, 0.0, 1.0, 1.0, 1.0, 0.0), gravity=(0.1, 0.2, -0.3))
+    mf = MatrixFill(p2)
+    rng = np.random.default_rng(5)
+    x1, x2 = rng.normal(size=n), rng.normal(size=n)
+    res = lambda x: mf.matrix_fill_full(x, assemble_jacobian=False)[2].copy()
+    r0, r1, r2, r12 = res(np.zeros(n)), res(x1), res(x2), res(x1 + x2)
+    assert np.abs(r12 - r1 - r2 + r0).max() < 1e-11 * np.abs(r12).max()
+    rs = res(x1 + uniform)
+    assert np.abs((rs - r1)[vel]).max() < 1e-11 * np.abs(r1).max()
+    # device-resident Jacobian: two fills, identical bits
+    bufs = mf.device_buffers()
+    d_a = device_view(bufs.d_a, mf.nnz_plus + 1, torch.device("cuda", 0))
+    mf.matrix_fill_full(x1, assemble_jacobian=False)  # x1 into HBM
+    assert mf.fill_device() == 0
+    torch.cuda.synchronize()
+    s1 = d_a.view(torch.int64).sum().item()
+    sa1 = float(d_a.abs().sum().item())
+    assert mf.fill_device() == 0
+    torch.cuda.synchronize()
+    assert d_a.view(torch.int64).sum().item() == s1 and np.isfinite(sa1) and sa1 > 0
+    mf.close()
