@@ -117,23 +117,42 @@ KernelEntry entry() {
 //                      DIM NN NGP  P1    ENERGY NSPEC ALE  TPE TI MINB
 int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
   const bool p1 = p.pressure_interp == GOMA_PRESSURE_P1;
-  if (p.ale) {  // pseudo-solid ARBITRARY mesh motion (config C4): Q2/P1, NS (+ energy)
+  if (p.ale) {  // pseudo-solid ARBITRARY mesh motion (config C4): Q2/P1, NS (+ energy) (+ species)
     if (!p1 || p.pspg) return fail(-2, "ALE is instantiated for Q2/P1 (QUAD9/HEX27) without PSPG only");
-    if (p.num_species) return fail(-2, "ALE with species is not instantiated");
+    const int fs = (p.energy ? 10 : 0) + p.num_species;  // field set: NS | NS+T | NS+Y | NS+T+2Y
+    if (fs != 0 && fs != 10 && fs != 1 && fs != 12)
+      return fail(-2, "ALE: instantiated field sets are NS, NS+T, NS+1 species, NS+T+2 species");
     if (p.elem_type == GOMA_GPU_QUAD9) {
-      k = p.energy ? entry<Cfg<2, 9, 9, true, true, 0, true, 96, 1, 4>>() : entry<Cfg<2, 9, 9, true, false, 0, true, 96, 1, 4>>();
+      k = fs == 0    ? entry<Cfg<2, 9, 9, true, false, 0, true, 96, 1, 4>>()
+          : fs == 10 ? entry<Cfg<2, 9, 9, true, true, 0, true, 96, 1, 4>>()
+          : fs == 1  ? entry<Cfg<2, 9, 9, true, false, 1, true, 96, 1, 4>>()
+                     : entry<Cfg<2, 9, 9, true, true, 2, true, 96, 1, 2>>();
       return 0;
     }
     if (p.elem_type == GOMA_GPU_HEX27) {
-      k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, true, 256, 1, 1>>()
-                   : entry<Cfg<3, 27, 27, true, false, 0, true, 256, 1, 1>>();
+      k = fs == 0    ? entry<Cfg<3, 27, 27, true, false, 0, true, 256, 1, 1>>()
+          : fs == 10 ? entry<Cfg<3, 27, 27, true, true, 0, true, 256, 1, 1>>()
+          : fs == 1  ? entry<Cfg<3, 27, 27, true, false, 1, true, 256, 1, 1>>()
+                     : entry<Cfg<3, 27, 27, true, true, 2, true, 256, 1, 1>>();
       return 0;
     }
     return fail(-2, "ALE needs QUAD9 or HEX27 elements");
   }
   if (p.pspg && p1) return fail(-2, "PSPG with P1 pressure is not supported by the GPU fill");
   if (!p1 && !p.pspg) return fail(-2, "equal-order velocity/pressure needs Pressure Stabilization (PSPG)");
-  if (p1 && p.num_species) return fail(-2, "species with Q2/P1 not instantiated yet");
+  if (p1 && p.num_species) {  // Q2/P1 with species (Fickian): generic block path, one node pair per thread
+    const int fs = (p.energy ? 10 : 0) + p.num_species;
+    if (fs != 1 && fs != 12) return fail(-2, "Q2/P1 with species: instantiated field sets are NS+1 species, NS+T+2 species");
+    if (p.elem_type == GOMA_GPU_QUAD9) {
+      k = fs == 1 ? entry<Cfg<2, 9, 9, true, false, 1, false, 96, 1, 4>>() : entry<Cfg<2, 9, 9, true, true, 2, false, 96, 1, 2>>();
+      return 0;
+    }
+    if (p.elem_type == GOMA_GPU_HEX27) {
+      k = fs == 1 ? entry<Cfg<3, 27, 27, true, false, 1, false, 256, 1, 1>>()
+                  : entry<Cfg<3, 27, 27, true, true, 2, false, 256, 1, 1>>();
+      return 0;
+    }
+  }
   if (p1 && p.elem_type == GOMA_GPU_QUAD9) {
     k = p.energy ? entry<Cfg<2, 9, 9, true, true, 0, false, 32, 3, 8>>()
                  : entry<Cfg<2, 9, 9, true, false, 0, false, 32, 3, 8>>();

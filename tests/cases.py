@@ -137,12 +137,25 @@ def build_case(name):
                         heat_source=0.6, etm_momentum=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0), etm_energy=(1.0,) * 5,
                         etm_mesh=(1.0, 1.0, 1.0, 1.0, 1.0), bcs=bcs2 + [Dirichlet("T", 1, 1.0)], **mat)
             return p, {"delta_t": 0.02, "theta": 0.5, "time": 0.1}
+    if name == "q2p1_quad9_species_ale_transient":
+        # Q2/P1 with energy and two Fickian species on a moving mesh: J_s_v, J_s_d, J_e_d and the v - xdot_mesh
+        # convection velocity in every transport equation
+        m = box_mesh("QUAD9", (4, 3), lo=(0, 0), hi=(2, 1), perturb=0.1, seed=21)
+        bcs = [Dirichlet("U", 1, 1.0), Dirichlet("V", 1, 0.0), Dirichlet("DX", 1, 0.0), Dirichlet("DY", 1, 0.0),
+               Dirichlet("DX", 3, 0.01, relax=1.0), Dirichlet("U", 4, 0.0), Dirichlet("T", 1, 1.0),
+               Dirichlet("Y", 3, 0.7, species=1), Dirichlet("Y", 2, 0.2, species=0, relax=1.0)]
+        p = Problem(m, ale=True, transient=True, energy=True, n_species=2, diffusivity=(0.05, 0.11, 1.0, 1.0),
+                    etm_momentum=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0), etm_energy=(1.0,) * 5, etm_species=(1.0,) * 5,
+                    etm_mesh=(1.0,) * 5, k=0.07, Cp=1.4, beta=0.8, Tref=0.3, ns_source="BOUSSINESQ", heat_source=0.6,
+                    rho=1.3, mu=0.7, gravity=(0.3, -0.2, 0.1), lame_mu=0.9, lame_lambda=1.7, bcs=bcs)
+        return p, {"delta_t": 0.02, "theta": 0.5, "time": 0.1}
     raise KeyError(name)
 
 
 GOLDEN_CASES = ["c1_quad9_ns", "c1_quad9_ns_transient", "c2_hex27_ns", "c3_hex27_boussinesq",
                 "c3_quad9_bouss_transient", "c5_hex8_pspg_local_transient", "c5_hex8_pspg_global",
-                "c5_quad4_pspg_local", "c4_quad9_ale", "c4_hex27_ale", "c4_quad9_ale_energy_transient"]
+                "c5_quad4_pspg_local", "c4_quad9_ale", "c4_hex27_ale", "c4_quad9_ale_energy_transient",
+                "q2p1_quad9_species_ale_transient"]
 
 
 def case_state(name):

@@ -479,3 +479,39 @@ def test_gpu_full_size_c2_properties(built):
     torch.cuda.synchronize()
     assert d_a.view(torch.int64).sum().item() == s1 and np.isfinite(sa1) and sa1 > 0
     mf.close()
+
+
+@pytest.mark.parametrize("et,n,energy,ns,ale,transient", [
+    ("QUAD9", (9, 6), False, 1, False, False), ("QUAD9", (7, 5), True, 2, False, True),
+    ("HEX27", (3, 3, 2), False, 1, False, True), ("HEX27", (3, 2, 2), True, 2, False, False),
+    ("QUAD9", (8, 5), False, 1, True, True), ("QUAD9", (6, 5), True, 2, True, False),
+    ("HEX27", (3, 2, 2), False, 1, True, False), ("HEX27", (2, 2, 2), True, 2, True, True)])
+def test_gpu_q2p1_species_field_sets_match_port_oracle(built, et, n, energy, ns, ale, transient):
+    """Q2/P1 with Fickian species (assemble_mass_transport, mm_fill_species.c:194; J_s_s, J_s_v and, on a moving
+    mesh, J_s_d :1103-1330), with and without energy and ALE, against the CPU restatement (pinned to the
+    reference on fixture q2p1_quad9_species_ale_transient and on live hex27 cases)."""
+    m = box_mesh(et, n, perturb=0.08, seed=51)
+    bcs = [Dirichlet("U", 1, 1.0), Dirichlet("V", 1, 0.0), Dirichlet("U", 4, 0.0, relax=1.0),
+           Dirichlet("Y", 3, 0.7, species=ns - 1), Dirichlet("Y", 2, 0.2, species=0, relax=1.0)]
+    if ale:
+        bcs += [Dirichlet("DX", 1, 0.0), Dirichlet("DY", 1, 0.0), Dirichlet("DX", 3, 0.01, relax=1.0)]
+    if energy:
+        bcs += [Dirichlet("T", 1, 1.0)]
+    kw = dict(etm_momentum=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0), etm_energy=(1.0,) * 5, etm_species=(1.0,) * 5,
+              etm_mesh=(1.0,) * 5) if transient else {}
+    p = Problem(m, ale=ale, transient=transient, energy=energy, n_species=ns, diffusivity=(0.05, 0.11, 1.0, 1.0),
+                k=0.07, Cp=1.4, beta=0.8, Tref=0.3, ns_source="BOUSSINESQ" if energy else "CONSTANT", heat_source=0.6,
+                rho=1.3, mu=0.7, gravity=(0.3, -0.2, 0.1), lame_mu=0.9, lame_lambda=1.7, bcs=bcs, **kw)
+    st = make_state(p, seed=29, transient=transient, delta_t=0.02, theta=0.5)
+    fkw = dict(delta_t=0.02, theta=0.5) if transient else {}
+    ija = capi.pattern_msr(p)
+    rc, a_ref, r_ref = port.port_fill(p, ija, st, **fkw)
+    assert rc == 0
+    mf = MatrixFill(p)
+    for scatter in (0, 2):
+        mf.set_option("scatter", scatter)
+        err, a, r = mf.matrix_fill_full(st["x"], st.get("x_old"), st.get("x_older"), st.get("xdot"), st.get("xdot_old"), **fkw)
+        assert err == 0
+        assert_close(a, a_ref, f"Jacobian scatter={scatter}")
+        assert_close(r, r_ref, f"residual scatter={scatter}")
+    mf.close()
