@@ -260,22 +260,19 @@ def allreduce_flags(flags, group=None):
     return t
 
 
-def setup_peer_exchange(mf, sub: Subdomain, group=None):
-    """Wire the ranks' GPU contexts together for ``MatrixFill.exchange_dof`` (``goma_gpu_exchange_*``).
-
-    Host plumbing only, once per problem: every rank publishes the CUDA IPC handles of its state vectors
-    and, per neighbour, its ``list_dof_send`` block (``dp_map_comm_vec.c:224-461``); the receiver hands that
-    block to the library as the list of neighbour-local indices that fill its external tail -- the same
-    pairing the reference's send/receive establishes (``dp_comm.c:77-96``).
-    """
-    import torch.distributed as dist
-
-    world = dist.get_world_size(group)
-    mine = {"handles": mf.exchange_export(), "neighbors": [int(p) for p in sub.neighbors],
+def peer_exchange_payload(sub: Subdomain, handles: bytes = b"") -> dict:
+    """What a rank publishes once for the peer-memory exchange: its IPC handles and, per neighbour, its
+    ``list_dof_send`` block (``dp_map_comm_vec.c:224-461``)."""
+    return {"handles": handles, "neighbors": [int(p) for p in sub.neighbors],
             "send": {int(p): np.asarray(sub.list_dof_send[int(sub.ptr_dof_send[k]):int(sub.ptr_dof_send[k + 1])], np.int32)
                      for k, p in enumerate(sub.neighbors)}}
-    everyone = [None] * world
-    dist.all_gather_object(everyone, mine, group=group)
+
+
+def peer_recv_lists(sub: Subdomain, everyone):
+    """From every rank's payload: (neighbour handles, my slot in each neighbour's list, recv_ptr, recv_list) where
+    ``recv_list`` holds, per neighbour and in the order of this rank's external tail, the dof indices IN THE
+    NEIGHBOUR'S NUMBERING to read -- the neighbour's send block for this rank: the pairing the reference's
+    send/receive establishes (``dp_comm.c:77-96``)."""
     handles, slots, recv_ptr, recv_list = [], [], [0], []
     for k, p in enumerate(sub.neighbors):
         other = everyone[int(p)]
@@ -286,6 +283,17 @@ def setup_peer_exchange(mf, sub: Subdomain, group=None):
             raise RuntimeError(f"rank {sub.rank}: neighbour {p} sends {len(block)} dofs, {int(sub.num_dofs_recv[k])} expected")
         recv_list.append(block)
         recv_ptr.append(recv_ptr[-1] + len(block))
-    rl = np.concatenate(recv_list) if recv_list else np.zeros(0, np.int32)
+    rl = np.concatenate(recv_list).astype(np.int32) if recv_list else np.zeros(0, np.int32)
+    return handles, slots, recv_ptr, rl
+
+
+def setup_peer_exchange(mf, sub: Subdomain, group=None):
+    """Wire the ranks' GPU contexts together for ``MatrixFill.exchange_dof`` (``goma_gpu_exchange_*``).
+    Host plumbing only, once per problem (``torch.distributed.all_gather_object`` as the set-up transport)."""
+    import torch.distributed as dist
+
+    everyone = [None] * dist.get_world_size(group)
+    dist.all_gather_object(everyone, peer_exchange_payload(sub, mf.exchange_export()), group=group)
+    handles, slots, recv_ptr, rl = peer_recv_lists(sub, everyone)
     mf.exchange_setup(handles, slots, recv_ptr, rl, sub.num_owned_dofs)
     dist.barrier(group=group)  # every flag block exists and is zero before the first epoch is published

@@ -124,3 +124,29 @@ def test_slab_subdomain_matches_general_decomposition(et, n, nranks):
         for k in a.problem.mesh.node_sets:
             np.testing.assert_array_equal(a.problem.mesh.node_sets[k], b.problem.mesh.node_sets[k])
         np.testing.assert_array_equal(a.problem.dirichlet_table()[0], b.problem.dirichlet_table()[0])
+
+
+@pytest.mark.parametrize("et,n,nranks", [("QUAD9", (9, 3), 3), ("HEX27", (4, 2, 2), 2), ("HEX27", (6, 2, 2), 3)])
+def test_peer_pull_lists_fill_the_external_tail(et, n, nranks):
+    """The lists handed to goma_gpu_exchange_setup: pulling ``x_neighbour[recv_list]`` into the external tail gives
+    every ghost dof its owner's value (what exchange_dof, dp_comm.c:48-102, achieves with send/receive)."""
+    from goma_b200.dp_comm import peer_exchange_payload, peer_recv_lists
+
+    p = _problem(et, n)
+    first_g = p.unknown_map()[0]
+    xg = np.random.default_rng(1).normal(size=int(first_g[-1]))
+    subs = decompose(p, slab_partition(p.mesh, nranks), nranks)
+    everyone = [peer_exchange_payload(s, b"h%d" % s.rank) for s in subs]
+    l2g = [_local_to_global_dofs(s, first_g) for s in subs]
+    for s in subs:
+        handles, slots, recv_ptr, rl = peer_recv_lists(s, everyone)
+        assert handles == [b"h%d" % q for q in s.neighbors]
+        x = xg[l2g[s.rank]].copy()
+        x[s.num_owned_dofs:] = np.nan  # stale ghosts
+        for k, q in enumerate(s.neighbors):
+            assert subs[q].neighbors[slots[k]] == s.rank
+            xq = xg[l2g[q]]
+            lst = rl[recv_ptr[k]:recv_ptr[k + 1]]
+            assert (lst < subs[q].num_owned_dofs).all()  # only owned values travel
+            x[s.num_owned_dofs + recv_ptr[k]: s.num_owned_dofs + recv_ptr[k + 1]] = xq[lst]
+        np.testing.assert_array_equal(x, xg[l2g[s.rank]])
