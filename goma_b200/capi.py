@@ -24,7 +24,8 @@ EXPORTED = [
     "goma_gpu_fill", "goma_gpu_fill_device_buffers", "goma_gpu_fill_device", "goma_gpu_global_h_U",
     "goma_gpu_pack_dofs", "goma_gpu_unpack_dofs", "goma_gpu_fill_last_stats", "goma_gpu_fill_set_option",
     "goma_gpu_last_error", "goma_gpu_pattern_msr", "goma_gpu_exchange_export", "goma_gpu_exchange_setup",
-    "goma_gpu_exchange_dof", "goma_gpu_row_sum_scale", "goma_gpu_scale_buffer", "goma_gpu_vector_norms",
+    "goma_gpu_exchange_dof", "goma_gpu_row_sum_scale", "goma_gpu_scale_buffer", "goma_gpu_vector_norms", "goma_gpu_csr_structure",
+    "goma_gpu_csr_values",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -59,6 +60,12 @@ class ExchangeHandles(C.Structure):
     """``struct goma_gpu_exchange_handles``: CUDA IPC handles of x, xdot, x_old and of the flag block."""
     _fields_ = [("vec", (C.c_ubyte * IPC_HANDLE_BYTES) * 3), ("flags", C.c_ubyte * IPC_HANDLE_BYTES),
                 ("device", C.c_int)]
+
+
+class Csr(C.Structure):
+    """``struct goma_gpu_csr``."""
+    _fields_ = [("num_rows", C.c_int), ("nnz", C.c_longlong), ("d_rowptr", C.c_void_p), ("d_colind", C.c_void_p),
+                ("d_values", C.c_void_p)]
 
 
 class DeviceBuffers(C.Structure):
@@ -97,6 +104,8 @@ def load_library():
     lib.goma_gpu_row_sum_scale.argtypes = [C.c_void_p, _dp, _ip]
     lib.goma_gpu_scale_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _ip]
     lib.goma_gpu_vector_norms.argtypes = [C.c_void_p, C.c_int, _dp]
+    lib.goma_gpu_csr_structure.argtypes = [C.c_void_p, C.POINTER(GomaGpuProblem), C.POINTER(Csr)]
+    lib.goma_gpu_csr_values.argtypes = [C.c_void_p]
     lib.goma_gpu_pack_dofs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.goma_gpu_unpack_dofs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.goma_gpu_fill_last_stats.argtypes = [C.c_void_p, _dp, _ip]

@@ -63,6 +63,10 @@ struct goma_gpu_ctx {
   int tail_begin = 0;
   unsigned long long epoch[3] = {0, 0, 0};
   double *d_sums = nullptr;  // goma_gpu_global_h_U
+  long long *d_csr_rowptr = nullptr;  // CSR hand-off
+  int *d_csr_colind = nullptr, *d_csr_dpos = nullptr;
+  double *d_csr_values = nullptr;
+  long long csr_nnz = 0;
   double *d_scale = nullptr;      // row-sum scale vector
   double *d_partials = nullptr;   // per-block partial norms
   int *d_zero_rows = nullptr;
@@ -340,6 +344,10 @@ extern "C" void goma_gpu_fill_destroy(goma_gpu_ctx *c) {
   if (c->d_xflags) cudaFree(c->d_xflags);
   if (c->d_recv_list) cudaFree(c->d_recv_list);
   if (c->d_sums) cudaFree(c->d_sums);
+  if (c->d_csr_rowptr) cudaFree(c->d_csr_rowptr);
+  if (c->d_csr_colind) cudaFree(c->d_csr_colind);
+  if (c->d_csr_dpos) cudaFree(c->d_csr_dpos);
+  if (c->d_csr_values) cudaFree(c->d_csr_values);
   if (c->d_scale) cudaFree(c->d_scale);
   if (c->d_partials) cudaFree(c->d_partials);
   if (c->d_zero_rows) cudaFree(c->d_zero_rows);
@@ -943,5 +951,117 @@ extern "C" int goma_gpu_vector_norms(goma_gpu_ctx *c, int which, double out[4]) 
     if (h[4 * b] > mx || (h[4 * b] == mx && h[4 * b + 3] >= 0.0 && (idx < 0.0 || h[4 * b + 3] < idx))) { mx = h[4 * b]; idx = h[4 * b + 3]; }
   }
   out[0] = mx; out[1] = l1; out[2] = l2; out[3] = idx;
+  return 0;
+}
+
+// ------------------------------------------------------------------ CSR hand-off to a GPU solver
+struct CsrKinds {
+  int num_unknowns[GOMA_GPU_MAX_KINDS];  // unknowns of a node of each kind
+  int num_pressure[GOMA_GPU_MAX_KINDS];  // ... of which pressure (last in the node)
+  int tslot[GOMA_GPU_MAX_KINDS];         // offset of T inside the node (-1: none): energy rows carry no P columns
+};
+
+// one thread per owned node: the rows of its unknowns share the node-node list (exo_conn.c build_node_node);
+// columns = the unknowns of the neighbour nodes in increasing node id (find_MSR_problem_graph), diagonal included
+__global__ void csr_structure_kernel(int num_owned_nodes, const long long *__restrict__ nn_ptr,
+                                     const int *__restrict__ nn_list, const int *__restrict__ first_unknown,
+                                     const unsigned char *__restrict__ node_kind, const __grid_constant__ CsrKinds K,
+                                     const long long *__restrict__ rowstart, long long msr0,
+                                     long long *__restrict__ rowptr, int *__restrict__ colind, int *__restrict__ dpos,
+                                     int num_rows) {
+  const int nd = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nd >= num_owned_nodes) return;
+  const int kd = node_kind[nd], fu = first_unknown[nd];
+  for (int s = 0; s < K.num_unknowns[kd]; s++) {
+    const int row = fu + s;
+    const long long base = rowstart[row] - msr0 + row;  // every earlier row adds its diagonal
+    rowptr[row] = base;
+    if (row == num_rows - 1) rowptr[num_rows] = rowstart[row + 1] - msr0 + row + 1;
+    const bool nop = K.tslot[kd] >= 0 && s == K.tslot[kd];
+    long long pos = base;
+    for (long long q = nn_ptr[nd]; q < nn_ptr[nd + 1]; q++) {
+      const int m = nn_list[q], km = node_kind[m], fm = first_unknown[m];
+      const int ncol = K.num_unknowns[km] - (nop ? K.num_pressure[km] : 0);
+      for (int c = 0; c < ncol; c++) {
+        if (fm + c == row) dpos[row] = (int)(pos - base);
+        colind[pos++] = fm + c;
+      }
+    }
+  }
+}
+
+// one warp per row: MSR row (diagonal apart) -> CSR row (diagonal at dpos)
+__global__ void csr_values_kernel(int num_rows, const long long *__restrict__ rowstart, const long long *__restrict__ rowptr,
+                                  const int *__restrict__ dpos, const double *__restrict__ a, double *__restrict__ v) {
+  const int lane = threadIdx.x & 31;
+  const int nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < num_rows; row += nwarp) {
+    const long long k0 = rowstart[row], c0 = rowptr[row];
+    const int len = (int)(rowptr[row + 1] - c0), d = dpos[row];
+    for (int t = lane; t < len; t += 32) v[c0 + t] = t < d ? a[k0 + t] : (t == d ? a[row] : a[k0 + t - 1]);
+  }
+}
+
+extern "C" int goma_gpu_csr_structure(goma_gpu_ctx *c, const goma_gpu_problem *p, goma_gpu_csr *out) {
+  if (!c || !p || !out) return fail(-2, "null argument");
+  CU(cudaSetDevice(c->device));
+  const int nrows = c->num_owned_unknowns;
+  if (!c->d_csr_rowptr) {
+    if (c->pat.nn_ptr.empty()) return fail(-2, "node-node lists are not available");
+    const long long msr0 = c->pat.rowstart[0];
+    c->csr_nnz = nrows > 0 ? (long long)(c->pat.rowstart[nrows] - msr0) + nrows : 0;
+    CsrKinds K;
+    memset(&K, 0, sizeof(K));
+    for (int k = 0; k < GOMA_GPU_MAX_KINDS; k++) {
+      K.tslot[k] = -1;
+      if (k >= p->num_kinds) continue;
+      K.num_unknowns[k] = p->kind_num_unknowns[k];
+      K.num_pressure[k] = kind_num_pressure(*p, k);
+      K.tslot[k] = p->energy ? p->kind_slot[k][GOMA_SLOT_T] : -1;
+    }
+    long long *d_nn_ptr = nullptr;
+    int *d_nn_list = nullptr;
+    CU(cudaMalloc((void **)&d_nn_ptr, c->pat.nn_ptr.size() * sizeof(long long)));
+    CU(cudaMalloc((void **)&d_nn_list, std::max<size_t>(c->pat.nn_list.size(), 1) * sizeof(int)));
+    CU(cudaMemcpy(d_nn_ptr, c->pat.nn_ptr.data(), c->pat.nn_ptr.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_nn_list, c->pat.nn_list.data(), c->pat.nn_list.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMalloc((void **)&c->d_csr_rowptr, ((size_t)nrows + 1) * sizeof(long long)));
+    CU(cudaMalloc((void **)&c->d_csr_colind, std::max<size_t>((size_t)c->csr_nnz, 1) * sizeof(int)));
+    CU(cudaMalloc((void **)&c->d_csr_dpos, std::max<size_t>((size_t)nrows, 1) * sizeof(int)));
+    CU(cudaMalloc((void **)&c->d_csr_values, std::max<size_t>((size_t)c->csr_nnz, 1) * sizeof(double)));
+    c->device_bytes += (size_t)c->csr_nnz * 12 + (size_t)nrows * 12;
+    CU(cudaMemset(c->d_csr_rowptr, 0, ((size_t)nrows + 1) * sizeof(long long)));
+    const int nown = c->prob.num_owned_nodes;
+    if (nown > 0 && nrows > 0) {
+      csr_structure_kernel<<<(nown + 127) / 128, 128, 0, c->stream>>>(nown, d_nn_ptr, d_nn_list, c->d_first, c->d_kind, K,
+                                                                      c->d_rowstart, msr0, c->d_csr_rowptr,
+                                                                      c->d_csr_colind, c->d_csr_dpos, nrows);
+      CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_nn_ptr);
+    cudaFree(d_nn_list);
+  }
+  out->num_rows = nrows;
+  out->nnz = c->csr_nnz;
+  out->d_rowptr = c->d_csr_rowptr;
+  out->d_colind = c->d_csr_colind;
+  out->d_values = c->d_csr_values;
+  return 0;
+}
+
+extern "C" int goma_gpu_csr_values(goma_gpu_ctx *c) {
+  if (!c) return fail(-2, "null context");
+  if (!c->d_csr_rowptr) return fail(-2, "call goma_gpu_csr_structure first");
+  CU(cudaSetDevice(c->device));
+  const int nrows = c->num_owned_unknowns;
+  if (nrows > 0) {
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    const int blocks = std::max(1, std::min(sms * 8, (nrows + 7) / 8));
+    csr_values_kernel<<<blocks, 256, 0, c->stream>>>(nrows, c->d_rowstart, c->d_csr_rowptr, c->d_csr_dpos, c->d_a, c->d_csr_values);
+    CU(cudaGetLastError());
+  }
+  CU(cudaStreamSynchronize(c->stream));
   return 0;
 }

@@ -124,6 +124,19 @@ class MatrixFill:
                    "goma_gpu_vector_norms")
         return float(out[0]), float(out[1]), float(np.sqrt(out[2])), int(out[3])
 
+    def csr(self, refresh_values=True):
+        """CSR view of the owned rows on the device (``goma_gpu_csr_structure`` / ``goma_gpu_csr_values``) as torch
+        tensors aliasing the library's buffers: (rowptr int64 [n+1], colind int32 [nnz], values float64 [nnz])."""
+        import torch
+
+        h = capi.Csr()
+        capi.check(self.lib.goma_gpu_csr_structure(self._ctx, C.byref(self._struct), C.byref(h)), "goma_gpu_csr_structure")
+        if refresh_values:
+            capi.check(self.lib.goma_gpu_csr_values(self._ctx), "goma_gpu_csr_values")
+        dev = torch.device("cuda", self.device)
+        return (device_view(h.d_rowptr, h.num_rows + 1, dev, "<i8"), device_view(h.d_colind, int(h.nnz), dev, "<i4"),
+                device_view(h.d_values, int(h.nnz), dev, "<f8"))
+
     def download_system(self):
         """D2H of the device-resident MSR values and residual (after row_sum_scale, say)."""
         import torch

@@ -180,6 +180,23 @@ int goma_gpu_row_sum_scale(goma_gpu_ctx *ctx, double *scale_out, int *zero_rows_
 int goma_gpu_scale_buffer(goma_gpu_ctx *ctx, double **d_scale, int *num_owned_unknowns);
 int goma_gpu_vector_norms(goma_gpu_ctx *ctx, int which, double out[4]);
 
+/* Device-resident hand-off to a GPU linear solver: a CSR view of the owned rows of the system --
+ * 64-bit row pointers, sorted 32-bit column indices with the diagonal in place (what cuSPARSE / AmgX / Ginkgo /
+ * an Epetra-Tpetra CRS view take; the reference's own plug-in point is the GomaSparseMatrix table,
+ * include/linalg/sparse_matrix.h:35-83).  goma_gpu_csr_structure builds rowptr / colind on the device from the
+ * node-node lists, exactly the column order of find_MSR_problem_graph (src/mm_fill_util.c:3229-3445) with the
+ * diagonal merged in, and allocates the value array; goma_gpu_csr_values re-gathers the values from the MSR
+ * storage after a fill (one read + one write of the matrix, HBM-bound).  Pointers stay valid for the context. */
+struct goma_gpu_csr {
+  int num_rows;        /* owned unknowns */
+  long long nnz;       /* entries of those rows, diagonal included */
+  long long *d_rowptr; /* [num_rows + 1] */
+  int *d_colind;       /* [nnz] local unknown numbers (external columns included) */
+  double *d_values;    /* [nnz] */
+};
+int goma_gpu_csr_structure(goma_gpu_ctx *ctx, const struct goma_gpu_problem *problem, struct goma_gpu_csr *out);
+int goma_gpu_csr_values(goma_gpu_ctx *ctx);
+
 /* exchange_dof() (src/dp_comm.c:48-102) over NVLink peer memory, one rank per GPU of one node.
  * Every rank exports CUDA IPC handles of its state vectors and of a small flag block
  * (goma_gpu_exchange_export); the host passes them round once (any transport) and each rank opens its

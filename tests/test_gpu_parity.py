@@ -515,3 +515,51 @@ def test_gpu_q2p1_species_field_sets_match_port_oracle(built, et, n, energy, ns,
         assert_close(a, a_ref, f"Jacobian scatter={scatter}")
         assert_close(r, r_ref, f"residual scatter={scatter}")
     mf.close()
+
+
+def _msr_to_csr_arrays(ija, a, nrows):
+    """(rowptr, colind, values) of the first nrows rows with the diagonal merged in, explicit zeros kept."""
+    ija = np.asarray(ija, np.int64)
+    N = int(ija[0]) - 1
+    cnt = np.diff(ija[: nrows + 1])
+    rows = np.concatenate([np.repeat(np.arange(nrows), cnt), np.arange(nrows)])
+    cols = np.concatenate([ija[ija[0]: ija[nrows]], np.arange(nrows)])
+    vals = np.concatenate([a[ija[0]: ija[nrows]], a[:nrows]])
+    order = np.lexsort((cols, rows))
+    rowptr = np.zeros(nrows + 1, np.int64)
+    np.cumsum(cnt + 1, out=rowptr[1:])
+    assert N >= nrows
+    return rowptr, cols[order].astype(np.int32), vals[order]
+
+
+@pytest.mark.parametrize("name", ["c3_hex27_boussinesq", "c5_hex8_pspg_global", "c4_quad9_ale"])
+def test_gpu_csr_handoff_matches_msr(built, name):
+    """the device-resident CSR view (sorted columns, diagonal in place) holds exactly the
+    assembled MSR system of the reference fixture; with ghost rows only the owned rows are exported."""
+    import torch
+
+    p, kw, st = case_state(name)
+    g = golden(name)
+    n = len(g["resid"])
+    mf = MatrixFill(p)
+    h, U = (p.global_h_elem_siz(), p.global_velocity_norm(st["x"])) if p.pspg else (0.0, 0.0)
+    err, a, r = mf.matrix_fill_full(st["x"], h_elem_avg=h, U_norm=U)
+    assert err == 0
+    rowptr, colind, values = (t.cpu().numpy() for t in mf.csr())
+    rp, ci, va = _msr_to_csr_arrays(g["ija"], g["a"], n)  # from the REFERENCE's graph and values
+    np.testing.assert_array_equal(rowptr, rp)
+    np.testing.assert_array_equal(colind, ci)
+    assert_close(values, va, "CSR values")
+    mf.close()
+    # owned rows only
+    owned = p.mesh.num_nodes - 7
+    n_owned = int(p.unknown_map()[0][owned])
+    mf = MatrixFill(p, num_owned_nodes=owned)
+    err, a, r = mf.matrix_fill_full(st["x"], h_elem_avg=h, U_norm=U)
+    rowptr, colind, values = (t.cpu().numpy() for t in mf.csr())
+    assert len(rowptr) == n_owned + 1
+    rp, ci, va = _msr_to_csr_arrays(mf.export_msr(), a, n_owned)
+    np.testing.assert_array_equal(rowptr, rp)
+    np.testing.assert_array_equal(colind, ci)
+    assert_close(values, va, "CSR values (owned rows)")
+    mf.close()
