@@ -1,25 +1,30 @@
-// Element assembly kernel for sm_100a: persistent CTAs, one element at a time per CTA, several CTAs
-// per SM.  Per element: operand tables (geometry, basis gradients, field values) are built in shared
-// memory, the node-pair Jacobian blocks are accumulated in registers over the Gauss points, staged
-// through shared memory and written out row by row so that a warp covers contiguous matrix slots.
+// Element assembly kernels for sm_100a: persistent CTAs, one element at a time per CTA, software-pipelined over
+// the elements a CTA owns.  Per element: the gather record (built once at init) arrives by a TMA bulk copy one
+// element ahead, the unknowns by cp.async under the previous element's Gauss loop; operand tables (geometry,
+// basis gradients, field values, per-Gauss-point terms) are built in shared memory; the node-pair Jacobian
+// blocks are accumulated in registers over the Gauss points and go straight from registers to their matrix
+// slots (slot map: no search, no staging).  fill_kernel is the default; fill_kernel_ws is a warp-specialised
+// variant (builder / multiplier warps over mbarrier-handed operand buffers) for the Q2/P1 Navier-Stokes block.
 //
 // What it replaces in the reference, per element (src/mm_fill.c:317 matrix_fill):
-//   BLOCK 1   load_elem_dofptr / load_ei          -> phase 0 gather through prebuilt tables
+//   BLOCK 1   load_elem_dofptr / load_ei          -> ElemRec (build_records_kernel) + gather_state
 //   per Gauss point (mm_fill.c:1253-2665):
 //     load_basis_functions (mm_fill_util.c:2608)  -> constant tables staged once per CTA by TMA
 //     beer_belly           (mm_fill_util.c:140)   -> phases 1-2 (J, detJ, B = J^-1 by cofactors)
 //     load_bf_grad         (mm_fill_util.c:1634)  -> phase 3  (grad_phi = B . dphi/dxi)
 //     load_fv / load_fv_grads (load_field_variables.c:128,2049) -> phase 4
 //     assemble_momentum    (mm_fill_momentum.c:100)   residual :534-662, J_m_v :1564-1735,
-//                                                     J_m_T :746-915, J_m_P :2052-2117
-//     assemble_continuity  (mm_fill_continuity.c:119) residual :435-613, J_c_v :665-761
-//     assemble_energy      (mm_fill_energy.c:109)     residual :322-381, J_e_T :425-487, J_e_v :628-692
+//                                                     J_m_T :746-915, J_m_P :2052-2117, J_m_d :2200-2442
+//     assemble_continuity  (mm_fill_continuity.c:119) residual :435-613, J_c_v :665-761, J_c_d :1004-1148,
+//                                                     PSPG calc_pspg (mm_fill_stabilization.c:852)
+//     assemble_energy      (mm_fill_energy.c:109)     residual :322-381, J_e_T :425-487, J_e_v :628-692, J_e_d :758-925
+//     assemble_mass_transport (mm_fill_species.c:194) Fickian: J_s_s, J_s_v, J_s_d :1103-1330
+//     assemble_mesh        (mm_fill_terms.c:111)      ARBITRARY / NONLINEAR: residual :421-428, J_d_d :529-576
 //   BLOCK 8   put_dirichlet_in_matrix (bc_dirich.c:44)
-//   load_lec  (mm_fill.c:5175, MSR branch :5241-5483) -> slot-mapped fp64 atomic scatter
+//   load_lec  (mm_fill.c:5175, MSR branch :5241-5483) -> slot-mapped scatter (atomic | coloured | first-touch)
 //
 // The Jacobian uses the Cartesian closed forms of SURVEY.md App. A instead of the reference's
-// zero-padded grad_phi_e / d_Pi tensors; the per-(i,j) node-pair block is accumulated in
-// registers over the Gauss points and written once.
+// zero-padded grad_phi_e / d_Pi tensors.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -920,7 +925,7 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
 
 // =====================================================================================
 // phase 6: node-pair blocks.  Thread = (row tile of TI nodes, one column node j); the TI x 1 tile of
-// NF x NF blocks is accumulated in registers over the Gauss points, then staged for the write-out.
+// NF x NF blocks is accumulated in registers over the Gauss points, then written to its matrix slots.
 // =====================================================================================
 template <class C>
 struct Tile {
