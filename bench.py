@@ -178,14 +178,14 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_baseline(budget_cores=None, nrep=2, energy=False):
+def cpu_baseline(budget_cores=None, nrep=8, energy=False):
     from oracle import ref_driver
 
     cores = budget_cores or host_cores()
     if ref_driver.ref_available():
-        v, step_s, ne = reference_sample(cores, 6, nrep, energy)
+        v, step_s, ne = reference_sample(cores, 8, nrep, energy)
         return {"value": v, "unit": "elements/s", "cores": cores, "kind": "reference",
-                "sample": f"{cores} single-rank processes of the reference's matrix_fill_full, one 6^3 hex27 "
+                "sample": f"{cores} single-rank processes of the reference's matrix_fill_full, one 8^3 hex27 "
                           f"sub-domain ({ne} elements) each, {nrep} fills, mean {step_s:.3f} s/fill"}
     v, step_s, ne = port_sample(6, nrep, energy)
     return {"value": v, "unit": "elements/s", "cores": 1, "kind": "port",
@@ -201,9 +201,9 @@ def run_reference_arm(args, rank):
     cores = host_cores()
     nrep = args.warmup + args.steps
     if ref_driver.ref_available():
-        v, step_s, ne = reference_sample(cores, 6, nrep, args.energy)
+        v, step_s, ne = reference_sample(cores, 8, nrep, args.energy)
         kind = "reference"
-        sample = (f"{cores} single-rank reference processes x one 6^3 hex27 sub-domain ({ne} elements) each; "
+        sample = (f"{cores} single-rank reference processes x one 8^3 hex27 sub-domain ({ne} elements) each; "
                   f"{nrep} fills per process, mean s/fill of the slowest process")
     else:
         v, step_s, ne = port_sample(6, nrep, args.energy)
