@@ -137,6 +137,26 @@ def build_case(name):
                         heat_source=0.6, etm_momentum=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0), etm_energy=(1.0,) * 5,
                         etm_mesh=(1.0, 1.0, 1.0, 1.0, 1.0), bcs=bcs2 + [Dirichlet("T", 1, 1.0)], **mat)
             return p, {"delta_t": 0.02, "theta": 0.5, "time": 0.1}
+    if name == "c2_hex27_ns_transient":
+        m = box_mesh("HEX27", (2, 2, 1), perturb=0.12, seed=31)
+        p = Problem(m, rho=1.0, mu=0.01, gravity=(0.0, 0.0, -0.4), transient=True,
+                    etm_momentum=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0), bcs=_bcs(3))
+        return p, {"delta_t": 0.005, "theta": 0.5, "time": 0.05}
+    if name == "c4_hex27_ale_energy_transient":
+        m = box_mesh("HEX27", (2, 1, 2), perturb=0.1, seed=32)
+        bcs = [Dirichlet("U", 1, 1.0), Dirichlet("V", 1, 0.0), Dirichlet("DX", 1, 0.0), Dirichlet("DY", 1, 0.0),
+               Dirichlet("DZ", 5, 0.0), Dirichlet("DX", 3, 0.01, relax=1.0), Dirichlet("W", 6, 0.5, relax=1.0),
+               Dirichlet("T", 1, 1.0), Dirichlet("T", 2, 0.0, relax=1.0)]
+        p = Problem(m, ale=True, transient=True, energy=True, k=0.07, Cp=1.4, beta=0.8, Tref=0.3, ns_source="BOUSSINESQ",
+                    heat_source=0.6, etm_momentum=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0), etm_energy=(1.0,) * 5,
+                    etm_mesh=(1.0,) * 5, rho=1.3, mu=0.7, gravity=(0.3, -0.2, 0.1), lame_mu=0.9, lame_lambda=1.7, bcs=bcs)
+        return p, {"delta_t": 0.02, "theta": 0.0, "time": 0.1}
+    if name == "c5_hex8_ns_pspg_local":
+        m = box_mesh("HEX8", (3, 2, 3), perturb=0.15, seed=33)
+        bcs = [Dirichlet("U", 1, 1.0), Dirichlet("V", 1, 0.0), Dirichlet("W", 5, 0.0), Dirichlet("U", 4, 0.0, relax=1.0),
+               Dirichlet("P", 7, 0.0)]
+        p = Problem(m, interp="Q1Q1", pspg="local", ps_scaling=0.2, rho=1.2, mu=0.3, gravity=(0.1, -0.2, -1.0), bcs=bcs)
+        return p, {}
     if name == "q2p1_quad9_species_ale_transient":
         # Q2/P1 with energy and two Fickian species on a moving mesh: J_s_v, J_s_d, J_e_d and the v - xdot_mesh
         # convection velocity in every transport equation
@@ -155,7 +175,8 @@ def build_case(name):
 GOLDEN_CASES = ["c1_quad9_ns", "c1_quad9_ns_transient", "c2_hex27_ns", "c3_hex27_boussinesq",
                 "c3_quad9_bouss_transient", "c5_hex8_pspg_local_transient", "c5_hex8_pspg_global",
                 "c5_quad4_pspg_local", "c4_quad9_ale", "c4_hex27_ale", "c4_quad9_ale_energy_transient",
-                "q2p1_quad9_species_ale_transient"]
+                "q2p1_quad9_species_ale_transient", "c2_hex27_ns_transient", "c4_hex27_ale_energy_transient",
+                "c5_hex8_ns_pspg_local"]
 
 
 def case_state(name):
