@@ -31,7 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # SURVEY.md §8(d) / BASELINE.md §3 per-element algorithmic work, fixed per config
-ALG_FLOPS_PER_ELEM = {"c2_hex27_ns": 1.2e6, "c3_hex27_ns_energy": 1.85e6, "c5_hex8_pspg_T_2Y": 0.25e6}
+ALG_FLOPS_PER_ELEM = {"c2_hex27_ns": 1.2e6, "c3_hex27_ns_energy": 1.85e6, "c5_hex8_pspg_T_2Y": 0.25e6,
+                      "c4_hex27_ale_ns": 3.6e6}  # C4: "3-4x the fixed-mesh count" (SURVEY.md §8d), lower end
 FP64_PEAK_NOMINAL_TFLOPS = 40.0  # BASELINE.json north_star; replaced by the DFMA micro-benchmark when it runs
 
 
@@ -59,6 +60,17 @@ def c5_problem_on(mesh):
     return Problem(mesh, interp="Q1Q1", pspg="local", ps_scaling=0.1, energy=True, n_species=2, rho=1.0, mu=0.01,
                    k=0.0141, Cp=1.0, beta=1.0, Tref=0.0, gravity=(0.0, 0.0, -1.0), ns_source="BOUSSINESQ",
                    diffusivity=(0.01, 0.02, 1.0, 1.0), bcs=bcs)
+
+
+def c4_problem_on(mesh):
+    """SURVEY.md §8d C4, 3-D variant: hex27 Q2/P1 Navier-Stokes on an ALE pseudo-solid mesh (ARBITRARY / NONLINEAR,
+    lambda = mu = 1), volumetric assembly with Dirichlet conditions on the displacements."""
+    from goma_b200.problem import Dirichlet, Problem
+
+    bcs = [Dirichlet(v, s, 0.0) for s in (1, 2, 3, 4, 5) for v in ("U", "V", "W", "DX", "DY", "DZ")]
+    bcs += [Dirichlet("U", 6, 1.0), Dirichlet("V", 6, 0.0), Dirichlet("W", 6, 0.0), Dirichlet("DZ", 6, 0.0),
+            Dirichlet("P", 7, 0.0)]
+    return Problem(mesh, ale=True, rho=1.0, mu=0.01, lame_mu=1.0, lame_lambda=1.0, bcs=bcs)
 
 
 def cavity_problem_on(mesh, energy=False):
@@ -219,6 +231,9 @@ def run_reference_arm(args, rank):
 
 
 def workload_name(args):
+    if getattr(args, "config", "c2") == "c4":
+        return (f"3D Navier-Stokes on an ALE pseudo-solid mesh, Q2/P1 hex27, {args.n}^3 elements per GPU (SURVEY C4, 3-D "
+                "variant; not the headline config)")
     if getattr(args, "config", "c2") == "c5":
         return (f"3D NS + energy + 2 species, PSPG Q1/Q1 hex8, {args.n}^3 elements per GPU (BASELINE.json configs[4]; "
                 "not the headline config)")
@@ -256,7 +271,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--edge", dest="n", type=int, default=100, help="elements per direction per GPU (100 -> 1M hex27 elements)")
     ap.add_argument("--energy", action="store_true", help="config C3 physics (NS + energy) instead of C2")
-    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 = headline (default); c3 = --energy; c5 = hex8 PSPG + T + 2 species (kernel number only)")
     ap.add_argument("--scatter", type=int, default=2,
                     help="0 fp64 atomics, 1 coloured load+add+store, 2 coloured first-touch stores (default)")
@@ -267,7 +282,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.config == "c3":
         args.energy = True
-    if args.config == "c5" and args.impl == "reference":
+    if args.config in ("c4", "c5") and args.impl == "reference":
         raise SystemExit("the reference arm is defined on the headline config (c2) and c3")
 
     rank = int(os.environ.get("RANK", "0"))
@@ -313,12 +328,13 @@ def main():
 
     t_setup = time.perf_counter()
     sub = None
-    make_on = c5_problem_on if args.config == "c5" else (lambda mesh: cavity_problem_on(mesh, args.energy))
+    make_on = (c5_problem_on if args.config == "c5" else c4_problem_on if args.config == "c4"
+               else (lambda mesh: cavity_problem_on(mesh, args.energy)))
     if world == 1:
-        if args.config == "c5":
+        if args.config in ("c4", "c5"):
             from goma_b200.mesh import box_mesh
 
-            problem = c5_problem_on(box_mesh("HEX8", (args.n,) * 3))
+            problem = make_on(box_mesh("HEX8" if args.config == "c5" else "HEX27", (args.n,) * 3))
         else:
             problem = cavity_problem(args.n, args.energy)
         num_owned_nodes = None
@@ -512,7 +528,7 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        key = "c5_hex8_pspg_T_2Y" if args.config == "c5" else ("c3_hex27_ns_energy" if args.energy else "c2_hex27_ns")
+        key = "c5_hex8_pspg_T_2Y" if args.config == "c5" else "c4_hex27_ale_ns" if args.config == "c4" else ("c3_hex27_ns_energy" if args.energy else "c2_hex27_ns")
         flops = ALG_FLOPS_PER_ELEM[key]
         bytes_per_elem = 8.0 * (nnz + n_unk) / ne + problem.mesh.npe * 4 + 8.0 * (3 * problem.mesh.num_nodes + n_unk) / ne
         kern_s = dev_ms * 1e-3
