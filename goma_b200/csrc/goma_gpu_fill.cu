@@ -63,6 +63,7 @@ struct goma_gpu_ctx {
   int tail_begin = 0;
   unsigned long long epoch[3] = {0, 0, 0};
   double *d_sums = nullptr;  // goma_gpu_global_h_U
+  unsigned char *d_elem_owned = nullptr;
   long long *d_csr_rowptr = nullptr;  // CSR hand-off
   int *d_csr_colind = nullptr, *d_csr_dpos = nullptr;
   double *d_csr_values = nullptr;
@@ -344,6 +345,7 @@ extern "C" void goma_gpu_fill_destroy(goma_gpu_ctx *c) {
   if (c->d_xflags) cudaFree(c->d_xflags);
   if (c->d_recv_list) cudaFree(c->d_recv_list);
   if (c->d_sums) cudaFree(c->d_sums);
+  if (c->d_elem_owned) cudaFree(c->d_elem_owned);
   if (c->d_csr_rowptr) cudaFree(c->d_csr_rowptr);
   if (c->d_csr_colind) cudaFree(c->d_csr_colind);
   if (c->d_csr_dpos) cudaFree(c->d_csr_dpos);
@@ -691,8 +693,9 @@ extern "C" int goma_gpu_global_h_U(goma_gpu_ctx *c, const unsigned char *elem_ow
   CU(cudaSetDevice(c->device));
   const goma_gpu_problem &p = c->prob;
   unsigned char *d_owned = nullptr;
-  if (elem_owned) {
-    CU(cudaMalloc((void **)&d_owned, std::max(1, p.num_elems)));
+  if (elem_owned) {  // the mask travels with every call (num_elems bytes); its buffer is kept
+    if (!c->d_elem_owned) CU(cudaMalloc((void **)&c->d_elem_owned, std::max(1, p.num_elems)));
+    d_owned = c->d_elem_owned;
     CU(cudaMemcpyAsync(d_owned, elem_owned, p.num_elems, cudaMemcpyHostToDevice, c->stream));
   }
   if (!c->d_sums) CU(cudaMalloc((void **)&c->d_sums, 4 * sizeof(double)));
@@ -706,7 +709,6 @@ extern "C" int goma_gpu_global_h_U(goma_gpu_ctx *c, const unsigned char *elem_ow
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(sums_out, c->d_sums, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  if (d_owned) cudaFree(d_owned);
   return 0;
 }
 
@@ -769,6 +771,11 @@ extern "C" int goma_gpu_exchange_setup(goma_gpu_ctx *c, int num_neighbors, const
   if (num_neighbors && (!nh || !my_slot_at_neighbor || !recv_ptr || !recv_list)) return fail(-2, "null argument");
   if (!c->d_xflags) return fail(-2, "call goma_gpu_exchange_export first");
   CU(cudaSetDevice(c->device));
+  for (int k = 0; k < c->num_neighbors; k++) {  // a second set-up replaces the first
+    for (int v = 0; v < 3; v++)
+      if (c->peer_vec[v][k]) cudaIpcCloseMemHandle(c->peer_vec[v][k]), c->peer_vec[v][k] = nullptr;
+    if (c->peer_flags[k]) cudaIpcCloseMemHandle(c->peer_flags[k]), c->peer_flags[k] = nullptr;
+  }
   c->num_neighbors = num_neighbors;
   c->tail_begin = tail_begin;
   c->recv_ptr.assign(recv_ptr, recv_ptr + num_neighbors + 1);

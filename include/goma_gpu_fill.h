@@ -207,7 +207,8 @@ int goma_gpu_csr_values(goma_gpu_ctx *ctx);
  * is complete" in the neighbours' flag blocks, waits for theirs and pulls the ghost values straight out of
  * the neighbours' HBM.  No host synchronisation, no staging buffer.  The caller must not overwrite a
  * vector again before every rank has finished the fill that follows the exchange (in Goma the linear
- * solve, a collective, sits in between).  which: 0 = x, 1 = xdot, 2 = x_old. */
+ * solve, a collective, sits in between).  The call is collective over the neighbourhood, like the reference's:
+ * a rank whose neighbour never calls it waits in the kernel.  which: 0 = x, 1 = xdot, 2 = x_old. */
 #define GOMA_GPU_IPC_HANDLE_BYTES 64
 #define GOMA_GPU_MAX_NEIGHBORS 32
 struct goma_gpu_exchange_handles {
