@@ -1,0 +1,75 @@
+// Private to the library: the context behind goma_gpu_ctx, error plumbing and small device-memory helpers shared
+// by the translation units (goma_gpu_fill.cu: init + assembly; exchange.cu: exchange_dof over peer memory;
+// post_fill.cu: PSPG norms, row-sum scaling, residual norms, CSR hand-off).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/goma_gpu_fill.h"
+#include "pattern.h"
+
+namespace goma_b200 {
+int fail(int code, const std::string &msg);  // records the message for goma_gpu_last_error(), returns code
+}
+using goma_b200::fail;
+
+#define CU(call)                                                                               \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(-3, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + \
+                          std::to_string(__LINE__));                                           \
+  } while (0)
+
+struct goma_gpu_ctx {
+  goma_gpu_problem prob;  // scalar members + kind tables only; pointers are not retained
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  goma_b200::Pattern pat;  // host copy kept for get_msr (nn lists) -- sized for test/bench meshes
+  // device arrays
+  int *d_conn = nullptr, *d_first = nullptr;
+  double *d_coord[3] = {nullptr, nullptr, nullptr};
+  unsigned char *d_kind = nullptr, *d_dbc_flag = nullptr;
+  double *d_dbc_value = nullptr;
+  long long *d_rowstart = nullptr;
+  unsigned short *d_pair_full = nullptr, *d_pair_p = nullptr;
+  unsigned *d_pair_first = nullptr, *d_node_first = nullptr;
+  double *d_tables = nullptr;
+  unsigned char *d_erec = nullptr;  // per-element gather records (ElemRec<C>)
+  double *d_x = nullptr, *d_x_old = nullptr, *d_x_older = nullptr, *d_xdot = nullptr, *d_xdot_old = nullptr;
+  double *d_a = nullptr, *d_resid = nullptr;
+  int *d_flags = nullptr;
+  long long *d_prof = nullptr;     // phase cycle counters (GOMA_GPU_PROFILE=1)
+  int *d_elem_list = nullptr;      // colour-ordered element list
+  // peer-memory exchange_dof
+  unsigned long long *d_xflags = nullptr;  // [3][GOMA_GPU_MAX_NEIGHBORS] epochs published by the neighbours
+  int num_neighbors = 0;
+  void *peer_vec[3][GOMA_GPU_MAX_NEIGHBORS] = {};
+  unsigned long long *peer_flags[GOMA_GPU_MAX_NEIGHBORS] = {};
+  int my_slot_at[GOMA_GPU_MAX_NEIGHBORS] = {};
+  int *d_recv_list = nullptr;
+  std::vector<int> recv_ptr;
+  int tail_begin = 0;
+  unsigned long long epoch[3] = {0, 0, 0};
+  double *d_sums = nullptr;  // goma_gpu_global_h_U
+  unsigned char *d_elem_owned = nullptr;
+  long long *d_csr_rowptr = nullptr;  // CSR hand-off
+  int *d_csr_colind = nullptr, *d_csr_dpos = nullptr;
+  double *d_csr_values = nullptr;
+  long long csr_nnz = 0;
+  double *d_scale = nullptr;      // row-sum scale vector
+  double *d_partials = nullptr;   // per-block partial norms
+  int *d_zero_rows = nullptr;
+  int num_owned_unknowns = 0;
+  std::vector<int> colour_begin;   // [ncolours+1]
+  int num_sms = 0, blocks_per_sm = 0;  // cached launch geometry (cudaGetDeviceProperties is slow)
+  int scatter_mode = 2;            // 0 fp64 atomics, 1 coloured load+add+store, 2 coloured first-touch stores
+  int grid_limit = 0;
+  double last_ms = 0.0;
+  int last_launches = 0;
+  size_t device_bytes = 0;
+};

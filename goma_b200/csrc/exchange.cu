@@ -1,0 +1,146 @@
+// exchange_dof() (src/dp_comm.c:48-102) on the device: the peer-memory pull kernel over CUDA IPC handles, and the
+// pack / unpack halves for a host that drives the transport itself.  See include/goma_gpu_fill.h.
+#include <cstring>
+
+#include "ctx.h"
+
+using namespace goma_b200;
+
+// ------------------------------------------------------------------ exchange_dof over peer memory
+struct ExchangeArgs {
+  int nn;
+  unsigned long long epoch;
+  unsigned long long *peer_ready[GOMA_GPU_MAX_NEIGHBORS];  // the slot of this rank in each neighbour's flag block
+  const unsigned long long *my_ready;                      // this rank's flag block, row of the vector
+  const double *peer_vec[GOMA_GPU_MAX_NEIGHBORS];
+  int recv_ptr[GOMA_GPU_MAX_NEIGHBORS + 1];
+  const int *recv_list;
+  double *tail;
+};
+
+__global__ void exchange_dof_kernel(const __grid_constant__ ExchangeArgs A) {
+  // publish: everything written to this rank's vector before this kernel (stream order) is visible to the
+  // neighbours once they observe the epoch
+  if (blockIdx.x == 0 && threadIdx.x < A.nn) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.peer_ready[threadIdx.x]), "l"(A.epoch) : "memory");
+  }
+  const int total = A.recv_ptr[A.nn];
+  for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+    const int k = base + threadIdx.x;
+    int nb = 0;
+    if (k < total) {
+      while (k >= A.recv_ptr[nb + 1]) nb++;
+      unsigned long long seen;
+      do {  // the neighbour's vector of this epoch is complete
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(A.my_ready + nb) : "memory");
+      } while (seen < A.epoch);
+      A.tail[k] = A.peer_vec[nb][A.recv_list[k]];
+    }
+  }
+}
+
+extern "C" int goma_gpu_exchange_export(goma_gpu_ctx *c, goma_gpu_exchange_handles *out) {
+  if (!c || !out) return fail(-2, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (!c->d_xflags) {
+    CU(cudaMalloc((void **)&c->d_xflags, 3 * GOMA_GPU_MAX_NEIGHBORS * sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_xflags, 0, 3 * GOMA_GPU_MAX_NEIGHBORS * sizeof(unsigned long long)));
+    CU(cudaDeviceSynchronize());
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == GOMA_GPU_IPC_HANDLE_BYTES, "IPC handle size");
+  memset(out, 0, sizeof(*out));
+  double *vecs[3] = {c->d_x, c->d_xdot, c->d_x_old};
+  for (int v = 0; v < 3; v++) CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->vec[v], vecs[v]));
+  CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)out->flags, c->d_xflags));
+  out->device = c->device;
+  return 0;
+}
+
+extern "C" int goma_gpu_exchange_setup(goma_gpu_ctx *c, int num_neighbors, const goma_gpu_exchange_handles *nh,
+                                       const int *my_slot_at_neighbor, const int *recv_ptr, const int *recv_list,
+                                       int tail_begin) {
+  if (!c) return fail(-2, "null context");
+  if (num_neighbors < 0 || num_neighbors > GOMA_GPU_MAX_NEIGHBORS) return fail(-2, "too many neighbours");
+  if (num_neighbors && (!nh || !my_slot_at_neighbor || !recv_ptr || !recv_list)) return fail(-2, "null argument");
+  if (!c->d_xflags) return fail(-2, "call goma_gpu_exchange_export first");
+  CU(cudaSetDevice(c->device));
+  for (int k = 0; k < c->num_neighbors; k++) {  // a second set-up replaces the first
+    for (int v = 0; v < 3; v++)
+      if (c->peer_vec[v][k]) cudaIpcCloseMemHandle(c->peer_vec[v][k]), c->peer_vec[v][k] = nullptr;
+    if (c->peer_flags[k]) cudaIpcCloseMemHandle(c->peer_flags[k]), c->peer_flags[k] = nullptr;
+  }
+  c->num_neighbors = num_neighbors;
+  c->tail_begin = tail_begin;
+  c->recv_ptr.assign(recv_ptr, recv_ptr + num_neighbors + 1);
+  if (tail_begin + c->recv_ptr[num_neighbors] > c->prob.num_unknowns) return fail(-2, "external tail exceeds the vector");
+  for (int k = 0; k < num_neighbors; k++) {
+    if (my_slot_at_neighbor[k] < 0 || my_slot_at_neighbor[k] >= GOMA_GPU_MAX_NEIGHBORS) return fail(-2, "bad neighbour slot");
+    c->my_slot_at[k] = my_slot_at_neighbor[k];
+    for (int v = 0; v < 3; v++)
+      CU(cudaIpcOpenMemHandle(&c->peer_vec[v][k], *(const cudaIpcMemHandle_t *)nh[k].vec[v], cudaIpcMemLazyEnablePeerAccess));
+    void *pf = nullptr;
+    CU(cudaIpcOpenMemHandle(&pf, *(const cudaIpcMemHandle_t *)nh[k].flags, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_flags[k] = (unsigned long long *)pf;
+  }
+  if (c->d_recv_list) cudaFree(c->d_recv_list);
+  c->d_recv_list = nullptr;
+  const int total = c->recv_ptr[num_neighbors];
+  CU(cudaMalloc((void **)&c->d_recv_list, std::max(1, total) * sizeof(int)));
+  if (total) CU(cudaMemcpy(c->d_recv_list, recv_list, (size_t)total * sizeof(int), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int goma_gpu_exchange_dof(goma_gpu_ctx *c, int which) {
+  if (!c) return fail(-2, "null context");
+  if (which < 0 || which > 2) return fail(-2, "which must be 0 (x), 1 (xdot) or 2 (x_old)");
+  if (c->num_neighbors == 0) return 0;
+  CU(cudaSetDevice(c->device));
+  ExchangeArgs A;
+  memset(&A, 0, sizeof(A));
+  A.nn = c->num_neighbors;
+  A.epoch = ++c->epoch[which];
+  double *vecs[3] = {c->d_x, c->d_xdot, c->d_x_old};
+  for (int k = 0; k < A.nn; k++) {
+    A.peer_ready[k] = c->peer_flags[k] + which * GOMA_GPU_MAX_NEIGHBORS + c->my_slot_at[k];
+    A.peer_vec[k] = (const double *)c->peer_vec[which][k];
+    A.recv_ptr[k] = c->recv_ptr[k];
+  }
+  A.recv_ptr[A.nn] = c->recv_ptr[A.nn];
+  A.my_ready = c->d_xflags + which * GOMA_GPU_MAX_NEIGHBORS;
+  A.recv_list = c->d_recv_list;
+  A.tail = vecs[which] + c->tail_begin;
+  const int total = c->recv_ptr[A.nn];
+  const int threads = 256, blocks = std::max(1, std::min(148, (total + threads - 1) / threads));
+  exchange_dof_kernel<<<blocks, threads, 0, c->stream>>>(A);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ exchange_dof halves
+__global__ void pack_dofs_kernel(const double *__restrict__ v, const int *__restrict__ list, int n,
+                                 double *__restrict__ buf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) buf[i] = v[list[i]];
+}
+__global__ void unpack_dofs_kernel(double *__restrict__ v, const int *__restrict__ list, int n,
+                                   const double *__restrict__ buf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[list[i]] = buf[i];
+}
+extern "C" int goma_gpu_pack_dofs(goma_gpu_ctx *c, const double *d_vec, const int *d_list, int n, double *d_buf) {
+  if (!c) return fail(-2, "null context");
+  if (n <= 0) return 0;
+  pack_dofs_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_vec, d_list, n, d_buf);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int goma_gpu_unpack_dofs(goma_gpu_ctx *c, double *d_vec, const int *d_list, int n, const double *d_buf) {
+  if (!c) return fail(-2, "null context");
+  if (n <= 0) return 0;
+  unpack_dofs_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_vec, d_list, n, d_buf);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}

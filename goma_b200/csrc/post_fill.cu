@@ -1,0 +1,337 @@
+// What surrounds matrix_fill_full in solve_nonlinear_problem, on the device-resident system: the PSPG global norms
+// before it (src/mm_fill_aux.c:1128,612), row-sum scaling and residual norms after it (src/sl_matrix_util.c:441,
+// src/mm_sol_nonlinear.c:3177-3375), and the CSR hand-off to a GPU solver.  See include/goma_gpu_fill.h.
+#include <cstring>
+
+#include "ctx.h"
+
+using namespace goma_b200;
+
+// ------------------------------------------------------------------ PSPG global norms
+// h_elem_siz (mm_fill_aux.c:844-1070): squared distances between opposite face centroids, from the vertex nodes
+__global__ void global_h_U_kernel(const int *__restrict__ conn, int npe, int dim, int num_elems,
+                                  const double *__restrict__ cx, const double *__restrict__ cy,
+                                  const double *__restrict__ cz, const unsigned char *__restrict__ elem_owned,
+                                  const int *__restrict__ first_unknown, const unsigned char *__restrict__ node_kind,
+                                  int slot_u0, int slot_u1, int slot_u2, int k0u, int k1u, int k2u, int k3u,
+                                  int num_owned_nodes, const double *__restrict__ x, double *__restrict__ sums) {
+  double h = 0.0, cnt = 0.0, vv = 0.0, nv = 0.0;
+  const int stride = gridDim.x * blockDim.x;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < num_elems; e += stride) {
+    if (elem_owned && !elem_owned[e]) continue;
+    const int *c = conn + (size_t)e * npe;
+    double hsq = 0.0;
+    for (int a = 0; a < dim; a++) {
+      const double *X = a == 0 ? cx : (a == 1 ? cy : cz);
+      if (dim == 2) {
+        const double x0 = X[c[0]], x1 = X[c[1]], x2 = X[c[2]], x3 = X[c[3]];
+        const double h0 = 0.5 * (x1 + x2) - 0.5 * (x0 + x3), h1 = 0.5 * (x0 + x1) - 0.5 * (x2 + x3);
+        hsq += h0 * h0 + h1 * h1;
+      } else {
+        double v[8];
+        for (int k = 0; k < 8; k++) v[k] = X[c[k]];
+        const double p1 = 0.25 * (v[0] + v[1] + v[2] + v[3]), p2 = 0.25 * (v[1] + v[2] + v[5] + v[6]);
+        const double p3 = 0.25 * (v[2] + v[3] + v[6] + v[7]), p4 = 0.25 * (v[0] + v[1] + v[4] + v[5]);
+        const double p5 = 0.25 * (v[0] + v[3] + v[4] + v[7]), p6 = 0.25 * (v[4] + v[5] + v[6] + v[7]);
+        hsq += (p2 - p5) * (p2 - p5) + (p3 - p4) * (p3 - p4) + (p1 - p6) * (p1 - p6);
+      }
+    }
+    h += sqrt(hsq / (double)dim);
+    cnt += 1.0;
+  }
+  const int ku[4][3] = {{k0u, k0u + 1, k0u + 2}, {k1u, k1u + 1, k1u + 2}, {k2u, k2u + 1, k2u + 2}, {k3u, k3u + 1, k3u + 2}};
+  (void)slot_u0; (void)slot_u1; (void)slot_u2;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < num_owned_nodes; n += stride) {
+    const int kd = node_kind[n];
+    if (ku[kd][0] < 0) continue;
+    const int f = first_unknown[n];
+    for (int a = 0; a < dim; a++) {
+      const double v = x[f + ku[kd][a]];
+      vv += v * v;
+      nv += 1.0;
+    }
+  }
+  double vals[4] = {h, cnt, vv, nv};
+  for (int q = 0; q < 4; q++) {
+    double v = vals[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&sums[q], v);
+  }
+}
+
+extern "C" int goma_gpu_global_h_U(goma_gpu_ctx *c, const unsigned char *elem_owned, double sums_out[4]) {
+  if (!c || !sums_out) return fail(-2, "null argument");
+  CU(cudaSetDevice(c->device));
+  const goma_gpu_problem &p = c->prob;
+  unsigned char *d_owned = nullptr;
+  if (elem_owned) {  // the mask travels with every call (num_elems bytes); its buffer is kept
+    if (!c->d_elem_owned) CU(cudaMalloc((void **)&c->d_elem_owned, std::max(1, p.num_elems)));
+    d_owned = c->d_elem_owned;
+    CU(cudaMemcpyAsync(d_owned, elem_owned, p.num_elems, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (!c->d_sums) CU(cudaMalloc((void **)&c->d_sums, 4 * sizeof(double)));
+  CU(cudaMemsetAsync(c->d_sums, 0, 4 * sizeof(double), c->stream));
+  int ku[4] = {-1, -1, -1, -1};  // offset of U inside a node of each kind (V, W follow it)
+  for (int k = 0; k < p.num_kinds && k < 4; k++) ku[k] = p.kind_slot[k][GOMA_SLOT_U];
+  const int threads = 256, blocks = std::max(1, std::min(148 * 8, (std::max(p.num_elems, p.num_owned_nodes) + threads - 1) / threads));
+  global_h_U_kernel<<<blocks, threads, 0, c->stream>>>(c->d_conn, p.elem_type, p.dim, p.num_elems, c->d_coord[0],
+                                                       c->d_coord[1], c->d_coord[2], d_owned, c->d_first, c->d_kind, 0, 1, 2,
+                                                       ku[0], ku[1], ku[2], ku[3], p.num_owned_nodes, c->d_x, c->d_sums);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(sums_out, c->d_sums, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------ after the fill: row-sum scaling, norms
+// One warp per owned row: the off-diagonal run of an MSR row is contiguous, lanes stride over it (coalesced),
+// the second sweep over the row (the division) hits L1/L2.  HBM-bound: reads and writes every value once.
+__global__ void __launch_bounds__(256, 6) row_sum_scale_kernel(int nrows, const long long *__restrict__ rowstart, double *__restrict__ a,
+                                     double *__restrict__ b, double *__restrict__ scale, int *__restrict__ zero_rows) {
+  const int lane = threadIdx.x & 31;
+  const int nwarp = (gridDim.x * blockDim.x) >> 5;
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  long long k0n = 0, k1n = 0;
+  if (row < nrows) {
+    k0n = rowstart[row];
+    k1n = rowstart[row + 1];
+  }
+  for (; row < nrows; row += nwarp) {
+    const long long k0 = k0n, k1 = k1n;
+    if (row + nwarp < nrows) {  // the next row's extent is on its way while this row streams
+      k0n = rowstart[row + nwarp];
+      k1n = rowstart[row + nwarp + 1];
+    }
+    double sum = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    long long k = k0 + lane;
+    for (; k + 96 < k1; k += 128) {  // four independent 256-byte requests in flight per warp
+      const double v0 = a[k], v1 = a[k + 32], v2 = a[k + 64], v3 = a[k + 96];
+      sum += fabs(v0);
+      s1 += fabs(v1);
+      s2 += fabs(v2);
+      s3 += fabs(v3);
+    }
+    for (; k < k1; k += 32) sum += fabs(a[k]);
+    sum = (sum + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const double diag = a[row];
+    double row_sum = fabs(diag) + sum;
+    if (fabs(diag) > 1.0e-200) row_sum = diag >= 0.0 ? row_sum : -row_sum;  // keep the diagonal positive (:547-549)
+    // the reference divides (a[k] /= row_sum); one reciprocal per row and a multiply per entry differ from that by
+    // at most 1 ulp (the parity tolerance is 1e-12) and take the fp64 divide sequence (~20 instructions per entry)
+    // off an HBM-bound pass
+    const double inv = 1.0 / row_sum;
+    k = k0 + lane;
+    for (; k + 96 < k1; k += 128) {
+      const double v0 = a[k], v1 = a[k + 32], v2 = a[k + 64], v3 = a[k + 96];
+      a[k] = v0 * inv;
+      a[k + 32] = v1 * inv;
+      a[k + 64] = v2 * inv;
+      a[k + 96] = v3 * inv;
+    }
+    for (; k < k1; k += 32) a[k] = a[k] * inv;
+    if (lane == 0) {
+      scale[row] = row_sum;
+      if (row_sum == 0.0) atomicAdd(zero_rows, 1);
+      a[row] = diag / row_sum;
+      b[row] = b[row] / row_sum;
+    }
+  }
+}
+
+extern "C" int goma_gpu_row_sum_scale(goma_gpu_ctx *c, double *scale_out, int *zero_rows_out) {
+  if (!c) return fail(-2, "null context");
+  CU(cudaSetDevice(c->device));
+  const int n = c->num_owned_unknowns;
+  if (!c->d_scale) CU(cudaMalloc((void **)&c->d_scale, std::max(1, c->prob.num_unknowns) * sizeof(double)));
+  if (!c->d_zero_rows) CU(cudaMalloc((void **)&c->d_zero_rows, sizeof(int)));
+  CU(cudaMemsetAsync(c->d_zero_rows, 0, sizeof(int), c->stream));
+  if (n > 0) {
+    const int threads = 256;
+    int per_sm = 0;  // a whole number of resident waves: the rows are handed out grid-stride
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)row_sum_scale_kernel, threads, 0));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    const int blocks = std::max(1, std::min(sms * std::max(per_sm, 1), (n + 7) / 8));
+    row_sum_scale_kernel<<<blocks, threads, 0, c->stream>>>(n, c->d_rowstart, c->d_a, c->d_resid, c->d_scale, c->d_zero_rows);
+    CU(cudaGetLastError());
+  }
+  int zr = 0;
+  CU(cudaMemcpyAsync(&zr, c->d_zero_rows, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (scale_out && n > 0) CU(cudaMemcpyAsync(scale_out, c->d_scale, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (zero_rows_out) *zero_rows_out = zr;
+  return 0;
+}
+
+extern "C" int goma_gpu_scale_buffer(goma_gpu_ctx *c, double **d_scale, int *num_owned_unknowns) {
+  if (!c) return fail(-2, "null context");
+  if (d_scale) *d_scale = c->d_scale;
+  if (num_owned_unknowns) *num_owned_unknowns = c->num_owned_unknowns;
+  return 0;
+}
+
+constexpr int NORM_BLOCKS = 592, NORM_THREADS = 256;
+__global__ void vector_norms_kernel(const double *__restrict__ v, int n, double *__restrict__ partials) {
+  __shared__ double sh[4][NORM_THREADS / 32];
+  double mx = -1.0, l1 = 0.0, l2 = 0.0, idx = -1.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double t = v[i], w = fabs(t);
+    l1 += w;
+    l2 += t * t;
+    if (w > mx) { mx = w; idx = (double)i; }  // first occurrence of the maximum, as the reference's strict '>'
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    l2 += __shfl_xor_sync(0xffffffffu, l2, o);
+    const double m2 = __shfl_xor_sync(0xffffffffu, mx, o), i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (m2 > mx || (m2 == mx && i2 >= 0.0 && (idx < 0.0 || i2 < idx))) { mx = m2; idx = i2; }
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sh[0][w] = mx; sh[1][w] = l1; sh[2][w] = l2; sh[3][w] = idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < NORM_THREADS / 32; k++) {
+      l1 += sh[1][k];
+      l2 += sh[2][k];
+      if (sh[0][k] > mx || (sh[0][k] == mx && sh[3][k] >= 0.0 && (idx < 0.0 || sh[3][k] < idx))) { mx = sh[0][k]; idx = sh[3][k]; }
+    }
+    double *o = partials + 4 * blockIdx.x;
+    o[0] = mx; o[1] = l1; o[2] = l2; o[3] = idx;
+  }
+}
+
+extern "C" int goma_gpu_vector_norms(goma_gpu_ctx *c, int which, double out[4]) {
+  if (!c || !out) return fail(-2, "null argument");
+  if (which < 0 || which > 2) return fail(-2, "which must be 0 (resid), 1 (x) or 2 (xdot)");
+  CU(cudaSetDevice(c->device));
+  const double *v = which == 0 ? c->d_resid : (which == 1 ? c->d_x : c->d_xdot);
+  if (!c->d_partials) CU(cudaMalloc((void **)&c->d_partials, 4 * NORM_BLOCKS * sizeof(double)));
+  vector_norms_kernel<<<NORM_BLOCKS, NORM_THREADS, 0, c->stream>>>(v, c->num_owned_unknowns, c->d_partials);
+  CU(cudaGetLastError());
+  std::vector<double> h(4 * NORM_BLOCKS);
+  CU(cudaMemcpyAsync(h.data(), c->d_partials, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  double mx = -1.0, l1 = 0.0, l2 = 0.0, idx = -1.0;
+  for (int b = 0; b < NORM_BLOCKS; b++) {  // fixed order: reproducible run to run
+    l1 += h[4 * b + 1];
+    l2 += h[4 * b + 2];
+    if (h[4 * b] > mx || (h[4 * b] == mx && h[4 * b + 3] >= 0.0 && (idx < 0.0 || h[4 * b + 3] < idx))) { mx = h[4 * b]; idx = h[4 * b + 3]; }
+  }
+  out[0] = mx; out[1] = l1; out[2] = l2; out[3] = idx;
+  return 0;
+}
+
+// ------------------------------------------------------------------ CSR hand-off to a GPU solver
+struct CsrKinds {
+  int num_unknowns[GOMA_GPU_MAX_KINDS];  // unknowns of a node of each kind
+  int num_pressure[GOMA_GPU_MAX_KINDS];  // ... of which pressure (last in the node)
+  int tslot[GOMA_GPU_MAX_KINDS];         // offset of T inside the node (-1: none): energy rows carry no P columns
+};
+
+// one thread per owned node: the rows of its unknowns share the node-node list (exo_conn.c build_node_node);
+// columns = the unknowns of the neighbour nodes in increasing node id (find_MSR_problem_graph), diagonal included
+__global__ void csr_structure_kernel(int num_owned_nodes, const long long *__restrict__ nn_ptr,
+                                     const int *__restrict__ nn_list, const int *__restrict__ first_unknown,
+                                     const unsigned char *__restrict__ node_kind, const __grid_constant__ CsrKinds K,
+                                     const long long *__restrict__ rowstart, long long msr0,
+                                     long long *__restrict__ rowptr, int *__restrict__ colind, int *__restrict__ dpos,
+                                     int num_rows) {
+  const int nd = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nd >= num_owned_nodes) return;
+  const int kd = node_kind[nd], fu = first_unknown[nd];
+  for (int s = 0; s < K.num_unknowns[kd]; s++) {
+    const int row = fu + s;
+    const long long base = rowstart[row] - msr0 + row;  // every earlier row adds its diagonal
+    rowptr[row] = base;
+    if (row == num_rows - 1) rowptr[num_rows] = rowstart[row + 1] - msr0 + row + 1;
+    const bool nop = K.tslot[kd] >= 0 && s == K.tslot[kd];
+    long long pos = base;
+    for (long long q = nn_ptr[nd]; q < nn_ptr[nd + 1]; q++) {
+      const int m = nn_list[q], km = node_kind[m], fm = first_unknown[m];
+      const int ncol = K.num_unknowns[km] - (nop ? K.num_pressure[km] : 0);
+      for (int c = 0; c < ncol; c++) {
+        if (fm + c == row) dpos[row] = (int)(pos - base);
+        colind[pos++] = fm + c;
+      }
+    }
+  }
+}
+
+// one warp per row: MSR row (diagonal apart) -> CSR row (diagonal at dpos)
+__global__ void csr_values_kernel(int num_rows, const long long *__restrict__ rowstart, const long long *__restrict__ rowptr,
+                                  const int *__restrict__ dpos, const double *__restrict__ a, double *__restrict__ v) {
+  const int lane = threadIdx.x & 31;
+  const int nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < num_rows; row += nwarp) {
+    const long long k0 = rowstart[row], c0 = rowptr[row];
+    const int len = (int)(rowptr[row + 1] - c0), d = dpos[row];
+    for (int t = lane; t < len; t += 32) v[c0 + t] = t < d ? a[k0 + t] : (t == d ? a[row] : a[k0 + t - 1]);
+  }
+}
+
+extern "C" int goma_gpu_csr_structure(goma_gpu_ctx *c, const goma_gpu_problem *p, goma_gpu_csr *out) {
+  if (!c || !p || !out) return fail(-2, "null argument");
+  CU(cudaSetDevice(c->device));
+  const int nrows = c->num_owned_unknowns;
+  if (!c->d_csr_rowptr) {
+    if (c->pat.nn_ptr.empty()) return fail(-2, "node-node lists are not available");
+    const long long msr0 = c->pat.rowstart[0];
+    c->csr_nnz = nrows > 0 ? (long long)(c->pat.rowstart[nrows] - msr0) + nrows : 0;
+    CsrKinds K;
+    memset(&K, 0, sizeof(K));
+    for (int k = 0; k < GOMA_GPU_MAX_KINDS; k++) {
+      K.tslot[k] = -1;
+      if (k >= p->num_kinds) continue;
+      K.num_unknowns[k] = p->kind_num_unknowns[k];
+      K.num_pressure[k] = kind_num_pressure(*p, k);
+      K.tslot[k] = p->energy ? p->kind_slot[k][GOMA_SLOT_T] : -1;
+    }
+    long long *d_nn_ptr = nullptr;
+    int *d_nn_list = nullptr;
+    CU(cudaMalloc((void **)&d_nn_ptr, c->pat.nn_ptr.size() * sizeof(long long)));
+    CU(cudaMalloc((void **)&d_nn_list, std::max<size_t>(c->pat.nn_list.size(), 1) * sizeof(int)));
+    CU(cudaMemcpy(d_nn_ptr, c->pat.nn_ptr.data(), c->pat.nn_ptr.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_nn_list, c->pat.nn_list.data(), c->pat.nn_list.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMalloc((void **)&c->d_csr_rowptr, ((size_t)nrows + 1) * sizeof(long long)));
+    CU(cudaMalloc((void **)&c->d_csr_colind, std::max<size_t>((size_t)c->csr_nnz, 1) * sizeof(int)));
+    CU(cudaMalloc((void **)&c->d_csr_dpos, std::max<size_t>((size_t)nrows, 1) * sizeof(int)));
+    CU(cudaMalloc((void **)&c->d_csr_values, std::max<size_t>((size_t)c->csr_nnz, 1) * sizeof(double)));
+    c->device_bytes += (size_t)c->csr_nnz * 12 + (size_t)nrows * 12;
+    CU(cudaMemset(c->d_csr_rowptr, 0, ((size_t)nrows + 1) * sizeof(long long)));
+    const int nown = c->prob.num_owned_nodes;
+    if (nown > 0 && nrows > 0) {
+      csr_structure_kernel<<<(nown + 127) / 128, 128, 0, c->stream>>>(nown, d_nn_ptr, d_nn_list, c->d_first, c->d_kind, K,
+                                                                      c->d_rowstart, msr0, c->d_csr_rowptr,
+                                                                      c->d_csr_colind, c->d_csr_dpos, nrows);
+      CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_nn_ptr);
+    cudaFree(d_nn_list);
+  }
+  out->num_rows = nrows;
+  out->nnz = c->csr_nnz;
+  out->d_rowptr = c->d_csr_rowptr;
+  out->d_colind = c->d_csr_colind;
+  out->d_values = c->d_csr_values;
+  return 0;
+}
+
+extern "C" int goma_gpu_csr_values(goma_gpu_ctx *c) {
+  if (!c) return fail(-2, "null context");
+  if (!c->d_csr_rowptr) return fail(-2, "call goma_gpu_csr_structure first");
+  CU(cudaSetDevice(c->device));
+  const int nrows = c->num_owned_unknowns;
+  if (nrows > 0) {
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    const int blocks = std::max(1, std::min(sms * 8, (nrows + 7) / 8));
+    csr_values_kernel<<<blocks, 256, 0, c->stream>>>(nrows, c->d_rowstart, c->d_csr_rowptr, c->d_csr_dpos, c->d_a, c->d_csr_values);
+    CU(cudaGetLastError());
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
