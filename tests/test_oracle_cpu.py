@@ -179,3 +179,16 @@ def test_post_fill_oracle_matches_reference_fixture():
     np.testing.assert_array_equal(a[: len(q["a"]) - 1], q["a"][:-1])
     loo, l1, l2, k = post_fill.norms(b, n)
     assert (loo, l1, l2, float(k)) == tuple(q["norms"])
+
+
+def test_header_is_valid_c_and_cxx(tmp_path):
+    """include/goma_gpu_fill.h compiles as C99 and as C++17 (extern "C" guards) on its own."""
+    import subprocess
+
+    hdr = os.path.join(ROOT, "include", "goma_gpu_fill.h")
+    c = tmp_path / "t.c"
+    c.write_text('#include "%s"\nint main(void) { struct goma_gpu_problem p; (void)p; return 0; }\n' % hdr)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", str(c)])
+    cxx = tmp_path / "t.cpp"
+    cxx.write_text('#include "%s"\nint main() { goma_gpu_csr a{}; const char *(*f)(void) = goma_gpu_last_error; (void)a; (void)f; return 0; }\n' % hdr)
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", str(cxx)])
