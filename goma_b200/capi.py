@@ -25,7 +25,7 @@ EXPORTED = [
     "goma_gpu_pack_dofs", "goma_gpu_unpack_dofs", "goma_gpu_fill_last_stats", "goma_gpu_fill_set_option",
     "goma_gpu_last_error", "goma_gpu_pattern_msr", "goma_gpu_exchange_export", "goma_gpu_exchange_setup",
     "goma_gpu_exchange_dof", "goma_gpu_row_sum_scale", "goma_gpu_scale_buffer", "goma_gpu_vector_norms", "goma_gpu_csr_structure",
-    "goma_gpu_csr_values",
+    "goma_gpu_csr_values", "goma_gpu_exchange_status", "goma_gpu_fill_device_async", "goma_gpu_fill_wait",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -49,6 +49,7 @@ class GomaGpuProblem(C.Structure):
         ("diffusivity", C.c_double * 4), ("momentum_source", C.c_double * 3), ("momentum_source_model", C.c_int),
         ("heat_source", C.c_double), ("lame_mu", C.c_double), ("lame_lambda", C.c_double),
         ("dbc_flag", _bp), ("dbc_value", _dp),
+        ("num_elem_blocks", C.c_int), ("num_materials", C.c_int),
     ]
 
 
@@ -97,10 +98,14 @@ def load_library():
     lib.goma_gpu_fill_device_buffers.argtypes = [C.c_void_p, C.POINTER(DeviceBuffers)]
     lib.goma_gpu_fill_device.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                          C.c_int, C.c_int, _ip]
+    lib.goma_gpu_fill_device_async.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                               C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.goma_gpu_fill_wait.argtypes = [C.c_void_p, _ip]
     lib.goma_gpu_global_h_U.argtypes = [C.c_void_p, _bp, _dp]
     lib.goma_gpu_exchange_export.argtypes = [C.c_void_p, C.POINTER(ExchangeHandles)]
     lib.goma_gpu_exchange_setup.argtypes = [C.c_void_p, C.c_int, C.POINTER(ExchangeHandles), _ip, _ip, _ip, C.c_int]
     lib.goma_gpu_exchange_dof.argtypes = [C.c_void_p, C.c_int]
+    lib.goma_gpu_exchange_status.argtypes = [C.c_void_p]
     lib.goma_gpu_row_sum_scale.argtypes = [C.c_void_p, _dp, _ip]
     lib.goma_gpu_scale_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _ip]
     lib.goma_gpu_vector_norms.argtypes = [C.c_void_p, C.c_int, _dp]
@@ -194,6 +199,8 @@ def make_problem_struct(problem, ija=None, num_owned_nodes=None):
     p.lame_mu, p.lame_lambda = problem.lame_mu, problem.lame_lambda
     p.dbc_flag = _ptr(keep["dbc_flag"], _bp)
     p.dbc_value = _ptr(keep["dbc_value"], _dp)
+    p.num_elem_blocks = int(getattr(m, "num_elem_blocks", 1))
+    p.num_materials = int(getattr(problem, "num_materials", 1))
     return p, keep
 
 

@@ -55,6 +55,7 @@ struct goma_gpu_ctx {
   std::vector<int> recv_ptr;
   int tail_begin = 0;
   unsigned long long epoch[3] = {0, 0, 0};
+  long long exchange_spin_limit = 40000000000LL;  // ~20 s of SM clock: bounded wait in exchange_dof_kernel
   double *d_sums = nullptr;  // goma_gpu_global_h_U
   unsigned char *d_elem_owned = nullptr;
   long long *d_csr_rowptr = nullptr;  // CSR hand-off
@@ -69,6 +70,10 @@ struct goma_gpu_ctx {
   int num_sms = 0, blocks_per_sm = 0;  // cached launch geometry (cudaGetDeviceProperties is slow)
   int scatter_mode = 2;            // 0 fp64 atomics, 1 coloured load+add+store, 2 coloured first-touch stores
   int grid_limit = 0;
+  bool rezero = false;       // zero the whole storage before the next first-touch fill
+  bool accumulate = false;   // goma_gpu_fill adds into the caller's a / resid_vector
+  bool preloaded = false;    // (internal) d_a / d_resid hold uploaded host values for this fill
+  bool fill_pending = false; // goma_gpu_fill_device_async launched, goma_gpu_fill_wait not yet called
   double last_ms = 0.0;
   int last_launches = 0;
   size_t device_bytes = 0;

@@ -16,6 +16,8 @@ struct ExchangeArgs {
   int recv_ptr[GOMA_GPU_MAX_NEIGHBORS + 1];
   const int *recv_list;
   double *tail;
+  unsigned long long *error;    // set when a neighbour never publishes this epoch (mismatched collective)
+  long long spin_limit;         // clock64 ticks a thread waits before it gives up
 };
 
 __global__ void exchange_dof_kernel(const __grid_constant__ ExchangeArgs A) {
@@ -32,10 +34,18 @@ __global__ void exchange_dof_kernel(const __grid_constant__ ExchangeArgs A) {
     if (k < total) {
       while (k >= A.recv_ptr[nb + 1]) nb++;
       unsigned long long seen;
+      const long long t0 = clock64();
+      bool ok = true;
       do {  // the neighbour's vector of this epoch is complete
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(A.my_ready + nb) : "memory");
-      } while (seen < A.epoch);
-      A.tail[k] = A.peer_vec[nb][A.recv_list[k]];
+        if (seen >= A.epoch) break;
+        if (clock64() - t0 > A.spin_limit) {  // bounded wait: report instead of hanging the device
+          ok = false;
+          *A.error = 1ull + (unsigned long long)nb;
+          break;
+        }
+      } while (true);
+      if (ok) A.tail[k] = A.peer_vec[nb][A.recv_list[k]];
     }
   }
 }
@@ -43,9 +53,9 @@ __global__ void exchange_dof_kernel(const __grid_constant__ ExchangeArgs A) {
 extern "C" int goma_gpu_exchange_export(goma_gpu_ctx *c, goma_gpu_exchange_handles *out) {
   if (!c || !out) return fail(-2, "null argument");
   CU(cudaSetDevice(c->device));
-  if (!c->d_xflags) {
-    CU(cudaMalloc((void **)&c->d_xflags, 3 * GOMA_GPU_MAX_NEIGHBORS * sizeof(unsigned long long)));
-    CU(cudaMemset(c->d_xflags, 0, 3 * GOMA_GPU_MAX_NEIGHBORS * sizeof(unsigned long long)));
+  if (!c->d_xflags) {  // [3][MAX_NEIGHBORS] epochs published by the neighbours + one error word
+    CU(cudaMalloc((void **)&c->d_xflags, (3 * GOMA_GPU_MAX_NEIGHBORS + 1) * sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_xflags, 0, (3 * GOMA_GPU_MAX_NEIGHBORS + 1) * sizeof(unsigned long long)));
     CU(cudaDeviceSynchronize());
   }
   static_assert(sizeof(cudaIpcMemHandle_t) == GOMA_GPU_IPC_HANDLE_BYTES, "IPC handle size");
@@ -70,10 +80,22 @@ extern "C" int goma_gpu_exchange_setup(goma_gpu_ctx *c, int num_neighbors, const
       if (c->peer_vec[v][k]) cudaIpcCloseMemHandle(c->peer_vec[v][k]), c->peer_vec[v][k] = nullptr;
     if (c->peer_flags[k]) cudaIpcCloseMemHandle(c->peer_flags[k]), c->peer_flags[k] = nullptr;
   }
-  c->num_neighbors = num_neighbors;
+  c->num_neighbors = 0;
+  // a (re-)set-up starts a new generation on every rank: epochs and the flag block restart from zero.  The host
+  // must put a barrier between the set-up of all ranks and the first exchange (dp_comm.setup_peer_exchange does),
+  // as it must between the reference's set_dof_communication and the first exchange_dof.
+  for (int v = 0; v < 3; v++) c->epoch[v] = 0;
+  CU(cudaMemset(c->d_xflags, 0, (3 * GOMA_GPU_MAX_NEIGHBORS + 1) * sizeof(unsigned long long)));
+  if (tail_begin < 0 || tail_begin > c->prob.num_unknowns) return fail(-2, "tail_begin outside the vector");
+  if (num_neighbors && recv_ptr[0] != 0) return fail(-2, "recv_ptr[0] must be 0");
+  for (int k = 0; k < num_neighbors; k++)
+    if (recv_ptr[k + 1] < recv_ptr[k]) return fail(-2, "recv_ptr must be non-decreasing");
   c->tail_begin = tail_begin;
   c->recv_ptr.assign(recv_ptr, recv_ptr + num_neighbors + 1);
-  if (tail_begin + c->recv_ptr[num_neighbors] > c->prob.num_unknowns) return fail(-2, "external tail exceeds the vector");
+  if (num_neighbors == 0) c->recv_ptr.assign(1, 0);
+  if ((long long)tail_begin + c->recv_ptr[num_neighbors] > c->prob.num_unknowns) return fail(-2, "external tail exceeds the vector");
+  for (int k = 0; k < c->recv_ptr[num_neighbors]; k++)
+    if (recv_list[k] < 0) return fail(-2, "negative dof index in recv_list");
   for (int k = 0; k < num_neighbors; k++) {
     if (my_slot_at_neighbor[k] < 0 || my_slot_at_neighbor[k] >= GOMA_GPU_MAX_NEIGHBORS) return fail(-2, "bad neighbour slot");
     c->my_slot_at[k] = my_slot_at_neighbor[k];
@@ -88,6 +110,7 @@ extern "C" int goma_gpu_exchange_setup(goma_gpu_ctx *c, int num_neighbors, const
   const int total = c->recv_ptr[num_neighbors];
   CU(cudaMalloc((void **)&c->d_recv_list, std::max(1, total) * sizeof(int)));
   if (total) CU(cudaMemcpy(c->d_recv_list, recv_list, (size_t)total * sizeof(int), cudaMemcpyHostToDevice));
+  c->num_neighbors = num_neighbors;
   return 0;
 }
 
@@ -110,6 +133,8 @@ extern "C" int goma_gpu_exchange_dof(goma_gpu_ctx *c, int which) {
   A.my_ready = c->d_xflags + which * GOMA_GPU_MAX_NEIGHBORS;
   A.recv_list = c->d_recv_list;
   A.tail = vecs[which] + c->tail_begin;
+  A.error = c->d_xflags + 3 * GOMA_GPU_MAX_NEIGHBORS;
+  A.spin_limit = c->exchange_spin_limit;
   const int total = c->recv_ptr[A.nn];
   const int threads = 256, blocks = std::max(1, std::min(148, (total + threads - 1) / threads));
   exchange_dof_kernel<<<blocks, threads, 0, c->stream>>>(A);
@@ -128,9 +153,21 @@ __global__ void unpack_dofs_kernel(double *__restrict__ v, const int *__restrict
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[list[i]] = buf[i];
 }
+extern "C" int goma_gpu_exchange_status(goma_gpu_ctx *c) {
+  if (!c) return fail(-2, "null context");
+  if (!c->d_xflags) return 0;
+  CU(cudaSetDevice(c->device));
+  unsigned long long e = 0;
+  CU(cudaMemcpyAsync(&e, c->d_xflags + 3 * GOMA_GPU_MAX_NEIGHBORS, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (e) return fail(-4, "exchange_dof: neighbour slot " + std::to_string(e - 1) + " never published its vector (timed out)");
+  return 0;
+}
+
 extern "C" int goma_gpu_pack_dofs(goma_gpu_ctx *c, const double *d_vec, const int *d_list, int n, double *d_buf) {
   if (!c) return fail(-2, "null context");
   if (n <= 0) return 0;
+  CU(cudaSetDevice(c->device));
   pack_dofs_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_vec, d_list, n, d_buf);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
@@ -139,6 +176,7 @@ extern "C" int goma_gpu_pack_dofs(goma_gpu_ctx *c, const double *d_vec, const in
 extern "C" int goma_gpu_unpack_dofs(goma_gpu_ctx *c, double *d_vec, const int *d_list, int n, const double *d_buf) {
   if (!c) return fail(-2, "null context");
   if (n <= 0) return 0;
+  CU(cudaSetDevice(c->device));
   unpack_dofs_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_vec, d_list, n, d_buf);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));

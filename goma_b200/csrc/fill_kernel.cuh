@@ -96,9 +96,13 @@ struct Cfg {
   static_assert(NN % TI == 0, "row tile must divide the node count");
   static_assert(TPE % 32 == 0, "whole warps");
   static constexpr int NWARP = TPE / 32;
-  static constexpr int TBL = NGP + NGP * NN + NGP * NN * DIM + NGP * (DIM + 1);
-  static constexpr int TBL_PAD = (TBL + 1) & ~1;  // 16-byte multiple for the bulk copy
-  static constexpr int T_WT = 0, T_PHI = NGP, T_DPHI = T_PHI + NGP * NN, T_PSI = T_DPHI + NGP * NN * DIM;
+  // constant tables in global memory: weights, dphi/dxi, P1 basis, phi.  The tensor-core configurations keep phi in
+  // their operand table (filled once per CTA), so only the part before T_PHI is staged into s.tbl
+  static constexpr int T_WT = 0, T_DPHI = NGP, T_PSI = T_DPHI + NGP * NN * DIM, T_PHI = T_PSI + NGP * (DIM + 1);
+  static constexpr int TBL = T_PHI + NGP * NN;
+  static constexpr bool PHI_IN_OPERANDS = NN == 27 && NGP == 27 && P1_ && NSPEC_ == 0 && !ALE_ && !WS_;  // == MMA below
+  static constexpr int TBL_PAD = ((PHI_IN_OPERANDS ? T_PHI : TBL) + 1) & ~1;  // staged doubles, 16-byte multiple for the bulk copy
+  static constexpr int TBL_GLOBAL = TBL + 2;
   // per-Gauss-point derived data (doubles): see phase 4b
   static constexpr int G_GV = 0;                                   // c_adv d_b v_a            [a][b]
   static constexpr int G_GT = G_GV + DIM * DIM;                    // ce_adv d_b T             [b]
@@ -123,6 +127,11 @@ struct Cfg {
   static constexpr int NROWS = NF * NN + NP;  // rows of the element block
   static constexpr int NPART = NGP >= 3 ? 3 : 1;  // Gauss-point thirds of the row sums
   static constexpr bool GENERAL = !P1 || NSPEC > 0 || ALE;  // generic block accumulation instead of the NS(+T) fast path
+  // hex27 Q2/P1 NS(+T): the node-pair blocks run on the FP64 tensor cores (mma.sync m8n8k4.f64, SASS DMMA): 8 x 8
+  // node blocks, K = Gauss points (27 -> 28); operand tables component-major with bank-conflict-free strides
+  static constexpr bool MMA = NN == 27 && NGP == 27 && P1 && !GENERAL && !WS_;
+  static_assert(MMA == PHI_IN_OPERANDS, "table staging and operand layout must agree");
+  static constexpr int NGK = MMA ? 28 : NGP;  // rows of the per-Gauss-point tables (row 27 = the zero K padding)
   __host__ __device__ static constexpr int slot(int f) {
     return f < DIM                       ? GOMA_SLOT_U + f
            : (ENERGY && f == F_T)        ? GOMA_SLOT_T
@@ -132,7 +141,7 @@ struct Cfg {
   }
 };
 
-template <class C>
+template <class C, bool MMA = C::MMA>
 struct Operands {
   // test-function side, component-major: SI[gp][0][i] = w phi_i, SI[gp][1+p][i] = w grad_phi_i[p].  A warp of the
   // Gauss loop spans at most two row tiles: each of these 8-byte loads is one shared-memory wavefront (a broadcast
@@ -144,6 +153,24 @@ struct Operands {
   double2 SJb[C::NGP][C::NN];  // (g_j[1], g_j[2])
   double VG[C::NGP][C::NN];    // v . grad_phi_j
 };
+// Tensor-core layout: SI[gp][c * 28 + i] (c = 0: w phi_i, 1..3: w grad_phi_i[p]) and SJ[gp][c * 28 + j] (c = 0: phi_j,
+// 1..3: grad_phi_j[p], 4: v . grad_phi_j).  A fragment of mma.m8n8k4 is (8 consecutive nodes) x (4 consecutive Gauss
+// points): with a Gauss-point stride of 4 (mod 8) doubles the 16 lanes of a half-warp hit 16 different bank pairs.
+// Column 27 of every component and row 27 (the K padding) stay zero from the kernel prologue on.
+template <class C>
+struct Operands<C, true> {
+  static constexpr int NNP = 28, SI_S = 4 * NNP + 4, SJ_S = 5 * NNP;
+  static_assert(SI_S % 8 == 4 && SJ_S % 8 == 4, "conflict-free fragment loads");
+  double SI[C::NGK][SI_S];
+  double SJ[C::NGK][SJ_S];
+};
+template <class C>
+__device__ __forceinline__ double op_si(const Operands<C> &op, int gp, int c, int i) {
+  if constexpr (C::MMA)
+    return op.SI[gp][c * 28 + i];
+  else
+    return op.SI[gp][c][i];
+}
 
 // Everything about one element that does not depend on the state vector, gathered once at init
 // (what load_ei / load_elem_dofptr, mm_fill_ptrs.c:170,1136, recompute per element and per Newton
@@ -171,7 +198,7 @@ struct alignas(16) Smem {
   double tbl[C::TBL_PAD];
   ElemRec<C> rec[C::NRECB];  // ring: the record of the next element lands while this one is assembled
   Operands<C> op[C::NOPB];
-  double GP[C::NOPB][C::NGP][C::GPD];   // per-Gauss-point derived quantities
+  double GP[C::NOPB][C::NGK][C::GPD];   // per-Gauss-point derived quantities
   double F[C::NGP][C::NF][C::DIM + 2];  // value, grad[DIM], time derivative
   double X[C::ALE ? C::DIM : 1][C::ALE ? C::NN : 1];  // ALE: displaced coordinates x = X + d
   double U[C::NRECB][C::NF][C::NN];     // nodal unknowns, buffered like rec (cp.async gather)
@@ -407,7 +434,8 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
   (void)stamps;
   constexpr int DIM = C::DIM, NN = C::NN, NGP = C::NGP, NF = C::NF, NP = C::NP, NT = C::TPE;
   const double *t_wt = s.tbl + C::T_WT;
-  const double *t_phi = s.tbl + C::T_PHI;    // [gp][NN]
+  const double *t_phi = s.tbl + (C::MMA ? 0 : C::T_PHI);  // [gp][NN] (tensor-core configurations: in op.SJ)
+  (void)t_phi;
   const double *t_dphi = s.tbl + C::T_DPHI;  // [gp][NN][DIM]
   const double *t_psi = s.tbl + C::T_PSI;    // [gp][DIM+1]
   const double rcp = P.rho * P.Cp;
@@ -538,19 +566,33 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
     int gp = idx / NN, i = idx - gp * NN;
     const double *B = s.B[gp];
     const double *dp = &t_dphi[(gp * NN + i) * DIM];
-    const double w = s.w[gp], ph = t_phi[gp * NN + i];
+    double ph;
+    if constexpr (C::MMA)
+      ph = op.SJ[gp][i];  // written once in the kernel prologue
+    else
+      ph = t_phi[gp * NN + i];
+    const double w = s.w[gp];
     double g[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int p = 0; p < DIM; p++) {
 #pragma unroll
       for (int q = 0; q < DIM; q++) g[p] += B[p * DIM + q] * dp[q];
     }
-    op.SJa[gp][i] = make_double2(ph, g[0]);
-    op.SJb[gp][i] = make_double2(g[1], g[2]);
-    op.SI[gp][0][i] = w * ph;
-    op.SI[gp][1][i] = w * g[0];
-    op.SI[gp][2][i] = w * g[1];
-    op.SI[gp][3][i] = w * g[2];
+    if constexpr (C::MMA) {
+      op.SI[gp][i] = w * ph;
+#pragma unroll
+      for (int p = 0; p < DIM; p++) {
+        op.SJ[gp][(1 + p) * 28 + i] = g[p];
+        op.SI[gp][(1 + p) * 28 + i] = w * g[p];
+      }
+    } else {
+      op.SJa[gp][i] = make_double2(ph, g[0]);
+      op.SJb[gp][i] = make_double2(g[1], g[2]);
+      op.SI[gp][0][i] = w * ph;
+      op.SI[gp][1][i] = w * g[0];
+      op.SI[gp][2][i] = w * g[1];
+      op.SI[gp][3][i] = w * g[2];
+    }
   }
   cta_sync<C>();
   GOMA_STAMP(3);
@@ -575,7 +617,14 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
       if (live) {
 #pragma unroll 2
         for (int kk = k0; kk < k1; kk++) {
-          const double2 a = op.SJa[gp][kk], b = op.SJb[gp][kk];
+          double2 a, b;
+          if constexpr (C::MMA) {
+            a = make_double2(op.SJ[gp][kk], op.SJ[gp][28 + kk]);
+            b = make_double2(op.SJ[gp][56 + kk], op.SJ[gp][84 + kk]);
+          } else {
+            a = op.SJa[gp][kk];
+            b = op.SJb[gp][kk];
+          }
 #pragma unroll
           for (int f = 0; f < NF; f++) {
             const double u = U[f][kk];
@@ -755,13 +804,22 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
   }
   for (int idx = tid; idx < NGP * NN; idx += NT) {
     int gp = idx / NN, j = idx - gp * NN;
-    const double2 ja = op.SJa[gp][j], jb = op.SJb[gp][j];
-    const double gj[3] = {ja.y, jb.x, jb.y};
+    double gj[3];
+    if constexpr (C::MMA) {
+#pragma unroll
+      for (int p = 0; p < 3; p++) gj[p] = op.SJ[gp][(1 + p) * 28 + j];
+    } else {
+      const double2 ja = op.SJa[gp][j], jb = op.SJb[gp][j];
+      gj[0] = ja.y, gj[1] = jb.x, gj[2] = jb.y;
+    }
     double acc = 0.0;
 #pragma unroll
     for (int p = 0; p < DIM; p++)
       acc += (s.F[gp][C::F_V + p][0] - (C::ALE ? s.F[gp][C::F_D + p][1 + DIM] : 0.0)) * gj[p];
-    op.VG[gp][j] = acc;
+    if constexpr (C::MMA)
+      op.SJ[gp][4 * 28 + j] = acc;
+    else
+      op.VG[gp][j] = acc;
   }
   cta_sync<C>();
   GOMA_STAMP(5);
@@ -793,8 +851,8 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
       for (int p = 0; p < NP; p++) S[a][p] = 0.0;
     }
     for (int gp = gp0; gp < gp1; gp++) {
-      const double2 s01 = make_double2(op.SI[gp][0][i], op.SI[gp][1][i]);
-      const double2 s23 = make_double2(op.SI[gp][2][i], op.SI[gp][3][i]);
+      const double2 s01 = make_double2(op_si<C>(op, gp, 0, i), op_si<C>(op, gp, 1, i));
+      const double2 s23 = make_double2(op_si<C>(op, gp, 2, i), op_si<C>(op, gp, 3, i));
       const double sg[3] = {s01.y, s23.x, s23.y};
       const double *G = s.GP[bo][gp];
       double ps[NP > 0 ? NP : 1];
@@ -837,8 +895,8 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
       const int q0 = isT ? C::G_RE : isY ? C::G_RY + (f - C::F_Y) : isP ? C::G_DIV : C::G_ZERO;
       const int q1 = isT ? C::G_RF : isY ? C::G_RFY + (f - C::F_Y) * DIM : isP ? C::G_PS : C::G_RD + (f - C::F_D) * DIM;
       for (int gp = gp0; gp < gp1; gp++) {
-        const double2 s01 = make_double2(op.SI[gp][0][i], op.SI[gp][1][i]);
-        const double2 s23 = make_double2(op.SI[gp][2][i], op.SI[gp][3][i]);
+        const double2 s01 = make_double2(op_si<C>(op, gp, 0, i), op_si<C>(op, gp, 1, i));
+        const double2 s23 = make_double2(op_si<C>(op, gp, 2, i), op_si<C>(op, gp, 3, i));
         const double sg[3] = {s01.y, s23.x, s23.y};
         const double *G = s.GP[bo][gp];
         double t = s01.x * G[q0];
@@ -1254,6 +1312,156 @@ __device__ __forceinline__ void write_tile_direct(const FillParams &P, const Ele
   }
 }
 
+
+// the same for ONE node pair (i, j): V[fr][fc] of the tensor-core path
+template <class C, int MODE>
+__device__ __forceinline__ void write_pair(const FillParams &P, const ElemRec<C> &s, int i, int j, const double (&V)[C::NF][C::NF]) {
+  constexpr int NF = C::NF;
+  const int rj = s.rank[j], ri = s.rank[i];
+  bool packed = true;
+#pragma unroll
+  for (int f = 1; f < NF; f++) packed = packed && (s.cs[j][f] == s.cs[j][0] + f);
+  const bool first = (s.first[i] >> j) & 1u;
+#pragma unroll
+  for (int fr = 0; fr < NF; fr++) {
+    const long long rstart = s.rs[fr][i];
+    if (rstart < 0) continue;
+    const bool rowT = C::ENERGY && fr == C::F_T;
+    const int row = s.gun[fr][i];
+    double *arow = P.a + rstart;
+    if (MODE == 2 && NF == 3 && !C::ENERGY && first && packed && rj != ri) {
+      double *dst = arow + s.po[i][j] + s.cs[j][0] - (rj > ri ? 1 : 0);
+      if ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
+        *reinterpret_cast<double2 *>(dst) = make_double2(V[fr][0], V[fr][1]);
+        dst[2] = V[fr][2];
+      } else {
+        dst[0] = V[fr][0];
+        *reinterpret_cast<double2 *>(dst + 1) = make_double2(V[fr][1], V[fr][2]);
+      }
+      continue;
+    }
+#pragma unroll
+    for (int fc = 0; fc < NF; fc++) {
+      int off = s.po[i][j] + s.cs[j][fc];
+      if (C::ENERGY && rowT) off -= s.pp[i][j];
+      double *dst;
+      if (rj != ri)
+        dst = arow + off - (rj > ri ? 1 : 0);
+      else
+        dst = (fc == fr) ? P.a + row : arow + off - (fc > fr ? 1 : 0);
+      slot_add_m<MODE>(dst, V[fr][fc], first);
+    }
+  }
+}
+
+// D (8x8) += A (8x4, row) * B (4x8, col) in fp64 on the tensor cores (SASS: DMMA.8x8x4).  Lane l holds
+// A[l/4][l%4], B[l%4][l/4] and D[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d[0]), "+d"(d[1])
+      : "d"(a), "d"(b));
+}
+
+// =====================================================================================
+// phase 6 on the FP64 tensor cores (hex27 Q2/P1 NS and NS+T).  For every component pair (a, b) the node-pair
+// block of J_m_v (mm_fill_momentum.c:1629-1712) is a 27 x 27 x (2 * 27) matrix product over the Gauss points:
+//     V_ab[i][j] = sum_gp  (w phi_i) . (phi_j c_adv d_b v_a  [+ delta_ab q_j])  +  (w grad_phi_i[b]) . (c_diff grad_phi_j[a])
+// with q_j = c_adv v.grad_phi_j + c_mass phi_j.  The delta_ab diffusion term is the trace over the three diagonal
+// products, kept in separate accumulators (KD) so that it costs no extra multiply.  A warp owns 8 x 8 node
+// blocks (27 -> 32 in both directions, K 27 -> 28): 18 DMMA per block and K step (23 with energy: J_m_T, J_e_v,
+// J_e_T from the products S1 = w phi_i . v.grad_phi_j, S3 = w phi_i . phi_j and w phi_i . phi_j ce_adv d_a T).
+// Shared-memory traffic per DMMA is one 8-byte fragment load per ~1 tensor instruction (a lane's fragment feeds
+// 8 FMAs) against one load per 2.9 FMAs of the scalar 3 x 1 register tile this replaces.
+// =====================================================================================
+template <class C, int MODE>
+__device__ __forceinline__ void gauss_blocks_mma(const FillParams &P, const Smem<C> &s, const ElemRec<C> &rec, int warp, int lane,
+                                                 long long *t_mma = nullptr) {
+  static_assert(C::MMA && C::DIM == 3, "tensor-core path: hex27 Q2/P1");
+  constexpr int NF = C::NF;
+  const Operands<C> &op = s.op[0];
+  const double tfac = P.transient ? (1.0 + 2.0 * P.theta) / P.delta_t : 0.0;
+  const double rcp = P.rho * P.Cp;
+  const double c_adv = -P.etm_mom[1] * P.rho, c_diff = -P.etm_mom[3] * P.mu, c_mass = -P.etm_mom[0] * P.rho * tfac;
+  const double ce_adv = -P.etm_energy[1] * rcp, ce_diff = -P.etm_energy[3] * P.k, ce_mass = -P.etm_energy[0] * rcp * tfac;
+  const int r = lane >> 2, kq = lane & 3;
+  const int nks = (P.debug & 2) ? 1 : 7;
+#pragma unroll 1
+  for (int blk = warp; blk < 16; blk += C::NWARP) {
+    const int I0 = (blk >> 2) * 8, J0 = (blk & 3) * 8;
+    const int ia = min(I0 + r, 27), jb = min(J0 + r, 27);  // rows / columns >= 27 read the zero padding
+#ifdef GOMA_PROFILE_PHASES
+    const long long t_blk0 = clock64();
+#endif
+    double T[3][3][2], KD[3][2], S1[2] = {0.0, 0.0}, S3[2] = {0.0, 0.0}, ET[3][2];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      KD[a][0] = KD[a][1] = 0.0;
+      ET[a][0] = ET[a][1] = 0.0;
+#pragma unroll
+      for (int b = 0; b < 3; b++) T[a][b][0] = T[a][b][1] = 0.0;
+    }
+#pragma unroll 1
+    for (int ks = 0; ks < nks; ks++) {
+      const int gp = 4 * ks + kq;
+      const double *si = &op.SI[gp][ia], *sj = &op.SJ[gp][jb];
+      const double *G = s.GP[0][gp];
+      const double aphi = si[0];
+      const double ag[3] = {si[28], si[56], si[84]};
+      const double bphi = sj[0];
+      const double bg[3] = {sj[28], sj[56], sj[84]};
+      const double bvg = sj[112];
+      const double bq = C::ENERGY ? 0.0 : c_adv * bvg + c_mass * bphi;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const double bgs = c_diff * bg[a];
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+          const double gv = G[C::G_GV + a * 3 + b];
+          const double bt = (a == b && !C::ENERGY) ? fma(bphi, gv, bq) : bphi * gv;
+          dmma884(T[a][b], aphi, bt);
+          if (a != b) dmma884(T[a][b], ag[b], bgs);
+        }
+        dmma884(KD[a], ag[a], bg[a]);
+        if (C::ENERGY) dmma884(ET[a], aphi, bphi * G[C::G_GT + a]);  // J_e_v (mm_fill_energy.c:640)
+      }
+      if (C::ENERGY) {
+        dmma884(S1, aphi, bvg);
+        dmma884(S3, aphi, bphi);
+      }
+    }
+#ifdef GOMA_PROFILE_PHASES
+    if (t_mma) *t_mma += clock64() - t_blk0;
+#endif
+    if (P.debug & 1) continue;
+    const int i = I0 + r;
+    if (i >= 27) continue;
+    double dfdT[3] = {0.0, 0.0, 0.0};
+    if (C::ENERGY && P.source_model != 0 && P.etm_mom[4] != 0.0) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) dfdT[a] = -P.g[a] * P.rho * P.beta * P.etm_mom[4];
+    }
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const int j = J0 + 2 * kq + c;
+      if (j >= 27) continue;
+      const double S2 = (KD[0][c] + KD[1][c]) + KD[2][c];  // sum_gp w grad_phi_i . grad_phi_j
+      const double dm = C::ENERGY ? c_adv * S1[c] + c_diff * S2 + c_mass * S3[c] : c_diff * S2;
+      double V[NF][NF];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int b = 0; b < 3; b++) V[a][b] = (a == b) ? T[a][a][c] + (c_diff * KD[a][c] + dm) : T[a][b][c];
+        if constexpr (C::ENERGY) {
+          V[a][C::F_T] = dfdT[a] * S3[c];  // J_m_T (mm_std_models.c:337)
+          V[C::F_T][a] = ET[a][c];
+        }
+      }
+      if constexpr (C::ENERGY) V[C::F_T][C::F_T] = ce_adv * S1[c] + ce_diff * S2 + ce_mass * S3[c];  // J_e_T
+      write_pair<C, MODE>(P, rec, i, j, V);
+    }
+  }
+}
+
 template <class C>
 __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_constant__ FillParams P) {
   constexpr int NN = C::NN, NF = C::NF, TI = C::TI, NT = C::TPE;
@@ -1273,6 +1481,15 @@ __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_cons
   }
   if (!P.transient)
     for (int idx = tid; idx < 2 * NF * NN; idx += NT) (&s.Udot[0][0][0])[idx] = 0.0;
+  if constexpr (C::MMA) {  // the padding row / column of the tensor-core operand tables is zero for the whole launch
+    for (int idx = tid; idx < (int)(sizeof(s.op) / 8); idx += NT) reinterpret_cast<double *>(&s.op)[idx] = 0.0;
+    for (int idx = tid; idx < (int)(sizeof(s.GP) / 8); idx += NT) (&s.GP[0][0][0])[idx] = 0.0;
+    __syncthreads();
+    for (int idx = tid; idx < C::NGP * NN; idx += NT) {  // phi_j at the Gauss points: the same for every element
+      const int gp = idx / NN, j = idx - gp * NN;
+      s.op[0].SJ[gp][j] = P.tables[C::T_PHI + idx];
+    }
+  }
   __syncthreads();
   if (ee >= P.elem_end) return;
   if (tid == 0) {
@@ -1289,7 +1506,7 @@ __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_cons
   __syncthreads();
 
   long long t_build = 0, t_rows = 0, t_loop = 0;
-  long long stamps_[6] = {0, 0, 0, 0, 0, 0};
+  long long stamps_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long *stamps = (P.prof && tid == 0) ? stamps_ : nullptr;
   int count = 0;
 #pragma unroll 1
@@ -1315,21 +1532,31 @@ __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_cons
     }
     if (P.assemble_jacobian) {
       const ElemRec<C> &rec = s.rec[buf];
-#pragma unroll 1
-      for (int t = tid; t < C::NTILE; t += NT) {
-        Tile<C> tile;
-        const int it = t / NN, j = t - it * NN, i = it * TI;
-        if (C::GENERAL)
-          gauss_loop_general<C>(P, s, i, j, tile);
-        else
-          gauss_loop<C>(P, s, i, j, tile);
-        if (P.debug & 1) continue;
+      if constexpr (C::MMA) {
+        long long *tm = stamps ? &stamps_[6] : nullptr;  // profiling build: cycles of the DMMA part (warp 0)
         if (P.scatter_mode == 2)
-          write_tile_direct<C, 2>(P, rec, i, j, tile);
+          gauss_blocks_mma<C, 2>(P, s, rec, tid >> 5, tid & 31, tm);
         else if (P.scatter_mode == 0)
-          write_tile_direct<C, 0>(P, rec, i, j, tile);
+          gauss_blocks_mma<C, 0>(P, s, rec, tid >> 5, tid & 31, tm);
         else
-          write_tile_direct<C, 1>(P, rec, i, j, tile);
+          gauss_blocks_mma<C, 1>(P, s, rec, tid >> 5, tid & 31, tm);
+      } else {
+#pragma unroll 1
+        for (int t = tid; t < C::NTILE; t += NT) {
+          Tile<C> tile;
+          const int it = t / NN, j = t - it * NN, i = it * TI;
+          if (C::GENERAL)
+            gauss_loop_general<C>(P, s, i, j, tile);
+          else
+            gauss_loop<C>(P, s, i, j, tile);
+          if (P.debug & 1) continue;
+          if (P.scatter_mode == 2)
+            write_tile_direct<C, 2>(P, rec, i, j, tile);
+          else if (P.scatter_mode == 0)
+            write_tile_direct<C, 0>(P, rec, i, j, tile);
+          else
+            write_tile_direct<C, 1>(P, rec, i, j, tile);
+        }
       }
     }
     cp_async_wait_all();
@@ -1342,7 +1569,7 @@ __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_cons
     long long *o = P.prof + blockIdx.x * 8;
     o[0] = t_build; o[1] = t_rows; o[2] = t_loop; o[3] = 0; o[6] = count;
     long long *o2 = P.prof + (4096 + blockIdx.x) * 8;
-    for (int k = 0; k < 6; k++) o2[k] = stamps_[k];
+    for (int k = 0; k < 7; k++) o2[k] = stamps_[k];
   }
 }
 

@@ -57,9 +57,9 @@ struct KernelEntry {
 template <class C>
 KernelEntry entry() {
   if constexpr (C::WS)
-    return {fill_kernel_ws<C>, build_records_kernel<C>, C::TPE + C::NMUL, sizeof(Smem<C>), C::TBL_PAD, sizeof(ElemRec<C>)};
+    return {fill_kernel_ws<C>, build_records_kernel<C>, C::TPE + C::NMUL, sizeof(Smem<C>), C::TBL_GLOBAL, sizeof(ElemRec<C>)};
   else
-    return {fill_kernel<C>, build_records_kernel<C>, C::TPE, sizeof(Smem<C>), C::TBL_PAD, sizeof(ElemRec<C>)};
+    return {fill_kernel<C>, build_records_kernel<C>, C::TPE, sizeof(Smem<C>), C::TBL_GLOBAL, sizeof(ElemRec<C>)};
 }
 
 // the instantiated physics/element combinations
@@ -148,6 +148,66 @@ static int validate(const goma_gpu_problem &p) {
   if (p.pressure_interp == GOMA_PRESSURE_P1 && !(et == GOMA_GPU_QUAD9 || et == GOMA_GPU_HEX27))
     return fail(-2, "P1 pressure needs a centroid node (QUAD9/HEX27)");
   if (p.num_owned_nodes < 0 || p.num_owned_nodes > p.num_nodes) return fail(-2, "num_owned_nodes out of range");
+  if (p.num_nodes < 0 || p.num_elems < 0 || p.num_unknowns < 0) return fail(-2, "negative size in goma_gpu_problem");
+  // one element block / one material (find_elemblock_index + Matilda[ebn] of mm_fill.c:224-235 are not restated)
+  if (p.num_elem_blocks > 1) return fail(-2, "meshes with more than one element block are not supported by the GPU fill");
+  if (p.num_materials > 1) return fail(-2, "more than one material is not supported by the GPU fill");
+
+  // ---- unknown map: everything build_pattern / build_records_kernel index with must be consistent
+  const int dim = p.dim, npe = p.elem_type;
+  for (int k = 0; k < p.num_kinds; k++) {
+    const int nu = p.kind_num_unknowns[k];
+    if (nu < 0 || nu > 64) return fail(-2, "kind_num_unknowns out of range");
+    const int np_ = p.pressure_interp == GOMA_PRESSURE_P1 ? dim + 1 : 1;
+    for (int sl = 0; sl < GOMA_NSLOT; sl++) {
+      const int off = p.kind_slot[k][sl];
+      if (off < -1 || off + (sl == GOMA_SLOT_P && off >= 0 ? np_ : 1) > nu + (off < 0 ? 1 : 0))
+        return fail(-2, "kind_slot does not fit kind_num_unknowns");
+    }
+  }
+  bool used[GOMA_GPU_MAX_KINDS] = {false, false, false, false};
+  for (int n = 0; n < p.num_nodes; n++) {
+    const int kd = p.node_kind[n];
+    if (kd >= p.num_kinds) return fail(-2, "node_kind[" + std::to_string(n) + "] >= num_kinds");
+    used[kd] = true;
+    const int fu = p.first_unknown[n];
+    if (fu < 0 || (long long)fu + p.kind_num_unknowns[kd] > p.num_unknowns)
+      return fail(-2, "first_unknown[" + std::to_string(n) + "] + its unknowns exceed num_unknowns");
+    if (n + 1 < p.num_nodes && p.first_unknown[n + 1] != fu + p.kind_num_unknowns[kd])
+      return fail(-2, "first_unknown is not the running sum of the nodal unknown counts at node " + std::to_string(n));
+  }
+  for (int u = 0; u < p.num_unknowns; u++)
+    if (p.dbc_flag[u] > 2) return fail(-2, "dbc_flag must be 0, 1 or 2");
+  // every field the selected kernel gathers must exist on every node kind in use (a node kind without T or Y,
+  // i.e. a variable not defined on all nodes, would be gathered from the neighbouring unknown)
+  const bool p1 = p.pressure_interp == GOMA_PRESSURE_P1;
+  for (int k = 0; k < p.num_kinds; k++) {
+    if (!used[k]) continue;
+    auto need = [&](int sl, const char *what) -> int {
+      return p.kind_slot[k][sl] < 0 ? fail(-2, std::string("node kind ") + std::to_string(k) + " carries no " + what +
+                                                   " unknown: variables must live on every node of the block")
+                                    : 0;
+    };
+    for (int d = 0; d < dim; d++)
+      if (int rc = need(GOMA_SLOT_U + d, "velocity")) return rc;
+    if (p.energy)
+      if (int rc = need(GOMA_SLOT_T, "temperature")) return rc;
+    for (int w = 0; w < p.num_species; w++)
+      if (int rc = need(GOMA_SLOT_Y0 + w, "species")) return rc;
+    if (p.ale)
+      for (int d = 0; d < dim; d++)
+        if (int rc = need(GOMA_SLOT_DX + d, "mesh displacement")) return rc;
+    if (!p1)
+      if (int rc = need(GOMA_SLOT_P, "pressure")) return rc;
+  }
+  for (long long k = 0; k < (long long)p.num_elems * npe; k++)
+    if (p.elem_connect[k] < 0 || p.elem_connect[k] >= p.num_nodes) return fail(-2, "element connectivity entry out of range");
+  if (p1) {
+    const int cen = npe == GOMA_GPU_QUAD9 ? 8 : 20;
+    for (int e = 0; e < p.num_elems; e++)
+      if (p.kind_slot[p.node_kind[p.elem_connect[(long long)e * npe + cen]]][GOMA_SLOT_P] < 0)
+        return fail(-2, "P1 pressure: the centroid node of element " + std::to_string(e) + " carries no pressure unknowns");
+  }
   return 0;
 }
 
@@ -163,31 +223,26 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
     return fail(-3, "no CUDA device: the goma_gpu_fill path has no CPU fallback");
   CU(cudaSetDevice(device));
 
-  goma_gpu_ctx *c = new goma_gpu_ctx();
+  struct Guard {  // every early return below destroys the half-built context
+    goma_gpu_ctx *c;
+    ~Guard() { if (c) goma_gpu_fill_destroy(c); }
+  } guard{new goma_gpu_ctx()};
+  goma_gpu_ctx *c = guard.c;
   c->prob = p;
   c->device = device;
   c->num_owned_unknowns = p.num_owned_nodes < p.num_nodes ? p.first_unknown[p.num_owned_nodes] : p.num_unknowns;
   int nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
   std::string perr = build_pattern(p, c->pat, std::min(nthreads, 32));
-  if (!perr.empty()) {
-    delete c;
-    return fail(-2, "sparsity pattern: " + perr);
-  }
+  if (!perr.empty()) return fail(-2, "sparsity pattern: " + perr);
   // optional bit-exact check against the host's own MSR graph
   if (p.ija) {
     const int N = p.num_unknowns;
-    if (c->pat.nnz_plus > 2147483647LL) {
-      delete c;
-      return fail(-2, "host ija given but nnz exceeds the 32-bit MSR limit");
-    }
+    if (c->pat.nnz_plus > 2147483647LL) return fail(-2, "host ija given but nnz exceeds the 32-bit MSR limit");
     std::vector<int> mine((size_t)c->pat.nnz_plus + 1, 0);
     emit_msr_columns(p, c->pat, mine.data());
     (void)N;
     for (long long k = 0; k < c->pat.nnz_plus; k++) {
-      if (mine[k] != p.ija[k]) {
-        delete c;
-        return fail(-2, "host MSR graph differs from the derived one at ija[" + std::to_string(k) + "]");
-      }
+      if (mine[k] != p.ija[k]) return fail(-2, "host MSR graph differs from the derived one at ija[" + std::to_string(k) + "]");
     }
   }
 
@@ -210,10 +265,7 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
   rc |= upload(&c->d_node_first, (const unsigned *)c->pat.node_first.data(), c->pat.node_first.size(), c);
   rc |= upload(&c->d_elem_list, c->pat.colour_order.data(), c->pat.colour_order.size(), c);
   c->colour_begin = c->pat.colour_begin;
-  if (rc) {
-    goma_gpu_fill_destroy(c);
-    return -3;
-  }
+  if (rc) return -3;
   // pair tables live on the device from here on
   std::vector<uint16_t>().swap(c->pat.pair_full);
   std::vector<uint16_t>().swap(c->pat.pair_p);
@@ -225,9 +277,9 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
   ElemTables t = make_tables(p.elem_type);
   std::vector<double> packed;
   packed.insert(packed.end(), t.wt.begin(), t.wt.end());
-  packed.insert(packed.end(), t.phi.begin(), t.phi.end());
   packed.insert(packed.end(), t.dphi.begin(), t.dphi.end());
   packed.insert(packed.end(), t.psi.begin(), t.psi.end());
+  packed.insert(packed.end(), t.phi.begin(), t.phi.end());
   packed.resize(ke.tbl_pad, 0.0);
   rc |= upload(&c->d_tables, packed.data(), packed.size(), c);
 
@@ -239,10 +291,7 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
   rc |= dalloc(&c->d_resid, N, c);
   rc |= dalloc(&c->d_a, (size_t)c->pat.nnz_plus + 1, c);
   rc |= dalloc(&c->d_flags, 4, c);
-  if (rc) {
-    goma_gpu_fill_destroy(c);
-    return -3;
-  }
+  if (rc) return -3;
 
   // per-element gather records: everything load_elem_dofptr would recompute per element and per
   // iteration, gathered once; afterwards the pair tables they were built from are dropped
@@ -264,11 +313,10 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
   if (getenv("GOMA_GPU_PROFILE")) rc |= dalloc(&c->d_prof, 2 * 8 * 4096, c);
   if (ke.smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute((const void *)ke.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ke.smem);
-    if (e != cudaSuccess) {
-      goma_gpu_fill_destroy(c);
-      return fail(-3, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    }
+    if (e != cudaSuccess) return fail(-3, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
   }
+  if (rc) return -3;
+  guard.c = nullptr;
   *out = c;
   return 0;
 }
@@ -342,6 +390,18 @@ extern "C" int goma_gpu_fill_set_option(goma_gpu_ctx *c, const char *name, int v
   }
   if (!strcmp(name, "grid_limit")) {
     c->grid_limit = value;
+    return 0;
+  }
+  if (!strcmp(name, "exchange_timeout_ms")) {  // bound of the wait inside goma_gpu_exchange_dof (default ~20 s)
+    c->exchange_spin_limit = (long long)std::max(1, value) * 2000000LL;
+    return 0;
+  }
+  if (!strcmp(name, "rezero")) {  // the next first-touch fill zeroes the whole matrix / residual storage first
+    c->rezero = value != 0;
+    return 0;
+  }
+  if (!strcmp(name, "accumulate")) {  // goma_gpu_fill adds into the caller's a / resid_vector (the reference's +=)
+    c->accumulate = value != 0;
     return 0;
   }
   return fail(-2, std::string("unknown option ") + name);
@@ -432,9 +492,12 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
   if (p.transient && !(delta_t > 0.0)) return fail(-2, "transient fill needs delta_t > 0");
 
   if (c->num_sms == 0) {
-    CU(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->blocks_per_sm, (const void *)ke.fn, ke.tpe, ke.smem));
-    if (c->blocks_per_sm < 1) return fail(-3, "fill kernel does not fit on an SM");
+    int sms = 0, bps = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void *)ke.fn, ke.tpe, ke.smem));
+    if (bps < 1 || sms < 1) return fail(-3, "fill kernel does not fit on an SM");
+    c->blocks_per_sm = bps;
+    c->num_sms = sms;  // cached only once the geometry is known to be valid
   }
   int max_grid = c->num_sms * c->blocks_per_sm;
   if (c->grid_limit > 0) max_grid = std::min(max_grid, c->grid_limit);
@@ -442,14 +505,23 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
   c->last_launches = 0;
   CU(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int), c->stream));
   CU(cudaEventRecord(c->ev0, c->stream));
-  P.scatter_mode = c->scatter_mode;
-  if (c->scatter_mode != 2) {
+  int mode = c->scatter_mode;
+  if (c->preloaded) mode = mode == 2 ? 1 : mode;  // accumulate into what the host uploaded: no store-over, no memset
+  P.scatter_mode = mode;
+  if (mode == 2 && c->rezero) {
+    // slots no element touches are zero from init; something (a row-sum scaling that met a zero row, a solver
+    // working in place) may have changed them since: zero everything once
+    CU(cudaMemsetAsync(c->d_resid, 0, (size_t)p.num_unknowns * sizeof(double), c->stream));
+    CU(cudaMemsetAsync(c->d_a, 0, ((size_t)c->pat.nnz_plus + 1) * sizeof(double), c->stream));
+    c->rezero = false;
+  }
+  if (mode != 2 && !c->preloaded) {
     // accumulate-into semantics need zeroed storage; the first-touch mode overwrites every slot the
     // elements touch and never writes the others (zeroed once at init), so it needs no memset
     if (assemble_residual) CU(cudaMemsetAsync(c->d_resid, 0, (size_t)p.num_unknowns * sizeof(double), c->stream));
     if (assemble_jacobian) CU(cudaMemsetAsync(c->d_a, 0, ((size_t)c->pat.nnz_plus + 1) * sizeof(double), c->stream));
   }
-  if (c->scatter_mode == 0) {
+  if (mode == 0) {
     P.elem_list = nullptr;
     P.elem_begin = 0;
     P.elem_end = p.num_elems;
@@ -476,8 +548,13 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
 
 static int finish_fill(goma_gpu_ctx *c, int flags_out[3]) {
   int h_flags[4] = {0, 0, 0, 0};
+  unsigned long long xerr = 0;
   CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
+  if (c->d_xflags && c->num_neighbors)
+    CU(cudaMemcpyAsync(&xerr, c->d_xflags + 3 * GOMA_GPU_MAX_NEIGHBORS, sizeof(xerr), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  c->fill_pending = false;
+  if (xerr) return fail(-4, "exchange_dof before this fill: neighbour slot " + std::to_string(xerr - 1) + " never published its vector");
   if (c->d_prof) {
     std::vector<long long> h(2 * 8 * 4096);
     CU(cudaMemcpy(h.data(), c->d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -487,11 +564,11 @@ static int finish_fill(goma_gpu_ctx *c, int flags_out[3]) {
       if (h[b * 8 + 6] > 0) {
         nb++;
         for (int k = 0; k < 6; k++) s[k] += (double)h[b * 8 + k] / (double)h[b * 8 + 6];
-        for (int k = 0; k < 6; k++) s2[k] += (double)h[(4096 + b) * 8 + k] / (double)h[b * 8 + 6];
+        for (int k = 0; k < 7; k++) s2[k] += (double)h[(4096 + b) * 8 + k] / (double)h[b * 8 + 6];
       }
     if (nb)
-      fprintf(stderr, "[goma_gpu profile] build split: ale-x %.0f J %.0f inv %.0f grads %.0f fields %.0f gp+vg %.0f\n",
-              s2[0] / nb, s2[1] / nb, s2[2] / nb, s2[3] / nb, s2[4] / nb, s2[5] / nb);
+      fprintf(stderr, "[goma_gpu profile] build split: ale-x %.0f J %.0f inv %.0f grads %.0f fields %.0f gp+vg %.0f | DMMA part of the loop (warp 0) %.0f\n",
+              s2[0] / nb, s2[1] / nb, s2[2] / nb, s2[3] / nb, s2[4] / nb, s2[5] / nb, s2[6] / nb);
     if (nb)
       fprintf(stderr, "[goma_gpu profile] cycles/element/CTA (mean over %d CTAs of the last launch): build %.0f rows %.0f "
                       "gauss loop + write-out %.0f\n", nb, s[0] / nb, s[1] / nb, s[2] / nb);
@@ -518,6 +595,28 @@ extern "C" int goma_gpu_fill_device(goma_gpu_ctx *c, double delta_t, double thet
   return finish_fill(c, flags_out);
 }
 
+// The same without the host synchronisation: everything is enqueued on the context's stream and the call returns.
+// *done_event (a cudaEvent_t owned by the context) is recorded behind the last assembly kernel: a solver on another
+// stream orders itself with cudaStreamWaitEvent.  goma_gpu_fill_wait collects the return code and the flags.
+extern "C" int goma_gpu_fill_device_async(goma_gpu_ctx *c, double delta_t, double theta, double time_value,
+                                          double h_elem_avg, double U_norm, int assemble_residual,
+                                          int assemble_jacobian, void **done_event) {
+  if (!c) return fail(-2, "null context");
+  CU(cudaSetDevice(c->device));
+  if (int rc = launch_fill(c, delta_t, theta, time_value, h_elem_avg, U_norm, assemble_residual, assemble_jacobian))
+    return rc;
+  c->fill_pending = true;
+  if (done_event) *done_event = (void *)c->ev1;
+  return 0;
+}
+
+extern "C" int goma_gpu_fill_wait(goma_gpu_ctx *c, int flags_out[3]) {
+  if (!c) return fail(-2, "null context");
+  if (!c->fill_pending) return fail(-2, "no asynchronous fill is pending");
+  CU(cudaSetDevice(c->device));
+  return finish_fill(c, flags_out);
+}
+
 extern "C" int goma_gpu_fill(goma_gpu_ctx *c, const double *x, const double *x_old, const double *x_older,
                              const double *xdot, const double *xdot_old, double delta_t, double theta,
                              double time_value, double h_elem_avg, double U_norm, int assemble_residual,
@@ -536,8 +635,20 @@ extern "C" int goma_gpu_fill(goma_gpu_ctx *c, const double *x, const double *x_o
     if (x_older) CU(cudaMemcpyAsync(c->d_x_older, x_older, nb, cudaMemcpyHostToDevice, c->stream));
     if (xdot_old) CU(cudaMemcpyAsync(c->d_xdot_old, xdot_old, nb, cudaMemcpyHostToDevice, c->stream));
   }
-  if (int rc = launch_fill(c, delta_t, theta, time_value, h_elem_avg, U_norm, assemble_residual, assemble_jacobian))
-    return rc;
+  if (c->accumulate) {
+    // the reference adds into caller-owned storage (mm_fill.c:5463 a[ja] +=, :5390 resid +=): upload what the
+    // caller holds and accumulate on top of it
+    if (assemble_jacobian)
+      CU(cudaMemcpyAsync(c->d_a, a, ((size_t)c->pat.nnz_plus + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (assemble_residual) CU(cudaMemcpyAsync(c->d_resid, resid_vector, nb, cudaMemcpyHostToDevice, c->stream));
+    c->preloaded = true;
+  }
+  int lrc = launch_fill(c, delta_t, theta, time_value, h_elem_avg, U_norm, assemble_residual, assemble_jacobian);
+  if (c->accumulate) {
+    c->preloaded = false;
+    c->rezero = true;  // the uploaded values sit in slots the first-touch mode never rewrites
+  }
+  if (lrc) return lrc;
   // one copy: the PCIe link is saturated by it (≈47 GB/s measured; two concurrent copy streams gave the same)
   if (assemble_jacobian)
     CU(cudaMemcpyAsync(a, c->d_a, ((size_t)c->pat.nnz_plus + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

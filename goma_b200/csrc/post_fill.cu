@@ -162,6 +162,9 @@ extern "C" int goma_gpu_row_sum_scale(goma_gpu_ctx *c, double *scale_out, int *z
   if (scale_out && n > 0) CU(cudaMemcpyAsync(scale_out, c->d_scale, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (zero_rows_out) *zero_rows_out = zr;
+  // a zero row sum turned its never-touched (zero) slots into 0 * inf = NaN, as in the reference -- but there the
+  // next fill starts from re-zeroed storage: make the next first-touch fill do the same
+  if (zr > 0) c->rezero = true;
   return 0;
 }
 

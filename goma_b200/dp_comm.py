@@ -130,6 +130,34 @@ def slab_partition(mesh: Mesh, nranks: int) -> np.ndarray:
     return (ix * nranks) // nx
 
 
+def brick_partition(mesh: Mesh, parts) -> np.ndarray:
+    """Element partition of a structured box into ``parts`` = (px, py[, pz]) bricks: in 3-D every brick of a
+    2 x 2 x 2 split touches all seven others (they share the centre node), the neighbourhood structure a
+    METIS k-way partition produces (``metis_decomp.c:449-466``) rather than the two neighbours of a slab."""
+    dim = len(mesh.shape)
+    parts = tuple(parts) + (1,) * (dim - len(parts))
+    idx = np.arange(mesh.num_elems)
+    rank = np.zeros(mesh.num_elems, np.int64)
+    mult = 1
+    for d in range(dim):
+        i_d = idx % mesh.shape[d]
+        idx = idx // mesh.shape[d]
+        rank += ((i_d * parts[d]) // mesh.shape[d]) * mult
+        mult *= parts[d]
+    return rank
+
+
+def scattered_partition(mesh: Mesh, nranks: int, seed: int = 0, block: int = 2) -> np.ndarray:
+    """A deliberately ragged element partition (random ranks per small block of elements): many neighbours per
+    rank, non-contiguous sub-domains, ranks that own nodes only through ghost elements -- the worst a graph
+    partitioner could hand to ``decompose``."""
+    rng = np.random.default_rng(seed)
+    nblk = (mesh.num_elems + block - 1) // block
+    r = rng.integers(0, nranks, nblk)
+    r[:nranks] = np.arange(nranks)  # every rank owns something
+    return np.repeat(r, block)[: mesh.num_elems]
+
+
 def slab_subdomain(make_problem, n, rank: int, nranks: int, elem_type: str = "HEX27") -> Subdomain:
     """Sub-domain ``rank`` of an ``nranks*n x n x n``-element box cut into x-slabs, built directly (the
     global mesh is never formed: this is how the weak-scaling bench gets 1M elements per GPU).

@@ -94,6 +94,22 @@ class MatrixFill:
                                                         int(assemble_jacobian),
                                                         self.flags.ctypes.data_as(capi._ip)), "goma_gpu_fill_device")
 
+    def fill_device_async(self, delta_t=0.0, theta=0.0, time_value=0.0, h_elem_avg=0.0, U_norm=0.0,
+                          assemble_residual=True, assemble_jacobian=True) -> int:
+        """Enqueue the device-resident assembly and return; the value is the cudaEvent_t (as int) recorded behind
+        it.  ``fill_wait`` collects the return code and the flags."""
+        ev = C.c_void_p()
+        capi.check(self.lib.goma_gpu_fill_device_async(self._ctx, float(delta_t), float(theta), float(time_value),
+                                                       float(h_elem_avg), float(U_norm), int(assemble_residual),
+                                                       int(assemble_jacobian), C.byref(ev)), "goma_gpu_fill_device_async")
+        return int(ev.value or 0)
+
+    def fill_wait(self) -> int:
+        return capi.check(self.lib.goma_gpu_fill_wait(self._ctx, self.flags.ctypes.data_as(capi._ip)), "goma_gpu_fill_wait")
+
+    def exchange_status(self) -> int:
+        return capi.check(self.lib.goma_gpu_exchange_status(self._ctx), "goma_gpu_exchange_status")
+
     def global_h_U(self, elem_owned=None):
         """Local sums of global_h_elem_siz / global_velocity_norm from the device-resident ``x``:
         (sum_h, n_elems, sum_v2, n_velocity_unknowns); the caller all-reduces and divides

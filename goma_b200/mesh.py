@@ -113,3 +113,130 @@ def box_mesh(elem_type: str, n, lo=None, hi=None, perturb: float = 0.0, seed: in
             h = (hi[d] - lo[d]) / (lat[d] - 1)
             coords[d, interior] += perturb * h * rng.uniform(-1, 1, interior.sum())
     return Mesh(elem_type, dim, np.ascontiguousarray(coords), conn, node_sets, n, lat)
+
+
+def patch_mesh(elem_type: str, verts, quads, refine: int = 0, nz: int = 0, height: float = 1.0) -> Mesh:
+    """Unstructured mesh from a quad4 topology: ``verts`` [nv, 2], ``quads`` [nq, 4] counter-clockwise.
+
+    What the reference reads from an arbitrary Exodus file (``rd_exo.c:99``) rather than from a lattice: vertex
+    valences other than 4 (three or five quads round a point), so node-node lists of irregular length and an
+    element colouring that a lattice formula cannot give.  ``refine`` splits every quad into 2x2 that many
+    times; QUAD9 adds the unique edge-midpoint and centre nodes; ``nz`` > 0 extrudes the plane mesh into
+    ``nz`` layers of HEX8 / HEX27 elements (Exodus node order, ``rf_shape.c:698,1105``).
+    Node sets: 1 = boundary of the plane mesh (all layers), 5 / 6 = bottom / top layer (3-D), 7 = pressure datum.
+    """
+    verts = [tuple(map(float, v)) for v in verts]
+    quads = [tuple(int(k) for k in q) for q in quads]
+    for _ in range(refine):
+        mids, nq = {}, []
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in mids:
+                verts.append(tuple(0.5 * (verts[a][d] + verts[b][d]) for d in range(2)))
+                mids[key] = len(verts) - 1
+            return mids[key]
+
+        for q in quads:
+            m = [mid(q[k], q[(k + 1) % 4]) for k in range(4)]
+            verts.append(tuple(0.25 * sum(verts[v][d] for v in q) for d in range(2)))
+            c = len(verts) - 1
+            nq += [(q[0], m[0], c, m[3]), (m[0], q[1], m[1], c), (c, m[1], q[2], m[2]), (m[3], c, m[2], q[3])]
+        quads = nq
+    order = 2 if elem_type in ("QUAD9", "HEX27") else 1
+    pts = list(verts)
+    conn2 = []
+    edge_count = {}
+    for q in quads:
+        for k in range(4):
+            key = (min(q[k], q[(k + 1) % 4]), max(q[k], q[(k + 1) % 4]))
+            edge_count[key] = edge_count.get(key, 0) + 1
+    if order == 1:
+        conn2 = [list(q) for q in quads]
+        emid = {}
+    else:
+        emid = {}
+        for q in quads:
+            row = list(q)
+            for k in range(4):
+                a, b = q[k], q[(k + 1) % 4]
+                key = (min(a, b), max(a, b))
+                if key not in emid:
+                    pts.append(tuple(0.5 * (verts[a][d] + verts[b][d]) for d in range(2)))
+                    emid[key] = len(pts) - 1
+                row.append(emid[key])
+            pts.append(tuple(0.25 * sum(verts[v][d] for v in q) for d in range(2)))
+            row.append(len(pts) - 1)
+            conn2.append(row)
+    bnd = set()
+    for (a, b), cnt in edge_count.items():
+        if cnt == 1:
+            bnd.update((a, b))
+            if (a, b) in emid:
+                bnd.add(emid[(a, b)])
+    pts = np.array(pts, float)
+    conn2 = np.array(conn2, np.int32)
+    n2 = len(pts)
+    if nz == 0:
+        et = "QUAD9" if order == 2 else "QUAD4"
+        assert elem_type == et
+        sets = {1: np.array(sorted(bnd), np.int32), 7: np.array([conn2[0, 8] if order == 2 else 0], np.int32)}
+        return Mesh(et, 2, np.ascontiguousarray(pts.T), conn2, sets, (len(conn2),), (n2,))
+    et = "HEX27" if order == 2 else "HEX8"
+    assert elem_type == et
+    nlay = order * nz + 1
+    zs = np.linspace(0.0, height, nlay)
+    coords = np.stack([np.tile(pts[:, 0], nlay), np.tile(pts[:, 1], nlay), np.repeat(zs, n2)])
+    q_of = {o: k for k, o in enumerate(_QUAD9 if order == 2 else _QUAD4)}
+    offs = _HEX27 if order == 2 else _HEX8
+    conn = np.empty((len(conn2) * nz, len(offs)), np.int32)
+    for lz in range(nz):
+        for k, (s, t, u) in enumerate(offs):
+            conn[lz * len(conn2):(lz + 1) * len(conn2), k] = conn2[:, q_of[(s, t)]] + (order * lz + u) * n2
+    b = np.array(sorted(bnd), np.int64)
+    sets = {1: np.sort((b[None, :] + n2 * np.arange(nlay)[:, None]).ravel()).astype(np.int32),
+            5: np.arange(n2, dtype=np.int32), 6: (np.arange(n2) + n2 * (nlay - 1)).astype(np.int32),
+            7: np.array([conn[0, 20] if order == 2 else 0], np.int32)}
+    for k in (2, 3, 4):
+        sets[k] = np.zeros(0, np.int32)
+    return Mesh(et, 3, np.ascontiguousarray(coords), conn, sets, (len(conn),), (coords.shape[1],))
+
+
+def star_mesh(elem_type: str, refine: int = 1, nz: int = 0, seed: int = 0, perturb: float = 0.0) -> Mesh:
+    """Two fans of quads sharing an edge region: five quads round one interior vertex (valence 5) and three round
+    another (valence 3) -- the smallest plane mesh with both irregular valences."""
+    import math
+
+    verts, quads = [(0.0, 0.0)], []
+    # valence-5 fan round vertex 0: corners v_k on the unit circle, mid-edge points m_k between them
+    ring = []
+    for k in range(5):
+        a0, a1 = 2 * math.pi * k / 5, 2 * math.pi * (k + 0.5) / 5
+        verts.append((math.cos(a0), math.sin(a0)))
+        verts.append((0.9 * math.cos(a1), 0.9 * math.sin(a1)))
+        ring += [len(verts) - 2, len(verts) - 1]
+    for k in range(5):
+        v, m_prev, m = ring[2 * k], ring[(2 * k - 1) % 10], ring[2 * k + 1]
+        quads.append((0, m_prev, v, m))
+    # valence-3 fan attached on the right: centre c3, sharing the edge (v_0, m_0)... built as a separate hexagon
+    cx = 2.2
+    verts.append((cx, 0.0))
+    c3 = len(verts) - 1
+    hexr = []
+    for k in range(6):
+        a = 2 * math.pi * k / 6 + math.pi
+        verts.append((cx + 1.0 * math.cos(a), math.sin(a)))
+        hexr.append(len(verts) - 1)
+    for k in range(3):
+        quads.append((c3, hexr[(2 * k - 1) % 6], hexr[2 * k], hexr[(2 * k + 1) % 6]))
+    # bridge quad between the fans: v_0 = ring[0] at (1, 0) and hexagon vertex hexr[0] at (cx - 1, 0)
+    m0, m9 = ring[1], ring[9]
+    quads.append((ring[0], m9, hexr[1], hexr[0]))
+    quads.append((ring[0], hexr[0], hexr[5], m0))
+    m = patch_mesh(elem_type, verts, quads, refine=refine, nz=nz)
+    if perturb > 0.0:
+        rng = np.random.default_rng(seed)
+        free = np.ones(m.num_nodes, bool)
+        free[m.node_sets[1]] = False
+        m.coords[:2, free] += perturb * 0.1 * rng.uniform(-1, 1, (2, int(free.sum())))
+    return m

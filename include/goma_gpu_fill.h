@@ -119,6 +119,12 @@ struct goma_gpu_problem {
   /* Dirichlet table: Nodes[]->DBC, BC_Types[].BC_Data_Float[0], BC_relax (bc_dirich.c:86-140) */
   const unsigned char *dbc_flag; /* [num_unknowns] 0 none, 1 residual = x - value, 2 hard set (residual 0) */
   const double *dbc_value; /* [num_unknowns] */
+
+  /* exo->num_elem_blocks and upd->Num_Mat of the host: the element loop here covers ONE element block with ONE
+   * material (find_elemblock_index / Matilda[ebn], src/mm_fill.c:224-235, are not restated); values > 1 are
+   * refused by goma_gpu_fill_init instead of being assembled with the wrong material.  0 = not stated. */
+  int num_elem_blocks;
+  int num_materials;
 };
 
 typedef struct goma_gpu_ctx goma_gpu_ctx;
@@ -153,6 +159,14 @@ int goma_gpu_fill_device_buffers(goma_gpu_ctx *ctx, struct goma_gpu_device_buffe
 int goma_gpu_fill_device(goma_gpu_ctx *ctx, double delta_t, double theta, double time_value,
                          double h_elem_avg, double U_norm, int assemble_residual,
                          int assemble_jacobian, int flags_out[3]);
+
+/* Asynchronous form for a GPU solver pipeline: enqueue the assembly on the context's stream and return.
+ * *done_event receives a cudaEvent_t (owned by the context) recorded behind the last assembly kernel;
+ * goma_gpu_fill_wait synchronises, returns what goma_gpu_fill_device would have and reports the flags. */
+int goma_gpu_fill_device_async(goma_gpu_ctx *ctx, double delta_t, double theta, double time_value,
+                               double h_elem_avg, double U_norm, int assemble_residual,
+                               int assemble_jacobian, void **done_event);
+int goma_gpu_fill_wait(goma_gpu_ctx *ctx, int flags_out[3]);
 
 /* global_h_elem_siz / global_velocity_norm (src/mm_fill_aux.c:1128-1207, :612-680) local sums over the
  * elements listed as owned and the owned nodes, from the device-resident x:
@@ -224,13 +238,24 @@ int goma_gpu_exchange_setup(goma_gpu_ctx *ctx, int num_neighbors,
                             const int *recv_list, /* neighbour-local dof indices, tail order */
                             int tail_begin /* first external unknown = num owned unknowns */);
 int goma_gpu_exchange_dof(goma_gpu_ctx *ctx, int which);
+/* The wait inside the exchange kernel is bounded (about 20 s of SM clock): a neighbour that never publishes its
+ * epoch -- a mismatched collective -- raises an error word instead of hanging the device.  This call (and every
+ * goma_gpu_fill* that follows an exchange) returns -4 with a message when that happened, 0 otherwise. */
+int goma_gpu_exchange_status(goma_gpu_ctx *ctx);
 
 /* timing / accounting of the last goma_gpu_fill*: device ms of the assembly kernel(s)
  * (CUDA events on the context's stream) and number of kernel launches */
 int goma_gpu_fill_last_stats(goma_gpu_ctx *ctx, double *kernel_ms, int *launches);
 
 /* options: "scatter" = 0 fp64 atomics into zeroed storage | 1 coloured load+add+store | 2 coloured first-touch
- * stores (default; no memset of the matrix, bit-reproducible);  "grid_limit" = cap on resident CTAs (tests). */
+ * stores (default; no memset of the matrix, bit-reproducible);  "grid_limit" = cap on resident CTAs (tests);
+ * "rezero" = 1: the next first-touch fill zeroes the whole device storage first -- needed after anything other
+ * than this library changed slots of d_a that no element touches (a solver factorising in place); the library sets
+ * it itself after a row-sum scaling that met a zero row;  "accumulate" = 1: goma_gpu_fill uploads the caller's a /
+ * resid_vector and ADDS the assembly to them, the literal semantics of the reference (src/mm_fill.c:5390,5463) for
+ * a host that pre-loads the residual; the default (0) overwrites, which equals the reference for the caller-zeroed
+ * storage of src/mm_sol_nonlinear.c:1109-1121 and saves a 45 GB upload;  "exchange_timeout_ms" = bound of the wait
+ * inside goma_gpu_exchange_dof, in milliseconds of a 2 GHz SM clock. */
 int goma_gpu_fill_set_option(goma_gpu_ctx *ctx, const char *name, int value);
 
 const char *goma_gpu_last_error(void);

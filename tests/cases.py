@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from goma_b200.mesh import box_mesh
+from goma_b200.mesh import box_mesh, star_mesh
 from goma_b200.problem import Dirichlet, Problem
 
 SEED = 20261017
@@ -43,7 +43,7 @@ def make_state(problem, seed=SEED, transient=False, delta_t=0.01, theta=0.0):
                 elif name.startswith("Y"):
                     v = 0.5 + 0.05 * noise
                 elif name.startswith("D"):
-                    h = 1.0 / max(m.lattice)
+                    h = 1.0 / max(max(m.lattice), 1)
                     v = 0.02 * h * noise
                 else:  # pressure dofs
                     v = noise
@@ -169,10 +169,30 @@ def build_case(name):
                     etm_mesh=(1.0,) * 5, k=0.07, Cp=1.4, beta=0.8, Tref=0.3, ns_source="BOUSSINESQ", heat_source=0.6,
                     rho=1.3, mu=0.7, gravity=(0.3, -0.2, 0.1), lame_mu=0.9, lame_lambda=1.7, bcs=bcs)
         return p, {"delta_t": 0.02, "theta": 0.5, "time": 0.1}
+    if name.startswith("irr_"):
+        # unstructured meshes: vertex valences 3 and 5 (node-node lists of irregular length, greedy colouring with
+        # more colours than a lattice needs) -- what an arbitrary Exodus file gives the reference
+        if name == "irr_quad9_star_ns":
+            m = star_mesh("QUAD9", refine=1, perturb=0.3, seed=1)
+            bcs = [Dirichlet("U", 1, 0.0), Dirichlet("V", 1, 0.5, relax=1.0), Dirichlet("P", 7, 0.0)]
+            return Problem(m, rho=1.1, mu=0.3, gravity=(0.1, -0.2, 0.0), bcs=bcs), {}
+        if name == "irr_hex27_star_bouss":
+            m = star_mesh("HEX27", refine=0, nz=2, perturb=0.3, seed=2)
+            bcs = [Dirichlet("U", 1, 0.0), Dirichlet("V", 1, 0.5, relax=1.0), Dirichlet("W", 5, 0.0),
+                   Dirichlet("T", 5, 1.0), Dirichlet("T", 6, 0.0, relax=1.0), Dirichlet("P", 7, 0.0)]
+            return Problem(m, energy=True, rho=1.1, mu=0.3, k=0.2, Cp=1.3, beta=0.5, Tref=0.1, ns_source="BOUSSINESQ",
+                           gravity=(0.1, -0.2, 0.3), heat_source=0.2, bcs=bcs), {}
+        if name == "irr_hex8_star_pspg":
+            m = star_mesh("HEX8", refine=1, nz=2, perturb=0.3, seed=3)
+            bcs = [Dirichlet("U", 1, 0.0), Dirichlet("V", 1, 0.5, relax=1.0), Dirichlet("W", 5, 0.0),
+                   Dirichlet("T", 5, 1.0), Dirichlet("Y", 6, 0.3, species=1), Dirichlet("P", 7, 0.0)]
+            return Problem(m, interp="Q1Q1", pspg="local", ps_scaling=0.1, energy=True, n_species=2, rho=1.2, mu=0.3,
+                           k=0.2, Cp=1.5, beta=0.4, Tref=0.2, diffusivity=(0.05, 0.11, 1.0, 1.0),
+                           gravity=(0.1, -0.2, -1.0), ns_source="BOUSSINESQ", heat_source=0.3, bcs=bcs), {}
     raise KeyError(name)
 
 
-GOLDEN_CASES = ["c1_quad9_ns", "c1_quad9_ns_transient", "c2_hex27_ns", "c3_hex27_boussinesq",
+GOLDEN_CASES = ["irr_quad9_star_ns", "irr_hex27_star_bouss", "irr_hex8_star_pspg","c1_quad9_ns", "c1_quad9_ns_transient", "c2_hex27_ns", "c3_hex27_boussinesq",
                 "c3_quad9_bouss_transient", "c5_hex8_pspg_local_transient", "c5_hex8_pspg_global",
                 "c5_quad4_pspg_local", "c4_quad9_ale", "c4_hex27_ale", "c4_quad9_ale_energy_transient",
                 "q2p1_quad9_species_ale_transient", "c2_hex27_ns_transient", "c4_hex27_ale_energy_transient",

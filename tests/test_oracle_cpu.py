@@ -192,3 +192,139 @@ def test_header_is_valid_c_and_cxx(tmp_path):
     cxx = tmp_path / "t.cpp"
     cxx.write_text('#include "%s"\nint main() { goma_gpu_csr a{}; const char *(*f)(void) = goma_gpu_last_error; (void)a; (void)f; return 0; }\n' % hdr)
     subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", str(cxx)])
+
+
+def _init_rc(st):
+    """goma_gpu_pattern_msr runs the same validate() as goma_gpu_fill_init and needs no device."""
+    nnz = ctypes.c_longlong()
+    lib = capi.load_library()
+    rc = lib.goma_gpu_pattern_msr(ctypes.byref(st), ctypes.byref(nnz), None)
+    return rc, lib.goma_gpu_last_error().decode()
+
+
+def test_inconsistent_unknown_map_is_refused(built):
+    """validate(): everything the pattern builder and the record kernel index with is checked first -- a node kind
+    out of range, a first_unknown that is not the running sum, a variable missing on a node kind (a multi-material
+    layout) and a bad Dirichlet flag are errors (-2), not out-of-bounds reads."""
+    p, _ = build_case("c3_hex27_boussinesq")
+    st, keep = capi.make_problem_struct(p)
+    assert _init_rc(st)[0] == 0
+    keep["kind"][5] = 3
+    rc, msg = _init_rc(st)
+    assert rc == -2 and "node_kind" in msg
+    keep["kind"][5] = 0
+    keep["first"][7] += 1
+    rc, msg = _init_rc(st)
+    assert rc == -2 and "first_unknown" in msg
+    keep["first"][7] -= 1
+    st.kind_slot[0][capi.SLOTS["T"]] = -1  # temperature not defined on the plain nodes
+    rc, msg = _init_rc(st)
+    assert rc == -2 and "temperature" in msg
+    st.kind_slot[0][capi.SLOTS["T"]] = 3
+    keep["dbc_flag"][0] = 9
+    rc, msg = _init_rc(st)
+    assert rc == -2 and "dbc_flag" in msg
+    keep["dbc_flag"][0] = 0
+    keep["conn"][0, 0] = 10 ** 6
+    rc, msg = _init_rc(st)
+    assert rc == -2 and "connectivity" in msg
+
+
+def test_multi_block_and_multi_material_meshes_are_refused(built):
+    """The ABI carries one element type and one material (find_elemblock_index / Matilda[ebn],
+    src/mm_fill.c:224-235, are not restated): a host that states two blocks or two materials is refused."""
+    p, _ = build_case("c1_quad9_ns")
+    st, keep = capi.make_problem_struct(p)
+    st.num_elem_blocks = 2
+    rc, msg = _init_rc(st)
+    assert rc == -2 and "element block" in msg
+    st.num_elem_blocks = 1
+    st.num_materials = 2
+    rc, msg = _init_rc(st)
+    assert rc == -2 and "material" in msg
+
+
+@pytest.mark.parametrize("et,nz", [("QUAD4", 0), ("QUAD9", 0), ("HEX8", 2), ("HEX27", 1)])
+def test_unstructured_mesh_generator(et, nz):
+    """star_mesh: valences 3 and 5, positive orientation, unique nodes, boundary node set closed."""
+    from collections import Counter
+
+    from goma_b200.mesh import star_mesh
+
+    m = star_mesh(et, refine=1, nz=nz, perturb=0.3, seed=1)
+    assert len(np.unique(m.conn)) == m.num_nodes
+    n2d = m.num_elems // max(nz, 1)
+    val = Counter(m.conn[:n2d, :4].ravel().tolist())
+    assert {3, 5} <= set(val.values())
+    c = m.conn[:, :4]
+    x, y = m.coords[0][c], m.coords[1][c]
+    area = 0.5 * sum(x[:, k] * y[:, (k + 1) % 4] - x[:, (k + 1) % 4] * y[:, k] for k in range(4))
+    assert (area > 0).all()
+
+
+@pytest.mark.skipif(not ref_driver.ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_unstructured_mesh_pattern_matches_reference_live(built):
+    """find_MSR_problem_graph of the reference on an irregular-valence hex8 mesh == the library's host pattern."""
+    from goma_b200.mesh import star_mesh
+    from goma_b200.problem import Dirichlet
+
+    m = star_mesh("HEX8", refine=2, nz=2, perturb=0.2, seed=4)
+    p = Problem(m, interp="Q1Q1", pspg="local", energy=True, ns_source="BOUSSINESQ", bcs=[Dirichlet("U", 1, 0.0)])
+    np.testing.assert_array_equal(ref_driver.run_map(p)["ija"][:-1], capi.pattern_msr(p))
+
+
+@pytest.mark.parametrize("parts,nranks", [((2, 2, 2), 8), (None, 5)])
+def test_irregular_partitions_reproduce_global_rows(built, parts, nranks):
+    """decompose() on partitions with many neighbours per rank (2x2x2 bricks: 7 each; a ragged random partition):
+    owner = lowest rank, one ghost layer, owned rows only -- the rows of all ranks are the global system, and the
+    peer-pull lists fill every external tail (dp_map_comm_vec.c:332-461, dp_comm.c:48-102)."""
+    from goma_b200.dp_comm import (brick_partition, decompose, peer_exchange_payload, peer_recv_lists,
+                                   scattered_partition)
+    from goma_b200.matrix_fill import msr_to_csr
+    from goma_b200.problem import Dirichlet
+    from tests.cases import make_state
+
+    m = box_mesh("HEX8", (4, 4, 4), perturb=0.1, seed=5)
+    p = Problem(m, interp="Q1Q1", pspg="global", energy=True, rho=1.1, mu=0.2, ns_source="BOUSSINESQ",
+                gravity=(0.1, -0.3, 0.2), bcs=[Dirichlet("U", 1, 1.0), Dirichlet("T", 2, 0.0, relax=1.0)])
+    st = make_state(p, seed=3)
+    first_g = p.unknown_map()[0]
+    ija_g = capi.pattern_msr(p)
+    h, U = p.global_h_elem_siz(), p.global_velocity_norm(st["x"])
+    rc, a_g, r_g = port.port_fill(p, ija_g, st, h_elem_avg=h, U_norm=U)
+    ng = len(r_g)
+    A_g = msr_to_csr(ija_g, a_g, ng)
+    part = brick_partition(m, parts) if parts else scattered_partition(m, nranks, seed=2)
+    subs = decompose(p, part, nranks)
+    if parts:
+        assert all(len(s.neighbors) == 7 for s in subs)
+    everyone = [peer_exchange_payload(s, b"h") for s in subs]
+    l2gs = []
+    for s in subs:
+        first_l = s.problem.unknown_map()[0]
+        l2g = np.empty(int(first_l[-1]), np.int64)
+        for k, g in enumerate(s.node_global):
+            l2g[first_l[k]:first_l[k + 1]] = np.arange(first_g[g], first_g[g + 1])
+        l2gs.append(l2g)
+    seen = np.zeros(ng, int)
+    for s, l2g in zip(subs, l2gs):
+        nown, nl = s.num_owned_dofs, len(l2g)
+        # ghost refresh through the pull lists
+        _, slots, recv_ptr, rl = peer_recv_lists(s, everyone)
+        x = st["x"][l2g].copy()
+        x[nown:] = np.nan
+        for k, q in enumerate(s.neighbors):
+            x[nown + recv_ptr[k]: nown + recv_ptr[k + 1]] = st["x"][l2gs[q]][rl[recv_ptr[k]:recv_ptr[k + 1]]]
+        np.testing.assert_array_equal(x, st["x"][l2g])
+        ija = capi.pattern_msr(s.problem)
+        rc, a, r = port.port_fill(s.problem, ija, {"x": x}, h_elem_avg=h, U_norm=U, num_owned_nodes=s.num_owned_nodes)
+        assert rc == 0
+        lrows = np.repeat(np.arange(nl), np.diff(ija[:nl + 1]))
+        lcols, vals = ija[nl + 1:], a[nl + 1:len(ija)]
+        own = lrows < nown
+        ref = np.asarray(A_g[l2g[lrows[own]], l2g[lcols[own]]]).ravel()
+        assert (not own.any() or np.abs(vals[own] - ref).max() < 1e-13) and not vals[~own].any()
+        np.testing.assert_allclose(a[:nown], a_g[l2g[:nown]], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(r[:nown], r_g[l2g[:nown]], rtol=0, atol=1e-13)
+        seen[l2g[:nown]] += 1
+    assert (seen == 1).all()
