@@ -158,9 +158,13 @@ def scattered_partition(mesh: Mesh, nranks: int, seed: int = 0, block: int = 2) 
     return np.repeat(r, block)[: mesh.num_elems]
 
 
-def slab_subdomain(make_problem, n, rank: int, nranks: int, elem_type: str = "HEX27") -> Subdomain:
+def slab_subdomain(make_problem, n, rank: int, nranks: int, elem_type: str = "HEX27", cols=None,
+                   x_len: float = None) -> Subdomain:
     """Sub-domain ``rank`` of an ``nranks*n x n x n``-element box cut into x-slabs, built directly (the
     global mesh is never formed: this is how the weak-scaling bench gets 1M elements per GPU).
+
+    ``cols`` (``nranks + 1`` increasing column boundaries) cuts a box of ``cols[-1]`` columns unevenly instead --
+    the strong-scaling split of ONE ``n^3`` cavity (``cols[-1] == n``, ``x_len = 1``) over the ranks.
 
     ``make_problem(mesh)`` returns the Problem on the local mesh.  Ownership and ordering follow
     :func:`decompose` exactly (checked against it in the tests): shared planes belong to the lower
@@ -170,18 +174,24 @@ def slab_subdomain(make_problem, n, rank: int, nranks: int, elem_type: str = "HE
     from .mesh import ELEM_TABLE, box_mesh
 
     dim, _, order, _ = ELEM_TABLE[elem_type]
-    c0 = rank * n
-    c1 = (rank + 1) * n + (1 if rank < nranks - 1 else 0)
+    if cols is None:
+        cols = [r * n for r in range(nranks + 1)]
+    total_cols = int(cols[-1])
+    if x_len is None:
+        x_len = total_cols / n
+    c0 = int(cols[rank])
+    n_own_cols = int(cols[rank + 1]) - c0
+    c1 = int(cols[rank + 1]) + (1 if rank < nranks - 1 else 0)
     ncol = c1 - c0
     shape = (ncol,) + (n,) * (dim - 1)
-    lo = (c0 / n,) + (0.0,) * (dim - 1)
-    hi = (c1 / n,) + (1.0,) * (dim - 1)
+    lo = (c0 * x_len / total_cols,) + (0.0,) * (dim - 1)
+    hi = (c1 * x_len / total_cols,) + (1.0,) * (dim - 1)
     m = box_mesh(elem_type, shape, lo=lo, hi=hi)
     LX = m.lattice[0]
     lx = np.arange(m.num_nodes) % LX
     has_left = rank > 0
     has_right = rank < nranks - 1
-    own_hi = order * n  # highest owned local plane
+    own_hi = order * n_own_cols  # highest owned local plane
     cat = np.zeros(m.num_nodes, np.int8)  # 0 internal, 1 boundary, 2 external-left, 3 external-right
     if has_left:
         cat[lx == 0] = 2
@@ -203,7 +213,7 @@ def slab_subdomain(make_problem, n, rank: int, nranks: int, elem_type: str = "HE
     n_int = int((cat == 0).sum())
     n_own = n_int + int((cat == 1).sum())
     # global ids (of the nranks*n-long box) for cross-checks
-    GLX = order * nranks * n + 1
+    GLX = order * total_cols + 1
     strides_l = np.array([1, LX, LX * m.lattice[1] if dim == 3 else 0][:dim])
     node_global = np.zeros(m.num_nodes, np.int64)
     rem = np.arange(m.num_nodes)
@@ -214,7 +224,7 @@ def slab_subdomain(make_problem, n, rank: int, nranks: int, elem_type: str = "HE
         node_global += (idx + (order * c0 if d == 0 else 0)) * gstr[d]
     sub = Subdomain(rank=rank, problem=problem, num_owned_nodes=n_own, num_internal_nodes=n_int,
                     node_global=node_global[perm], elem_global=np.zeros(0, np.int64),
-                    elem_owned=(np.arange(m.num_elems) % ncol) < n)
+                    elem_owned=(np.arange(m.num_elems) % ncol) < n_own_cols)
     first_l = problem.unknown_map()[0]
 
     def dofs_of(local_nodes_sorted):

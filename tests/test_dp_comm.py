@@ -150,3 +150,30 @@ def test_peer_pull_lists_fill_the_external_tail(et, n, nranks):
             assert (lst < subs[q].num_owned_dofs).all()  # only owned values travel
             x[s.num_owned_dofs + recv_ptr[k]: s.num_owned_dofs + recv_ptr[k + 1]] = xq[lst]
         np.testing.assert_array_equal(x, xg[l2g[s.rank]])
+
+
+@pytest.mark.parametrize("et,n,cols", [("HEX27", 3, [0, 1, 3]), ("HEX8", 5, [0, 2, 3, 5]), ("QUAD9", 7, [0, 2, 4, 5, 7])])
+def test_uneven_slab_split_matches_general_decomposition(et, n, cols):
+    """Strong scaling: ONE n^dim box cut into x-slabs of unequal width (bench.py --scaling strong) == decompose()."""
+    dim = 2 if et == "QUAD9" else 3
+    nranks = len(cols) - 1
+    gm = box_mesh(et, (n,) * dim)
+    q1 = et == "HEX8"
+    bcs = [Dirichlet("U", 1, 1.0), Dirichlet("V", 2, 0.0, relax=1.0), Dirichlet("U", 3, 0.0), Dirichlet("P", 7, 0.3)]
+    mk = lambda mesh: Problem(mesh, interp="Q1Q1" if q1 else "Q2P1", pspg="global" if q1 else None, rho=1.1, mu=0.2, bcs=bcs)
+    ix = np.arange(gm.num_elems) % n
+    part = np.searchsorted(np.asarray(cols[1:]), ix, side="right")
+    subs = decompose(mk(gm), part, nranks)
+    for r in range(nranks):
+        a, b = subs[r], slab_subdomain(mk, n, r, nranks, et, cols=cols, x_len=1.0)
+        assert (a.num_owned_nodes, a.num_internal_nodes, a.neighbors) == (b.num_owned_nodes, b.num_internal_nodes, b.neighbors)
+        np.testing.assert_array_equal(a.node_global, b.node_global)
+        np.testing.assert_allclose(a.problem.mesh.coords, b.problem.mesh.coords, atol=1e-14)
+        assert {tuple(row) for row in a.problem.mesh.conn.tolist()} == {tuple(row) for row in b.problem.mesh.conn.tolist()}
+        np.testing.assert_array_equal(a.list_dof_send, b.list_dof_send)
+        np.testing.assert_array_equal(a.ptr_dof_send, b.ptr_dof_send)
+        np.testing.assert_array_equal(a.num_dofs_recv, b.num_dofs_recv)
+        # (decompose marks an element by the lowest owner of its nodes, rd_dpi.c:322-336; the slab constructor by
+        # the column it lies in: both count every element exactly once over the ranks)
+        assert int(b.elem_owned.sum()) == (cols[r + 1] - cols[r]) * n ** (dim - 1)
+        np.testing.assert_array_equal(a.problem.dirichlet_table()[0], b.problem.dirichlet_table()[0])
