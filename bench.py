@@ -30,10 +30,29 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# SURVEY.md §8(d) / BASELINE.md §3 per-element algorithmic work, fixed per config
+# SURVEY.md §8(d) / BASELINE.md §3 per-element algorithmic work, fixed per config: the contract's
+# numerator of `roofline.achieved`.  C4: "3-4x the fixed-mesh count" (SURVEY.md §8d), lower end.
 ALG_FLOPS_PER_ELEM = {"c2_hex27_ns": 1.2e6, "c3_hex27_ns_energy": 1.85e6, "c5_hex8_pspg_T_2Y": 0.25e6,
-                      "c4_hex27_ale_ns": 3.6e6}  # C4: "3-4x the fixed-mesh count" (SURVEY.md §8d), lower end
+                      "c4_hex27_ale_ns": 3.6e6}
+# Counted, not estimated (BASELINE.md §3 "instrumented CPU restatement"):
+#  restatement = floating-point operations oracle/fill_port.c executes per element, counted by running it with an
+#                operation-counting number type (oracle/flop_count.cpp; `python bench.py --count-flops` re-counts).  The
+#                restatement evaluates every (i,a; j,b) entry of App. A as written -- no factoring across (a,b) --
+#                so it is an UPPER bound of the algorithmic work, 3x the survey's figure on the hex27 configs;
+#  executed    = what the CUDA kernel issues per element, padding of the tensor-core tiles included.
+COUNTED_FLOPS_PER_ELEM = {
+    "c2_hex27_ns": {"restatement": 3.70e6, "executed": 1.18e6},
+    "c3_hex27_ns_energy": {"restatement": 4.88e6, "executed": 1.47e6},
+    "c5_hex8_pspg_T_2Y": {"restatement": 0.290e6, "executed": None},
+    "c4_hex27_ale_ns": {"restatement": 29.2e6, "executed": None},
+}
 FP64_PEAK_NOMINAL_TFLOPS = 40.0  # BASELINE.json north_star; replaced by the DFMA micro-benchmark when it runs
+CONFIGS = {  # name -> (roofline key, element type, default edge = the size BASELINE.json / SURVEY.md §8d name)
+    "c2": ("c2_hex27_ns", "HEX27", 100),
+    "c3": ("c3_hex27_ns_energy", "HEX27", 126),
+    "c4": ("c4_hex27_ale_ns", "HEX27", 32),
+    "c5": ("c5_hex8_pspg_T_2Y", "HEX8", 100),
+}
 
 
 def cavity_problem(n, energy=False, x_len=1.0):
@@ -87,7 +106,7 @@ def cavity_problem_on(mesh, energy=False):
 
 
 def synthetic_state(problem, seed):
-    from tests.cases import make_state
+    from tests.cases import make_state  # the seeded state of SURVEY.md §8d, shared with the parity tests
 
     return make_state(problem, seed=seed)["x"]
 
@@ -224,21 +243,21 @@ def run_reference_arm(args, rank):
     line = {"impl": "reference", "metric": "jacobian_residual_elements_per_s", "value": v, "unit": "elements/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "elements_per_step": cores * ne},
+            "config": {"workload": workload_name(args.config, args.n), "elements_per_step": cores * ne},
             "cpu_baseline": {"value": v, "unit": "elements/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_name(args):
-    if getattr(args, "config", "c2") == "c4":
-        return (f"3D Navier-Stokes on an ALE pseudo-solid mesh, Q2/P1 hex27, {args.n}^3 elements per GPU (SURVEY C4, 3-D "
-                "variant; not the headline config)")
-    if getattr(args, "config", "c2") == "c5":
-        return (f"3D NS + energy + 2 species, PSPG Q1/Q1 hex8, {args.n}^3 elements per GPU (BASELINE.json configs[4]; "
-                "not the headline config)")
-    phys = "NS+energy (Boussinesq)" if args.energy else "Navier-Stokes"
-    return f"3D lid-driven cavity {phys}, Q2/P1 hex27, {args.n}^3 elements per GPU (BASELINE.json configs[1])"
+def workload_name(cfg, n, scaling="weak", world=1):
+    per = f"{n}^3 elements per GPU" if scaling == "weak" else f"ONE {n}^3 mesh split over {world} GPUs (x-slabs)"
+    if cfg == "c4":
+        return f"3D Navier-Stokes on an ALE pseudo-solid mesh, Q2/P1 hex27, {per} (SURVEY C4, 3-D variant)"
+    if cfg == "c5":
+        return f"3D NS + energy + 2 species, PSPG Q1/Q1 hex8, {per} (BASELINE.json configs[4])"
+    if cfg == "c3":
+        return f"3D Boussinesq natural convection NS+energy, Q2/P1 hex27, {per} (BASELINE.json configs[2])"
+    return f"3D lid-driven cavity Navier-Stokes, Q2/P1 hex27, {per} (BASELINE.json configs[1])"
 
 
 def fp64_peak_tflops(device):
@@ -263,25 +282,134 @@ def fp64_peak_tflops(device):
     return best
 
 
+def problem_maker(cfg):
+    if cfg == "c5":
+        return c5_problem_on
+    if cfg == "c4":
+        return c4_problem_on
+    return lambda mesh: cavity_problem_on(mesh, cfg == "c3")
+
+
+class Workload:
+    """One config on this rank: problem, GPU context, sub-domain (N > 1)."""
+
+    def __init__(self, cfg, n, rank, world, local_rank, scaling, scatter):
+        from goma_b200.matrix_fill import MatrixFill
+        from goma_b200.mesh import box_mesh
+
+        self.cfg, self.n, self.rank, self.world = cfg, n, rank, world
+        self.key, elem, _ = CONFIGS[cfg]
+        make_on = problem_maker(cfg)
+        t0 = time.perf_counter()
+        self.sub = None
+        if world == 1:
+            self.problem = make_on(box_mesh(elem, (n,) * 3))
+            owned_nodes = None
+            self.ne_owned = self.problem.mesh.num_elems
+        else:
+            from goma_b200.dp_comm import slab_subdomain
+
+            if scaling == "strong":  # ONE n^3 cavity cut into x-slabs of (almost) equal width
+                cols = [round(r * n / world) for r in range(world + 1)]
+                self.sub = slab_subdomain(make_on, n, rank, world, elem_type=elem, cols=cols, x_len=1.0)
+            else:  # weak: rank r owns the r-th n^3 slab of a (world*n) x n x n box, plus its ghost column
+                self.sub = slab_subdomain(make_on, n, rank, world, elem_type=elem)
+            self.problem = self.sub.problem
+            owned_nodes = self.sub.num_owned_nodes
+            self.ne_owned = int(self.sub.elem_owned.sum())
+        self.x = synthetic_state(self.problem, 20261017 + rank)
+        self.mesh_gen_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        self.mf = MatrixFill(self.problem, device=local_rank, num_owned_nodes=owned_nodes)
+        self.init_s = time.perf_counter() - t0
+        self.mf.set_option("scatter", scatter)
+        self.ne = self.problem.mesh.num_elems  # assembled per step on this rank (owned + ghost elements)
+        self.n_unk, self.nnz = self.mf.num_unknowns, self.mf.nnz_plus
+        self.hU = [0.0, 0.0]
+
+    def step(self, dist=None, dev=None):
+        mf = self.mf
+        if self.sub is not None:
+            mf.exchange_dof(0)  # ghost refresh (mm_sol_nonlinear.c:1273): own stream, overlaps the interior classes
+        if self.problem.pspg:  # global_h_elem_siz / global_velocity_norm on the device (mm_sol_nonlinear.c:1184-1192)
+            sums = mf.global_h_U(None if self.sub is None else self.sub.elem_owned)
+            if self.world > 1:
+                import torch
+
+                t = torch.tensor(sums, dtype=torch.float64, device=dev)
+                dist.all_reduce(t)
+                sums = t.cpu().numpy()
+            self.hU[0], self.hU[1] = sums[0] / sums[1], sums[2] / sums[3]
+        mf.fill_device(h_elem_avg=self.hU[0], U_norm=self.hU[1])
+
+
+def roofline_of(w, dev_ms, fp64_peak, hbm_peak, hbm_src, traffic=None):
+    flops = ALG_FLOPS_PER_ELEM[w.key]
+    bpe = 8.0 * (w.nnz + w.n_unk) / w.ne + w.problem.mesh.npe * 4 + 8.0 * (3 * w.problem.mesh.num_nodes + w.n_unk) / w.ne
+    kern_s = dev_ms * 1e-3
+    ach_tf = flops * w.ne / kern_s / 1e12
+    ach_gbs = bpe * w.ne / kern_s / 1e9
+    counted = COUNTED_FLOPS_PER_ELEM[w.key]
+    roof = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+            "traffic": traffic, "peak_source": "fp64 matmul micro-benchmark in this run (nominal %.0f)" % FP64_PEAK_NOMINAL_TFLOPS,
+            "flops_per_element": flops, "flops_per_element_source": "SURVEY.md §8d (the contract's per-unit figure)",
+            "flops_per_element_counted": counted,
+            "frac_executed": (counted["executed"] * w.ne / kern_s / 1e12 / fp64_peak) if counted["executed"] else None,
+            "note": "binding roof is the FP64 pipe (AI ~25 flop/B, SURVEY.md §8d); frac_executed counts what the kernel "
+                    "issues (tensor-core tile padding included)"}
+    roof_hbm = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                "traffic": traffic, "peak_source": hbm_src, "bytes_per_element": bpe}
+    return roof, roof_hbm
+
+
+def count_flops():
+    """Re-count the restatement's operations per element (small meshes; the count per element is size-independent
+    up to the Dirichlet rows)."""
+    from goma_b200.mesh import box_mesh
+    from oracle import port
+    from tests.cases import make_state
+
+    out = {}
+    for cfg, (key, elem, _) in CONFIGS.items():
+        p = problem_maker(cfg)(box_mesh(elem, (8,) * 3 if elem == "HEX8" else (4,) * 3))
+        st = make_state(p, seed=1)
+        h, U = (p.global_h_elem_siz(), p.global_velocity_norm(st["x"])) if p.pspg else (0.0, 0.0)
+        f, tot = port.port_flops(p, st, h_elem_avg=h, U_norm=U)
+        out[key] = {"flops_per_element": f, "ops": tot, "elements": p.mesh.num_elems}
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--edge", dest="n", type=int, default=100, help="elements per direction per GPU (100 -> 1M hex27 elements)")
+    ap.add_argument("--edge", dest="n", type=int, default=None,
+                    help="elements per direction (default: the size the config is named on: c2 100, c3 126, c4 32, c5 100)")
     ap.add_argument("--energy", action="store_true", help="config C3 physics (NS + energy) instead of C2")
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
-                    help="c2 = headline (default); c3 = --energy; c5 = hex8 PSPG + T + 2 species (kernel number only)")
+                    help="c2 = headline (default); c3 = NS + energy; c4 = ALE; c5 = hex8 PSPG + T + 2 species")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = `edge`^3 elements per GPU (default); strong = ONE `edge`^3 mesh split over the GPUs")
     ap.add_argument("--scatter", type=int, default=2,
                     help="0 fp64 atomics, 1 coloured load+add+store, 2 coloured first-touch stores (default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="N = 1, headline config: skip the device-timed C3 / C5 / C4 lines under `configs`")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--count-flops", action="store_true", help="re-count the restatement's flops per element and exit")
     args = ap.parse_args()
+    if args.count_flops:
+        count_flops()
+        return
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    if args.config == "c3":
-        args.energy = True
+    if args.energy:
+        args.config = "c3"
+    args.energy = args.config == "c3"
+    if args.n is None:
+        args.n = CONFIGS[args.config][2]
     if args.config in ("c4", "c5") and args.impl == "reference":
         raise SystemExit("the reference arm is defined on the headline config (c2) and c3")
 
@@ -296,7 +424,6 @@ def main():
     import torch.distributed as dist
 
     import __graft_entry__ as ge
-    from goma_b200.matrix_fill import MatrixFill
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the GPU fill has no CPU fallback")
@@ -326,44 +453,40 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    t_setup = time.perf_counter()
-    sub = None
-    make_on = (c5_problem_on if args.config == "c5" else c4_problem_on if args.config == "c4"
-               else (lambda mesh: cavity_problem_on(mesh, args.energy)))
-    if world == 1:
-        if args.config in ("c4", "c5"):
-            from goma_b200.mesh import box_mesh
-
-            problem = make_on(box_mesh("HEX8" if args.config == "c5" else "HEX27", (args.n,) * 3))
-        else:
-            problem = cavity_problem(args.n, args.energy)
-        num_owned_nodes = None
-        ne_owned = problem.mesh.num_elems
-    else:
-        # weak scaling: rank r owns the r-th n^3 slab of a (world*n) x n x n cavity, plus its ghost column
-        from goma_b200.dp_comm import exchange_dof, setup_peer_exchange, slab_subdomain
-
-        sub = slab_subdomain(make_on, args.n, rank, world, elem_type="HEX8" if args.config == "c5" else "HEX27")
-        problem = sub.problem
-        num_owned_nodes = sub.num_owned_nodes
-        ne_owned = int(sub.elem_owned.sum())
-    x = synthetic_state(problem, 20261017 + rank)
-    mf = MatrixFill(problem, device=local_rank, num_owned_nodes=num_owned_nodes)
-    mf.set_option("scatter", args.scatter)
-    ne = problem.mesh.num_elems  # assembled per step on this rank (owned + ghost elements)
-    n_unk, nnz = mf.num_unknowns, mf.nnz_plus
-    t_setup = time.perf_counter() - t_setup
+    def timed_steps(w, steps, warmup, sampler=None):
+        """`warmup` untimed + `steps` timed device-resident fills: (s/step wall max over ranks, device ms/step, launches)."""
+        w.mf.matrix_fill_full(w.x, assemble_jacobian=False)  # state into HBM once (one residual-only host call)
+        for _ in range(warmup):
+            w.step(dist, dev)
+        if sampler:
+            sampler.mark()
+        barrier()
+        t0 = time.perf_counter()
+        kernel_ms, launches = 0.0, 0
+        for _ in range(steps):
+            w.step(dist, dev)
+            ms, nl = w.mf.last_stats()
+            kernel_ms += ms
+            launches += nl
+        barrier()
+        step_s = max_over_ranks((time.perf_counter() - t0) / steps)
+        return step_s, max_over_ranks(kernel_ms / steps), launches
 
     from goma_b200.matrix_fill import device_view
 
+    w = Workload(args.config, args.n, rank, world, local_rank, args.scaling, args.scatter)
+    mf, sub, problem = w.mf, w.sub, w.problem
+    ne, n_unk, nnz, ne_owned, x = w.ne, w.n_unk, w.nnz, w.ne_owned, w.x
+    setup = mf.setup_stats()
     bufs = mf.device_buffers()
     d_x = device_view(bufs.d_x, n_unk, dev)
 
-    trace = [] if os.environ.get("GOMA_BENCH_TRACE") else None
     halo = None
     if sub is not None:
         # ghost refresh = goma_gpu_exchange_dof: one kernel pulling the ghost values out of the neighbours'
         # HBM over NVLink.  Checked once against the torch.distributed (NCCL send/recv) restatement.
+        from goma_b200.dp_comm import exchange_dof, setup_peer_exchange
+
         setup_peer_exchange(mf, sub)
         mf.matrix_fill_full(x, assemble_jacobian=False)  # state into HBM
         ref = d_x.clone()
@@ -371,51 +494,15 @@ def main():
         torch.cuda.synchronize(dev)
         mf.exchange_dof(0)
         torch.cuda.synchronize(dev)
-        same = bool(torch.equal(ref, d_x))
-        if not same:
+        if not bool(torch.equal(ref, d_x)):
             raise SystemExit(f"rank {rank}: peer-memory exchange_dof differs from the NCCL send/recv result")
-        halo = "goma_gpu_exchange_dof (one pull kernel over NVLink peer memory) before every fill; checked == NCCL send/recv"
+        halo = ("goma_gpu_exchange_dof (one pull kernel over NVLink peer memory) on its own stream before every fill, "
+                "overlapped with the interior element classes; checked == NCCL send/recv")
 
-    hU = [0.0, 0.0]
-
-    def step():
-        t0 = time.perf_counter()
-        if sub is not None:
-            mf.exchange_dof(0)  # ghost refresh before the fill (mm_sol_nonlinear.c:1273), same stream as the fill
-        if problem.pspg:  # global_h_elem_siz / global_velocity_norm on the device (mm_sol_nonlinear.c:1184-1192)
-            sums = mf.global_h_U(None if sub is None else sub.elem_owned)
-            if world > 1:
-                t = torch.tensor(sums, dtype=torch.float64, device=dev)
-                dist.all_reduce(t)
-                sums = t.cpu().numpy()
-            hU[0], hU[1] = sums[0] / sums[1], sums[2] / sums[3]
-        t1 = time.perf_counter()
-        mf.fill_device(h_elem_avg=hU[0], U_norm=hU[1])
-        if trace is not None:
-            trace.append((t1 - t0, time.perf_counter() - t1))
-
-    # state into HBM once (one residual-only host call), then the device-resident steps
     sampler = ClockSampler(local_rank)
     sampler.start()
-    mf.matrix_fill_full(x, assemble_jacobian=False)
-    for _ in range(args.warmup):
-        step()
-    sampler.mark()
-    barrier()
-    t0 = time.perf_counter()
-    kernel_ms, launches = 0.0, 0
-    for _ in range(args.steps):
-        step()
-        ms, nl = mf.last_stats()
-        kernel_ms += ms
-        launches += nl
-    barrier()
-    step_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    step_s, dev_ms, launches = timed_steps(w, args.steps, args.warmup, sampler)
     clocks = sampler.stop()
-    if trace is not None:
-        print(f"[bench trace rank {rank}] (exchange_s, fill_s) per step:", [(round(a * 1e3, 3), round(b * 1e3, 3)) for a, b in trace[-args.steps:]],
-              file=sys.stderr)
-    dev_ms = max_over_ranks(kernel_ms / args.steps)  # CUDA events on the library's stream: memsets + kernel(s)
     total_elems = sum_over_ranks(float(ne_owned))  # ghost elements are assembled twice but counted once
     value = total_elems / step_s
 
@@ -438,7 +525,7 @@ def main():
                 "note": "row_sum_scaling_scale on device: one read + one write of the MSR values"}
         # CSR hand-off to a GPU solver (§8f-2): structure once, values re-gathered after every fill
         free_b, _ = torch.cuda.mem_get_info(dev)
-        if 12.0 * (nnz + n_unk) + 4.0 * nnz / 8 > 0.9 * free_b:  # colind + values (+ transient node-node lists)
+        if 12.0 * (nnz + n_unk) > 0.9 * free_b:  # colind + values
             post["csr"] = "skipped: %.0f GB free on the device, the CSR copy needs %.0f GB" % (free_b / 1e9, 12e-9 * nnz)
             return_csr = False
         else:
@@ -513,61 +600,90 @@ def main():
             mf.fill_raw(ptrs)
         barrier()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+        # the host-copy roof beside it: what one D2H of the matrix alone takes on this link
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d_a = device_view(bufs.d_a, nnz + 1, dev)
+        ev0.record()
+        ha.copy_(d_a, non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        d2h_ms = max_over_ranks(ev0.elapsed_time(ev1))
         e2e = {"value": total_elems / e2e_s, "unit": "elements/s", "h2d_bytes_per_step": 8 * n_unk,
                "d2h_bytes_per_step": 8 * (nnz + 1) + 8 * n_unk, "ms_per_step": e2e_s * 1e3,
                "host_buffers": "pinned" if pinned else "pageable", "steps": args.e2e_steps,
-               "resid_checksum": float(hr.numpy().sum())}
-        del hx, ha, hr
+               "resid_checksum": float(hr.numpy().sum()),
+               "host_copy_roof": {"d2h_matrix_ms": d2h_ms, "GB/s": 8e-6 * (nnz + 1) / d2h_ms,
+                                  "elements_per_s_at_roof": total_elems / (d2h_ms * 1e-3),
+                                  "note": "one cudaMemcpy D2H of the MSR values alone, all ranks at once (max over ranks): "
+                                          "the floor of any host-buffer step"}}
+        del hx, ha, hr, d_a
 
     line = None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    traffic_tbl = {}
+    try:
+        traffic_tbl = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except OSError:
+        pass
+
+    def traffic_of(wk, nlaunch, nsteps):  # measured DRAM bytes per launch (ncu capture summarised under profiles/)
+        if wk.key in traffic_tbl and nlaunch:
+            return traffic_tbl[wk.key]["bytes_per_element"] * wk.ne * nsteps / nlaunch
+        return None
+
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        key = "c5_hex8_pspg_T_2Y" if args.config == "c5" else "c4_hex27_ale_ns" if args.config == "c4" else ("c3_hex27_ns_energy" if args.energy else "c2_hex27_ns")
-        flops = ALG_FLOPS_PER_ELEM[key]
-        bytes_per_elem = 8.0 * (nnz + n_unk) / ne + problem.mesh.npe * 4 + 8.0 * (3 * problem.mesh.num_nodes + n_unk) / ne
-        kern_s = dev_ms * 1e-3
-        traffic = None  # measured DRAM bytes per launch (ncu capture summarised under profiles/)
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
-            if key in tj and launches:
-                traffic = tj[key]["bytes_per_element"] * ne * args.steps / launches
-        except OSError:
-            pass
-        fp64_meas = fp64_peak_tflops(dev)
-        fp64_peak = max(fp64_meas, 1e-9)
-        ach_tf = flops * ne / kern_s / 1e12
-        ach_gbs = bytes_per_elem * ne / kern_s / 1e9
+        fp64_peak = max(fp64_peak_tflops(dev), 1e-9)
+        roof, roof_hbm = roofline_of(w, dev_ms, fp64_peak, hbm_peak, hbm_src, traffic_of(w, launches, args.steps))
         line = {
             "metric": "jacobian_residual_elements_per_s", "value": value, "unit": "elements/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "elements_per_gpu": ne_owned,
+            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.config, args.n, args.scaling, world), "elements_per_gpu": ne_owned,
                        "elements_assembled_per_gpu": ne, "unknowns_per_gpu": n_unk,
                        "halo": halo,
                        "nnz_per_gpu": nnz, "scatter": ["fp64 atomics", "coloured load+add+store", "coloured first-touch stores"][args.scatter],
                        "l2": "inputs larger than L2 (MSR values %.1f GB per GPU rewritten every step)" % (8e-9 * nnz),
-                       "setup_s": round(t_setup, 1)},
+                       "setup_s": round(w.init_s, 2),
+                       "setup": {"goma_gpu_fill_init_s": round(w.init_s, 3), **{k: round(v, 3) for k, v in setup.items()},
+                                 "synthetic_mesh_and_state_s (python harness, not the product)": round(w.mesh_gen_s, 2)}},
             "clocks": clocks, "gpu_launches": launches, "device_ms_per_step": dev_ms,
-            "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": ach_tf / fp64_peak, "traffic": traffic,
-                         "peak_source": "fp64 matmul micro-benchmark in this run (nominal %.0f)" % FP64_PEAK_NOMINAL_TFLOPS,
-                         "flops_per_element": flops,
-                         "note": "binding roof of the hex27 fill is the FP64 pipe (AI ~27 flop/B, SURVEY.md §8d)"},
-            "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
-                             "bytes_per_element": bytes_per_elem},
+            "roofline": roof, "roofline_hbm": roof_hbm,
         }
         if post:
             post["hbm_frac"] = post["GB/s"] / hbm_peak
             line["post_fill"] = post
         if e2e:
             line["e2e"] = e2e
+    mf.close()
+    del mf, d_x
+    torch.cuda.empty_cache()
+
+    # ---- the other named configs, device-timed, one after the other on the freed GPU (N = 1, headline run only)
+    if world == 1 and args.config == "c2" and not args.no_extra_configs and rank == 0:
+        extra = {}
+        for cfg in ("c3", "c5", "c4"):
+            try:
+                wk = Workload(cfg, CONFIGS[cfg][2], 0, 1, local_rank, "weak", args.scatter)
+                s_s, d_ms, nl = timed_steps(wk, 3, 3)
+                r, rh = roofline_of(wk, d_ms, fp64_peak, hbm_peak, hbm_src, traffic_of(wk, nl, 3))
+                extra[cfg] = {"workload": workload_name(cfg, wk.n), "value": wk.ne_owned / s_s, "unit": "elements/s",
+                              "ms_per_step": s_s * 1e3, "device_ms_per_step": d_ms, "steps": 3, "warmup": 3,
+                              "gpu_launches": nl, "elements": wk.ne, "unknowns": wk.n_unk, "nnz": wk.nnz,
+                              "setup_s": round(wk.init_s, 2), "roofline": r, "roofline_hbm": rh}
+                wk.mf.close()
+                del wk
+                torch.cuda.empty_cache()
+            except Exception as ex:  # an extra line must never take the headline down with it
+                extra[cfg] = {"error": str(ex)[:300]}
+        line["configs"] = extra
+
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(energy=args.energy)
@@ -575,7 +691,6 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": "elements/s", "cores": 0, "kind": "reference",
                                         "sample": f"failed: {ex}"}
         print(json.dumps(line))
-    mf.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -25,7 +25,7 @@ EXPORTED = [
     "goma_gpu_pack_dofs", "goma_gpu_unpack_dofs", "goma_gpu_fill_last_stats", "goma_gpu_fill_set_option",
     "goma_gpu_last_error", "goma_gpu_pattern_msr", "goma_gpu_exchange_export", "goma_gpu_exchange_setup",
     "goma_gpu_exchange_dof", "goma_gpu_row_sum_scale", "goma_gpu_scale_buffer", "goma_gpu_vector_norms", "goma_gpu_csr_structure",
-    "goma_gpu_csr_values", "goma_gpu_exchange_status", "goma_gpu_fill_device_async", "goma_gpu_fill_wait",
+    "goma_gpu_csr_values", "goma_gpu_exchange_status", "goma_gpu_fill_device_async", "goma_gpu_fill_wait", "goma_gpu_fill_setup_stats",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -114,6 +114,7 @@ def load_library():
     lib.goma_gpu_pack_dofs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.goma_gpu_unpack_dofs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.goma_gpu_fill_last_stats.argtypes = [C.c_void_p, _dp, _ip]
+    lib.goma_gpu_fill_setup_stats.argtypes = [C.c_void_p, _dp]
     lib.goma_gpu_fill_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     _lib = lib
     return lib

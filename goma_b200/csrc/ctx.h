@@ -24,20 +24,48 @@ using goma_b200::fail;
                           std::to_string(__LINE__));                                           \
   } while (0)
 
+namespace goma_b200 {
+struct KindInfo {  // per node kind: unknowns, of which pressure (last in the node), offset of T (-1: none)
+  int nunk[GOMA_GPU_MAX_KINDS], npress[GOMA_GPU_MAX_KINDS], tslot[GOMA_GPU_MAX_KINDS];
+};
+// device-resident topology built by build_pattern_device (pattern_gpu.cu)
+struct DevPattern {
+  int *ne_ptr = nullptr, *ne_list = nullptr;            // node -> elements, ascending
+  long long *nn_ptr = nullptr;                          // node-node lists (exo_conn.c build_node_node), sorted
+  int *nn_list = nullptr;
+  unsigned short *cum_full = nullptr, *cum_p = nullptr;  // per list entry: unknowns / pressure unknowns of earlier neighbours
+  int *row_full = nullptr, *row_p = nullptr;            // per node: unknowns / pressure unknowns of all neighbours
+  unsigned *pair_first = nullptr, *node_first = nullptr;  // first-touch masks
+  unsigned char *cls = nullptr;                         // class (colour, + ncol for border elements) of each element
+  long long nn_total = 0;
+};
+}  // namespace goma_b200
+struct goma_gpu_ctx;
+namespace goma_b200 {
+KindInfo make_kind_info(const goma_gpu_problem &p);
+int build_pattern_device(goma_gpu_ctx *c);
+void free_device_pattern(goma_gpu_ctx *c, bool keep_node_node);
+int download_pattern(goma_gpu_ctx *c, Pattern &out);
+}  // namespace goma_b200
+
 struct goma_gpu_ctx {
   goma_gpu_problem prob;  // scalar members + kind tables only; pointers are not retained
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  goma_b200::Pattern pat;  // host copy kept for get_msr (nn lists) -- sized for test/bench meshes
+  goma_b200::DevPattern dpat;
+  long long nnz_plus = 0;          // == ija[N] of the MSR graph
+  int num_colours = 0;             // element colours; classes [0, ncol) interior, [ncol, 2 ncol) border elements
+  int first_border_class = 0;      // classes from here on touch external nodes: they wait for the ghost exchange
+  cudaStream_t xstream = nullptr;  // exchange_dof runs here, overlapped with the interior classes
+  cudaEvent_t ev_x = nullptr, ev_pre = nullptr;
+  bool exchange_in_flight = false;
   // device arrays
   int *d_conn = nullptr, *d_first = nullptr;
   double *d_coord[3] = {nullptr, nullptr, nullptr};
   unsigned char *d_kind = nullptr, *d_dbc_flag = nullptr;
   double *d_dbc_value = nullptr;
   long long *d_rowstart = nullptr;
-  unsigned short *d_pair_full = nullptr, *d_pair_p = nullptr;
-  unsigned *d_pair_first = nullptr, *d_node_first = nullptr;
   double *d_tables = nullptr;
   unsigned char *d_erec = nullptr;  // per-element gather records (ElemRec<C>)
   double *d_x = nullptr, *d_x_old = nullptr, *d_x_older = nullptr, *d_xdot = nullptr, *d_xdot_old = nullptr;
@@ -77,4 +105,5 @@ struct goma_gpu_ctx {
   double last_ms = 0.0;
   int last_launches = 0;
   size_t device_bytes = 0;
+  double setup_s[5] = {0, 0, 0, 0, 0};  // goma_gpu_fill_init: total, validation, uploads, pattern (device), tables + state + records
 };

@@ -136,9 +136,16 @@ extern "C" int goma_gpu_exchange_dof(goma_gpu_ctx *c, int which) {
   A.error = c->d_xflags + 3 * GOMA_GPU_MAX_NEIGHBORS;
   A.spin_limit = c->exchange_spin_limit;
   const int total = c->recv_ptr[A.nn];
-  const int threads = 256, blocks = std::max(1, std::min(148, (total + threads - 1) / threads));
-  exchange_dof_kernel<<<blocks, threads, 0, c->stream>>>(A);
+  // The pull runs on its own stream, behind everything enqueued so far on the context's stream (the solver update
+  // that produced the vector); the next fill assembles its interior classes meanwhile and makes its border classes
+  // wait for ev_x.  Few blocks: a block waiting for a late neighbour holds registers a fill CTA could use.
+  const int threads = 256, blocks = std::max(1, std::min(32, (total + threads - 1) / threads));
+  CU(cudaEventRecord(c->ev_pre, c->stream));
+  CU(cudaStreamWaitEvent(c->xstream, c->ev_pre, 0));
+  exchange_dof_kernel<<<blocks, threads, 0, c->xstream>>>(A);
   CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ev_x, c->xstream));
+  c->exchange_in_flight = true;
   return 0;
 }
 
@@ -158,6 +165,7 @@ extern "C" int goma_gpu_exchange_status(goma_gpu_ctx *c) {
   if (!c->d_xflags) return 0;
   CU(cudaSetDevice(c->device));
   unsigned long long e = 0;
+  CU(cudaStreamSynchronize(c->xstream));
   CU(cudaMemcpyAsync(&e, c->d_xflags + 3 * GOMA_GPU_MAX_NEIGHBORS, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (e) return fail(-4, "exchange_dof: neighbour slot " + std::to_string(e - 1) + " never published its vector (timed out)");

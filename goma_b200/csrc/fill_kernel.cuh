@@ -41,8 +41,10 @@ struct FillParams {
   const unsigned char *node_kind;
   int kind_slot[GOMA_GPU_MAX_KINDS][GOMA_NSLOT];
   const long long *rowstart;
-  const unsigned short *pair_full;
-  const unsigned short *pair_p;
+  const long long *nn_ptr;         // node-node lists with the running unknown counts along them (init only:
+  const int *nn_list;              // build_records_kernel turns them into the per-element slot map)
+  const unsigned short *cum_full;
+  const unsigned short *cum_p;
   const unsigned *pair_first;  // first-touch masks (write-once scatter)
   const unsigned *node_first;
   const unsigned char *dbc_flag;
@@ -125,8 +127,9 @@ struct Cfg {
   static constexpr int G_C1 = G_CM + (ALE ? DIM * DIM : 0);        // ed3 lambda vc^2 vc^(-2/3)
   static constexpr int GPD = (G_C1 + (ALE ? 1 : 0) + 1) & ~1;
   static constexpr int NROWS = NF * NN + NP;  // rows of the element block
-  static constexpr int NPART = NGP >= 3 ? 3 : 1;  // Gauss-point thirds of the row sums
   static constexpr bool GENERAL = !P1 || NSPEC > 0 || ALE;  // generic block accumulation instead of the NS(+T) fast path
+  // Gauss-point thirds of the row sums (the tensor-core configurations sum the rows in one product)
+  static constexpr int NPART = (PHI_IN_OPERANDS || NGP < 3) ? 1 : 3;
   // hex27 Q2/P1 NS(+T): the node-pair blocks run on the FP64 tensor cores (mma.sync m8n8k4.f64, SASS DMMA): 8 x 8
   // node blocks, K = Gauss points (27 -> 28); operand tables component-major with bank-conflict-free strides
   static constexpr bool MMA = NN == 27 && NGP == 27 && P1 && !GENERAL && !WS_;
@@ -329,6 +332,14 @@ __device__ __forceinline__ void momentum_source(const FillParams &P, double T, d
   }
 }
 
+// D (8x8) += A (8x4, row) * B (4x8, col) in fp64 on the tensor cores (SASS: DMMA.8x8x4).  Lane l holds
+// A[l/4][l%4], B[l%4][l/4] and D[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d[0]), "+d"(d[1])
+      : "d"(a), "d"(b));
+}
+
 // length-N dot product with three independent accumulation chains (hides DFMA latency in the
 // low-parallelism set-up phases)
 template <int N>
@@ -374,9 +385,27 @@ __global__ void build_records_kernel(const FillParams P, int num_elems) {
     for (int d = 0; d < DIM; d++) r.X[d][k] = P.coord[d][nd];
   }
   r.node_first = P.node_first ? P.node_first[e] : 0u;
-  for (int idx = 0; idx < NN * NN; idx++) {
-    (&r.po[0][0])[idx] = P.pair_full[(size_t)e * NN * NN + idx];
-    if (C::ENERGY) (&r.pp[0][0])[idx] = P.pair_p[(size_t)e * NN * NN + idx];
+  // slot map: column offset of node j's first unknown in a row of node i = the running unknown count at node j's
+  // position in node i's sorted neighbour list (replaces the in_list search of load_lec, mm_fill.c:5461)
+  for (int i = 0; i < NN; i++) {
+    const long long b = P.nn_ptr[node[i]];
+    const int len = (int)(P.nn_ptr[node[i] + 1] - b);
+    for (int j = 0; j < NN; j++) {
+      int lo = 0, hi = len;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (P.nn_list[b + mid] < node[j])
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      if (lo >= len || P.nn_list[b + lo] != node[j]) {
+        P.flags[3] = 1;  // "Could not find vbl in sparse matrix"
+        lo = 0;
+      }
+      r.po[i][j] = P.cum_full[b + lo];
+      if (C::ENERGY) r.pp[i][j] = P.cum_p[b + lo];
+    }
   }
   for (int k = 0; k < NN; k++) {
     int rk = 0;
@@ -456,6 +485,29 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
   }
   GOMA_STAMP(0);
   // ---- phase 1: J[a][b] = sum_k x_b,k dphi_k/dxi_a   (beer_belly, mm_fill_util.c:258-276)
+  if constexpr (C::MMA) {
+    // tensor cores: rows m = (Gauss point, a) (81 -> 88), columns b (3 -> 8), K = nodes (27 -> 28)
+    const int warp = tid >> 5, lane = tid & 31, r = lane >> 2, kq = lane & 3;
+    for (int mt = warp; mt < 11; mt += C::NWARP) {
+      const int m = min(mt * 8 + r, 80);
+      const double *arow = &t_dphi[(m / 3) * NN * DIM + (m % 3)];  // + 3 * node
+      double acc[2] = {0.0, 0.0};
+#pragma unroll
+      for (int ks = 0; ks < 7; ks++) {
+        const int k = 4 * ks + kq;
+        const bool live = k < NN;
+        const double av = live ? arow[3 * k] : 0.0;
+        const double bv = (live && r < DIM) ? rec.X[r][k] : 0.0;
+        dmma884(acc, av, bv);
+      }
+      const int mo = mt * 8 + r;
+      if (mo < 81) {
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+          if (2 * kq + c < DIM) (&s.B[0][0])[mo * DIM + 2 * kq + c] = acc[c];
+      }
+    }
+  } else
   //      one thread per (Gauss point, a, third of the nodes): each dphi load feeds DIM FMAs
   {
     constexpr int NITEM = NGP * DIM, Q = (NN + 3) / 4;
@@ -516,7 +568,8 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
       J[7] = -(j00 * j21 - j20 * j01) * rd;
       J[8] = (j00 * j11 - j10 * j01) * rd;
     }
-    if (fabs(det) < 1.e-10) P.flags[2] = 1;  // zero_detJ (mm_fill_util.c:335-343)
+    // (zero_detJ, mm_fill_util.c:335-343, is only ever raised inside beer_belly's SHELL / TRISHELL branch (:312-344):
+    //  for the continuum elements of this path the reference assembles whatever |detJ| is, and so does this kernel)
     s.w[tid] = det * t_wt[tid];  // d_area = detJ * wt * h3, h3 = 1 (Cartesian)
   }
   if (!C::P1 && tid == NT - 1) {
@@ -597,6 +650,34 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
   cta_sync<C>();
   GOMA_STAMP(3);
   // ---- phase 4: field values, gradients, time derivatives at the Gauss points (load_fv, load_fv_grads)
+  if constexpr (C::MMA) {
+    // tensor cores: F_q[gp][f] = sum_k SJ_q[gp][k] U[f][k], q = value | grad_0..2 | time derivative (phi with Udot):
+    // rows = Gauss points (27 -> 32), columns = fields (NF -> 8), K = nodes (27 -> 28)
+    const int warp = tid >> 5, lane = tid & 31, r = lane >> 2, kq = lane & 3;
+    const int nq = P.transient ? 5 : 4;
+    for (int job = warp; job < 4 * nq; job += C::NWARP) {
+      const int mt = job & 3, q = job >> 2;
+      const int gpr = min(mt * 8 + r, 27);  // row 27 of the tables is zero
+      const double *arow = &op.SJ[gpr][(q == 4 ? 0 : q) * 28];
+      const double (*Usrc)[NN] = q == 4 ? Udot : U;
+      double acc[2] = {0.0, 0.0};
+#pragma unroll
+      for (int ks = 0; ks < 7; ks++) {
+        const int k = 4 * ks + kq;
+        const double av = arow[k];  // column 27 is zero
+        const double bv = (k < NN && r < NF) ? Usrc[r][k] : 0.0;
+        dmma884(acc, av, bv);
+      }
+      const int gp = mt * 8 + r;
+      if (gp < NGP) {
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+          if (2 * kq + c < NF) s.F[gp][2 * kq + c][q == 4 ? 1 + DIM : q] = acc[c];
+      }
+    }
+    if (!P.transient)
+      for (int idx = tid; idx < NGP * NF; idx += NT) s.F[idx / NF][idx % NF][1 + DIM] = 0.0;
+  } else
   //      four lanes per Gauss point, each over a quarter of the nodes for ALL fields (one load of the basis
   //      functions feeds NF x (DIM+2) FMAs), combined by shuffles
   {
@@ -839,6 +920,55 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
   //      points by one thread; the velocity rows accumulate the P1 pressure coupling on the way:
   //      S[i][a][p] = sum_gp w grad_phi_i[a] psi_p, shared by J_m_P (mm_fill_momentum.c:2091-2104) and
   //      J_c_v (mm_fill_continuity.c:686-716)
+  if constexpr (C::MMA) {
+    // tensor cores.  Warps 0-3: the velocity (and temperature) rows of 8 nodes each,
+    //   R[i][n] = sum_gp sum_c SI_c[gp][i] Gc[gp][n],  n = a: (G_RQ+a | G_RP+3a+p),  n = 3: (G_RE | G_RF+p)
+    // warps 4-7: the P1 coupling sums S[a][i][p] = sum_gp SI_{1+a}[gp][i] psi[gp][p] (12 tiles of 8 nodes x 4)
+    const int warp = tid >> 5, lane = tid & 31, r = lane >> 2, kq = lane & 3;
+    if (warp < 4) {
+      const int ia = min(warp * 8 + r, 27);
+      const int n = r;  // column of the B fragment this lane feeds
+      const bool nv = n < DIM, nT = C::ENERGY && n == C::F_T;
+      const int q0 = nv ? C::G_RQ + n : C::G_RE, q1 = nv ? C::G_RP + n * DIM : C::G_RF;
+      double acc[2] = {0.0, 0.0};
+#pragma unroll 1
+      for (int ks = 0; ks < 7; ks++) {
+        const int gp = 4 * ks + kq;  // row 27 of SI and GP is zero
+        const double *si = &op.SI[gp][ia];
+        const double *G = s.GP[bo][gp];
+        const bool on = nv || nT;
+        dmma884(acc, si[0], on ? G[q0] : 0.0);
+#pragma unroll
+        for (int p = 0; p < DIM; p++) dmma884(acc, si[28 * (1 + p)], on ? G[q1 + p] : 0.0);
+      }
+      const int i = warp * 8 + r;
+      if (i < NN) {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const int col = 2 * kq + c;
+          if (col < DIM || (C::ENERGY && col == C::F_T)) s.redR[0][col * NN + i] = acc[c];
+        }
+      }
+    } else {
+      for (int job = warp - 4; job < 4 * DIM; job += 4) {
+        const int mt = job & 3, a = job >> 2;
+        const int ia = min(mt * 8 + r, 27);
+        double acc[2] = {0.0, 0.0};
+#pragma unroll
+        for (int ks = 0; ks < 7; ks++) {
+          const int gp = 4 * ks + kq;
+          const double bv = (gp < NGP && r < NP) ? t_psi[gp * (DIM + 1) + r] : 0.0;
+          dmma884(acc, op.SI[gp][(1 + a) * 28 + ia], bv);
+        }
+        const int i = mt * 8 + r;
+        if (i < NN) {
+#pragma unroll
+          for (int c = 0; c < 2; c++)
+            if (2 * kq + c < NP) s.redS[0][a * NN + i][2 * kq + c] = acc[c];
+        }
+      }
+    }
+  } else
   //      velocity rows: one thread per (node i, third) does all DIM components off one load of the test functions
   for (int idx = tid; idx < NN * NPART; idx += NT) {
     const int c = idx / NN, i = idx - c * NN;
@@ -878,6 +1008,7 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
   //      the other rows: one thread per (row, third)
   for (int idx = tid; idx < (NROW - DIM * NN) * NPART; idx += NT) {
     const int c = idx / (NROW - DIM * NN), r = DIM * NN + idx - c * (NROW - DIM * NN);
+    if (C::MMA && r < NF * NN) continue;  // temperature rows: summed with the velocity rows on the tensor cores
     const int gp0 = c * NGP / NPART, gp1 = (c + 1) * NGP / NPART;
     const bool prow = r >= NF * NN;  // P1 continuity row
     const int f = prow ? 0 : r / NN;
@@ -1354,13 +1485,6 @@ __device__ __forceinline__ void write_pair(const FillParams &P, const ElemRec<C>
   }
 }
 
-// D (8x8) += A (8x4, row) * B (4x8, col) in fp64 on the tensor cores (SASS: DMMA.8x8x4).  Lane l holds
-// A[l/4][l%4], B[l%4][l/4] and D[l/4][2*(l%4) + {0,1}].
-__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-      : "+d"(d[0]), "+d"(d[1])
-      : "d"(a), "d"(b));
-}
 
 // =====================================================================================
 // phase 6 on the FP64 tensor cores (hex27 Q2/P1 NS and NS+T).  For every component pair (a, b) the node-pair
@@ -1440,6 +1564,13 @@ __device__ __forceinline__ void gauss_blocks_mma(const FillParams &P, const Smem
 #pragma unroll
       for (int a = 0; a < 3; a++) dfdT[a] = -P.g[a] * P.rho * P.beta * P.etm_mom[4];
     }
+    // write-out: the node's fields are consecutive unknowns (checked at init), so the NF entries of (row, column
+    // node j) are contiguous; everything that depends on the row node only is fetched once per block
+    long long rsv[NF];
+#pragma unroll
+    for (int fr = 0; fr < NF; fr++) rsv[fr] = rec.rs[fr][i];
+    const int ri = rec.rank[i];
+    const unsigned fi = rec.first[i];
 #pragma unroll
     for (int c = 0; c < 2; c++) {
       const int j = J0 + 2 * kq + c;
@@ -1457,7 +1588,21 @@ __device__ __forceinline__ void gauss_blocks_mma(const FillParams &P, const Smem
         }
       }
       if constexpr (C::ENERGY) V[C::F_T][C::F_T] = ce_adv * S1[c] + ce_diff * S2 + ce_mass * S3[c];  // J_e_T
-      write_pair<C, MODE>(P, rec, i, j, V);
+      const int rj = rec.rank[j];
+      if (rj == ri) {  // the diagonal node pair: the diagonal entries live in a[0..N), the rest shifts
+        write_pair<C, MODE>(P, rec, i, j, V);
+        continue;
+      }
+      const bool first = (fi >> j) & 1u;
+      const int off = rec.po[i][j] + rec.cs[j][0] - (rj > ri ? 1 : 0);
+      const int offT = C::ENERGY ? off - rec.pp[i][j] : off;  // energy rows carry no pressure columns
+#pragma unroll
+      for (int fr = 0; fr < NF; fr++) {
+        if (rsv[fr] < 0) continue;
+        double *dst = P.a + rsv[fr] + ((C::ENERGY && fr == C::F_T) ? offT : off);
+#pragma unroll
+        for (int fc = 0; fc < NF; fc++) slot_add_m<MODE>(dst + fc, V[fr][fc], first);
+      }
     }
   }
 }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -108,6 +109,15 @@ int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
     return 0;
   }
   if (p1 && p.elem_type == GOMA_GPU_HEX27) {
+    // the tensor-core write-out stores the fields of a node as one run: U, V, W(, T) must be consecutive unknowns
+    // (they are in the reference's ordering: variables by increasing id, include/rf_fem_const.h:174-200)
+    for (int k = 0; k < p.num_kinds; k++) {
+      const int u = p.kind_slot[k][GOMA_SLOT_U];
+      if (u < 0) continue;
+      if (p.kind_slot[k][GOMA_SLOT_V] != u + 1 || p.kind_slot[k][GOMA_SLOT_W] != u + 2 ||
+          (p.energy && p.kind_slot[k][GOMA_SLOT_T] != u + 3))
+        return fail(-2, "velocity (and temperature) unknowns must be consecutive inside a node");
+    }
     // config C2 (Q2/P1 Navier-Stokes): warp-specialised kernel, 192 builder + 128 multiplier threads, one CTA per SM
     static const bool ws = getenv("GOMA_GPU_WS") ? atoi(getenv("GOMA_GPU_WS")) != 0 : false;
     k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2>>()
@@ -214,6 +224,7 @@ static int validate(const goma_gpu_problem &p) {
 extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, goma_gpu_ctx **out) {
   if (!problem || !out) return fail(-2, "null argument");
   *out = nullptr;
+  const auto t_init0 = std::chrono::steady_clock::now();
   const goma_gpu_problem &p = *problem;
   if (int rc = validate(p)) return rc;
   KernelEntry ke;
@@ -231,47 +242,45 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
   c->prob = p;
   c->device = device;
   c->num_owned_unknowns = p.num_owned_nodes < p.num_nodes ? p.first_unknown[p.num_owned_nodes] : p.num_unknowns;
-  int nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
-  std::string perr = build_pattern(p, c->pat, std::min(nthreads, 32));
-  if (!perr.empty()) return fail(-2, "sparsity pattern: " + perr);
-  // optional bit-exact check against the host's own MSR graph
-  if (p.ija) {
-    const int N = p.num_unknowns;
-    if (c->pat.nnz_plus > 2147483647LL) return fail(-2, "host ija given but nnz exceeds the 32-bit MSR limit");
-    std::vector<int> mine((size_t)c->pat.nnz_plus + 1, 0);
-    emit_msr_columns(p, c->pat, mine.data());
-    (void)N;
-    for (long long k = 0; k < c->pat.nnz_plus; k++) {
-      if (mine[k] != p.ija[k]) return fail(-2, "host MSR graph differs from the derived one at ija[" + std::to_string(k) + "]");
-    }
-  }
-
   const int nn = p.num_nodes, ne = p.num_elems, npe = p.elem_type, N = p.num_unknowns;
   int rc = 0;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double>(b - a).count();
+  };
+  const auto t_upload = now();
+  c->setup_s[1] = secs(t_init0, t_upload);  // validate()
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
+  CU(cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_pre, cudaEventDisableTiming));
   rc |= upload(&c->d_conn, p.elem_connect, (size_t)ne * npe, c);
   rc |= upload(&c->d_first, p.first_unknown, nn, c);
   for (int d = 0; d < p.dim; d++) rc |= upload(&c->d_coord[d], p.coord[d], nn, c);
   rc |= upload(&c->d_kind, p.node_kind, nn, c);
   rc |= upload(&c->d_dbc_flag, p.dbc_flag, N, c);
   rc |= upload(&c->d_dbc_value, p.dbc_value, N, c);
-  static_assert(sizeof(long long) == sizeof(int64_t), "64-bit row pointers");
-  rc |= upload(&c->d_rowstart, (const long long *)c->pat.rowstart.data(), (size_t)N + 1, c);
-  rc |= upload(&c->d_pair_full, (const unsigned short *)c->pat.pair_full.data(), c->pat.pair_full.size(), c);
-  rc |= upload(&c->d_pair_p, (const unsigned short *)c->pat.pair_p.data(), c->pat.pair_p.size(), c);
-  rc |= upload(&c->d_pair_first, (const unsigned *)c->pat.pair_first.data(), c->pat.pair_first.size(), c);
-  rc |= upload(&c->d_node_first, (const unsigned *)c->pat.node_first.data(), c->pat.node_first.size(), c);
-  rc |= upload(&c->d_elem_list, c->pat.colour_order.data(), c->pat.colour_order.size(), c);
-  c->colour_begin = c->pat.colour_begin;
   if (rc) return -3;
-  // pair tables live on the device from here on
-  std::vector<uint16_t>().swap(c->pat.pair_full);
-  std::vector<uint16_t>().swap(c->pat.pair_p);
-  std::vector<uint32_t>().swap(c->pat.pair_first);
-  std::vector<uint32_t>().swap(c->pat.node_first);
-  std::vector<int>().swap(c->pat.colour_order);
+  // node-element / node-node lists, MSR row starts, element colouring and first-touch masks: built on the device
+  // from the arrays just uploaded (pattern_gpu.cu)
+  const auto t_pat = now();
+  c->setup_s[2] = secs(t_upload, t_pat);
+  if (int prc = build_pattern_device(c)) return prc;
+  const auto t_pat1 = now();
+  c->setup_s[3] = secs(t_pat, t_pat1);
+  // optional bit-exact check against the host's own MSR graph
+  if (p.ija) {
+    if (c->nnz_plus > 2147483647LL) return fail(-2, "host ija given but nnz exceeds the 32-bit MSR limit");
+    Pattern hp;
+    if (int drc = download_pattern(c, hp)) return drc;
+    std::vector<int> mine((size_t)c->nnz_plus + 1, 0);
+    emit_msr_columns(p, hp, mine.data());
+    for (long long k = 0; k < c->nnz_plus; k++) {
+      if (mine[k] != p.ija[k]) return fail(-2, "host MSR graph differs from the derived one at ija[" + std::to_string(k) + "]");
+    }
+  }
 
   // quadrature / basis tables, packed in the order Smem<C>::tbl expects
   ElemTables t = make_tables(p.elem_type);
@@ -289,7 +298,7 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
   rc |= dalloc(&c->d_xdot, N, c);
   rc |= dalloc(&c->d_xdot_old, N, c);
   rc |= dalloc(&c->d_resid, N, c);
-  rc |= dalloc(&c->d_a, (size_t)c->pat.nnz_plus + 1, c);
+  rc |= dalloc(&c->d_a, (size_t)c->nnz_plus + 1, c);
   rc |= dalloc(&c->d_flags, 4, c);
   if (rc) return -3;
 
@@ -300,14 +309,15 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
     c->device_bytes += (size_t)ne * ke.rec_bytes;
     FillParams P;
     static_params(c, P);
+    P.flags = c->d_flags;
     if (ne > 0) ke.build_records<<<(ne + 127) / 128, 128, 0, c->stream>>>(P, ne);
     CU(cudaGetLastError());
+    int h_flags[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    void *drop[] = {c->d_pair_full, c->d_pair_p, c->d_pair_first, c->d_node_first};
-    for (void *q : drop)
-      if (q) cudaFree(q);
-    c->d_pair_full = c->d_pair_p = nullptr;
-    c->d_pair_first = c->d_node_first = nullptr;
+    if (h_flags[3]) return fail(-2, "sparsity pattern: Could not find vbl in sparse matrix");  // mm_fill.c:5462 wording
+    // the node-node lists stay (CSR structure, ija export); everything else of the topology is dropped
+    free_device_pattern(c, true);
   }
 
   if (getenv("GOMA_GPU_PROFILE")) rc |= dalloc(&c->d_prof, 2 * 8 * 4096, c);
@@ -316,6 +326,8 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
     if (e != cudaSuccess) return fail(-3, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
   }
   if (rc) return -3;
+  c->setup_s[4] = secs(t_pat1, now());
+  c->setup_s[0] = secs(t_init0, now());
   guard.c = nullptr;
   *out = c;
   return 0;
@@ -325,7 +337,7 @@ extern "C" void goma_gpu_fill_destroy(goma_gpu_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   void *ptrs[] = {c->d_conn, c->d_first, c->d_coord[0], c->d_coord[1], c->d_coord[2], c->d_kind, c->d_dbc_flag,
-                  c->d_dbc_value, c->d_rowstart, c->d_pair_full, c->d_pair_p, c->d_pair_first, c->d_node_first, c->d_prof, c->d_tables, c->d_erec, c->d_x, c->d_x_old,
+                  c->d_dbc_value, c->d_rowstart, c->d_prof, c->d_tables, c->d_erec, c->d_x, c->d_x_old,
                   c->d_x_older, c->d_xdot, c->d_xdot_old, c->d_a, c->d_resid, c->d_flags, c->d_elem_list};
   for (void *q : ptrs)
     if (q) cudaFree(q);
@@ -345,6 +357,10 @@ extern "C" void goma_gpu_fill_destroy(goma_gpu_ctx *c) {
   if (c->d_scale) cudaFree(c->d_scale);
   if (c->d_partials) cudaFree(c->d_partials);
   if (c->d_zero_rows) cudaFree(c->d_zero_rows);
+  free_device_pattern(c, false);
+  if (c->ev_x) cudaEventDestroy(c->ev_x);
+  if (c->ev_pre) cudaEventDestroy(c->ev_pre);
+  if (c->xstream) cudaStreamDestroy(c->xstream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -353,15 +369,18 @@ extern "C" void goma_gpu_fill_destroy(goma_gpu_ctx *c) {
 
 extern "C" int goma_gpu_fill_get_msr(goma_gpu_ctx *c, long long *nnz_plus) {
   if (!c) return fail(-2, "null context");
-  if (nnz_plus) *nnz_plus = c->pat.nnz_plus;
+  if (nnz_plus) *nnz_plus = c->nnz_plus;
   return 0;
 }
 
 // ija export needs the host arrays again (they are not retained in the context)
 extern "C" int goma_gpu_fill_export_msr(goma_gpu_ctx *c, const goma_gpu_problem *p, int *ija_out) {
   if (!c || !p || !ija_out) return fail(-2, "null argument");
-  if (c->pat.nnz_plus > 2147483647LL) return fail(-2, "nnz exceeds the 32-bit MSR limit of ija");
-  emit_msr_columns(*p, c->pat, ija_out);
+  if (c->nnz_plus > 2147483647LL) return fail(-2, "nnz exceeds the 32-bit MSR limit of ija");
+  CU(cudaSetDevice(c->device));
+  Pattern hp;
+  if (int drc = download_pattern(c, hp)) return drc;
+  emit_msr_columns(*p, hp, ija_out);
   return 0;
 }
 
@@ -430,10 +449,12 @@ static void static_params(const goma_gpu_ctx *c, FillParams &P) {
   P.node_kind = c->d_kind;
   memcpy(P.kind_slot, p.kind_slot, sizeof(P.kind_slot));
   P.rowstart = c->d_rowstart;
-  P.pair_full = c->d_pair_full;
-  P.pair_p = c->d_pair_p;
-  P.pair_first = c->d_pair_first;
-  P.node_first = c->d_node_first;
+  P.nn_ptr = c->dpat.nn_ptr;
+  P.nn_list = c->dpat.nn_list;
+  P.cum_full = c->dpat.cum_full;
+  P.cum_p = c->dpat.cum_p;
+  P.pair_first = c->dpat.pair_first;
+  P.node_first = c->dpat.node_first;
   P.dbc_flag = c->d_dbc_flag;
   P.dbc_value = c->d_dbc_value;
   P.num_owned_nodes = p.num_owned_nodes;
@@ -512,16 +533,24 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
     // slots no element touches are zero from init; something (a row-sum scaling that met a zero row, a solver
     // working in place) may have changed them since: zero everything once
     CU(cudaMemsetAsync(c->d_resid, 0, (size_t)p.num_unknowns * sizeof(double), c->stream));
-    CU(cudaMemsetAsync(c->d_a, 0, ((size_t)c->pat.nnz_plus + 1) * sizeof(double), c->stream));
+    CU(cudaMemsetAsync(c->d_a, 0, ((size_t)c->nnz_plus + 1) * sizeof(double), c->stream));
     c->rezero = false;
   }
   if (mode != 2 && !c->preloaded) {
     // accumulate-into semantics need zeroed storage; the first-touch mode overwrites every slot the
     // elements touch and never writes the others (zeroed once at init), so it needs no memset
     if (assemble_residual) CU(cudaMemsetAsync(c->d_resid, 0, (size_t)p.num_unknowns * sizeof(double), c->stream));
-    if (assemble_jacobian) CU(cudaMemsetAsync(c->d_a, 0, ((size_t)c->pat.nnz_plus + 1) * sizeof(double), c->stream));
+    if (assemble_jacobian) CU(cudaMemsetAsync(c->d_a, 0, ((size_t)c->nnz_plus + 1) * sizeof(double), c->stream));
   }
+  auto wait_for_exchange = [&]() -> int {  // the ghost values must have landed before an element reads them
+    if (c->exchange_in_flight) {
+      CU(cudaStreamWaitEvent(c->stream, c->ev_x, 0));
+      c->exchange_in_flight = false;
+    }
+    return 0;
+  };
   if (mode == 0) {
+    if (int wrc = wait_for_exchange()) return wrc;
     P.elem_list = nullptr;
     P.elem_begin = 0;
     P.elem_end = p.num_elems;
@@ -529,9 +558,13 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
     ke.fn<<<grid, ke.tpe, ke.smem, c->stream>>>(P);
     c->last_launches++;
   } else {
-    // colour classes in increasing order, one launch each: stream order is the inter-colour barrier
+    // classes in increasing order, one launch each: stream order is the inter-class barrier.  Classes
+    // [0, first_border_class) hold the elements with owned nodes only: they run while exchange_dof is in flight
+    // on its own stream; the border classes wait for it (hide the exchange behind the interior)
     P.elem_list = c->d_elem_list;
     for (size_t col = 0; col + 1 < c->colour_begin.size(); col++) {
+      if ((int)col == c->first_border_class)
+        if (int wrc = wait_for_exchange()) return wrc;
       P.elem_begin = c->colour_begin[col];
       P.elem_end = c->colour_begin[col + 1];
       int n = P.elem_end - P.elem_begin;
@@ -541,6 +574,7 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
       c->last_launches++;
     }
   }
+  if (int wrc = wait_for_exchange()) return wrc;  // (no border class: nothing read the tail, keep the order anyway)
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev1, c->stream));
   return 0;
@@ -639,7 +673,7 @@ extern "C" int goma_gpu_fill(goma_gpu_ctx *c, const double *x, const double *x_o
     // the reference adds into caller-owned storage (mm_fill.c:5463 a[ja] +=, :5390 resid +=): upload what the
     // caller holds and accumulate on top of it
     if (assemble_jacobian)
-      CU(cudaMemcpyAsync(c->d_a, a, ((size_t)c->pat.nnz_plus + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      CU(cudaMemcpyAsync(c->d_a, a, ((size_t)c->nnz_plus + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     if (assemble_residual) CU(cudaMemcpyAsync(c->d_resid, resid_vector, nb, cudaMemcpyHostToDevice, c->stream));
     c->preloaded = true;
   }
@@ -651,9 +685,15 @@ extern "C" int goma_gpu_fill(goma_gpu_ctx *c, const double *x, const double *x_o
   if (lrc) return lrc;
   // one copy: the PCIe link is saturated by it (≈47 GB/s measured; two concurrent copy streams gave the same)
   if (assemble_jacobian)
-    CU(cudaMemcpyAsync(a, c->d_a, ((size_t)c->pat.nnz_plus + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(a, c->d_a, ((size_t)c->nnz_plus + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (assemble_residual) CU(cudaMemcpyAsync(resid_vector, c->d_resid, nb, cudaMemcpyDeviceToHost, c->stream));
   return finish_fill(c, flags_out);
+}
+
+extern "C" int goma_gpu_fill_setup_stats(goma_gpu_ctx *c, double out[5]) {
+  if (!c || !out) return fail(-2, "null argument");
+  for (int k = 0; k < 5; k++) out[k] = c->setup_s[k];
+  return 0;
 }
 
 extern "C" int goma_gpu_fill_last_stats(goma_gpu_ctx *c, double *kernel_ms, int *launches) {

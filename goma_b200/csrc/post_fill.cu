@@ -228,24 +228,19 @@ extern "C" int goma_gpu_vector_norms(goma_gpu_ctx *c, int which, double out[4]) 
 }
 
 // ------------------------------------------------------------------ CSR hand-off to a GPU solver
-struct CsrKinds {
-  int num_unknowns[GOMA_GPU_MAX_KINDS];  // unknowns of a node of each kind
-  int num_pressure[GOMA_GPU_MAX_KINDS];  // ... of which pressure (last in the node)
-  int tslot[GOMA_GPU_MAX_KINDS];         // offset of T inside the node (-1: none): energy rows carry no P columns
-};
 
 // one thread per owned node: the rows of its unknowns share the node-node list (exo_conn.c build_node_node);
 // columns = the unknowns of the neighbour nodes in increasing node id (find_MSR_problem_graph), diagonal included
 __global__ void csr_structure_kernel(int num_owned_nodes, const long long *__restrict__ nn_ptr,
                                      const int *__restrict__ nn_list, const int *__restrict__ first_unknown,
-                                     const unsigned char *__restrict__ node_kind, const __grid_constant__ CsrKinds K,
+                                     const unsigned char *__restrict__ node_kind, const __grid_constant__ KindInfo K,
                                      const long long *__restrict__ rowstart, long long msr0,
                                      long long *__restrict__ rowptr, int *__restrict__ colind, int *__restrict__ dpos,
                                      int num_rows) {
   const int nd = blockIdx.x * blockDim.x + threadIdx.x;
   if (nd >= num_owned_nodes) return;
   const int kd = node_kind[nd], fu = first_unknown[nd];
-  for (int s = 0; s < K.num_unknowns[kd]; s++) {
+  for (int s = 0; s < K.nunk[kd]; s++) {
     const int row = fu + s;
     const long long base = rowstart[row] - msr0 + row;  // every earlier row adds its diagonal
     rowptr[row] = base;
@@ -254,7 +249,7 @@ __global__ void csr_structure_kernel(int num_owned_nodes, const long long *__res
     long long pos = base;
     for (long long q = nn_ptr[nd]; q < nn_ptr[nd + 1]; q++) {
       const int m = nn_list[q], km = node_kind[m], fm = first_unknown[m];
-      const int ncol = K.num_unknowns[km] - (nop ? K.num_pressure[km] : 0);
+      const int ncol = K.nunk[km] - (nop ? K.npress[km] : 0);
       for (int c = 0; c < ncol; c++) {
         if (fm + c == row) dpos[row] = (int)(pos - base);
         colind[pos++] = fm + c;
@@ -280,24 +275,15 @@ extern "C" int goma_gpu_csr_structure(goma_gpu_ctx *c, const goma_gpu_problem *p
   CU(cudaSetDevice(c->device));
   const int nrows = c->num_owned_unknowns;
   if (!c->d_csr_rowptr) {
-    if (c->pat.nn_ptr.empty()) return fail(-2, "node-node lists are not available");
-    const long long msr0 = c->pat.rowstart[0];
-    c->csr_nnz = nrows > 0 ? (long long)(c->pat.rowstart[nrows] - msr0) + nrows : 0;
-    CsrKinds K;
-    memset(&K, 0, sizeof(K));
-    for (int k = 0; k < GOMA_GPU_MAX_KINDS; k++) {
-      K.tslot[k] = -1;
-      if (k >= p->num_kinds) continue;
-      K.num_unknowns[k] = p->kind_num_unknowns[k];
-      K.num_pressure[k] = kind_num_pressure(*p, k);
-      K.tslot[k] = p->energy ? p->kind_slot[k][GOMA_SLOT_T] : -1;
-    }
-    long long *d_nn_ptr = nullptr;
-    int *d_nn_list = nullptr;
-    CU(cudaMalloc((void **)&d_nn_ptr, c->pat.nn_ptr.size() * sizeof(long long)));
-    CU(cudaMalloc((void **)&d_nn_list, std::max<size_t>(c->pat.nn_list.size(), 1) * sizeof(int)));
-    CU(cudaMemcpy(d_nn_ptr, c->pat.nn_ptr.data(), c->pat.nn_ptr.size() * sizeof(long long), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d_nn_list, c->pat.nn_list.data(), c->pat.nn_list.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!c->dpat.nn_ptr || !c->dpat.nn_list) return fail(-2, "node-node lists are not available");
+    long long h_rs[2] = {0, 0};
+    CU(cudaMemcpy(&h_rs[0], c->d_rowstart, sizeof(long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&h_rs[1], c->d_rowstart + nrows, sizeof(long long), cudaMemcpyDeviceToHost));
+    const long long msr0 = h_rs[0];
+    c->csr_nnz = nrows > 0 ? (h_rs[1] - msr0) + nrows : 0;
+    const KindInfo K = make_kind_info(*p);
+    long long *d_nn_ptr = c->dpat.nn_ptr;
+    int *d_nn_list = c->dpat.nn_list;
     CU(cudaMalloc((void **)&c->d_csr_rowptr, ((size_t)nrows + 1) * sizeof(long long)));
     CU(cudaMalloc((void **)&c->d_csr_colind, std::max<size_t>((size_t)c->csr_nnz, 1) * sizeof(int)));
     CU(cudaMalloc((void **)&c->d_csr_dpos, std::max<size_t>((size_t)nrows, 1) * sizeof(int)));
@@ -312,8 +298,6 @@ extern "C" int goma_gpu_csr_structure(goma_gpu_ctx *c, const goma_gpu_problem *p
       CU(cudaGetLastError());
     }
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(d_nn_ptr);
-    cudaFree(d_nn_list);
   }
   out->num_rows = nrows;
   out->nnz = c->csr_nnz;

@@ -185,6 +185,12 @@ class MatrixFill:
         """Ghost refresh of x (0), xdot (1) or x_old (2): one kernel on the context's stream, no host sync."""
         capi.check(self.lib.goma_gpu_exchange_dof(self._ctx, int(which)), "goma_gpu_exchange_dof")
 
+    def setup_stats(self):
+        """Wall seconds of goma_gpu_fill_init: total, validation, uploads, device pattern, tables + records."""
+        out = np.zeros(5)
+        capi.check(self.lib.goma_gpu_fill_setup_stats(self._ctx, out.ctypes.data_as(capi._dp)), "setup_stats")
+        return dict(zip(("total_s", "validate_s", "upload_s", "pattern_s", "records_s"), out.tolist()))
+
     def last_stats(self):
         ms, n = C.c_double(), C.c_int()
         capi.check(self.lib.goma_gpu_fill_last_stats(self._ctx, C.byref(ms), C.byref(n)), "last_stats")

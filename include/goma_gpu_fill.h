@@ -246,6 +246,9 @@ int goma_gpu_exchange_status(goma_gpu_ctx *ctx);
 /* timing / accounting of the last goma_gpu_fill*: device ms of the assembly kernel(s)
  * (CUDA events on the context's stream) and number of kernel launches */
 int goma_gpu_fill_last_stats(goma_gpu_ctx *ctx, double *kernel_ms, int *launches);
+/* wall seconds of goma_gpu_fill_init: out = { total, validation of the snapshot (host), uploads, sparsity pattern +
+ * colouring + first-touch masks (device), tables + state / matrix allocation + gather records } */
+int goma_gpu_fill_setup_stats(goma_gpu_ctx *ctx, double out[5]);
 
 /* options: "scatter" = 0 fp64 atomics into zeroed storage | 1 coloured load+add+store | 2 coloured first-touch
  * stores (default; no memset of the matrix, bit-reproducible);  "grid_limit" = cap on resident CTAs (tests);

@@ -244,7 +244,8 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
         B[2][1] = -(Jm[0][0] * Jm[2][1] - Jm[2][0] * Jm[0][1]) / det;
         B[2][2] = (Jm[0][0] * Jm[1][1] - Jm[1][0] * Jm[0][1]) / det;
       }
-      if (fabs(det) < 1.e-10) { rc = -1; goto done; } /* zero_detJ (mm_fill_util.c:335-343; mm_fill.c:256,308) */
+      /* zero_detJ (mm_fill_util.c:335-343) is raised only inside beer_belly's SHELL / TRISHELL branch (:312-344):
+       * continuum elements are assembled whatever |detJ| is */
       const double d_area = det * wt; /* h3 = 1 */
       for (int i = 0; i < nn; i++)
         for (int q = 0; q < dim; q++) {

@@ -44,6 +44,28 @@ __global__ void dfma_kernel(double *out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// DMMA and DFMA interleaved in one instruction stream (8 + 16 independent accumulators): if the tensor sub-pipe and
+// the FP64 pipe were separate units the sum would exceed either peak
+__global__ void mixed_kernel(double *out, int iters) {
+  double c[8][2], d[16];
+  for (int t = 0; t < 8; t++) c[t][0] = c[t][1] = 0.0;
+  for (int t = 0; t < 16; t++) d[t] = t;
+  double a0 = threadIdx.x * 1e-3, b0 = 0.5, b = 0.999;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[t][0]), "+d"(c[t][1]) : "d"(a0), "d"(b0));
+      d[2 * t] = fma(d[2 * t], b, a0);
+      d[2 * t + 1] = fma(d[2 * t + 1], b, a0);
+    }
+  }
+  double s = 0.0;
+  for (int t = 0; t < 8; t++) s += c[t][0] + c[t][1];
+  for (int t = 0; t < 16; t++) s += d[t];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <class F>
 float time_ms(F f) {
   cudaEvent_t e0, e1;
@@ -74,6 +96,10 @@ int main() {
     printf("warps/SM %2d  DMMA m8n8k4    %7.2f TFLOP/s\n", warps, 2.0 * 256 * 8 * iters * (double)warps * grid / ms / 1e9);
     ms = time_ms([&] { dmma_kernel<1684, 8><<<grid, threads>>>(out, iters); });
     printf("warps/SM %2d  DMMA m16n8k4   %7.2f TFLOP/s\n", warps, 2.0 * 512 * 8 * iters * (double)warps * grid / ms / 1e9);
+    ms = time_ms([&] { mixed_kernel<<<grid, threads>>>(out, iters); });
+    printf("warps/SM %2d  DMMA + DFMA    %7.2f TFLOP/s  (DMMA part %.2f, DFMA part %.2f)\n", warps,
+           (2.0 * 256 * 8 * warps + 2.0 * 16 * threads) * iters * (double)grid / ms / 1e9,
+           2.0 * 256 * 8 * iters * (double)warps * grid / ms / 1e9, 2.0 * 16 * iters * (double)threads * grid / ms / 1e9);
     ms = time_ms([&] { dmma_kernel<1688, 8><<<grid, threads>>>(out, iters); });
     printf("warps/SM %2d  DMMA m16n8k8   %7.2f TFLOP/s\n", warps, 2.0 * 1024 * 8 * iters * (double)warps * grid / ms / 1e9);
   }

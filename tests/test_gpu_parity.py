@@ -610,25 +610,32 @@ def test_gpu_matches_reference_live_cavity(built, n, energy):
 
 
 @pytest.mark.parametrize("et", ["HEX27", "QUAD9", "HEX8"])
-def test_gpu_zero_detJ_is_a_domain_failure(built, et):
-    """|detJ| < 1e-10 at a Gauss point: beer_belly sets zero_detJ and matrix_fill_full returns -1
-    (mm_fill_util.c:335-343, mm_fill.c:256,308).  A mesh small enough that every detJ is below the threshold."""
+def test_gpu_tiny_detJ_is_assembled_like_the_reference(built, et):
+    """|detJ| < 1e-10 at every Gauss point (a mesh in micrometre-sized units).  The reference raises zero_detJ only
+    inside beer_belly's shell-element branch (mm_fill_util.c:312-344): continuum elements are assembled normally,
+    return 0, and so must the GPU path (round 1 wrongly flagged them).  Per-row tolerance: the entries are ~1e-12."""
     dim = 2 if et == "QUAD9" else 3
-    L = 2e-5 if dim == 2 else 8e-4  # detJ = (h/2)^dim with h = L/2
-    m = box_mesh(et, (2,) * dim, hi=(L,) * dim)
+    L = 3e-5 if dim == 2 else 8e-4  # detJ = prod(h_d / 2) < 2e-11
+    m = box_mesh(et, (4, 3) if dim == 2 else (2, 2, 2), hi=(L,) * dim, perturb=0.1, seed=3)
     q1 = et == "HEX8"
-    p = Problem(m, interp="Q1Q1" if q1 else "Q2P1", pspg="global" if q1 else None, bcs=[Dirichlet("U", 1, 1.0)])
+    p = Problem(m, interp="Q1Q1" if q1 else "Q2P1", pspg="global" if q1 else None, rho=1.1, mu=0.3,
+                gravity=(0.1, -0.2, 0.3 if dim == 3 else 0.0), bcs=[Dirichlet("U", 1, 1.0)])
     st = make_state(p, seed=1)
     ija = capi.pattern_msr(p)
-    rc, _, _ = port.port_fill(p, ija, st, h_elem_avg=L / 2, U_norm=1.0)
-    assert rc == -1
+    h, U = (p.global_h_elem_siz(), p.global_velocity_norm(st["x"])) if q1 else (0.0, 0.0)
+    rc, a_ref, r_ref = port.port_fill(p, ija, st, h_elem_avg=h, U_norm=U)
+    assert rc == 0
     mf = MatrixFill(p)
-    err, _, _ = mf.matrix_fill_full(st["x"], h_elem_avg=L / 2, U_norm=1.0)
-    assert err == -1 and mf.flags[2] == 1 and mf.flags[0] == 0
-    mf.close()
+    err, a, r = mf.matrix_fill_full(st["x"], h_elem_avg=h, U_norm=U)
+    assert err == 0 and not mf.flags.any()
+    assert_close(a, a_ref, "Jacobian", ija=ija)
+    assert_close(r, r_ref, "residual")
     if ref_driver.ref_available():
         ref = ref_driver.run_fill(p, [st])[0]
-        assert ref["err"] == -1 and ref["zero_detJ"] == 1
+        assert ref["err"] == 0 and ref["zero_detJ"] == 0
+        assert_close(a, ref["a"], "Jacobian vs live reference", ija=ija)
+        assert_close(r, ref["resid"], "residual vs live reference")
+    mf.close()
 
 
 def test_gpu_irregular_valence_mesh_all_scatter_modes(built):
