@@ -26,6 +26,7 @@ EXPORTED = [
     "goma_gpu_last_error", "goma_gpu_pattern_msr", "goma_gpu_exchange_export", "goma_gpu_exchange_setup",
     "goma_gpu_exchange_dof", "goma_gpu_row_sum_scale", "goma_gpu_scale_buffer", "goma_gpu_vector_norms", "goma_gpu_csr_structure",
     "goma_gpu_csr_values", "goma_gpu_exchange_status", "goma_gpu_fill_device_async", "goma_gpu_fill_wait", "goma_gpu_fill_setup_stats",
+    "goma_gpu_fill_value_count", "goma_gpu_csr_rows", "goma_gpu_node_graph",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -49,7 +50,7 @@ class GomaGpuProblem(C.Structure):
         ("diffusivity", C.c_double * 4), ("momentum_source", C.c_double * 3), ("momentum_source_model", C.c_int),
         ("heat_source", C.c_double), ("lame_mu", C.c_double), ("lame_lambda", C.c_double),
         ("dbc_flag", _bp), ("dbc_value", _dp),
-        ("num_elem_blocks", C.c_int), ("num_materials", C.c_int),
+        ("num_elem_blocks", C.c_int), ("num_materials", C.c_int), ("matrix_layout", C.c_int),
     ]
 
 
@@ -115,6 +116,9 @@ def load_library():
     lib.goma_gpu_unpack_dofs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.goma_gpu_fill_last_stats.argtypes = [C.c_void_p, _dp, _ip]
     lib.goma_gpu_fill_setup_stats.argtypes = [C.c_void_p, _dp]
+    lib.goma_gpu_fill_value_count.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+    lib.goma_gpu_csr_rows.argtypes = [C.c_void_p, C.POINTER(Csr)]
+    lib.goma_gpu_node_graph.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.goma_gpu_fill_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     _lib = lib
     return lib
@@ -136,7 +140,10 @@ def _ptr(a, typ):
     return a.ctypes.data_as(typ) if a is not None else typ()
 
 
-def make_problem_struct(problem, ija=None, num_owned_nodes=None):
+LAYOUT_MSR, LAYOUT_CSR = 0, 1
+
+
+def make_problem_struct(problem, ija=None, num_owned_nodes=None, layout="msr"):
     """Fill ``struct goma_gpu_problem`` from a :class:`goma_b200.problem.Problem`.
 
     Returns (struct, keepalive) -- keepalive holds the numpy arrays the struct points into.
@@ -202,6 +209,7 @@ def make_problem_struct(problem, ija=None, num_owned_nodes=None):
     p.dbc_value = _ptr(keep["dbc_value"], _dp)
     p.num_elem_blocks = int(getattr(m, "num_elem_blocks", 1))
     p.num_materials = int(getattr(problem, "num_materials", 1))
+    p.matrix_layout = {"msr": LAYOUT_MSR, "csr": LAYOUT_CSR}[layout]
     return p, keep
 
 

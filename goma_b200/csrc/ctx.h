@@ -46,6 +46,7 @@ KindInfo make_kind_info(const goma_gpu_problem &p);
 int build_pattern_device(goma_gpu_ctx *c);
 void free_device_pattern(goma_gpu_ctx *c, bool keep_node_node);
 int download_pattern(goma_gpu_ctx *c, Pattern &out);
+int build_csr_dpos(goma_gpu_ctx *c);  // post_fill.cu: diagonal offsets of the CSR layout (needs the init-time lists)
 }  // namespace goma_b200
 
 struct goma_gpu_ctx {
@@ -55,6 +56,9 @@ struct goma_gpu_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   goma_b200::DevPattern dpat;
   long long nnz_plus = 0;          // == ija[N] of the MSR graph
+  int layout = 0;                  // GOMA_GPU_LAYOUT_*: how d_a is laid out
+  long long a_len = 0;             // doubles in d_a: nnz_plus + 1 (MSR) or csr_nnz (CSR)
+  int *d_dpos = nullptr;           // CSR layout: offset of the diagonal inside each owned row
   int num_colours = 0;             // element colours; classes [0, ncol) interior, [ncol, 2 ncol) border elements
   int first_border_class = 0;      // classes from here on touch external nodes: they wait for the ghost exchange
   cudaStream_t xstream = nullptr;  // exchange_dof runs here, overlapped with the interior classes

@@ -62,6 +62,11 @@ struct FillParams {
   // switches
   int assemble_residual, assemble_jacobian, transient;
   int scatter_mode;  // 0 fp64 atomics (any order), 1 coloured load+add+store, 2 coloured first-touch stores
+  // value layout: 0 = MSR (diagonal in a[0..N), off-diagonals of row r at a[ija[r]..ija[r+1]), the reference's
+  // ams->val); 1 = CSR of the owned rows with the diagonal in place (what Epetra's SumIntoGlobalValues target or a
+  // GPU solver takes): position = rowptr[r] + offset of the column in the row's sorted list, no diagonal shift
+  int csr;
+  long long msr0;  // ija[0] = N + 1: rowptr_csr[r] = rowstart[r] - msr0 + r
   // constants
   double etm_mom[6], etm_cont[2], etm_energy[5], etm_species[5], etm_mesh[5];
   double rho, mu, k, Cp, beta, Tref, heat_source;
@@ -419,7 +424,7 @@ __global__ void build_records_kernel(const FillParams P, int num_elems) {
       r.cs[k][f] = (unsigned char)cs;
       r.gun[f][k] = gun;
       r.flag[f][k] = (unsigned char)(dbc | (owned ? 4 : 0));
-      r.rs[f][k] = (owned && dbc == 0) ? P.rowstart[gun] : -1;
+      r.rs[f][k] = (owned && dbc == 0) ? (P.csr ? P.rowstart[gun] - P.msr0 + gun : P.rowstart[gun]) : -1;
     }
     r.cs[k][NF] = 0;
   }
@@ -436,7 +441,7 @@ __global__ void build_records_kernel(const FillParams P, int num_elems) {
       const int gun = r.gunP + p;
       const int dbc = P.dbc_flag[gun];
       r.flagP[p] = (unsigned char)(dbc | (owned ? 4 : 0));
-      r.rsP[p] = (owned && dbc == 0) ? P.rowstart[gun] : -1;
+      r.rsP[p] = (owned && dbc == 0) ? (P.csr ? P.rowstart[gun] - P.msr0 + gun : P.rowstart[gun]) : -1;
     }
   }
 }
@@ -1051,7 +1056,15 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
     const int dbc = flag & 3;
     if (dbc) {
       if (P.assemble_residual) slot_add(P, &P.resid[gun], dbc == 1 ? P.x[gun] - P.dbc_value[gun] : 0.0, first);
-      if (P.assemble_jacobian) slot_add(P, &P.a[gun], 1.0, first);
+      if (P.assemble_jacobian) {
+        long long dpos = gun;  // MSR: the diagonal lives in a[0..N)
+        if (P.csr) {           // CSR: at its sorted position inside the row
+          const int before = prow ? rec.po[C::CEN][C::CEN] + rec.poffP + (r - NF * NN)
+                                  : rec.po[i][i] + rec.cs[i][f] - ((C::ENERGY && f == C::F_T) ? rec.pp[i][i] : 0);
+          dpos = P.rowstart[gun] - P.msr0 + gun + before;
+        }
+        slot_add(P, &P.a[dpos], 1.0, first);
+      }
       continue;
     }
     if (!P.assemble_residual) continue;
@@ -1078,13 +1091,13 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
       // (row velocity a of node i, column pressure p of the centroid node)
       if (rec.rs[a][i] >= 0) {
         const int row = rec.gun[a][i], col = rec.gunP + p;
-        const long long pos = rec.rs[a][i] + rec.po[i][C::CEN] + poff + p - (col > row ? 1 : 0);
+        const long long pos = rec.rs[a][i] + rec.po[i][C::CEN] + poff + p - ((!P.csr && col > row) ? 1 : 0);
         slot_add(P, &P.a[pos], P.etm_mom[3] * S, true);
       }
       // (row pressure p of the centroid node, column velocity a of node i)
       if (rec.rsP[p] >= 0) {
         const int row = rec.gunP + p, col = rec.gun[a][i];
-        const long long pos = rec.rsP[p] + rec.po[C::CEN][i] + rec.cs[i][a] - (col > row ? 1 : 0);
+        const long long pos = rec.rsP[p] + rec.po[C::CEN][i] + rec.cs[i][a] - ((!P.csr && col > row) ? 1 : 0);
         slot_add(P, &P.a[pos], P.etm_cont[0] * S, true);
       }
     }
@@ -1105,7 +1118,7 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
           acc += s.w[gp] * t_psi[gp * (DIM + 1) + p] * (P.etm_cont[0] * ddiv + s.GP[bo][gp][C::G_DIV] * gj[b]);
         }
         const int row = rec.gunP + p, col = rec.gun[C::F_D + b][j];
-        const long long pos = rec.rsP[p] + rec.po[C::CEN][j] + rec.cs[j][C::F_D + b] - (col > row ? 1 : 0);
+        const long long pos = rec.rsP[p] + rec.po[C::CEN][j] + rec.cs[j][C::F_D + b] - ((!P.csr && col > row) ? 1 : 0);
         slot_add(P, &P.a[pos], acc, true);
       }
     }
@@ -1417,7 +1430,7 @@ __device__ __forceinline__ void write_tile_direct(const FillParams &P, const Ele
       const int row = s.gun[fr][i];
       double *arow = P.a + rstart;
       if (MODE == 2 && NF == 3 && !C::ENERGY && first && packed && rj != ri) {
-        double *dst = arow + s.po[i][j] + s.cs[j][0] - (rj > ri ? 1 : 0);
+        double *dst = arow + s.po[i][j] + s.cs[j][0] - ((!P.csr && rj > ri) ? 1 : 0);
         if ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
           *reinterpret_cast<double2 *>(dst) = make_double2(t.V[ii][fr][0], t.V[ii][fr][1]);
           dst[2] = t.V[ii][fr][2];
@@ -1433,7 +1446,9 @@ __device__ __forceinline__ void write_tile_direct(const FillParams &P, const Ele
         int off = s.po[i][j] + s.cs[j][fc];
         if (C::ENERGY && rowT) off -= s.pp[i][j];
         double *dst;
-        if (rj != ri)
+        if (P.csr)
+          dst = arow + off;
+        else if (rj != ri)
           dst = arow + off - (rj > ri ? 1 : 0);
         else
           dst = (fc == fr) ? P.a + row : arow + off - (fc > fr ? 1 : 0);
@@ -1461,7 +1476,7 @@ __device__ __forceinline__ void write_pair(const FillParams &P, const ElemRec<C>
     const int row = s.gun[fr][i];
     double *arow = P.a + rstart;
     if (MODE == 2 && NF == 3 && !C::ENERGY && first && packed && rj != ri) {
-      double *dst = arow + s.po[i][j] + s.cs[j][0] - (rj > ri ? 1 : 0);
+      double *dst = arow + s.po[i][j] + s.cs[j][0] - ((!P.csr && rj > ri) ? 1 : 0);
       if ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
         *reinterpret_cast<double2 *>(dst) = make_double2(V[fr][0], V[fr][1]);
         dst[2] = V[fr][2];
@@ -1476,7 +1491,9 @@ __device__ __forceinline__ void write_pair(const FillParams &P, const ElemRec<C>
       int off = s.po[i][j] + s.cs[j][fc];
       if (C::ENERGY && rowT) off -= s.pp[i][j];
       double *dst;
-      if (rj != ri)
+      if (P.csr)
+        dst = arow + off;
+      else if (rj != ri)
         dst = arow + off - (rj > ri ? 1 : 0);
       else
         dst = (fc == fr) ? P.a + row : arow + off - (fc > fr ? 1 : 0);
@@ -1594,14 +1611,25 @@ __device__ __forceinline__ void gauss_blocks_mma(const FillParams &P, const Smem
         continue;
       }
       const bool first = (fi >> j) & 1u;
-      const int off = rec.po[i][j] + rec.cs[j][0] - (rj > ri ? 1 : 0);
+      const int off = rec.po[i][j] + rec.cs[j][0] - ((!P.csr && rj > ri) ? 1 : 0);
       const int offT = C::ENERGY ? off - rec.pp[i][j] : off;  // energy rows carry no pressure columns
+      // one branch on `first` per pair (not per entry): a warp whose lanes disagree runs each side once
+      if (MODE == 2 && first) {
 #pragma unroll
-      for (int fr = 0; fr < NF; fr++) {
-        if (rsv[fr] < 0) continue;
-        double *dst = P.a + rsv[fr] + ((C::ENERGY && fr == C::F_T) ? offT : off);
+        for (int fr = 0; fr < NF; fr++) {
+          if (rsv[fr] < 0) continue;
+          double *dst = P.a + rsv[fr] + ((C::ENERGY && fr == C::F_T) ? offT : off);
 #pragma unroll
-        for (int fc = 0; fc < NF; fc++) slot_add_m<MODE>(dst + fc, V[fr][fc], first);
+          for (int fc = 0; fc < NF; fc++) dst[fc] = V[fr][fc];
+        }
+      } else {
+#pragma unroll
+        for (int fr = 0; fr < NF; fr++) {
+          if (rsv[fr] < 0) continue;
+          double *dst = P.a + rsv[fr] + ((C::ENERGY && fr == C::F_T) ? offT : off);
+#pragma unroll
+          for (int fc = 0; fc < NF; fc++) slot_add_m<MODE>(dst + fc, V[fr][fc], false);
+        }
       }
     }
   }

@@ -162,6 +162,8 @@ static int validate(const goma_gpu_problem &p) {
   // one element block / one material (find_elemblock_index + Matilda[ebn] of mm_fill.c:224-235 are not restated)
   if (p.num_elem_blocks > 1) return fail(-2, "meshes with more than one element block are not supported by the GPU fill");
   if (p.num_materials > 1) return fail(-2, "more than one material is not supported by the GPU fill");
+  if (p.matrix_layout != GOMA_GPU_LAYOUT_MSR && p.matrix_layout != GOMA_GPU_LAYOUT_CSR)
+    return fail(-2, "matrix_layout must be GOMA_GPU_LAYOUT_MSR or GOMA_GPU_LAYOUT_CSR");
 
   // ---- unknown map: everything build_pattern / build_records_kernel index with must be consistent
   const int dim = p.dim, npe = p.elem_type;
@@ -298,7 +300,16 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
   rc |= dalloc(&c->d_xdot, N, c);
   rc |= dalloc(&c->d_xdot_old, N, c);
   rc |= dalloc(&c->d_resid, N, c);
-  rc |= dalloc(&c->d_a, (size_t)c->nnz_plus + 1, c);
+  c->layout = p.matrix_layout;
+  {
+    // CSR of the owned rows: every row gains its diagonal, rows of external unknowns do not exist
+    long long rs_owned = 0;
+    const int no = c->num_owned_unknowns;
+    CU(cudaMemcpy(&rs_owned, c->d_rowstart + no, sizeof(long long), cudaMemcpyDeviceToHost));
+    c->csr_nnz = (rs_owned - ((long long)N + 1)) + no;
+  }
+  c->a_len = c->layout == GOMA_GPU_LAYOUT_CSR ? c->csr_nnz : c->nnz_plus + 1;
+  rc |= dalloc(&c->d_a, (size_t)c->a_len, c);
   rc |= dalloc(&c->d_flags, 4, c);
   if (rc) return -3;
 
@@ -310,6 +321,9 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
     FillParams P;
     static_params(c, P);
     P.flags = c->d_flags;
+    if (c->layout == GOMA_GPU_LAYOUT_CSR) {
+      if (int drc = build_csr_dpos(c)) return drc;
+    }
     if (ne > 0) ke.build_records<<<(ne + 127) / 128, 128, 0, c->stream>>>(P, ne);
     CU(cudaGetLastError());
     int h_flags[4] = {0, 0, 0, 0};
@@ -353,7 +367,8 @@ extern "C" void goma_gpu_fill_destroy(goma_gpu_ctx *c) {
   if (c->d_csr_rowptr) cudaFree(c->d_csr_rowptr);
   if (c->d_csr_colind) cudaFree(c->d_csr_colind);
   if (c->d_csr_dpos) cudaFree(c->d_csr_dpos);
-  if (c->d_csr_values) cudaFree(c->d_csr_values);
+  if (c->d_csr_values && c->d_csr_values != c->d_a) cudaFree(c->d_csr_values);
+  if (c->d_dpos) cudaFree(c->d_dpos);
   if (c->d_scale) cudaFree(c->d_scale);
   if (c->d_partials) cudaFree(c->d_partials);
   if (c->d_zero_rows) cudaFree(c->d_zero_rows);
@@ -370,6 +385,12 @@ extern "C" void goma_gpu_fill_destroy(goma_gpu_ctx *c) {
 extern "C" int goma_gpu_fill_get_msr(goma_gpu_ctx *c, long long *nnz_plus) {
   if (!c) return fail(-2, "null context");
   if (nnz_plus) *nnz_plus = c->nnz_plus;
+  return 0;
+}
+
+extern "C" int goma_gpu_fill_value_count(goma_gpu_ctx *c, long long *count) {
+  if (!c || !count) return fail(-2, "null argument");
+  *count = c->a_len;
   return 0;
 }
 
@@ -459,6 +480,8 @@ static void static_params(const goma_gpu_ctx *c, FillParams &P) {
   P.dbc_value = c->d_dbc_value;
   P.num_owned_nodes = p.num_owned_nodes;
   P.erec = c->d_erec;
+  P.csr = c->layout == GOMA_GPU_LAYOUT_CSR ? 1 : 0;
+  P.msr0 = (long long)p.num_unknowns + 1;
 }
 
 // ------------------------------------------------------------------ the fill
@@ -533,14 +556,14 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
     // slots no element touches are zero from init; something (a row-sum scaling that met a zero row, a solver
     // working in place) may have changed them since: zero everything once
     CU(cudaMemsetAsync(c->d_resid, 0, (size_t)p.num_unknowns * sizeof(double), c->stream));
-    CU(cudaMemsetAsync(c->d_a, 0, ((size_t)c->nnz_plus + 1) * sizeof(double), c->stream));
+    CU(cudaMemsetAsync(c->d_a, 0, (size_t)c->a_len * sizeof(double), c->stream));
     c->rezero = false;
   }
   if (mode != 2 && !c->preloaded) {
     // accumulate-into semantics need zeroed storage; the first-touch mode overwrites every slot the
     // elements touch and never writes the others (zeroed once at init), so it needs no memset
     if (assemble_residual) CU(cudaMemsetAsync(c->d_resid, 0, (size_t)p.num_unknowns * sizeof(double), c->stream));
-    if (assemble_jacobian) CU(cudaMemsetAsync(c->d_a, 0, ((size_t)c->nnz_plus + 1) * sizeof(double), c->stream));
+    if (assemble_jacobian) CU(cudaMemsetAsync(c->d_a, 0, (size_t)c->a_len * sizeof(double), c->stream));
   }
   auto wait_for_exchange = [&]() -> int {  // the ghost values must have landed before an element reads them
     if (c->exchange_in_flight) {
@@ -673,7 +696,7 @@ extern "C" int goma_gpu_fill(goma_gpu_ctx *c, const double *x, const double *x_o
     // the reference adds into caller-owned storage (mm_fill.c:5463 a[ja] +=, :5390 resid +=): upload what the
     // caller holds and accumulate on top of it
     if (assemble_jacobian)
-      CU(cudaMemcpyAsync(c->d_a, a, ((size_t)c->nnz_plus + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      CU(cudaMemcpyAsync(c->d_a, a, (size_t)c->a_len * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     if (assemble_residual) CU(cudaMemcpyAsync(c->d_resid, resid_vector, nb, cudaMemcpyHostToDevice, c->stream));
     c->preloaded = true;
   }
@@ -685,7 +708,7 @@ extern "C" int goma_gpu_fill(goma_gpu_ctx *c, const double *x, const double *x_o
   if (lrc) return lrc;
   // one copy: the PCIe link is saturated by it (≈47 GB/s measured; two concurrent copy streams gave the same)
   if (assemble_jacobian)
-    CU(cudaMemcpyAsync(a, c->d_a, ((size_t)c->nnz_plus + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(a, c->d_a, (size_t)c->a_len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (assemble_residual) CU(cudaMemcpyAsync(resid_vector, c->d_resid, nb, cudaMemcpyDeviceToHost, c->stream));
   return finish_fill(c, flags_out);
 }

@@ -179,47 +179,48 @@ __global__ void rowstart_kernel(int nn, int N, const unsigned char *__restrict__
   if (nd == nn - 1) rowstart[N] = (long long)N + 1 + node_off[nd] + node_len[nd];
 }
 
-// ---- colouring: one Jones-Plassmann round.  An element takes the smallest colour none of its coloured neighbours
-//      holds once every uncoloured neighbour has a lower priority.
-__global__ void jp_round_kernel(int ne, int npe, const int *__restrict__ conn, const int *__restrict__ ne_ptr,
-                                const int *__restrict__ ne_list, const signed char *__restrict__ col_in,
-                                signed char *__restrict__ col_out, int *__restrict__ remaining, int *__restrict__ err) {
+// ---- colouring: one round.  An element takes the smallest colour none of its coloured neighbours holds once every
+//      neighbour that precedes it is coloured.  BY_ID: "precedes" = lower element number, which reproduces the serial
+//      greedy colouring in element order exactly (8 colours on a structured hex mesh, 4 on quads) -- the number of
+//      rounds is the depth of that dependence (a diagonal wavefront, nx + 2 ny + 4 nz on a lattice).  Otherwise
+//      "precedes" = higher hashed priority (Jones-Plassmann, O(log n) rounds): the finish for meshes whose numbering
+//      makes the greedy dependence too deep.  In place: a neighbour that must come later can never be coloured
+//      before this element, so the colours an element sees are final and the result does not depend on timing.
+template <bool BY_ID>
+__global__ void colour_round_kernel(int ne, int npe, const int *__restrict__ conn, const int *__restrict__ ne_ptr,
+                                    const int *__restrict__ ne_list, volatile signed char *col, int *__restrict__ remaining,
+                                    int count, int *__restrict__ err) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= ne) return;
-  const int c0 = col_in[e];
-  if (c0 >= 0) {
-    col_out[e] = (signed char)c0;
-    return;
-  }
+  if (e >= ne || col[e] >= 0) return;
   const unsigned pe = hash32((unsigned)e);
   unsigned long long used = 0ull;
-  bool blocked = false;
-  for (int i = 0; i < npe && !blocked; i++) {
+  for (int i = 0; i < npe; i++) {
     const int nd = conn[(size_t)e * npe + i];
     for (int q = ne_ptr[nd]; q < ne_ptr[nd + 1]; q++) {
       const int e2 = ne_list[q];
       if (e2 == e) continue;
-      const int c2 = col_in[e2];
-      if (c2 >= 0)
+      const int c2 = col[e2];
+      if (c2 >= 0) {
         used |= 1ull << c2;
+        continue;
+      }
+      bool before;
+      if (BY_ID)
+        before = e2 < e;
       else {
         const unsigned p2 = hash32((unsigned)e2);
-        if (p2 > pe || (p2 == pe && e2 > e)) {
-          blocked = true;
-          break;
-        }
+        before = p2 > pe || (p2 == pe && e2 > e);
+      }
+      if (before) {  // wait for it
+        if (count) *remaining = 1;  // (the host only asks whether anybody is still waiting)
+        return;
       }
     }
-  }
-  if (blocked) {
-    col_out[e] = -1;
-    atomicAdd(remaining, 1);
-    return;
   }
   int c = 0;
   while (c < 63 && ((used >> c) & 1ull)) c++;
   if (c >= 63) atomicMax(err, 3);
-  col_out[e] = (signed char)c;
+  col[e] = (signed char)c;
 }
 
 // class of an element = colour, or colour + ncol when it touches an external node (needs the ghost exchange)
@@ -447,23 +448,32 @@ int build_pattern_device(goma_gpu_ctx *c) {
   }
 
   // ---- colouring, classes, processing order
-  signed char *d_col[2] = {nullptr, nullptr};
+  signed char *d_colour = nullptr;
   int *d_counters = nullptr;  // [0] remaining, [1] max colour, [2..] class histogram (128)
-  CU(cudaMalloc((void **)&d_col[0], std::max(ne, 1)));
-  CU(cudaMalloc((void **)&d_col[1], std::max(ne, 1)));
+  CU(cudaMalloc((void **)&d_colour, std::max(ne, 1)));
   CU(cudaMalloc((void **)&d_counters, (2 + 128) * sizeof(int)));
-  CU(cudaMemsetAsync(d_col[0], 0xff, std::max(ne, 1), st));
-  int rounds = 0, remaining = ne > 0 ? 1 : 0, cur = 0;
-  while (remaining > 0) {
-    if (++rounds > 4096) return fail(-3, "element colouring did not converge");
-    CU(cudaMemsetAsync(d_counters, 0, sizeof(int), st));
-    jp_round_kernel<<<(ne + 127) / 128, 128, 0, st>>>(ne, npe, c->d_conn, d.ne_ptr, d.ne_list, d_col[cur], d_col[cur ^ 1], d_counters, d_err);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(&remaining, d_counters, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    cur ^= 1;
+  CU(cudaMemsetAsync(d_colour, 0xff, std::max(ne, 1), st));
+  {
+    // rounds are enqueued in groups; the host looks at the count of waiting elements once per group
+    const int group = 64, greedy_rounds = 4096, max_rounds = 4096 + 4096;
+    int rounds = 0, remaining = ne > 0 ? 1 : 0;
+    while (remaining > 0) {
+      if (rounds >= max_rounds) return fail(-3, "element colouring did not converge");
+      const bool by_id = rounds < greedy_rounds;
+      for (int k = 0; k < group; k++, rounds++) {
+        if (k == group - 1) CU(cudaMemsetAsync(d_counters, 0, sizeof(int), st));
+        if (by_id)
+          colour_round_kernel<true><<<(ne + 127) / 128, 128, 0, st>>>(ne, npe, c->d_conn, d.ne_ptr, d.ne_list, d_colour, d_counters,
+                                                                      k == group - 1, d_err);
+        else
+          colour_round_kernel<false><<<(ne + 127) / 128, 128, 0, st>>>(ne, npe, c->d_conn, d.ne_ptr, d.ne_list, d_colour, d_counters,
+                                                                       k == group - 1, d_err);
+      }
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(&remaining, d_counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+    }
   }
-  const signed char *d_colour = d_col[cur];
   int maxc = -1;
   {
     int init = -1;
@@ -509,8 +519,7 @@ int build_pattern_device(goma_gpu_ctx *c) {
   int h_err[4] = {0, 0, 0, 0};
   CU(cudaMemcpyAsync(h_err, d_err, sizeof(h_err), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  cudaFree(d_col[0]);
-  cudaFree(d_col[1]);
+  cudaFree(d_colour);
   cudaFree(d_counters);
   cudaFree(d_ids);
   switch (h_err[0]) {

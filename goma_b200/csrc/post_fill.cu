@@ -84,60 +84,107 @@ extern "C" int goma_gpu_global_h_U(goma_gpu_ctx *c, const unsigned char *elem_ow
 }
 
 // ------------------------------------------------------------------ after the fill: row-sum scaling, norms
-// One warp per owned row: the off-diagonal run of an MSR row is contiguous, lanes stride over it (coalesced),
-// the second sweep over the row (the division) hits L1/L2.  HBM-bound: reads and writes every value once.
-__global__ void __launch_bounds__(256, 6) row_sum_scale_kernel(int nrows, const long long *__restrict__ rowstart, double *__restrict__ a,
-                                     double *__restrict__ b, double *__restrict__ scale, int *__restrict__ zero_rows) {
-  const int lane = threadIdx.x & 31;
-  const int nwarp = (gridDim.x * blockDim.x) >> 5;
-  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  long long k0n = 0, k1n = 0;
-  if (row < nrows) {
-    k0n = rowstart[row];
-    k1n = rowstart[row + 1];
-  }
-  for (; row < nrows; row += nwarp) {
-    const long long k0 = k0n, k1 = k1n;
-    if (row + nwarp < nrows) {  // the next row's extent is on its way while this row streams
-      k0n = rowstart[row + nwarp];
-      k1n = rowstart[row + nwarp + 1];
+// row_sum_scale_MSR (src/sl_matrix_util.c:507-600).  Consecutive rows are contiguous in memory (MSR off-diagonals as
+// well as CSR rows), so a CTA stages a BATCH of rows in shared memory with asynchronous copies (cp.async: the whole
+// batch, ~25 KB, is in flight at once), sums and scales it there (one warp per row) and streams it back with
+// coalesced stores: exactly one read and one write of every value, no reliance on L1/L2 for the second sweep.
+constexpr int RSS_ROWS = 8, RSS_THREADS = 256, RSS_CAP = 5120;  // rows per batch, capacity of the staging buffer (doubles)
+
+__device__ __forceinline__ void rss_cp_async8(void *dst, const void *src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+
+template <bool CSR>
+__global__ void __launch_bounds__(RSS_THREADS) row_sum_scale_kernel(int nrows, const long long *__restrict__ rowstart, long long msr0,
+                                                                    const int *__restrict__ dpos, double *__restrict__ a,
+                                                                    double *__restrict__ b, double *__restrict__ scale,
+                                                                    int *__restrict__ zero_rows) {
+  __shared__ double buf[RSS_CAP];
+  __shared__ long long rs[RSS_ROWS + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nbatch = (nrows + RSS_ROWS - 1) / RSS_ROWS;
+  for (int bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
+    const int r0 = bt * RSS_ROWS, nr = min(RSS_ROWS, nrows - r0);
+    if (tid <= nr) rs[tid] = CSR ? rowstart[r0 + tid] - msr0 + (r0 + tid) : rowstart[r0 + tid];
+    __syncthreads();
+    const long long k0 = rs[0];
+    const int len = (int)(rs[nr] - k0);
+    const bool staged = len <= RSS_CAP;  // (rows longer than the buffer go through global memory twice)
+    if (staged) {
+      for (int k = tid; k < len; k += RSS_THREADS) rss_cp_async8(&buf[k], &a[k0 + k]);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_all;" ::: "memory");
     }
-    double sum = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    long long k = k0 + lane;
-    for (; k + 96 < k1; k += 128) {  // four independent 256-byte requests in flight per warp
-      const double v0 = a[k], v1 = a[k + 32], v2 = a[k + 64], v3 = a[k + 96];
-      sum += fabs(v0);
-      s1 += fabs(v1);
-      s2 += fabs(v2);
-      s3 += fabs(v3);
-    }
-    for (; k < k1; k += 32) sum += fabs(a[k]);
-    sum = (sum + s1) + (s2 + s3);
+    __syncthreads();
+    if (warp < nr) {
+      const int row = r0 + warp;
+      const int o0 = (int)(rs[warp] - k0), o1 = (int)(rs[warp + 1] - k0);
+      double sum = 0.0;
+      if (staged)
+        for (int k = o0 + lane; k < o1; k += 32) sum += fabs(buf[k]);
+      else
+        for (long long k = rs[warp] + lane; k < rs[warp + 1]; k += 32) sum += fabs(a[k]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const double diag = a[row];
-    double row_sum = fabs(diag) + sum;
-    if (fabs(diag) > 1.0e-200) row_sum = diag >= 0.0 ? row_sum : -row_sum;  // keep the diagonal positive (:547-549)
-    // the reference divides (a[k] /= row_sum); one reciprocal per row and a multiply per entry differ from that by
-    // at most 1 ulp (the parity tolerance is 1e-12) and take the fp64 divide sequence (~20 instructions per entry)
-    // off an HBM-bound pass
-    const double inv = 1.0 / row_sum;
-    k = k0 + lane;
-    for (; k + 96 < k1; k += 128) {
-      const double v0 = a[k], v1 = a[k + 32], v2 = a[k + 64], v3 = a[k + 96];
-      a[k] = v0 * inv;
-      a[k + 32] = v1 * inv;
-      a[k + 64] = v2 * inv;
-      a[k + 96] = v3 * inv;
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      // MSR: the diagonal lives apart in a[row]; CSR: it is one of the staged entries (already in the sum)
+      const double diag = CSR ? (staged ? buf[o0 + dpos[row]] : a[rs[warp] + dpos[row]]) : a[row];
+      double row_sum = CSR ? sum : fabs(diag) + sum;
+      if (fabs(diag) > 1.0e-200) row_sum = diag >= 0.0 ? row_sum : -row_sum;  // keep the diagonal positive (:547-549)
+      // one reciprocal per row and a multiply per entry differ from the reference's divide by at most 1 ulp (parity
+      // tolerance 1e-12) and keep the fp64 divide sequence off an HBM-bound pass
+      const double inv = 1.0 / row_sum;
+      if (staged)
+        for (int k = o0 + lane; k < o1; k += 32) buf[k] *= inv;
+      else
+        for (long long k = rs[warp] + lane; k < rs[warp + 1]; k += 32) a[k] *= inv;
+      if (lane == 0) {
+        scale[row] = row_sum;
+        if (row_sum == 0.0) atomicAdd(zero_rows, 1);
+        if (!CSR) a[row] = diag / row_sum;
+        b[row] = b[row] / row_sum;
+      }
     }
-    for (; k < k1; k += 32) a[k] = a[k] * inv;
-    if (lane == 0) {
-      scale[row] = row_sum;
-      if (row_sum == 0.0) atomicAdd(zero_rows, 1);
-      a[row] = diag / row_sum;
-      b[row] = b[row] / row_sum;
-    }
+    __syncthreads();
+    if (staged)
+      for (int k = tid; k < len; k += RSS_THREADS) a[k0 + k] = buf[k];
+    __syncthreads();
   }
+}
+
+// CSR layout: offset of the diagonal inside every owned row, from the node-node lists (init only)
+__global__ void csr_dpos_kernel(int num_owned_nodes, const long long *__restrict__ nn_ptr, const int *__restrict__ nn_list,
+                                const unsigned short *__restrict__ cum_full, const unsigned short *__restrict__ cum_p,
+                                const int *__restrict__ first_unknown, const unsigned char *__restrict__ node_kind,
+                                const __grid_constant__ KindInfo K, int *__restrict__ dpos) {
+  const int nd = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nd >= num_owned_nodes) return;
+  const long long b = nn_ptr[nd];
+  int lo = 0, hi = (int)(nn_ptr[nd + 1] - b);
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (nn_list[b + mid] < nd)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  const int kd = node_kind[nd], fu = first_unknown[nd];
+  for (int s = 0; s < K.nunk[kd]; s++)
+    dpos[fu + s] = cum_full[b + lo] + s - ((K.tslot[kd] >= 0 && s == K.tslot[kd]) ? cum_p[b + lo] : 0);
+}
+
+int goma_b200::build_csr_dpos(goma_gpu_ctx *c) {
+  const int no = c->num_owned_unknowns, nown = c->prob.num_owned_nodes;
+  if (c->d_dpos) return 0;
+  CU(cudaMalloc((void **)&c->d_dpos, std::max<size_t>(no, 1) * sizeof(int)));
+  c->device_bytes += (size_t)no * sizeof(int);
+  if (nown > 0) {
+    const KindInfo K = make_kind_info(c->prob);
+    csr_dpos_kernel<<<(nown + 127) / 128, 128, 0, c->stream>>>(nown, c->dpat.nn_ptr, c->dpat.nn_list, c->dpat.cum_full, c->dpat.cum_p,
+                                                                c->d_first, c->d_kind, K, c->d_dpos);
+    CU(cudaGetLastError());
+  }
+  return 0;
 }
 
 extern "C" int goma_gpu_row_sum_scale(goma_gpu_ctx *c, double *scale_out, int *zero_rows_out) {
@@ -148,13 +195,20 @@ extern "C" int goma_gpu_row_sum_scale(goma_gpu_ctx *c, double *scale_out, int *z
   if (!c->d_zero_rows) CU(cudaMalloc((void **)&c->d_zero_rows, sizeof(int)));
   CU(cudaMemsetAsync(c->d_zero_rows, 0, sizeof(int), c->stream));
   if (n > 0) {
-    const int threads = 256;
-    int per_sm = 0;  // a whole number of resident waves: the rows are handed out grid-stride
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)row_sum_scale_kernel, threads, 0));
+    const bool csr = c->layout == GOMA_GPU_LAYOUT_CSR;
+    int per_sm = 0;  // a whole number of resident waves: the batches are handed out grid-stride
+    if (csr)
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)row_sum_scale_kernel<true>, RSS_THREADS, 0));
+    else
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)row_sum_scale_kernel<false>, RSS_THREADS, 0));
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-    const int blocks = std::max(1, std::min(sms * std::max(per_sm, 1), (n + 7) / 8));
-    row_sum_scale_kernel<<<blocks, threads, 0, c->stream>>>(n, c->d_rowstart, c->d_a, c->d_resid, c->d_scale, c->d_zero_rows);
+    const int blocks = std::max(1, std::min(sms * std::max(per_sm, 1), (n + RSS_ROWS - 1) / RSS_ROWS));
+    const long long msr0 = (long long)c->prob.num_unknowns + 1;
+    if (csr)
+      row_sum_scale_kernel<true><<<blocks, RSS_THREADS, 0, c->stream>>>(n, c->d_rowstart, msr0, c->d_dpos, c->d_a, c->d_resid, c->d_scale, c->d_zero_rows);
+    else
+      row_sum_scale_kernel<false><<<blocks, RSS_THREADS, 0, c->stream>>>(n, c->d_rowstart, msr0, nullptr, c->d_a, c->d_resid, c->d_scale, c->d_zero_rows);
     CU(cudaGetLastError());
   }
   int zr = 0;
@@ -274,7 +328,7 @@ extern "C" int goma_gpu_csr_structure(goma_gpu_ctx *c, const goma_gpu_problem *p
   if (!c || !p || !out) return fail(-2, "null argument");
   CU(cudaSetDevice(c->device));
   const int nrows = c->num_owned_unknowns;
-  if (!c->d_csr_rowptr) {
+  if (!c->d_csr_colind) {
     if (!c->dpat.nn_ptr || !c->dpat.nn_list) return fail(-2, "node-node lists are not available");
     long long h_rs[2] = {0, 0};
     CU(cudaMemcpy(&h_rs[0], c->d_rowstart, sizeof(long long), cudaMemcpyDeviceToHost));
@@ -284,11 +338,14 @@ extern "C" int goma_gpu_csr_structure(goma_gpu_ctx *c, const goma_gpu_problem *p
     const KindInfo K = make_kind_info(*p);
     long long *d_nn_ptr = c->dpat.nn_ptr;
     int *d_nn_list = c->dpat.nn_list;
-    CU(cudaMalloc((void **)&c->d_csr_rowptr, ((size_t)nrows + 1) * sizeof(long long)));
+    if (!c->d_csr_rowptr) CU(cudaMalloc((void **)&c->d_csr_rowptr, ((size_t)nrows + 1) * sizeof(long long)));
     CU(cudaMalloc((void **)&c->d_csr_colind, std::max<size_t>((size_t)c->csr_nnz, 1) * sizeof(int)));
     CU(cudaMalloc((void **)&c->d_csr_dpos, std::max<size_t>((size_t)nrows, 1) * sizeof(int)));
-    CU(cudaMalloc((void **)&c->d_csr_values, std::max<size_t>((size_t)c->csr_nnz, 1) * sizeof(double)));
-    c->device_bytes += (size_t)c->csr_nnz * 12 + (size_t)nrows * 12;
+    if (c->layout == GOMA_GPU_LAYOUT_CSR)
+      c->d_csr_values = c->d_a;  // the fill scatters straight into the CSR values: no second copy of the matrix
+    else
+      CU(cudaMalloc((void **)&c->d_csr_values, std::max<size_t>((size_t)c->csr_nnz, 1) * sizeof(double)));
+    c->device_bytes += (size_t)c->csr_nnz * (c->layout == GOMA_GPU_LAYOUT_CSR ? 4 : 12) + (size_t)nrows * 12;
     CU(cudaMemset(c->d_csr_rowptr, 0, ((size_t)nrows + 1) * sizeof(long long)));
     const int nown = c->prob.num_owned_nodes;
     if (nown > 0 && nrows > 0) {
@@ -309,6 +366,7 @@ extern "C" int goma_gpu_csr_structure(goma_gpu_ctx *c, const goma_gpu_problem *p
 
 extern "C" int goma_gpu_csr_values(goma_gpu_ctx *c) {
   if (!c) return fail(-2, "null context");
+  if (c->layout == GOMA_GPU_LAYOUT_CSR) return 0;  // the values are assembled in place
   if (!c->d_csr_rowptr) return fail(-2, "call goma_gpu_csr_structure first");
   CU(cudaSetDevice(c->device));
   const int nrows = c->num_owned_unknowns;
@@ -320,5 +378,38 @@ extern "C" int goma_gpu_csr_values(goma_gpu_ctx *c) {
     CU(cudaGetLastError());
   }
   CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+__global__ void csr_rowptr_kernel(int nrows, const long long *__restrict__ rowstart, long long msr0, long long *__restrict__ rowptr) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r <= nrows) rowptr[r] = rowstart[r] - msr0 + r;
+}
+
+extern "C" int goma_gpu_csr_rows(goma_gpu_ctx *c, goma_gpu_csr *out) {
+  if (!c || !out) return fail(-2, "null argument");
+  if (c->layout != GOMA_GPU_LAYOUT_CSR)
+    return fail(-2, "goma_gpu_csr_rows needs matrix_layout = GOMA_GPU_LAYOUT_CSR (use goma_gpu_csr_structure / _values for MSR)");
+  CU(cudaSetDevice(c->device));
+  const int nrows = c->num_owned_unknowns;
+  if (!c->d_csr_rowptr) {
+    CU(cudaMalloc((void **)&c->d_csr_rowptr, ((size_t)nrows + 1) * sizeof(long long)));
+    csr_rowptr_kernel<<<(nrows + 256) / 256, 256, 0, c->stream>>>(nrows, c->d_rowstart, (long long)c->prob.num_unknowns + 1, c->d_csr_rowptr);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  out->num_rows = nrows;
+  out->nnz = c->csr_nnz;
+  out->d_rowptr = c->d_csr_rowptr;
+  out->d_colind = c->d_csr_colind;  // NULL unless goma_gpu_csr_structure ran
+  out->d_values = c->d_a;
+  return 0;
+}
+
+extern "C" int goma_gpu_node_graph(goma_gpu_ctx *c, long long **d_nn_ptr, int **d_nn_list) {
+  if (!c) return fail(-2, "null context");
+  if (!c->dpat.nn_ptr) return fail(-2, "node-node lists are not resident");
+  if (d_nn_ptr) *d_nn_ptr = c->dpat.nn_ptr;
+  if (d_nn_list) *d_nn_list = c->dpat.nn_list;
   return 0;
 }

@@ -18,17 +18,22 @@ from . import capi
 
 
 class MatrixFill:
-    def __init__(self, problem, device: int = 0, ija=None, num_owned_nodes=None):
+    def __init__(self, problem, device: int = 0, ija=None, num_owned_nodes=None, layout: str = "msr"):
+        """``layout``: "msr" = the reference's ``ams->val`` (default); "csr" = CSR of the owned rows with the diagonal in
+        place, assembled directly (``goma_gpu_problem.matrix_layout``)."""
         self.lib = capi.load_library()
         self.problem = problem
         self.device = int(device)
-        self._struct, self._keep = capi.make_problem_struct(problem, ija=ija, num_owned_nodes=num_owned_nodes)
+        self.layout = layout
+        self._struct, self._keep = capi.make_problem_struct(problem, ija=ija, num_owned_nodes=num_owned_nodes, layout=layout)
         self._ctx = C.c_void_p()
         capi.check(self.lib.goma_gpu_fill_init(C.byref(self._struct), device, C.byref(self._ctx)),
                    "goma_gpu_fill_init")
         nnz = C.c_longlong()
         capi.check(self.lib.goma_gpu_fill_get_msr(self._ctx, C.byref(nnz)), "goma_gpu_fill_get_msr")
         self.nnz_plus = int(nnz.value)
+        capi.check(self.lib.goma_gpu_fill_value_count(self._ctx, C.byref(nnz)), "goma_gpu_fill_value_count")
+        self.value_count = int(nnz.value)  # doubles in `a`: nnz_plus + 1 (MSR) or the CSR nnz
         self.num_unknowns = int(self._struct.num_unknowns)
         self.flags = np.zeros(3, np.int32)
 
@@ -58,7 +63,7 @@ class MatrixFill:
 
         x, x_old, x_older, xdot, xdot_old = (prep(v) for v in (x, x_old, x_older, xdot, xdot_old))
         if a is None and assemble_jacobian:
-            a = np.empty(self.nnz_plus + 1, np.float64)
+            a = np.empty(self.value_count, np.float64)
         if resid_vector is None and assemble_residual:
             resid_vector = np.empty(n, np.float64)
         p = lambda v: capi._ptr(v, capi._dp)
@@ -153,13 +158,23 @@ class MatrixFill:
         return (device_view(h.d_rowptr, h.num_rows + 1, dev, "<i8"), device_view(h.d_colind, int(h.nnz), dev, "<i4"),
                 device_view(h.d_values, int(h.nnz), dev, "<f8"))
 
+    def csr_rows(self):
+        """CSR layout only: (rowptr int64 [n+1], values float64 [nnz]) aliasing the library's buffers -- no column array
+        (``goma_gpu_csr_rows``); ``node_graph`` describes the columns at node level."""
+        import torch
+
+        h = capi.Csr()
+        capi.check(self.lib.goma_gpu_csr_rows(self._ctx, C.byref(h)), "goma_gpu_csr_rows")
+        dev = torch.device("cuda", self.device)
+        return device_view(h.d_rowptr, h.num_rows + 1, dev, "<i8"), device_view(h.d_values, int(h.nnz), dev, "<f8")
+
     def download_system(self):
         """D2H of the device-resident MSR values and residual (after row_sum_scale, say)."""
         import torch
 
         b = self.device_buffers()
         dev = torch.device("cuda", self.device)
-        a = device_view(b.d_a, self.nnz_plus + 1, dev).cpu().numpy()
+        a = device_view(b.d_a, self.value_count, dev).cpu().numpy()
         r = device_view(b.d_resid, self.num_unknowns, dev).cpu().numpy()
         return a, r
 

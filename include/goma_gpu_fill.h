@@ -125,7 +125,17 @@ struct goma_gpu_problem {
    * refused by goma_gpu_fill_init instead of being assembled with the wrong material.  0 = not stated. */
   int num_elem_blocks;
   int num_materials;
+
+  /* Layout of the assembled values.  GOMA_GPU_LAYOUT_MSR (0): the reference's ams->val -- diagonal a[0..N), a[N]
+   * unused, off-diagonals of row r at a[ija[r]..ija[r+1]) (src/mm_fill_util.c:2865-3031).  GOMA_GPU_LAYOUT_CSR (1):
+   * CSR of the OWNED rows with the diagonal at its sorted position -- the element blocks are scattered straight into
+   * the array a GPU solver or an Epetra/Tpetra CRS matrix consumes (the target of SumIntoGlobalValues,
+   * src/linalg/sparse_matrix_epetra.cpp:111-118), no second copy of the matrix: goma_gpu_fill's `a` and d_a then
+   * hold goma_gpu_csr::nnz values, goma_gpu_csr_structure's d_values IS d_a and goma_gpu_csr_values is a no-op. */
+  int matrix_layout;
 };
+#define GOMA_GPU_LAYOUT_MSR 0
+#define GOMA_GPU_LAYOUT_CSR 1
 
 typedef struct goma_gpu_ctx goma_gpu_ctx;
 
@@ -135,6 +145,8 @@ void goma_gpu_fill_destroy(goma_gpu_ctx *ctx);
 /* MSR graph as built by the library: nnz_plus = ija[num_unknowns].  export_msr writes the
  * whole ija[0..nnz_plus) (needs the host arrays of `problem` again; fails beyond 2^31-1). */
 int goma_gpu_fill_get_msr(goma_gpu_ctx *ctx, long long *nnz_plus);
+/* doubles in the value array (`a` of goma_gpu_fill, d_a): nnz_plus + 1 for the MSR layout, goma_gpu_csr::nnz for CSR */
+int goma_gpu_fill_value_count(goma_gpu_ctx *ctx, long long *count);
 int goma_gpu_fill_export_msr(goma_gpu_ctx *ctx, const struct goma_gpu_problem *problem, int *ija_out);
 
 /* Host-only (no device): the MSR graph the library derives from mesh + unknown map, i.e. what
@@ -205,10 +217,16 @@ struct goma_gpu_csr {
   int num_rows;        /* owned unknowns */
   long long nnz;       /* entries of those rows, diagonal included */
   long long *d_rowptr; /* [num_rows + 1] */
-  int *d_colind;       /* [nnz] local unknown numbers (external columns included) */
+  int *d_colind;       /* [nnz] local unknown numbers (external columns included); NULL from goma_gpu_csr_rows */
   double *d_values;    /* [nnz] */
 };
 int goma_gpu_csr_structure(goma_gpu_ctx *ctx, const struct goma_gpu_problem *problem, struct goma_gpu_csr *out);
+/* The same without the 4-byte-per-entry column array (C3 at 2M elements: 75 GB that do not fit beside the 150 GB
+ * of values): row pointers and values only.  The columns of a row are then described by the node-level lists every
+ * row of a node shares -- goma_gpu_node_graph: the sorted neighbour nodes of each node (exo_conn.c build_node_node),
+ * whose unknowns, in node order, are the row's columns (energy rows skip pressure unknowns). */
+int goma_gpu_csr_rows(goma_gpu_ctx *ctx, struct goma_gpu_csr *out);
+int goma_gpu_node_graph(goma_gpu_ctx *ctx, long long **d_nn_ptr, int **d_nn_list);
 int goma_gpu_csr_values(goma_gpu_ctx *ctx);
 
 /* exchange_dof() (src/dp_comm.c:48-102) over NVLink peer memory, one rank per GPU of one node.

@@ -723,3 +723,64 @@ def test_gpu_zero_row_scaling_does_not_poison_later_fills(built):
     err, a2, r2 = mf.matrix_fill_full(st["x"])
     assert err == 0 and not np.isnan(a2).any() and not a2.any()
     mf.close()
+
+
+@pytest.mark.parametrize("name", ["c2_hex27_ns", "c3_hex27_boussinesq", "c5_hex8_pspg_global", "c4_quad9_ale",
+                                  "c1_quad9_ns_transient", "irr_hex27_star_bouss", "q2p1_quad9_species_ale_transient"])
+@pytest.mark.parametrize("scatter", [0, 2], ids=["atomic", "first_touch"])
+def test_gpu_csr_layout_is_assembled_in_place(built, name, scatter):
+    """matrix_layout = CSR: the element blocks are scattered straight into the CSR value array (diagonal at its sorted
+    position, owned rows only) -- no second copy of the matrix.  The values equal the reference fixture's MSR system
+    re-ordered; rowptr / colind equal the reference graph; the residual is the same; with ghost nodes only owned rows
+    exist; row-sum scaling works on the CSR array in place."""
+    p, kw, st = case_state(name)
+    g = golden(name)
+    n = len(g["resid"])
+    fkw = dict(delta_t=kw.get("delta_t", 0.0), theta=kw.get("theta", 0.0), time_value=kw.get("time", 0.0))
+    h, U = (p.global_h_elem_siz(), p.global_velocity_norm(st["x"])) if p.pspg else (0.0, 0.0)
+    args = (st["x"], st.get("x_old"), st.get("x_older"), st.get("xdot"), st.get("xdot_old"))
+    mf = MatrixFill(p, layout="csr")
+    mf.set_option("scatter", scatter)
+    rp, ci, va = _msr_to_csr_arrays(g["ija"], g["a"], n)  # from the REFERENCE's graph and values
+    assert mf.value_count == len(va)
+    err, a, r = mf.matrix_fill_full(*args, h_elem_avg=h, U_norm=U, **fkw)
+    assert err == 0 and len(a) == len(va)
+    csr_ija = np.concatenate([[n + 1], n + 1 + np.cumsum(np.diff(rp) - 1)])  # per-row scale of the check below
+    scale = np.maximum.reduceat(np.abs(va), rp[:-1])
+    assert (np.abs(a - va) <= TOL * np.repeat(scale, np.diff(rp))).all(), "CSR values vs reference (per-row tolerance)"
+    assert_close(r, g["resid"], "residual")
+    rowptr, colind, values = (t.cpu().numpy() for t in mf.csr())
+    np.testing.assert_array_equal(rowptr, rp)
+    np.testing.assert_array_equal(colind, ci)
+    np.testing.assert_array_equal(values, a)  # the CSR view IS the assembled array
+    rowptr2, values2 = (t.cpu().numpy() for t in mf.csr_rows())
+    np.testing.assert_array_equal(rowptr2, rp)
+    np.testing.assert_array_equal(values2, a)
+    # row-sum scaling in place on the CSR array == the MSR path's result re-ordered
+    mf_m = MatrixFill(p)
+    mf_m.matrix_fill_full(*args, h_elem_avg=h, U_norm=U, **fkw)
+    s_m, z_m = mf_m.row_sum_scale()
+    am, rm = mf_m.download_system()
+    s_c, z_c = mf.row_sum_scale()
+    ac, rc_ = mf.download_system()
+    assert z_m == z_c == 0
+    assert_close(s_c, s_m, "scale")
+    _, _, vam = _msr_to_csr_arrays(g["ija"], am, n)
+    assert_close(ac, vam, "scaled CSR values")
+    assert_close(rc_, rm, "scaled residual")
+    mf.close()
+    mf_m.close()
+    assert len(csr_ija) == n + 1
+    # owned rows only
+    owned = p.mesh.num_nodes - 5
+    n_owned = int(p.unknown_map()[0][owned])
+    mf = MatrixFill(p, num_owned_nodes=owned, layout="csr")
+    mf_m = MatrixFill(p, num_owned_nodes=owned)
+    err, a, r = mf.matrix_fill_full(*args, h_elem_avg=h, U_norm=U, **fkw)
+    _, am, rm = mf_m.matrix_fill_full(*args, h_elem_avg=h, U_norm=U, **fkw)
+    rp, ci, va = _msr_to_csr_arrays(mf_m.export_msr(), am, n_owned)
+    assert len(a) == len(va) == rp[-1]
+    assert_close(a, va, "CSR values, owned rows")
+    assert_close(r, rm, "residual, owned rows")
+    mf.close()
+    mf_m.close()
