@@ -282,6 +282,30 @@ def fp64_peak_tflops(device):
     return best
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank (and with it the pinned host buffers it allocates: first touch) to the CPUs of the NUMA node its
+    GPU hangs off, so that 8 ranks copying 45 GB each to the host do not all cross one socket's memory controller."""
+    try:
+        import torch
+
+        prop = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        pass
+    return None
+
+
 def problem_maker(cfg):
     if cfg == "c5":
         return c5_problem_on
@@ -430,6 +454,7 @@ def main():
     ge.build(quiet=True)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -646,7 +671,7 @@ def main():
             "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.config, args.n, args.scaling, world), "elements_per_gpu": ne_owned,
                        "elements_assembled_per_gpu": ne, "unknowns_per_gpu": n_unk,
-                       "halo": halo,
+                       "halo": halo, "numa_binding": numa,
                        "nnz_per_gpu": nnz, "scatter": ["fp64 atomics", "coloured load+add+store", "coloured first-touch stores"][args.scatter],
                        "l2": "inputs larger than L2 (MSR values %.1f GB per GPU rewritten every step)" % (8e-9 * nnz),
                        "setup_s": round(setup["total_s"], 2),

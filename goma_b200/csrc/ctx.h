@@ -36,7 +36,7 @@ struct DevPattern {
   unsigned short *cum_full = nullptr, *cum_p = nullptr;  // per list entry: unknowns / pressure unknowns of earlier neighbours
   int *row_full = nullptr, *row_p = nullptr;            // per node: unknowns / pressure unknowns of all neighbours
   unsigned *pair_first = nullptr, *node_first = nullptr;  // first-touch masks
-  unsigned char *cls = nullptr;                         // class (colour, + ncol for border elements) of each element
+  unsigned *cls = nullptr;                              // class ((border, chunk, colour) key) of each element
   long long nn_total = 0;
 };
 }  // namespace goma_b200
@@ -59,7 +59,9 @@ struct goma_gpu_ctx {
   int layout = 0;                  // GOMA_GPU_LAYOUT_*: how d_a is laid out
   long long a_len = 0;             // doubles in d_a: nnz_plus + 1 (MSR) or csr_nnz (CSR)
   int *d_dpos = nullptr;           // CSR layout: offset of the diagonal inside each owned row
-  int num_colours = 0;             // element colours; classes [0, ncol) interior, [ncol, 2 ncol) border elements
+  int num_colours = 0;             // element colours; class = ((border ? nchunk : 0) + chunk) * ncol + colour
+  int num_chunks = 1;              // chunks of consecutive elements swept one after the other (L2-sized; 1 = off)
+  int chunk_elems_option = 0;      // "chunk_elems" option at init: 0 auto, > 0 elements per chunk, < 0 off
   int first_border_class = 0;      // classes from here on touch external nodes: they wait for the ghost exchange
   cudaStream_t xstream = nullptr;  // exchange_dof runs here, overlapped with the interior classes
   cudaEvent_t ev_x = nullptr, ev_pre = nullptr;

@@ -1159,11 +1159,18 @@ __device__ __forceinline__ void gauss_loop(const FillParams &P, const Smem<C> &s
   const int ngp_run = (P.debug & 2) ? 1 : NGP;
 #pragma unroll 1
   for (int gp = 0; gp < ngp_run; gp++) {
-    const double2 j01 = op.SJa[gp][j];
-    const double2 j23 = op.SJb[gp][j];
-    const double phi_j = j01.x;
-    const double gj[3] = {j01.y, j23.x, j23.y};
-    const double vgj = op.VG[gp][j];
+    double phi_j, gj[3], vgj;
+    if constexpr (C::MMA) {  // tensor-core table layout (the remainder tiles of gauss_blocks_mma)
+      phi_j = op.SJ[gp][j];
+      gj[0] = op.SJ[gp][28 + j], gj[1] = op.SJ[gp][56 + j], gj[2] = op.SJ[gp][84 + j];
+      vgj = op.SJ[gp][112 + j];
+    } else {
+      const double2 j01 = op.SJa[gp][j];
+      const double2 j23 = op.SJb[gp][j];
+      phi_j = j01.x;
+      gj[0] = j01.y, gj[1] = j23.x, gj[2] = j23.y;
+      vgj = op.VG[gp][j];
+    }
     const double qj = c_adv * vgj + c_mass * phi_j;
     double gjs[DIM], GV[DIM][DIM], GT[DIM];
     const double *G = s.GP[bo][gp];
@@ -1176,8 +1183,8 @@ __device__ __forceinline__ void gauss_loop(const FillParams &P, const Smem<C> &s
     }
 #pragma unroll
     for (int ii = 0; ii < TI; ii++) {
-      const double2 i01 = make_double2(op.SI[gp][0][i0 + ii], op.SI[gp][1][i0 + ii]);
-      const double2 i23 = make_double2(op.SI[gp][2][i0 + ii], op.SI[gp][3][i0 + ii]);
+      const double2 i01 = make_double2(op_si<C>(op, gp, 0, i0 + ii), op_si<C>(op, gp, 1, i0 + ii));
+      const double2 i23 = make_double2(op_si<C>(op, gp, 2, i0 + ii), op_si<C>(op, gp, 3, i0 + ii));
       const double wphi = i01.x;
       const double wg[3] = {i01.y, i23.x, i23.y};
       const double pp = wphi * phi_j;
@@ -1526,9 +1533,24 @@ __device__ __forceinline__ void gauss_blocks_mma(const FillParams &P, const Smem
   const double ce_adv = -P.etm_energy[1] * rcp, ce_diff = -P.etm_energy[3] * P.k, ce_mass = -P.etm_energy[0] * rcp * tfac;
   const int r = lane >> 2, kq = lane & 3;
   const int nks = (P.debug & 2) ? 1 : 7;
+  // 27 = 3 * 8 + 3: the nine full 8 x 8 node blocks run on the tensor cores (warps 0 .. NWARP-3); padding the
+  // remaining 3 nodes to a fourth block row / column would spend 16/9 of that work on the pipe the kernel is bound by,
+  // so the 153 node pairs with a node >= 24 are done by the last two warps as scalar 3 x 1 register tiles
+  // (gauss_loop): 51 tiles, 20-23 FMAs per pair and Gauss point, about as long as two tensor-core blocks
+  constexpr int NMW = C::NWARP - 2;
+  if (warp >= NMW) {
+    const int t = (warp - NMW) * 32 + lane;
+    if (t < 27 + 24) {
+      const int i0 = t < 27 ? 24 : ((t - 27) / 3) * 3, j = t < 27 ? t : 24 + (t - 27) % 3;
+      Tile<C> tile;
+      gauss_loop<C>(P, s, i0, j, tile);
+      if (!(P.debug & 1)) write_tile_direct<C, MODE>(P, rec, i0, j, tile);
+    }
+    return;
+  }
 #pragma unroll 1
-  for (int blk = warp; blk < 16; blk += C::NWARP) {
-    const int I0 = (blk >> 2) * 8, J0 = (blk & 3) * 8;
+  for (int blk = warp; blk < 9; blk += NMW) {
+    const int I0 = (blk / 3) * 8, J0 = (blk % 3) * 8;
     const int ia = min(I0 + r, 27), jb = min(J0 + r, 27);  // rows / columns >= 27 read the zero padding
 #ifdef GOMA_PROFILE_PHASES
     const long long t_blk0 = clock64();

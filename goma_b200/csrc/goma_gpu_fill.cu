@@ -243,6 +243,7 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
   goma_gpu_ctx *c = guard.c;
   c->prob = p;
   c->device = device;
+  if (const char *ce = getenv("GOMA_GPU_CHUNK_ELEMS")) c->chunk_elems_option = atoi(ce);  // experiments: 0 auto, < 0 off
   c->num_owned_unknowns = p.num_owned_nodes < p.num_nodes ? p.first_unknown[p.num_owned_nodes] : p.num_unknowns;
   const int nn = p.num_nodes, ne = p.num_elems, npe = p.elem_type, N = p.num_unknowns;
   int rc = 0;

@@ -230,16 +230,18 @@ __global__ void max_colour_kernel(int ne, const signed char *__restrict__ col, i
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m >= 0) atomicMax(maxc, m);
 }
-__global__ void class_kernel(int ne, int npe, int ncol, int num_owned_nodes, int split_border, const int *__restrict__ conn,
-                             const signed char *__restrict__ col, unsigned char *__restrict__ cls, int *__restrict__ ids,
-                             int *__restrict__ hist) {
+__global__ void class_kernel(int ne, int npe, int ncol, int nchunk, int chunk_elems, int num_owned_nodes, int split_border,
+                             const int *__restrict__ conn, const signed char *__restrict__ col, unsigned *__restrict__ cls,
+                             int *__restrict__ ids, int *__restrict__ hist) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ne) return;
   bool border = false;
   if (split_border)
     for (int i = 0; i < npe; i++) border = border || conn[(size_t)e * npe + i] >= num_owned_nodes;
-  const int k = col[e] + (border ? ncol : 0);
-  cls[e] = (unsigned char)k;
+  // processing order: interior elements before border elements (the ghost exchange overlaps the former); inside each,
+  // chunks of consecutive elements whose matrix rows fit the L2 cache, one colour after the other
+  const int k = ((border ? nchunk : 0) + e / chunk_elems) * ncol + col[e];
+  cls[e] = (unsigned)k;
   ids[e] = e;
   atomicAdd(&hist[k], 1);
 }
@@ -247,7 +249,7 @@ __global__ void class_kernel(int ne, int npe, int ncol, int num_owned_nodes, int
 // ---- first-touch masks: the pair (i, j) of element e is NOT a first touch iff an element of a lower class holds
 //      both nodes (elements of one class share no node: classes are colours)
 __global__ void first_touch_kernel(int ne, int npe, const int *__restrict__ conn, const int *__restrict__ ne_ptr,
-                                   const int *__restrict__ ne_list, const unsigned char *__restrict__ cls,
+                                   const int *__restrict__ ne_list, const unsigned *__restrict__ cls,
                                    unsigned *__restrict__ pair_first, unsigned *__restrict__ node_first,
                                    int *__restrict__ err) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -256,7 +258,7 @@ __global__ void first_touch_kernel(int ne, int npe, const int *__restrict__ conn
   int ids[MAXNB];
   unsigned masks[MAXNB];
   int nnb = 0;
-  const int ce = cls[e];
+  const unsigned ce = cls[e];
   for (int i = 0; i < npe; i++) {
     const int nd = conn[(size_t)e * npe + i];
     for (int q = ne_ptr[nd]; q < ne_ptr[nd + 1]; q++) {
@@ -449,9 +451,9 @@ int build_pattern_device(goma_gpu_ctx *c) {
 
   // ---- colouring, classes, processing order
   signed char *d_colour = nullptr;
-  int *d_counters = nullptr;  // [0] remaining, [1] max colour, [2..] class histogram (128)
+  int *d_counters = nullptr;  // [0] remaining, [1] max colour
   CU(cudaMalloc((void **)&d_colour, std::max(ne, 1)));
-  CU(cudaMalloc((void **)&d_counters, (2 + 128) * sizeof(int)));
+  CU(cudaMalloc((void **)&d_counters, 2 * sizeof(int)));
   CU(cudaMemsetAsync(d_colour, 0xff, std::max(ne, 1), st));
   {
     // rounds are enqueued in groups; the host looks at the count of waiting elements once per group
@@ -478,38 +480,62 @@ int build_pattern_device(goma_gpu_ctx *c) {
   {
     int init = -1;
     CU(cudaMemcpyAsync(d_counters + 1, &init, sizeof(int), cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(d_counters + 2, 0, 128 * sizeof(int), st));
     if (ne > 0) max_colour_kernel<<<grid_for(ne, 256), 256, 0, st>>>(ne, d_colour, d_counters + 1);
     CU(cudaMemcpyAsync(&maxc, d_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
   }
   const int ncol = maxc + 1;
   const int split_border = p.num_owned_nodes < p.num_nodes ? 1 : 0;
-  const int ncls = ncol * (split_border ? 2 : 1);
-  if (ncls > 126) return fail(-2, "element colouring needs more than 63 colours");
-  int *d_ids = nullptr;
+  // Chunks: when many elements contribute to the same matrix slots (hex8 / quad4: 2-8 elements per node pair), a
+  // colour sweep over the whole mesh reads and writes every shared sector once per contribution from DRAM.  Sweeping
+  // the colours chunk by chunk, with the rows of a chunk small enough to stay in L2, lets the contributions meet there.
+  // Only worth it while a (chunk, colour) launch still fills the GPU: not for hex27 (45-75 KB of matrix per element).
+  int chunk_elems = std::max(ne, 1);
+  {
+    int l2 = 0, sms = 0;
+    CU(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, c->device));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    const double bytes_per_elem = ne > 0 ? 8.0 * (double)c->nnz_plus / ne : 1.0;
+    long long want = c->chunk_elems_option > 0 ? c->chunk_elems_option : (long long)(0.5 * l2 / bytes_per_elem);
+    const bool many_writers = npe == GOMA_GPU_HEX8 || npe == GOMA_GPU_QUAD4;
+    const bool on = c->chunk_elems_option > 0 || (c->chunk_elems_option == 0 && many_writers && want >= 4LL * sms * std::max(ncol, 1));
+    if (on && want < ne) chunk_elems = (int)std::max<long long>(want, 1);
+  }
+  const int nchunk = ne > 0 ? (ne + chunk_elems - 1) / chunk_elems : 1;
+  const long long ncls_ll = (long long)ncol * nchunk * (split_border ? 2 : 1);
+  if (ncol > 63) return fail(-2, "element colouring needs more than 63 colours");
+  if (ncls_ll > (1LL << 24)) return fail(-2, "too many (chunk, colour) classes");
+  const int ncls = (int)ncls_ll;
+  int *d_ids = nullptr, *d_hist = nullptr;
   if (dev_alloc(&d.cls, (size_t)ne, c)) return -3;
   CU(cudaMalloc((void **)&d_ids, std::max(ne, 1) * sizeof(int)));
+  CU(cudaMalloc((void **)&d_hist, std::max(ncls, 1) * sizeof(int)));
+  CU(cudaMemsetAsync(d_hist, 0, std::max(ncls, 1) * sizeof(int), st));
   if (dev_alloc(&c->d_elem_list, (size_t)ne, c)) return -3;
-  std::vector<int> hist(128, 0);
+  std::vector<int> hist(std::max(ncls, 1), 0);
   if (ne > 0) {
-    class_kernel<<<(ne + 255) / 256, 256, 0, st>>>(ne, npe, ncol, p.num_owned_nodes, split_border, c->d_conn, d_colour, d.cls, d_ids, d_counters + 2);
-    unsigned char *d_cls_out = nullptr;
-    CU(cudaMalloc((void **)&d_cls_out, ne));
+    class_kernel<<<(ne + 255) / 256, 256, 0, st>>>(ne, npe, ncol, nchunk, chunk_elems, p.num_owned_nodes, split_border, c->d_conn, d_colour,
+                                                   d.cls, d_ids, d_hist);
+    unsigned *d_cls_out = nullptr;
+    CU(cudaMalloc((void **)&d_cls_out, (size_t)ne * sizeof(unsigned)));
+    int bits = 1;
+    while ((1LL << bits) < std::max(ncls, 2)) bits++;
     size_t need = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, need, d.cls, d_cls_out, d_ids, c->d_elem_list, ne, 0, 8, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, need, d.cls, d_cls_out, d_ids, c->d_elem_list, ne, 0, bits, st);
     if (temp(need)) return -3;
     size_t tb = temp_bytes;
-    cub::DeviceRadixSort::SortPairs(d_temp, tb, d.cls, d_cls_out, d_ids, c->d_elem_list, ne, 0, 8, st);
+    cub::DeviceRadixSort::SortPairs(d_temp, tb, d.cls, d_cls_out, d_ids, c->d_elem_list, ne, 0, bits, st);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(hist.data(), d_counters + 2, 128 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hist.data(), d_hist, (size_t)ncls * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     cudaFree(d_cls_out);
   }
+  cudaFree(d_hist);
   c->colour_begin.assign(ncls + 1, 0);
   for (int k = 0; k < ncls; k++) c->colour_begin[k + 1] = c->colour_begin[k] + hist[k];
-  c->first_border_class = split_border ? ncol : ncls;
+  c->first_border_class = split_border ? ncol * nchunk : ncls;
   c->num_colours = ncol;
+  c->num_chunks = nchunk;
 
   // ---- first-touch masks
   if (npe > 32) return fail(-2, "first-touch masks need <= 32 nodes per element");
