@@ -300,9 +300,16 @@ __device__ __forceinline__ void slot_add(const FillParams &P, double *addr, doub
     *addr += val;
   }
 }
+#ifdef GOMA_PROFILE_PHASES
+__constant__ int g_store_debug;  // profiling build only: bit 2 (4) drops the reductions, bit 3 (8) the first-touch stores
+#endif
 // the same with the scatter mode fixed at compile time (the node-pair write-out issues thousands per element)
 template <int MODE>
 __device__ __forceinline__ void slot_add_m(double *addr, double val, bool first) {
+#ifdef GOMA_PROFILE_PHASES
+  if ((g_store_debug & 4) && !first) return;
+  if ((g_store_debug & 8) && first) return;
+#endif
   if (MODE == 2) {
     if (first)
       *addr = val;
@@ -1642,7 +1649,12 @@ __device__ __forceinline__ void gauss_blocks_mma(const FillParams &P, const Smem
           if (rsv[fr] < 0) continue;
           double *dst = P.a + rsv[fr] + ((C::ENERGY && fr == C::F_T) ? offT : off);
 #pragma unroll
-          for (int fc = 0; fc < NF; fc++) dst[fc] = V[fr][fc];
+          for (int fc = 0; fc < NF; fc++) {
+#ifdef GOMA_PROFILE_PHASES
+            if (g_store_debug & 8) continue;
+#endif
+            dst[fc] = V[fr][fc];
+          }
         }
       } else {
 #pragma unroll

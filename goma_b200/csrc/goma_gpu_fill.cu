@@ -534,6 +534,9 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
   P.ps_scaling = p.ps_scaling;
   P.prof = c->d_prof;
   P.debug = getenv("GOMA_GPU_DEBUG") ? atoi(getenv("GOMA_GPU_DEBUG")) : 0;
+#ifdef GOMA_PROFILE_PHASES
+  CU(cudaMemcpyToSymbolAsync(g_store_debug, &P.debug, sizeof(int), 0, cudaMemcpyHostToDevice, c->stream));
+#endif
   if (p.transient && !(delta_t > 0.0)) return fail(-2, "transient fill needs delta_t > 0");
 
   if (c->num_sms == 0) {
