@@ -105,10 +105,14 @@ struct Cfg {
   static constexpr int NWARP = TPE / 32;
   // constant tables in global memory: weights, dphi/dxi, P1 basis, phi.  The tensor-core configurations keep phi in
   // their operand table (filled once per CTA), so only the part before T_PHI is staged into s.tbl
-  static constexpr int T_WT = 0, T_DPHI = NGP, T_PSI = T_DPHI + NGP * NN * DIM, T_PHI = T_PSI + NGP * (DIM + 1);
+  // order: weights, P1 basis, the 1-D Lagrange factors L[point][node], dL[point][node] (18), dphi/dxi, phi.  The
+  // tensor-core configurations form dphi/dxi from the 1-D factors on the fly (two multiplies per value instead of
+  // 17 KB of shared memory) and stage only what precedes T_DPHI
+  static constexpr int T_WT = 0, T_PSI = NGP, T_L1D = T_PSI + NGP * (DIM + 1), T_DPHI = T_L1D + 18,
+                       T_PHI = T_DPHI + NGP * NN * DIM;
   static constexpr int TBL = T_PHI + NGP * NN;
   static constexpr bool PHI_IN_OPERANDS = NN == 27 && NGP == 27 && P1_ && NSPEC_ == 0 && !ALE_ && !WS_;  // == MMA below
-  static constexpr int TBL_PAD = ((PHI_IN_OPERANDS ? T_PHI : TBL) + 1) & ~1;  // staged doubles, 16-byte multiple for the bulk copy
+  static constexpr int TBL_PAD = ((PHI_IN_OPERANDS ? T_DPHI : TBL) + 1) & ~1;  // staged doubles, 16-byte multiple for the bulk copy
   static constexpr int TBL_GLOBAL = TBL + 2;
   // per-Gauss-point derived data (doubles): see phase 4b
   static constexpr int G_GV = 0;                                   // c_adv d_b v_a            [a][b]
@@ -161,21 +165,23 @@ struct Operands {
   double2 SJb[C::NGP][C::NN];  // (g_j[1], g_j[2])
   double VG[C::NGP][C::NN];    // v . grad_phi_j
 };
-// Tensor-core layout: SI[gp][c * 28 + i] (c = 0: w phi_i, 1..3: w grad_phi_i[p]) and SJ[gp][c * 28 + j] (c = 0: phi_j,
-// 1..3: grad_phi_j[p], 4: v . grad_phi_j).  A fragment of mma.m8n8k4 is (8 consecutive nodes) x (4 consecutive Gauss
-// points): with a Gauss-point stride of 4 (mod 8) doubles the 16 lanes of a half-warp hit 16 different bank pairs.
-// Column 27 of every component and row 27 (the K padding) stay zero from the kernel prologue on.
+// Tensor-core layout: ONE table SJ[gp][c * 28 + node], c = 0: phi (the same for every element, written once per
+// CTA), 1..3: grad_phi[p], 4: v . grad_phi.  Test- and trial-function side read the same values: the quadrature
+// weight w(gp) is folded into the other operand of every product (the lane that forms a B fragment multiplies it by
+// the w of its Gauss point).  A fragment of mma.m8n8k4 is (8 consecutive nodes) x (4 consecutive Gauss points): with
+// a Gauss-point stride of 4 (mod 8) doubles the 16 lanes of a half-warp hit 16 different bank pairs.  Column 27 of
+// every component and row 27 (the K padding) stay zero from the kernel prologue on.  31 KB instead of the 52 KB of
+// separate w-scaled and raw tables: three CTAs fit on an SM.
 template <class C>
 struct Operands<C, true> {
-  static constexpr int NNP = 28, SI_S = 4 * NNP + 4, SJ_S = 5 * NNP;
-  static_assert(SI_S % 8 == 4 && SJ_S % 8 == 4, "conflict-free fragment loads");
-  double SI[C::NGK][SI_S];
+  static constexpr int NNP = 28, SJ_S = 5 * NNP;
+  static_assert(SJ_S % 8 == 4, "conflict-free fragment loads");
   double SJ[C::NGK][SJ_S];
 };
 template <class C>
 __device__ __forceinline__ double op_si(const Operands<C> &op, int gp, int c, int i) {
   if constexpr (C::MMA)
-    return op.SI[gp][c * 28 + i];
+    return op.SJ[gp][c * 28 + i];  // (unweighted: the tensor-core configurations fold w into the other operand)
   else
     return op.SI[gp][c][i];
 }
@@ -212,12 +218,13 @@ struct alignas(16) Smem {
   double U[C::NRECB][C::NF][C::NN];     // nodal unknowns, buffered like rec (cp.async gather)
   double Udot[C::NRECB][C::NF][C::NN];
   double Pd[C::NRECB][C::NP > 0 ? C::NP : 2];
-  double w[C::NGP];
+  double w[C::NGK];  // w(gp) = detJ * weight; entry 27 (K padding of the tensor-core tables) stays zero
   double B[C::NGP][C::DIM * C::DIM];
   double Pgp[C::NGP];
   double tau, dtau[3];  // PSPG tau and d tau / d v_avg[b] (element level)
   double redR[C::NPART][C::NROWS];  // partial row sums (element_rows)
   double redS[C::NPART][C::P1 ? C::DIM * C::NN : 1][C::NP > 0 ? C::NP : 1];
+  unsigned char lat[32];  // tensor-core configurations: lattice position o0 + 3 o1 + 9 o2 of the local nodes
   unsigned long long mbar;
   unsigned long long mbar_rec[C::NRECB];
   unsigned long long full[2], empty[2];  // WS: operand buffer hand-off between builders and multipliers
@@ -352,6 +359,21 @@ __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
       : "d"(a), "d"(b));
 }
 
+// HEX27 local node -> lattice position o0 + 3 o1 + 9 o2 (Exodus / PATRAN order, rf_shape.c:1105-1200; tables.h)
+__device__ const unsigned char HEX27_LATTICE[27] = {0, 2, 8, 6, 18, 20, 26, 24, 1, 5, 7, 3, 9, 11, 17, 15, 19, 23, 25, 21, 13, 4, 22, 12, 14, 10, 16};
+
+// dphi_k / dxi_a at Gauss point gp from the 1-D Lagrange factors: the product make_tables() evaluates
+// ((x0 * x1) * x2, x_d = dL or L of direction d), so the value has the bits of the table entry
+__device__ __forceinline__ double dphi_from_1d(const double *__restrict__ l1d, const unsigned char *__restrict__ lat, int gp, int k, int a) {
+  const int o = lat[k];
+  const int o0 = o % 3, o1 = (o / 3) % 3, o2 = o / 9;
+  const int p0 = gp % 3, p1 = (gp / 3) % 3, p2 = gp / 9;
+  const double x0 = l1d[(a == 0 ? 9 : 0) + p0 * 3 + o0];
+  const double x1 = l1d[(a == 1 ? 9 : 0) + p1 * 3 + o1];
+  const double x2 = l1d[(a == 2 ? 9 : 0) + p2 * 3 + o2];
+  return (x0 * x1) * x2;
+}
+
 // length-N dot product with three independent accumulation chains (hides DFMA latency in the
 // low-parallelism set-up phases)
 template <int N>
@@ -477,7 +499,8 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
   const double *t_wt = s.tbl + C::T_WT;
   const double *t_phi = s.tbl + (C::MMA ? 0 : C::T_PHI);  // [gp][NN] (tensor-core configurations: in op.SJ)
   (void)t_phi;
-  const double *t_dphi = s.tbl + C::T_DPHI;  // [gp][NN][DIM]
+  const double *t_dphi = s.tbl + (C::MMA ? 0 : C::T_DPHI);  // [gp][NN][DIM] (tensor-core configurations: dphi_from_1d)
+  (void)t_dphi;
   const double *t_psi = s.tbl + C::T_PSI;    // [gp][DIM+1]
   const double rcp = P.rho * P.Cp;
   const double c_adv = -P.etm_mom[1] * P.rho;
@@ -502,13 +525,12 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
     const int warp = tid >> 5, lane = tid & 31, r = lane >> 2, kq = lane & 3;
     for (int mt = warp; mt < 11; mt += C::NWARP) {
       const int m = min(mt * 8 + r, 80);
-      const double *arow = &t_dphi[(m / 3) * NN * DIM + (m % 3)];  // + 3 * node
       double acc[2] = {0.0, 0.0};
 #pragma unroll
       for (int ks = 0; ks < 7; ks++) {
         const int k = 4 * ks + kq;
         const bool live = k < NN;
-        const double av = live ? arow[3 * k] : 0.0;
+        const double av = live ? dphi_from_1d(s.tbl + C::T_L1D, s.lat, m / 3, k, m % 3) : 0.0;
         const double bv = (live && r < DIM) ? rec.X[r][k] : 0.0;
         dmma884(acc, av, bv);
       }
@@ -630,7 +652,15 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
   for (int idx = tid; idx < NGP * NN; idx += NT) {
     int gp = idx / NN, i = idx - gp * NN;
     const double *B = s.B[gp];
-    const double *dp = &t_dphi[(gp * NN + i) * DIM];
+    double dpv[3] = {0.0, 0.0, 0.0};
+    if constexpr (C::MMA) {
+#pragma unroll
+      for (int q = 0; q < DIM; q++) dpv[q] = dphi_from_1d(s.tbl + C::T_L1D, s.lat, gp, i, q);
+    } else {
+#pragma unroll
+      for (int q = 0; q < DIM; q++) dpv[q] = t_dphi[(gp * NN + i) * DIM + q];
+    }
+    const double *dp = dpv;
     double ph;
     if constexpr (C::MMA)
       ph = op.SJ[gp][i];  // written once in the kernel prologue
@@ -644,12 +674,10 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
       for (int q = 0; q < DIM; q++) g[p] += B[p * DIM + q] * dp[q];
     }
     if constexpr (C::MMA) {
-      op.SI[gp][i] = w * ph;
 #pragma unroll
-      for (int p = 0; p < DIM; p++) {
-        op.SJ[gp][(1 + p) * 28 + i] = g[p];
-        op.SI[gp][(1 + p) * 28 + i] = w * g[p];
-      }
+      for (int p = 0; p < DIM; p++) op.SJ[gp][(1 + p) * 28 + i] = g[p];
+      (void)w;
+      (void)ph;
     } else {
       op.SJa[gp][i] = make_double2(ph, g[0]);
       op.SJb[gp][i] = make_double2(g[1], g[2]);
@@ -945,13 +973,13 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
       double acc[2] = {0.0, 0.0};
 #pragma unroll 1
       for (int ks = 0; ks < 7; ks++) {
-        const int gp = 4 * ks + kq;  // row 27 of SI and GP is zero
-        const double *si = &op.SI[gp][ia];
+        const int gp = 4 * ks + kq;  // row 27 of the tables and w[27] are zero
+        const double *si = &op.SJ[gp][ia];
         const double *G = s.GP[bo][gp];
-        const bool on = nv || nT;
-        dmma884(acc, si[0], on ? G[q0] : 0.0);
+        const double wv = (nv || nT) ? s.w[gp] : 0.0;  // the quadrature weight rides on the B operand
+        dmma884(acc, si[0], wv * G[q0]);
 #pragma unroll
-        for (int p = 0; p < DIM; p++) dmma884(acc, si[28 * (1 + p)], on ? G[q1 + p] : 0.0);
+        for (int p = 0; p < DIM; p++) dmma884(acc, si[28 * (1 + p)], wv * G[q1 + p]);
       }
       const int i = warp * 8 + r;
       if (i < NN) {
@@ -969,8 +997,8 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
 #pragma unroll
         for (int ks = 0; ks < 7; ks++) {
           const int gp = 4 * ks + kq;
-          const double bv = (gp < NGP && r < NP) ? t_psi[gp * (DIM + 1) + r] : 0.0;
-          dmma884(acc, op.SI[gp][(1 + a) * 28 + ia], bv);
+          const double bv = (gp < NGP && r < NP) ? s.w[gp] * t_psi[gp * (DIM + 1) + r] : 0.0;
+          dmma884(acc, op.SJ[gp][(1 + a) * 28 + ia], bv);
         }
         const int i = mt * 8 + r;
         if (i < NN) {
@@ -1166,18 +1194,11 @@ __device__ __forceinline__ void gauss_loop(const FillParams &P, const Smem<C> &s
   const int ngp_run = (P.debug & 2) ? 1 : NGP;
 #pragma unroll 1
   for (int gp = 0; gp < ngp_run; gp++) {
-    double phi_j, gj[3], vgj;
-    if constexpr (C::MMA) {  // tensor-core table layout (the remainder tiles of gauss_blocks_mma)
-      phi_j = op.SJ[gp][j];
-      gj[0] = op.SJ[gp][28 + j], gj[1] = op.SJ[gp][56 + j], gj[2] = op.SJ[gp][84 + j];
-      vgj = op.SJ[gp][112 + j];
-    } else {
-      const double2 j01 = op.SJa[gp][j];
-      const double2 j23 = op.SJb[gp][j];
-      phi_j = j01.x;
-      gj[0] = j01.y, gj[1] = j23.x, gj[2] = j23.y;
-      vgj = op.VG[gp][j];
-    }
+    const double2 j01 = op.SJa[gp][j];
+    const double2 j23 = op.SJb[gp][j];
+    const double phi_j = j01.x;
+    const double gj[3] = {j01.y, j23.x, j23.y};
+    const double vgj = op.VG[gp][j];
     const double qj = c_adv * vgj + c_mass * phi_j;
     double gjs[DIM], GV[DIM][DIM], GT[DIM];
     const double *G = s.GP[bo][gp];
@@ -1546,12 +1567,61 @@ __device__ __forceinline__ void gauss_blocks_mma(const FillParams &P, const Smem
   // (gauss_loop): 51 tiles, 20-23 FMAs per pair and Gauss point, about as long as two tensor-core blocks
   constexpr int NMW = C::NWARP - 2;
   if (warp >= NMW) {
-    const int t = (warp - NMW) * 32 + lane;
-    if (t < 27 + 24) {
-      const int i0 = t < 27 ? 24 : ((t - 27) / 3) * 3, j = t < 27 ? t : 24 + (t - 27) % 3;
-      Tile<C> tile;
-      gauss_loop<C>(P, s, i0, j, tile);
-      if (!(P.debug & 1)) write_tile_direct<C, MODE>(P, rec, i0, j, tile);
+    // 153 pairs with a node >= 24 over 64 threads: (i >= 24, any j) first, then (i < 24, j >= 24)
+#pragma unroll 1
+    for (int t = (warp - NMW) * 32 + lane; t < 81 + 72; t += 64) {
+      const int i = t < 81 ? 24 + t / 27 : (t - 81) / 3, j = t < 81 ? t % 27 : 24 + (t - 81) % 3;
+      double A[3][3], D = 0.0, S1 = 0.0, S2 = 0.0, S3 = 0.0, ET[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) A[a][b] = 0.0;
+      const int ngp_run = (P.debug & 2) ? 1 : 27;
+#pragma unroll 1
+      for (int gp = 0; gp < ngp_run; gp++) {
+        const double *G = s.GP[0][gp];
+        const double wv = s.w[gp];
+        const double phi_i = op.SJ[gp][i], gi[3] = {op.SJ[gp][28 + i], op.SJ[gp][56 + i], op.SJ[gp][84 + i]};
+        const double phj = wv * op.SJ[gp][j], vgj = wv * op.SJ[gp][112 + j];
+        const double gj[3] = {wv * op.SJ[gp][28 + j], wv * op.SJ[gp][56 + j], wv * op.SJ[gp][84 + j]};
+        const double pp = phi_i * phj;
+        double gij = 0.0;
+#pragma unroll
+        for (int p = 0; p < 3; p++) gij += gi[p] * gj[p];
+        if (C::ENERGY) {
+          S1 += phi_i * vgj;
+          S2 += gij;
+          S3 += pp;
+        } else {
+          D += phi_i * (c_adv * vgj + c_mass * phj) + c_diff * gij;
+        }
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          const double gjs = c_diff * gj[a];
+#pragma unroll
+          for (int b = 0; b < 3; b++) A[a][b] += pp * G[C::G_GV + a * 3 + b] + gi[b] * gjs;
+          if (C::ENERGY) ET[a] += pp * G[C::G_GT + a];
+        }
+      }
+      if (P.debug & 1) continue;
+      double dfdT[3] = {0.0, 0.0, 0.0};
+      if (C::ENERGY && P.source_model != 0 && P.etm_mom[4] != 0.0) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) dfdT[a] = -P.g[a] * P.rho * P.beta * P.etm_mom[4];
+      }
+      const double dm = C::ENERGY ? c_adv * S1 + c_diff * S2 + c_mass * S3 : D;
+      double V[NF][NF];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int b = 0; b < 3; b++) V[a][b] = A[a][b] + (a == b ? dm : 0.0);
+        if constexpr (C::ENERGY) {
+          V[a][C::F_T] = dfdT[a] * S3;
+          V[C::F_T][a] = ET[a];
+        }
+      }
+      if constexpr (C::ENERGY) V[C::F_T][C::F_T] = ce_adv * S1 + ce_diff * S2 + ce_mass * S3;
+      write_pair<C, MODE>(P, rec, i, j, V);
     }
     return;
   }
@@ -1573,13 +1643,14 @@ __device__ __forceinline__ void gauss_blocks_mma(const FillParams &P, const Smem
 #pragma unroll 1
     for (int ks = 0; ks < nks; ks++) {
       const int gp = 4 * ks + kq;
-      const double *si = &op.SI[gp][ia], *sj = &op.SJ[gp][jb];
+      const double *si = &op.SJ[gp][ia], *sj = &op.SJ[gp][jb];
       const double *G = s.GP[0][gp];
+      const double wv = s.w[gp];  // the weight of this lane's Gauss point rides on the B fragments (w[27] = 0)
       const double aphi = si[0];
       const double ag[3] = {si[28], si[56], si[84]};
-      const double bphi = sj[0];
-      const double bg[3] = {sj[28], sj[56], sj[84]};
-      const double bvg = sj[112];
+      const double bphi = wv * sj[0];
+      const double bg[3] = {wv * sj[28], wv * sj[56], wv * sj[84]};
+      const double bvg = wv * sj[112];
       const double bq = C::ENERGY ? 0.0 : c_adv * bvg + c_mass * bphi;
 #pragma unroll
       for (int a = 0; a < 3; a++) {
@@ -1691,6 +1762,8 @@ __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_cons
   if constexpr (C::MMA) {  // the padding row / column of the tensor-core operand tables is zero for the whole launch
     for (int idx = tid; idx < (int)(sizeof(s.op) / 8); idx += NT) reinterpret_cast<double *>(&s.op)[idx] = 0.0;
     for (int idx = tid; idx < (int)(sizeof(s.GP) / 8); idx += NT) (&s.GP[0][0][0])[idx] = 0.0;
+    if (tid == 0) s.w[C::NGK - 1] = 0.0;
+    if (tid < 27) s.lat[tid] = HEX27_LATTICE[tid];
     __syncthreads();
     for (int idx = tid; idx < C::NGP * NN; idx += NT) {  // phi_j at the Gauss points: the same for every element
       const int gp = idx / NN, j = idx - gp * NN;

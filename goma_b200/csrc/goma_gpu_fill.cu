@@ -120,9 +120,11 @@ int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
     }
     // config C2 (Q2/P1 Navier-Stokes): warp-specialised kernel, 192 builder + 128 multiplier threads, one CTA per SM
     static const bool ws = getenv("GOMA_GPU_WS") ? atoi(getenv("GOMA_GPU_WS")) != 0 : false;
-    k = p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2>>()
+    static const int c3_minb = getenv("GOMA_GPU_C3_MINB") ? atoi(getenv("GOMA_GPU_C3_MINB")) : 3;  // experiments
+    k = (p.energy && c3_minb == 2) ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2>>()
+        : p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 3>>()
         : ws     ? entry<Cfg<3, 27, 27, true, false, 0, false, 192, 3, 1, true>>()
-                 : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2>>();
+                 : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 3>>();
     return 0;
   }
   if (!p1 && p.elem_type == GOMA_GPU_HEX8) {  // Q1/Q1 PSPG (config C5 and its sub-cases)
@@ -289,8 +291,9 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
   ElemTables t = make_tables(p.elem_type);
   std::vector<double> packed;
   packed.insert(packed.end(), t.wt.begin(), t.wt.end());
-  packed.insert(packed.end(), t.dphi.begin(), t.dphi.end());
   packed.insert(packed.end(), t.psi.begin(), t.psi.end());
+  packed.insert(packed.end(), t.l1d.begin(), t.l1d.end());
+  packed.insert(packed.end(), t.dphi.begin(), t.dphi.end());
   packed.insert(packed.end(), t.phi.begin(), t.phi.end());
   packed.resize(ke.tbl_pad, 0.0);
   rc |= upload(&c->d_tables, packed.data(), packed.size(), c);

@@ -21,6 +21,7 @@ struct ElemTables {
   std::vector<double> phi;   // [ngp][nn]
   std::vector<double> dphi;  // [ngp][nn][dim]
   std::vector<double> psi;   // [ngp][dim+1]  P1 basis
+  std::vector<double> l1d;   // [2][3][3]: 1-D Lagrange factors L[point][node] and dL[point][node] at the 1-D Gauss points
   // basis at the element centroid xi = 0 (PSPG block 1.5, mm_fill.c:754-787)
   std::vector<double> phi0, dphi0;
 };
@@ -109,6 +110,15 @@ inline ElemTables make_tables(int elem_type) {
     eval_basis(elem_type, xi, &t.phi[g * t.nn], &t.dphi[g * t.nn * t.dim]);
     t.psi[g * (t.dim + 1) + 0] = 1.0;
     for (int d = 0; d < t.dim; d++) t.psi[g * (t.dim + 1) + 1 + d] = xi[d];
+  }
+  t.l1d.assign(18, 0.0);
+  for (int pt = 0; pt < n1; pt++) {
+    double L[3] = {0, 0, 0}, dL[3] = {0, 0, 0};
+    lagrange1d(order, pts[pt], L, dL);
+    for (int n = 0; n < n1; n++) {
+      t.l1d[pt * 3 + n] = L[n];
+      t.l1d[9 + pt * 3 + n] = dL[n];
+    }
   }
   t.phi0.resize(t.nn);
   t.dphi0.resize(t.nn * t.dim);
