@@ -81,8 +81,9 @@ struct FillParams {
   int debug;        // experiments only: bit0 = drop the matrix stores, bit1 = skip the Gauss loop
 };
 
-template <int DIM_, int NN_, int NGP_, bool P1_, bool ENERGY_, int NSPEC_, bool ALE_, int TPE_, int TI_, int MINB_, bool WS_ = false>
+template <int DIM_, int NN_, int NGP_, bool P1_, bool ENERGY_, int NSPEC_, bool ALE_, int TPE_, int TI_, int MINB_, bool WS_ = false, int VAR_ = 0>
 struct Cfg {
+  static constexpr int VAR = VAR_;  // experiment switches of the tensor-core kernels: bit 0 = all 16 padded blocks on the tensor cores (no scalar remainder)
   static constexpr int DIM = DIM_, NN = NN_, NGP = NGP_, NSPEC = NSPEC_, TI = TI_, TPE = TPE_, MINB = MINB_;
   static constexpr bool P1 = P1_, ENERGY = ENERGY_, ALE = ALE_;
   static constexpr int F_V = 0;
@@ -1565,8 +1566,9 @@ __device__ __forceinline__ void gauss_blocks_mma(const FillParams &P, const Smem
   // remaining 3 nodes to a fourth block row / column would spend 16/9 of that work on the pipe the kernel is bound by,
   // so the 153 node pairs with a node >= 24 are done by the last two warps as scalar 3 x 1 register tiles
   // (gauss_loop): 51 tiles, 20-23 FMAs per pair and Gauss point, about as long as two tensor-core blocks
-  constexpr int NMW = C::NWARP - 2;
-  if (warp >= NMW) {
+  constexpr bool REM = !(C::VAR & 1);
+  constexpr int NMW = REM ? C::NWARP - 2 : C::NWARP, NBLK = REM ? 9 : 16, NBS = REM ? 3 : 4;
+  if (REM && warp >= NMW) {
     // 153 pairs with a node >= 24 over 64 threads: (i >= 24, any j) first, then (i < 24, j >= 24)
 #pragma unroll 1
     for (int t = (warp - NMW) * 32 + lane; t < 81 + 72; t += 64) {
@@ -1626,8 +1628,8 @@ __device__ __forceinline__ void gauss_blocks_mma(const FillParams &P, const Smem
     return;
   }
 #pragma unroll 1
-  for (int blk = warp; blk < 9; blk += NMW) {
-    const int I0 = (blk / 3) * 8, J0 = (blk % 3) * 8;
+  for (int blk = warp; blk < NBLK; blk += NMW) {
+    const int I0 = (blk / NBS) * 8, J0 = (blk % NBS) * 8;
     const int ia = min(I0 + r, 27), jb = min(J0 + r, 27);  // rows / columns >= 27 read the zero padding
 #ifdef GOMA_PROFILE_PHASES
     const long long t_blk0 = clock64();

@@ -118,13 +118,22 @@ int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
           (p.energy && p.kind_slot[k][GOMA_SLOT_T] != u + 3))
         return fail(-2, "velocity (and temperature) unknowns must be consecutive inside a node");
     }
-    // config C2 (Q2/P1 Navier-Stokes): warp-specialised kernel, 192 builder + 128 multiplier threads, one CTA per SM
+    // experiments: GOMA_GPU_VARIANT bit 0 = 16 padded tensor-core blocks instead of 9 + scalar remainder, bit 1 = two
+    // CTAs per SM at 128 registers instead of three at 80
+    static const int var = getenv("GOMA_GPU_VARIANT") ? atoi(getenv("GOMA_GPU_VARIANT")) : 0;
     static const bool ws = getenv("GOMA_GPU_WS") ? atoi(getenv("GOMA_GPU_WS")) != 0 : false;
-    static const int c3_minb = getenv("GOMA_GPU_C3_MINB") ? atoi(getenv("GOMA_GPU_C3_MINB")) : 3;  // experiments
-    k = (p.energy && c3_minb == 2) ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2>>()
-        : p.energy ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 3>>()
-        : ws     ? entry<Cfg<3, 27, 27, true, false, 0, false, 192, 3, 1, true>>()
-                 : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 3>>();
+    if (p.energy)
+      k = var == 1   ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 3, false, 1>>()
+          : var == 2 ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2, false, 0>>()
+          : var == 3 ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2, false, 1>>()
+                     : entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 3, false, 0>>();
+    else if (ws)
+      k = entry<Cfg<3, 27, 27, true, false, 0, false, 192, 3, 1, true>>();
+    else
+      k = var == 1   ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 3, false, 1>>()
+          : var == 2 ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2, false, 0>>()
+          : var == 3 ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2, false, 1>>()
+                     : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 3, false, 0>>();
     return 0;
   }
   if (!p1 && p.elem_type == GOMA_GPU_HEX8) {  // Q1/Q1 PSPG (config C5 and its sub-cases)
