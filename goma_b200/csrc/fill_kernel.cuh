@@ -83,7 +83,11 @@ struct FillParams {
 
 template <int DIM_, int NN_, int NGP_, bool P1_, bool ENERGY_, int NSPEC_, bool ALE_, int TPE_, int TI_, int MINB_, bool WS_ = false, int VAR_ = 0>
 struct Cfg {
-  static constexpr int VAR = VAR_;  // experiment switches of the tensor-core kernels: bit 0 = all 16 padded blocks on the tensor cores (no scalar remainder)
+  // variants of the hex27 Q2/P1 kernels (A/B runs): bit 0 = all 16 padded node blocks on the tensor cores
+  // (no scalar remainder); bit 2 = scalar set-up phases (Jacobian of the map, field interpolation, row sums) instead of
+  // the tensor-core ones; bit 3 = no tensor cores at all (the round-1 scalar 3 x 1 register-tile kernel)
+  static constexpr int VAR = VAR_;
+  static constexpr bool MMA_SETUP = !(VAR_ & 4);
   static constexpr int DIM = DIM_, NN = NN_, NGP = NGP_, NSPEC = NSPEC_, TI = TI_, TPE = TPE_, MINB = MINB_;
   static constexpr bool P1 = P1_, ENERGY = ENERGY_, ALE = ALE_;
   static constexpr int F_V = 0;
@@ -112,7 +116,7 @@ struct Cfg {
   static constexpr int T_WT = 0, T_PSI = NGP, T_L1D = T_PSI + NGP * (DIM + 1), T_DPHI = T_L1D + 18,
                        T_PHI = T_DPHI + NGP * NN * DIM;
   static constexpr int TBL = T_PHI + NGP * NN;
-  static constexpr bool PHI_IN_OPERANDS = NN == 27 && NGP == 27 && P1_ && NSPEC_ == 0 && !ALE_ && !WS_;  // == MMA below
+  static constexpr bool PHI_IN_OPERANDS = NN == 27 && NGP == 27 && P1_ && NSPEC_ == 0 && !ALE_ && !WS_ && !(VAR_ & 8);  // == MMA below
   static constexpr int TBL_PAD = ((PHI_IN_OPERANDS ? T_DPHI : TBL) + 1) & ~1;  // staged doubles, 16-byte multiple for the bulk copy
   static constexpr int TBL_GLOBAL = TBL + 2;
   // per-Gauss-point derived data (doubles): see phase 4b
@@ -139,10 +143,10 @@ struct Cfg {
   static constexpr int NROWS = NF * NN + NP;  // rows of the element block
   static constexpr bool GENERAL = !P1 || NSPEC > 0 || ALE;  // generic block accumulation instead of the NS(+T) fast path
   // Gauss-point thirds of the row sums (the tensor-core configurations sum the rows in one product)
-  static constexpr int NPART = (PHI_IN_OPERANDS || NGP < 3) ? 1 : 3;
+  static constexpr int NPART = ((PHI_IN_OPERANDS && !(VAR_ & 4)) || NGP < 3) ? 1 : 3;
   // hex27 Q2/P1 NS(+T): the node-pair blocks run on the FP64 tensor cores (mma.sync m8n8k4.f64, SASS DMMA): 8 x 8
   // node blocks, K = Gauss points (27 -> 28); operand tables component-major with bank-conflict-free strides
-  static constexpr bool MMA = NN == 27 && NGP == 27 && P1 && !GENERAL && !WS_;
+  static constexpr bool MMA = NN == 27 && NGP == 27 && P1 && !GENERAL && !WS_ && !(VAR_ & 8);
   static_assert(MMA == PHI_IN_OPERANDS, "table staging and operand layout must agree");
   static constexpr int NGK = MMA ? 28 : NGP;  // rows of the per-Gauss-point tables (row 27 = the zero K padding)
   __host__ __device__ static constexpr int slot(int f) {
@@ -521,7 +525,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
   }
   GOMA_STAMP(0);
   // ---- phase 1: J[a][b] = sum_k x_b,k dphi_k/dxi_a   (beer_belly, mm_fill_util.c:258-276)
-  if constexpr (C::MMA) {
+  if constexpr (C::MMA && C::MMA_SETUP) {
     // tensor cores: rows m = (Gauss point, a) (81 -> 88), columns b (3 -> 8), K = nodes (27 -> 28)
     const int warp = tid >> 5, lane = tid & 31, r = lane >> 2, kq = lane & 3;
     for (int mt = warp; mt < 11; mt += C::NWARP) {
@@ -559,7 +563,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
         const double *dp = &t_dphi[gp * NN * DIM + a];
 #pragma unroll 4
         for (int k = k0; k < k1; k++) {
-          const double d = dp[k * DIM];
+          const double d = C::MMA ? dphi_from_1d(s.tbl + C::T_L1D, s.lat, gp, k, a) : dp[k * DIM];
 #pragma unroll
           for (int b = 0; b < DIM; b++) acc[b] += (C::ALE ? s.X[b][k] : rec.X[b][k]) * d;
         }
@@ -691,7 +695,7 @@ __device__ __forceinline__ void build_element(const FillParams &P, Smem<C> &s, i
   cta_sync<C>();
   GOMA_STAMP(3);
   // ---- phase 4: field values, gradients, time derivatives at the Gauss points (load_fv, load_fv_grads)
-  if constexpr (C::MMA) {
+  if constexpr (C::MMA && C::MMA_SETUP) {
     // tensor cores: F_q[gp][f] = sum_k SJ_q[gp][k] U[f][k], q = value | grad_0..2 | time derivative (phi with Udot):
     // rows = Gauss points (27 -> 32), columns = fields (NF -> 8), K = nodes (27 -> 28)
     const int warp = tid >> 5, lane = tid & 31, r = lane >> 2, kq = lane & 3;
@@ -961,7 +965,7 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
   //      points by one thread; the velocity rows accumulate the P1 pressure coupling on the way:
   //      S[i][a][p] = sum_gp w grad_phi_i[a] psi_p, shared by J_m_P (mm_fill_momentum.c:2091-2104) and
   //      J_c_v (mm_fill_continuity.c:686-716)
-  if constexpr (C::MMA) {
+  if constexpr (C::MMA && C::MMA_SETUP) {
     // tensor cores.  Warps 0-3: the velocity (and temperature) rows of 8 nodes each,
     //   R[i][n] = sum_gp sum_c SI_c[gp][i] Gc[gp][n],  n = a: (G_RQ+a | G_RP+3a+p),  n = 3: (G_RE | G_RF+p)
     // warps 4-7: the P1 coupling sums S[a][i][p] = sum_gp SI_{1+a}[gp][i] psi[gp][p] (12 tiles of 8 nodes x 4)
@@ -1022,8 +1026,9 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
       for (int p = 0; p < NP; p++) S[a][p] = 0.0;
     }
     for (int gp = gp0; gp < gp1; gp++) {
-      const double2 s01 = make_double2(op_si<C>(op, gp, 0, i), op_si<C>(op, gp, 1, i));
-      const double2 s23 = make_double2(op_si<C>(op, gp, 2, i), op_si<C>(op, gp, 3, i));
+      const double wq = C::MMA ? s.w[gp] : 1.0;  // (the tensor-core table is unweighted)
+      const double2 s01 = make_double2(wq * op_si<C>(op, gp, 0, i), wq * op_si<C>(op, gp, 1, i));
+      const double2 s23 = make_double2(wq * op_si<C>(op, gp, 2, i), wq * op_si<C>(op, gp, 3, i));
       const double sg[3] = {s01.y, s23.x, s23.y};
       const double *G = s.GP[bo][gp];
       double ps[NP > 0 ? NP : 1];
@@ -1049,7 +1054,7 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
   //      the other rows: one thread per (row, third)
   for (int idx = tid; idx < (NROW - DIM * NN) * NPART; idx += NT) {
     const int c = idx / (NROW - DIM * NN), r = DIM * NN + idx - c * (NROW - DIM * NN);
-    if (C::MMA && r < NF * NN) continue;  // temperature rows: summed with the velocity rows on the tensor cores
+    if (C::MMA && C::MMA_SETUP && r < NF * NN) continue;  // temperature rows: summed with the velocity rows on the tensor cores
     const int gp0 = c * NGP / NPART, gp1 = (c + 1) * NGP / NPART;
     const bool prow = r >= NF * NN;  // P1 continuity row
     const int f = prow ? 0 : r / NN;
@@ -1067,8 +1072,9 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
       const int q0 = isT ? C::G_RE : isY ? C::G_RY + (f - C::F_Y) : isP ? C::G_DIV : C::G_ZERO;
       const int q1 = isT ? C::G_RF : isY ? C::G_RFY + (f - C::F_Y) * DIM : isP ? C::G_PS : C::G_RD + (f - C::F_D) * DIM;
       for (int gp = gp0; gp < gp1; gp++) {
-        const double2 s01 = make_double2(op_si<C>(op, gp, 0, i), op_si<C>(op, gp, 1, i));
-        const double2 s23 = make_double2(op_si<C>(op, gp, 2, i), op_si<C>(op, gp, 3, i));
+        const double wq = C::MMA ? s.w[gp] : 1.0;
+        const double2 s01 = make_double2(wq * op_si<C>(op, gp, 0, i), wq * op_si<C>(op, gp, 1, i));
+        const double2 s23 = make_double2(wq * op_si<C>(op, gp, 2, i), wq * op_si<C>(op, gp, 3, i));
         const double sg[3] = {s01.y, s23.x, s23.y};
         const double *G = s.GP[bo][gp];
         double t = s01.x * G[q0];

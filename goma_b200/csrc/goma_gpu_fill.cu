@@ -122,18 +122,25 @@ int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
     // CTAs per SM at 128 registers instead of three at 80
     static const int var = getenv("GOMA_GPU_VARIANT") ? atoi(getenv("GOMA_GPU_VARIANT")) : 0;
     static const bool ws = getenv("GOMA_GPU_WS") ? atoi(getenv("GOMA_GPU_WS")) != 0 : false;
+    // (variant numbers: see Cfg::VAR; 1xx = two CTAs per SM at 128 registers instead of three at 80)
     if (p.energy)
-      k = var == 1   ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 3, false, 1>>()
-          : var == 2 ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2, false, 0>>()
-          : var == 3 ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2, false, 1>>()
-                     : entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 3, false, 0>>();
+      k = var == 1     ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 3, false, 1>>()
+          : var == 100 ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2, false, 0>>()
+          : var == 101 ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2, false, 1>>()
+          : var == 105 ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2, false, 5>>()
+          : var == 104 ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2, false, 4>>()
+          : var == 108 ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2, false, 8>>()
+                       : entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 3, false, 0>>();
     else if (ws)
       k = entry<Cfg<3, 27, 27, true, false, 0, false, 192, 3, 1, true>>();
     else
-      k = var == 1   ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 3, false, 1>>()
-          : var == 2 ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2, false, 0>>()
-          : var == 3 ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2, false, 1>>()
-                     : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 3, false, 0>>();
+      k = var == 1     ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 3, false, 1>>()
+          : var == 100 ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2, false, 0>>()
+          : var == 101 ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2, false, 1>>()
+          : var == 105 ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2, false, 5>>()
+          : var == 104 ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2, false, 4>>()
+          : var == 108 ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2, false, 8>>()
+                       : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 3, false, 0>>();
     return 0;
   }
   if (!p1 && p.elem_type == GOMA_GPU_HEX8) {  // Q1/Q1 PSPG (config C5 and its sub-cases)
