@@ -1449,6 +1449,30 @@ __device__ __forceinline__ void gauss_loop_general(const FillParams &P, const Sm
   (void)NN;
 }
 
+// first-touch store of the NF consecutive entries of one (row, column node) run, as 16-byte vectors where possible
+template <int NF>
+__device__ __forceinline__ void store_run(double *dst, const double *v) {
+  const bool al = (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0;
+  if (NF == 3) {
+    if (al) {
+      *reinterpret_cast<double2 *>(dst) = make_double2(v[0], v[1]);
+      dst[2] = v[2];
+    } else {
+      dst[0] = v[0];
+      *reinterpret_cast<double2 *>(dst + 1) = make_double2(v[1], v[2]);
+    }
+  } else {
+    if (al) {
+      *reinterpret_cast<double2 *>(dst) = make_double2(v[0], v[1]);
+      *reinterpret_cast<double2 *>(dst + 2) = make_double2(v[2], v[3]);
+    } else {
+      dst[0] = v[0];
+      *reinterpret_cast<double2 *>(dst + 1) = make_double2(v[1], v[2]);
+      dst[3] = v[3];
+    }
+  }
+}
+
 // write-out of one node-pair tile straight from registers: one thread per (row tile, column node j).  In a
 // row (i, fr) the entries of column node j are contiguous; when the tile is the first writer of the pair and
 // the fields of node j sit next to each other, the NF doubles go out as 16-byte + 8-byte stores (fewer LSU
@@ -1471,15 +1495,9 @@ __device__ __forceinline__ void write_tile_direct(const FillParams &P, const Ele
       const bool rowT = C::ENERGY && fr == C::F_T;
       const int row = s.gun[fr][i];
       double *arow = P.a + rstart;
-      if (MODE == 2 && NF == 3 && !C::ENERGY && first && packed && rj != ri) {
-        double *dst = arow + s.po[i][j] + s.cs[j][0] - ((!P.csr && rj > ri) ? 1 : 0);
-        if ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
-          *reinterpret_cast<double2 *>(dst) = make_double2(t.V[ii][fr][0], t.V[ii][fr][1]);
-          dst[2] = t.V[ii][fr][2];
-        } else {
-          dst[0] = t.V[ii][fr][0];
-          *reinterpret_cast<double2 *>(dst + 1) = make_double2(t.V[ii][fr][1], t.V[ii][fr][2]);
-        }
+      if (MODE == 2 && (NF == 3 || (NF == 4 && C::P1)) && first && packed && (rj != ri || P.csr)) {
+        double *dst = arow + s.po[i][j] + s.cs[j][0] - ((!P.csr && rj > ri) ? 1 : 0) - ((C::ENERGY && rowT) ? s.pp[i][j] : 0);
+        store_run<NF>(dst, &t.V[ii][fr][0]);
         continue;
       }
 #pragma unroll
@@ -1517,15 +1535,9 @@ __device__ __forceinline__ void write_pair(const FillParams &P, const ElemRec<C>
     const bool rowT = C::ENERGY && fr == C::F_T;
     const int row = s.gun[fr][i];
     double *arow = P.a + rstart;
-    if (MODE == 2 && NF == 3 && !C::ENERGY && first && packed && rj != ri) {
-      double *dst = arow + s.po[i][j] + s.cs[j][0] - ((!P.csr && rj > ri) ? 1 : 0);
-      if ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
-        *reinterpret_cast<double2 *>(dst) = make_double2(V[fr][0], V[fr][1]);
-        dst[2] = V[fr][2];
-      } else {
-        dst[0] = V[fr][0];
-        *reinterpret_cast<double2 *>(dst + 1) = make_double2(V[fr][1], V[fr][2]);
-      }
+    if (MODE == 2 && (NF == 3 || (NF == 4 && C::P1)) && first && packed && (rj != ri || P.csr)) {
+      double *dst = arow + s.po[i][j] + s.cs[j][0] - ((!P.csr && rj > ri) ? 1 : 0) - ((C::ENERGY && rowT) ? s.pp[i][j] : 0);
+      store_run<NF>(dst, &V[fr][0]);
       continue;
     }
 #pragma unroll
@@ -1723,17 +1735,16 @@ __device__ __forceinline__ void gauss_blocks_mma(const FillParams &P, const Smem
       const int offT = C::ENERGY ? off - rec.pp[i][j] : off;  // energy rows carry no pressure columns
       // one branch on `first` per pair (not per entry): a warp whose lanes disagree runs each side once
       if (MODE == 2 && first) {
+        // first touch: plain stores, as 16-byte vectors where the run allows (the store path -- L1 tag stage, one
+        // crossbar packet per instruction and sector -- is what this phase is bound by: fewer, wider requests)
 #pragma unroll
         for (int fr = 0; fr < NF; fr++) {
           if (rsv[fr] < 0) continue;
           double *dst = P.a + rsv[fr] + ((C::ENERGY && fr == C::F_T) ? offT : off);
-#pragma unroll
-          for (int fc = 0; fc < NF; fc++) {
 #ifdef GOMA_PROFILE_PHASES
-            if (g_store_debug & 8) continue;
+          if (g_store_debug & 8) continue;
 #endif
-            dst[fc] = V[fr][fc];
-          }
+          store_run<NF>(dst, &V[fr][0]);
         }
       } else {
 #pragma unroll

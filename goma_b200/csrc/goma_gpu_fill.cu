@@ -118,8 +118,8 @@ int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
           (p.energy && p.kind_slot[k][GOMA_SLOT_T] != u + 3))
         return fail(-2, "velocity (and temperature) unknowns must be consecutive inside a node");
     }
-    // experiments: GOMA_GPU_VARIANT bit 0 = 16 padded tensor-core blocks instead of 9 + scalar remainder, bit 1 = two
-    // CTAs per SM at 128 registers instead of three at 80
+    // default: 16 padded node blocks on the tensor cores, tensor-core set-up phases, two CTAs per SM (the fastest of
+    // the A/B runs under profiles/r2*_variants*); GOMA_GPU_VARIANT selects the others for experiments
     static const int var = getenv("GOMA_GPU_VARIANT") ? atoi(getenv("GOMA_GPU_VARIANT")) : 0;
     static const bool ws = getenv("GOMA_GPU_WS") ? atoi(getenv("GOMA_GPU_WS")) != 0 : false;
     // (variant numbers: see Cfg::VAR; 1xx = two CTAs per SM at 128 registers instead of three at 80)
@@ -130,7 +130,8 @@ int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
           : var == 105 ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2, false, 5>>()
           : var == 104 ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2, false, 4>>()
           : var == 108 ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2, false, 8>>()
-                       : entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 3, false, 0>>();
+          : var == 3   ? entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 3, false, 0>>()
+                       : entry<Cfg<3, 27, 27, true, true, 0, false, 256, 3, 2, false, 1>>();
     else if (ws)
       k = entry<Cfg<3, 27, 27, true, false, 0, false, 192, 3, 1, true>>();
     else
@@ -140,7 +141,8 @@ int pick_kernel(const goma_gpu_problem &p, KernelEntry &k) {
           : var == 105 ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2, false, 5>>()
           : var == 104 ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2, false, 4>>()
           : var == 108 ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2, false, 8>>()
-                       : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 3, false, 0>>();
+          : var == 3   ? entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 3, false, 0>>()
+                       : entry<Cfg<3, 27, 27, true, false, 0, false, 256, 3, 2, false, 1>>();
     return 0;
   }
   if (!p1 && p.elem_type == GOMA_GPU_HEX8) {  // Q1/Q1 PSPG (config C5 and its sub-cases)
