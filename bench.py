@@ -249,8 +249,9 @@ def run_reference_arm(args, rank):
     print(json.dumps(line))
 
 
-def workload_name(cfg, n, scaling="weak", world=1):
-    per = f"{n}^3 elements per GPU" if scaling == "weak" else f"ONE {n}^3 mesh split over {world} GPUs (x-slabs)"
+def workload_name(cfg, n, scaling="weak", world=1, partition="brick"):
+    per = (f"{n}^3 elements per GPU" if scaling == "weak" else
+           f"ONE {n}^3 mesh split over {world} GPUs ({'bricks' if partition == 'brick' and world in (2, 4, 8) else 'x-slabs'})")
     if cfg == "c4":
         return f"3D Navier-Stokes on an ALE pseudo-solid mesh, Q2/P1 hex27, {per} (SURVEY C4, 3-D variant)"
     if cfg == "c5":
@@ -292,7 +293,7 @@ def bind_to_gpu_numa_node(local_rank):
         bus = "%04x:%02x:%02x.0" % (getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id)
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
         if node < 0:
-            return None
+            return {"numa_node": node, "note": "the box exposes no NUMA affinity for the GPU: ranks left unbound"}
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
@@ -317,7 +318,7 @@ def problem_maker(cfg):
 class Workload:
     """One config on this rank: problem, GPU context, sub-domain (N > 1)."""
 
-    def __init__(self, cfg, n, rank, world, local_rank, scaling, scatter, layout="msr"):
+    def __init__(self, cfg, n, rank, world, local_rank, scaling, scatter, layout="msr", partition="brick"):
         from goma_b200.matrix_fill import MatrixFill
         from goma_b200.mesh import box_mesh
 
@@ -333,7 +334,14 @@ class Workload:
         else:
             from goma_b200.dp_comm import slab_subdomain
 
-            if scaling == "strong":  # ONE n^3 cavity cut into x-slabs of (almost) equal width
+            if scaling == "strong" and partition == "brick" and world in (2, 4, 8):
+                # ONE n^3 cavity cut into bricks (2x2x2 at 8 GPUs: every rank has 7 neighbours, ghost layers on its
+                # three high sides: (n/2 + 1)^3 / (n/2)^3 = 6 % redundant elements against 12 % for x-slabs)
+                from goma_b200.dp_comm import brick_subdomain
+
+                self.parts = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+                self.sub = brick_subdomain(make_on, n, rank, self.parts, elem_type=elem)
+            elif scaling == "strong":  # ... or into x-slabs of (almost) equal width
                 cols = [round(r * n / world) for r in range(world + 1)]
                 self.sub = slab_subdomain(make_on, n, rank, world, elem_type=elem, cols=cols, x_len=1.0)
             else:  # weak: rank r owns the r-th n^3 slab of a (world*n) x n x n box, plus its ghost column
@@ -416,6 +424,8 @@ def main():
                     help="c2 = headline (default); c3 = NS + energy; c4 = ALE; c5 = hex8 PSPG + T + 2 species")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = `edge`^3 elements per GPU (default); strong = ONE `edge`^3 mesh split over the GPUs")
+    ap.add_argument("--partition", default="brick", choices=["brick", "slab"],
+                    help="--scaling strong: 2x2x2 bricks (default at 2, 4, 8 GPUs) or x-slabs")
     ap.add_argument("--scatter", type=int, default=2,
                     help="0 fp64 atomics, 1 coloured load+add+store, 2 coloured first-touch stores (default)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -499,7 +509,7 @@ def main():
 
     from goma_b200.matrix_fill import device_view
 
-    w = Workload(args.config, args.n, rank, world, local_rank, args.scaling, args.scatter)
+    w = Workload(args.config, args.n, rank, world, local_rank, args.scaling, args.scatter, partition=args.partition)
     mf, sub, problem = w.mf, w.sub, w.problem
     ne, n_unk, nnz, ne_owned, x = w.ne, w.n_unk, w.nnz, w.ne_owned, w.x
     setup = mf.setup_stats()
@@ -669,7 +679,8 @@ def main():
             "metric": "jacobian_residual_elements_per_s", "value": value, "unit": "elements/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
             "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.config, args.n, args.scaling, world), "elements_per_gpu": ne_owned,
+            "config": {"workload": workload_name(args.config, args.n, args.scaling, world, args.partition), "elements_per_gpu": ne_owned,
+                       "neighbors": (len(sub.neighbors) if sub is not None else 0),
                        "elements_assembled_per_gpu": ne, "unknowns_per_gpu": n_unk,
                        "halo": halo, "numa_binding": numa,
                        "nnz_per_gpu": nnz, "scatter": ["fp64 atomics", "coloured load+add+store", "coloured first-touch stores"][args.scatter],

@@ -1136,12 +1136,19 @@ __device__ __forceinline__ void element_rows(const FillParams &P, Smem<C> &s, in
         const long long pos = rec.rs[a][i] + rec.po[i][C::CEN] + poff + p - ((!P.csr && col > row) ? 1 : 0);
         slot_add(P, &P.a[pos], P.etm_mom[3] * S, true);
       }
-      // (row pressure p of the centroid node, column velocity a of node i)
-      if (rec.rsP[p] >= 0) {
-        const int row = rec.gunP + p, col = rec.gun[a][i];
-        const long long pos = rec.rsP[p] + rec.po[C::CEN][i] + rec.cs[i][a] - ((!P.csr && col > row) ? 1 : 0);
-        slot_add(P, &P.a[pos], P.etm_cont[0] * S, true);
-      }
+    }
+    // (row pressure p of the centroid node, column velocity a of node i): a runs fastest over the lanes, so that the
+    // three entries of a column node leave in one store request
+    for (int idx = tid; idx < NN * DIM * NP; idx += NT) {
+      const int p = idx / (NN * DIM), r = idx - p * NN * DIM;
+      const int i = r / DIM, a = r - i * DIM;
+      if (rec.rsP[p] < 0) continue;
+      double S = s.redS[0][a * NN + i][p];
+#pragma unroll
+      for (int c = 1; c < NPART; c++) S += s.redS[c][a * NN + i][p];
+      const int row = rec.gunP + p, col = rec.gun[a][i];
+      const long long pos = rec.rsP[p] + rec.po[C::CEN][i] + rec.cs[i][a] - ((!P.csr && col > row) ? 1 : 0);
+      slot_add(P, &P.a[pos], P.etm_cont[0] * S, true);
     }
     if constexpr (C::ALE) {
       // J_c_d (mm_fill_continuity.c:1004-1148): d(div v)/d d_bj + div v d|J|/d d_bj, with
@@ -1473,6 +1480,21 @@ __device__ __forceinline__ void store_run(double *dst, const double *v) {
   }
 }
 
+// the same for a run of N doubles (equal-order / species / ALE blocks: N = 5 .. 10)
+template <int N>
+__device__ __forceinline__ void store_run_n(double *dst, const double *v) {
+  if ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
+#pragma unroll
+    for (int k = 0; k + 1 < N; k += 2) *reinterpret_cast<double2 *>(dst + k) = make_double2(v[k], v[k + 1]);
+    if (N & 1) dst[N - 1] = v[N - 1];
+  } else {
+    dst[0] = v[0];
+#pragma unroll
+    for (int k = 1; k + 1 < N; k += 2) *reinterpret_cast<double2 *>(dst + k) = make_double2(v[k], v[k + 1]);
+    if (!(N & 1)) dst[N - 1] = v[N - 1];
+  }
+}
+
 // write-out of one node-pair tile straight from registers: one thread per (row tile, column node j).  In a
 // row (i, fr) the entries of column node j are contiguous; when the tile is the first writer of the pair and
 // the fields of node j sit next to each other, the NF doubles go out as 16-byte + 8-byte stores (fewer LSU
@@ -1498,6 +1520,16 @@ __device__ __forceinline__ void write_tile_direct(const FillParams &P, const Ele
       if (MODE == 2 && (NF == 3 || (NF == 4 && C::P1)) && first && packed && (rj != ri || P.csr)) {
         double *dst = arow + s.po[i][j] + s.cs[j][0] - ((!P.csr && rj > ri) ? 1 : 0) - ((C::ENERGY && rowT) ? s.pp[i][j] : 0);
         store_run<NF>(dst, &t.V[ii][fr][0]);
+        continue;
+      }
+      if (MODE == 2 && NF > 4 && first && packed && (rj != ri || P.csr)) {
+        // general field sets: the entries of (row, column node) are one run; energy rows of the equal-order
+        // configurations end before the pressure column (the last field of the node)
+        double *dst = arow + s.po[i][j] + s.cs[j][0] - ((!P.csr && rj > ri) ? 1 : 0) - ((C::ENERGY && rowT) ? s.pp[i][j] : 0);
+        if (rowT && !C::P1)
+          store_run_n<NF - 1>(dst, &t.V[ii][fr][0]);
+        else
+          store_run_n<NF>(dst, &t.V[ii][fr][0]);
         continue;
       }
 #pragma unroll

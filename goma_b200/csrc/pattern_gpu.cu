@@ -498,7 +498,10 @@ int build_pattern_device(goma_gpu_ctx *c) {
     const double bytes_per_elem = ne > 0 ? 8.0 * (double)c->nnz_plus / ne : 1.0;
     long long want = c->chunk_elems_option > 0 ? c->chunk_elems_option : (long long)(0.5 * l2 / bytes_per_elem);
     const bool many_writers = npe == GOMA_GPU_HEX8 || npe == GOMA_GPU_QUAD4;
-    const bool on = c->chunk_elems_option > 0 || (c->chunk_elems_option == 0 && many_writers && want >= 4LL * sms * std::max(ncol, 1));
+    // measured (profiles/r2d_c5_chunks.txt): on B200 the extra launches cost more than the L2 hits save -- off unless asked for
+    const bool on = c->chunk_elems_option > 0;
+    (void)many_writers;
+    (void)sms;
     if (on && want < ne) chunk_elems = (int)std::max<long long>(want, 1);
   }
   const int nchunk = ne > 0 ? (ne + chunk_elems - 1) / chunk_elems : 1;

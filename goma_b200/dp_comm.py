@@ -253,6 +253,136 @@ def slab_subdomain(make_problem, n, rank: int, nranks: int, elem_type: str = "HE
     return sub
 
 
+def brick_subdomain(make_problem, n, rank: int, parts, elem_type: str = "HEX27") -> Subdomain:
+    """Sub-domain ``rank`` of ONE ``n^3``-element unit cube cut into ``parts = (px, py, pz)`` bricks, built directly
+    (the strong-scaling bench at 1M elements: the global mesh is never formed).  Same rules as :func:`decompose`
+    (checked against it in the tests): a node belongs to the lowest rank touching it, i.e. to the brick whose
+    half-open lattice interval (lo, hi] contains it in every direction; a rank keeps one ghost element layer on each
+    of its high sides; local order internal, boundary, external (by owner, then global id)."""
+    from .mesh import ELEM_TABLE, box_mesh
+
+    dim, _, order, _ = ELEM_TABLE[elem_type]
+    parts = tuple(parts) + (1,) * (dim - len(parts))
+    nranks = int(np.prod(parts))
+    b = []
+    rr = rank
+    for d in range(dim):
+        b.append(rr % parts[d])
+        rr //= parts[d]
+    cuts = [[-((-k * n) // parts[d]) for k in range(parts[d] + 1)] for d in range(dim)]  # == brick_partition
+    c0 = [cuts[d][b[d]] for d in range(dim)]
+    c1 = [cuts[d][b[d] + 1] for d in range(dim)]
+    has_low = [b[d] > 0 for d in range(dim)]
+    has_high = [b[d] < parts[d] - 1 for d in range(dim)]
+    ncol = [c1[d] - c0[d] + (1 if has_high[d] else 0) for d in range(dim)]
+    lo = tuple(c0[d] / n for d in range(dim))
+    hi = tuple((c0[d] + ncol[d]) / n for d in range(dim))
+    m = box_mesh(elem_type, tuple(ncol), lo=lo, hi=hi)
+    lat = m.lattice
+    nid = np.arange(m.num_nodes)
+    l = []
+    stride = 1
+    for d in range(dim):
+        l.append((nid // stride) % lat[d])
+        stride *= lat[d]
+    own_hi = [order * (c1[d] - c0[d]) for d in range(dim)]
+    owned = np.ones(m.num_nodes, bool)
+    bnd = np.zeros(m.num_nodes, bool)
+    owner_b = []
+    for d in range(dim):
+        low_face = has_low[d] & (l[d] == 0)
+        beyond = has_high[d] & (l[d] > own_hi[d])
+        owned &= ~low_face & ~beyond
+        bnd |= (has_low[d] & (l[d] <= order)) | (has_high[d] & (l[d] == own_hi[d]))
+        owner_b.append(np.where(low_face, b[d] - 1, np.where(beyond, b[d] + 1, b[d])))
+    # a node outside r's half-open box belongs to the brick that contains it in EVERY direction
+    owner = np.zeros(m.num_nodes, np.int64)
+    mult = 1
+    for d in range(dim):
+        owner += owner_b[d] * mult
+        mult *= parts[d]
+    GL = [order * n + 1 for _ in range(dim)]
+    gid = np.zeros(m.num_nodes, np.int64)
+    mult = 1
+    for d in range(dim):
+        gid += (order * c0[d] + l[d]) * mult
+        mult *= GL[d]
+    cat = np.where(owned, np.where(bnd, 1, 0), 2)
+    key_owner = np.where(owned, 0, owner)
+    perm = np.lexsort((gid, key_owner, cat))  # category, then owner (externals), then global id
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    node_sets = {}
+    for k, nodes in m.node_sets.items():
+        if 1 <= k <= 2 * dim:
+            d, high = (k - 1) // 2, (k - 1) % 2 == 1
+            if (high and c0[d] + ncol[d] != n) or (not high and c0[d] != 0):  # the local face is not a global one
+                nodes = nodes[:0]
+        if k == 7 and rank != 0:
+            nodes = nodes[:0]
+        node_sets[k] = np.sort(inv[nodes]).astype(np.int32)
+    lmesh = Mesh(elem_type, dim, np.ascontiguousarray(m.coords[:, perm]), inv[m.conn].astype(np.int32), node_sets,
+                 tuple(ncol), m.lattice)
+    problem = make_problem(lmesh)
+    n_int = int((cat == 0).sum())
+    n_own = n_int + int((cat == 1).sum())
+    eidx = np.arange(m.num_elems)
+    e_owned = np.ones(m.num_elems, bool)
+    stride = 1
+    for d in range(dim):
+        e_owned &= ((eidx // stride) % ncol[d]) < (c1[d] - c0[d])
+        stride *= ncol[d]
+    sub = Subdomain(rank=rank, problem=problem, num_owned_nodes=n_own, num_internal_nodes=n_int, node_global=gid[perm],
+                    elem_global=np.zeros(0, np.int64), elem_owned=e_owned)
+    first_l = problem.unknown_map()[0]
+
+    def dofs_of(local_nodes):
+        f0, f1 = first_l[local_nodes], first_l[local_nodes + 1]
+        if len(f0) == 0:
+            return np.zeros(0, np.int32)
+        cnt = f1 - f0
+        out = np.repeat(f0, cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))
+        return out.astype(np.int32)
+
+    # what each neighbour brick q sees of my owned nodes: my owned nodes inside q's local lattice box
+    import itertools
+
+    glat = [order * c0[d] + l[d] for d in range(dim)]
+    sends, recvs, nbrs = {}, {}, set()
+    for off in itertools.product((-1, 0, 1), repeat=dim):
+        if not any(off):
+            continue
+        qb = [b[d] + off[d] for d in range(dim)]
+        if any(qb[d] < 0 or qb[d] >= parts[d] for d in range(dim)):
+            continue
+        q = 0
+        mult = 1
+        for d in range(dim):
+            q += qb[d] * mult
+            mult *= parts[d]
+        inside = owned.copy()
+        for d in range(dim):
+            q0 = order * cuts[d][qb[d]]
+            q1 = order * (cuts[d][qb[d] + 1] + (1 if qb[d] < parts[d] - 1 else 0))
+            inside &= (glat[d] >= q0) & (glat[d] <= q1)
+        nodes = np.nonzero(inside)[0]
+        if len(nodes):
+            nodes = nodes[np.argsort(gid[nodes])]
+            sends[q] = dofs_of(inv[nodes])
+            nbrs.add(q)
+        ext_q = np.nonzero(~owned & (owner == q))[0]
+        if len(ext_q):
+            recvs[q] = int((first_l[inv[ext_q] + 1] - first_l[inv[ext_q]]).sum())
+            nbrs.add(q)
+    sub.neighbors = sorted(nbrs)
+    send_lists = [sends.get(q, np.zeros(0, np.int32)) for q in sub.neighbors]
+    sub.list_dof_send = np.concatenate(send_lists).astype(np.int32) if send_lists else np.zeros(0, np.int32)
+    sub.ptr_dof_send = np.concatenate([[0], np.cumsum([len(v) for v in send_lists])]).astype(np.int64)
+    sub.num_dofs_recv = np.array([recvs.get(q, 0) for q in sub.neighbors], np.int64)
+    assert nranks >= 1
+    return sub
+
+
 def exchange_dof(x, sub: Subdomain, group=None, pack=None):
     """Refresh the external (ghost) tail of the local vector ``x`` (torch tensor, CPU or CUDA).
 

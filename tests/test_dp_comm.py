@@ -177,3 +177,33 @@ def test_uneven_slab_split_matches_general_decomposition(et, n, cols):
         # the column it lies in: both count every element exactly once over the ranks)
         assert int(b.elem_owned.sum()) == (cols[r + 1] - cols[r]) * n ** (dim - 1)
         np.testing.assert_array_equal(a.problem.dirichlet_table()[0], b.problem.dirichlet_table()[0])
+
+
+@pytest.mark.parametrize("et,n,parts", [("HEX27", 4, (2, 2, 2)), ("HEX8", 5, (2, 2, 2)), ("HEX27", 3, (3, 1, 2)),
+                                        ("QUAD9", 6, (2, 3)), ("HEX8", 4, (2, 2, 1))])
+def test_brick_subdomain_matches_general_decomposition(et, n, parts):
+    """The direct brick constructor of the strong-scaling bench (up to 26 neighbours per rank) == decompose() of the
+    global mesh along brick_partition: ownership, local order, send / receive lists, node sets."""
+    from goma_b200.dp_comm import brick_partition, brick_subdomain
+
+    dim = 2 if et == "QUAD9" else 3
+    nranks = int(np.prod(parts))
+    gm = box_mesh(et, (n,) * dim)
+    q1 = et == "HEX8"
+    bcs = [Dirichlet("U", 1, 1.0), Dirichlet("V", 2, 0.0, relax=1.0), Dirichlet("U", 3, 0.0), Dirichlet("V", 4, 0.5),
+           Dirichlet("P", 7, 0.3)] + ([Dirichlet("W", 6, 0.2)] if dim == 3 else [])
+    mk = lambda mesh: Problem(mesh, interp="Q1Q1" if q1 else "Q2P1", pspg="global" if q1 else None, rho=1.1, mu=0.2, bcs=bcs)
+    subs = decompose(mk(gm), brick_partition(gm, parts), nranks)
+    for r in range(nranks):
+        a, b = subs[r], brick_subdomain(mk, n, r, parts, et)
+        assert (a.num_owned_nodes, a.num_internal_nodes, a.neighbors) == (b.num_owned_nodes, b.num_internal_nodes, b.neighbors)
+        np.testing.assert_array_equal(a.node_global, b.node_global)
+        np.testing.assert_allclose(a.problem.mesh.coords, b.problem.mesh.coords, atol=1e-14)
+        assert {tuple(row) for row in a.problem.mesh.conn.tolist()} == {tuple(row) for row in b.problem.mesh.conn.tolist()}
+        np.testing.assert_array_equal(a.list_dof_send, b.list_dof_send)
+        np.testing.assert_array_equal(a.ptr_dof_send, b.ptr_dof_send)
+        np.testing.assert_array_equal(a.num_dofs_recv, b.num_dofs_recv)
+        for k in a.problem.mesh.node_sets:
+            np.testing.assert_array_equal(a.problem.mesh.node_sets[k], b.problem.mesh.node_sets[k])
+        np.testing.assert_array_equal(a.problem.dirichlet_table()[0], b.problem.dirichlet_table()[0])
+    assert sum(int(brick_subdomain(mk, n, r, parts, et).elem_owned.sum()) for r in range(nranks)) == gm.num_elems
