@@ -39,12 +39,15 @@ ALG_FLOPS_PER_ELEM = {"c2_hex27_ns": 1.2e6, "c3_hex27_ns_energy": 1.85e6, "c5_he
 #                operation-counting number type (oracle/flop_count.cpp; `python bench.py --count-flops` re-counts).  The
 #                restatement evaluates every (i,a; j,b) entry of App. A as written -- no factoring across (a,b) --
 #                so it is an UPPER bound of the algorithmic work, 3x the survey's figure on the hex27 configs;
-#  executed    = what the CUDA kernel issues per element, padding of the tensor-core tiles included.
+#  executed    = what the CUDA kernel issues per element.  hex27 tensor-core kernels: DMMA count x 512
+#                flop (2016 node-pair + 385 set-up instructions on C2, 2576 + 420 on C3; the 27 -> 32 and 3 -> 8 tile
+#                padding included) + the scalar FP64 instructions; C5 / C4: FP64-pipe active cycles of the ncu capture
+#                x 64 lanes x 2 (an upper bound: every instruction counted as an FMA), profiles/r2j_fill_kernel_c*.txt.
 COUNTED_FLOPS_PER_ELEM = {
-    "c2_hex27_ns": {"restatement": 3.70e6, "executed": 1.18e6},
-    "c3_hex27_ns_energy": {"restatement": 4.88e6, "executed": 1.47e6},
-    "c5_hex8_pspg_T_2Y": {"restatement": 0.290e6, "executed": None},
-    "c4_hex27_ale_ns": {"restatement": 29.2e6, "executed": None},
+    "c2_hex27_ns": {"restatement": 3.70e6, "executed": 1.33e6},
+    "c3_hex27_ns_energy": {"restatement": 4.88e6, "executed": 1.65e6},
+    "c5_hex8_pspg_T_2Y": {"restatement": 0.290e6, "executed": 0.21e6},
+    "c4_hex27_ale_ns": {"restatement": 29.2e6, "executed": 14.1e6},
 }
 FP64_PEAK_NOMINAL_TFLOPS = 40.0  # BASELINE.json north_star; replaced by the DFMA micro-benchmark when it runs
 CONFIGS = {  # name -> (roofline key, element type, default edge = the size BASELINE.json / SURVEY.md §8d name)
@@ -106,7 +109,7 @@ def cavity_problem_on(mesh, energy=False):
 
 
 def synthetic_state(problem, seed):
-    from tests.cases import make_state  # the seeded state of SURVEY.md §8d, shared with the parity tests
+    from goma_b200.state import make_state  # the seeded state of SURVEY.md §8d, shared with the parity tests
 
     return make_state(problem, seed=seed)["x"]
 
@@ -399,7 +402,7 @@ def count_flops():
     up to the Dirichlet rows)."""
     from goma_b200.mesh import box_mesh
     from oracle import port
-    from tests.cases import make_state
+    from goma_b200.state import make_state
 
     out = {}
     for cfg, (key, elem, _) in CONFIGS.items():

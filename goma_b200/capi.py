@@ -26,7 +26,7 @@ EXPORTED = [
     "goma_gpu_last_error", "goma_gpu_pattern_msr", "goma_gpu_exchange_export", "goma_gpu_exchange_setup",
     "goma_gpu_exchange_dof", "goma_gpu_row_sum_scale", "goma_gpu_scale_buffer", "goma_gpu_vector_norms", "goma_gpu_csr_structure",
     "goma_gpu_csr_values", "goma_gpu_exchange_status", "goma_gpu_fill_device_async", "goma_gpu_fill_wait", "goma_gpu_fill_setup_stats",
-    "goma_gpu_fill_value_count", "goma_gpu_csr_rows", "goma_gpu_node_graph",
+    "goma_gpu_fill_value_count", "goma_gpu_csr_rows", "goma_gpu_node_graph", "goma_gpu_exchange_fence",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -107,6 +107,7 @@ def load_library():
     lib.goma_gpu_exchange_setup.argtypes = [C.c_void_p, C.c_int, C.POINTER(ExchangeHandles), _ip, _ip, _ip, C.c_int]
     lib.goma_gpu_exchange_dof.argtypes = [C.c_void_p, C.c_int]
     lib.goma_gpu_exchange_status.argtypes = [C.c_void_p]
+    lib.goma_gpu_exchange_fence.argtypes = [C.c_void_p, C.c_int]
     lib.goma_gpu_row_sum_scale.argtypes = [C.c_void_p, _dp, _ip]
     lib.goma_gpu_scale_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _ip]
     lib.goma_gpu_vector_norms.argtypes = [C.c_void_p, C.c_int, _dp]

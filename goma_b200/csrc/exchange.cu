@@ -7,6 +7,10 @@
 using namespace goma_b200;
 
 // ------------------------------------------------------------------ exchange_dof over peer memory
+// flag block of a rank: [3][MAX_NEIGHBORS] epochs "neighbour k's vector is complete" (written by the neighbours),
+// [3][MAX_NEIGHBORS] epochs "neighbour k has pulled my vector" (written by the neighbours), one error word
+constexpr int XFLAG_DONE = 3 * GOMA_GPU_MAX_NEIGHBORS, XFLAG_ERR = 6 * GOMA_GPU_MAX_NEIGHBORS, XFLAG_WORDS = XFLAG_ERR + 1;
+
 struct ExchangeArgs {
   int nn;
   unsigned long long epoch;
@@ -50,12 +54,32 @@ __global__ void exchange_dof_kernel(const __grid_constant__ ExchangeArgs A) {
   }
 }
 
+// after the pull (stream order): tell every neighbour that its vector of this epoch has been read
+__global__ void exchange_done_kernel(const __grid_constant__ ExchangeArgs A) {
+  if (threadIdx.x < A.nn) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.peer_ready[threadIdx.x] + XFLAG_DONE), "l"(A.epoch) : "memory");
+  }
+}
+// the owner's side: wait until every neighbour has pulled the vector of the current epoch
+__global__ void exchange_fence_kernel(int nn, const unsigned long long *done, unsigned long long epoch, long long spin_limit,
+                                      unsigned long long *error) {
+  if (threadIdx.x >= nn) return;
+  const long long t0 = clock64();
+  unsigned long long seen;
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(done + threadIdx.x) : "memory");
+    if (seen >= epoch) return;
+  } while (clock64() - t0 <= spin_limit);
+  *error = 1ull + (unsigned long long)threadIdx.x;
+}
+
 extern "C" int goma_gpu_exchange_export(goma_gpu_ctx *c, goma_gpu_exchange_handles *out) {
   if (!c || !out) return fail(-2, "null argument");
   CU(cudaSetDevice(c->device));
   if (!c->d_xflags) {  // [3][MAX_NEIGHBORS] epochs published by the neighbours + one error word
-    CU(cudaMalloc((void **)&c->d_xflags, (3 * GOMA_GPU_MAX_NEIGHBORS + 1) * sizeof(unsigned long long)));
-    CU(cudaMemset(c->d_xflags, 0, (3 * GOMA_GPU_MAX_NEIGHBORS + 1) * sizeof(unsigned long long)));
+    CU(cudaMalloc((void **)&c->d_xflags, XFLAG_WORDS * sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_xflags, 0, XFLAG_WORDS * sizeof(unsigned long long)));
     CU(cudaDeviceSynchronize());
   }
   static_assert(sizeof(cudaIpcMemHandle_t) == GOMA_GPU_IPC_HANDLE_BYTES, "IPC handle size");
@@ -85,7 +109,7 @@ extern "C" int goma_gpu_exchange_setup(goma_gpu_ctx *c, int num_neighbors, const
   // must put a barrier between the set-up of all ranks and the first exchange (dp_comm.setup_peer_exchange does),
   // as it must between the reference's set_dof_communication and the first exchange_dof.
   for (int v = 0; v < 3; v++) c->epoch[v] = 0;
-  CU(cudaMemset(c->d_xflags, 0, (3 * GOMA_GPU_MAX_NEIGHBORS + 1) * sizeof(unsigned long long)));
+  CU(cudaMemset(c->d_xflags, 0, XFLAG_WORDS * sizeof(unsigned long long)));
   if (tail_begin < 0 || tail_begin > c->prob.num_unknowns) return fail(-2, "tail_begin outside the vector");
   if (num_neighbors && recv_ptr[0] != 0) return fail(-2, "recv_ptr[0] must be 0");
   for (int k = 0; k < num_neighbors; k++)
@@ -133,7 +157,7 @@ extern "C" int goma_gpu_exchange_dof(goma_gpu_ctx *c, int which) {
   A.my_ready = c->d_xflags + which * GOMA_GPU_MAX_NEIGHBORS;
   A.recv_list = c->d_recv_list;
   A.tail = vecs[which] + c->tail_begin;
-  A.error = c->d_xflags + 3 * GOMA_GPU_MAX_NEIGHBORS;
+  A.error = c->d_xflags + XFLAG_ERR;
   A.spin_limit = c->exchange_spin_limit;
   const int total = c->recv_ptr[A.nn];
   // The pull runs on its own stream, behind everything enqueued so far on the context's stream (the solver update
@@ -143,6 +167,8 @@ extern "C" int goma_gpu_exchange_dof(goma_gpu_ctx *c, int which) {
   CU(cudaEventRecord(c->ev_pre, c->stream));
   CU(cudaStreamWaitEvent(c->xstream, c->ev_pre, 0));
   exchange_dof_kernel<<<blocks, threads, 0, c->xstream>>>(A);
+  CU(cudaGetLastError());
+  exchange_done_kernel<<<1, GOMA_GPU_MAX_NEIGHBORS, 0, c->xstream>>>(A);
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev_x, c->xstream));
   c->exchange_in_flight = true;
@@ -160,13 +186,24 @@ __global__ void unpack_dofs_kernel(double *__restrict__ v, const int *__restrict
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[list[i]] = buf[i];
 }
+extern "C" int goma_gpu_exchange_fence(goma_gpu_ctx *c, int which) {
+  if (!c) return fail(-2, "null context");
+  if (which < 0 || which > 2) return fail(-2, "which must be 0 (x), 1 (xdot) or 2 (x_old)");
+  if (c->num_neighbors == 0 || c->epoch[which] == 0) return 0;
+  CU(cudaSetDevice(c->device));
+  exchange_fence_kernel<<<1, GOMA_GPU_MAX_NEIGHBORS, 0, c->stream>>>(c->num_neighbors, c->d_xflags + XFLAG_DONE + which * GOMA_GPU_MAX_NEIGHBORS,
+                                                                  c->epoch[which], c->exchange_spin_limit, c->d_xflags + XFLAG_ERR);
+  CU(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int goma_gpu_exchange_status(goma_gpu_ctx *c) {
   if (!c) return fail(-2, "null context");
   if (!c->d_xflags) return 0;
   CU(cudaSetDevice(c->device));
   unsigned long long e = 0;
   CU(cudaStreamSynchronize(c->xstream));
-  CU(cudaMemcpyAsync(&e, c->d_xflags + 3 * GOMA_GPU_MAX_NEIGHBORS, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&e, c->d_xflags + XFLAG_ERR, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (e) return fail(-4, "exchange_dof: neighbour slot " + std::to_string(e - 1) + " never published its vector (timed out)");
   return 0;

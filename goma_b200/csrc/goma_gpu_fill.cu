@@ -633,7 +633,7 @@ static int finish_fill(goma_gpu_ctx *c, int flags_out[3]) {
   unsigned long long xerr = 0;
   CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
   if (c->d_xflags && c->num_neighbors)
-    CU(cudaMemcpyAsync(&xerr, c->d_xflags + 3 * GOMA_GPU_MAX_NEIGHBORS, sizeof(xerr), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&xerr, c->d_xflags + 6 * GOMA_GPU_MAX_NEIGHBORS, sizeof(xerr), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   c->fill_pending = false;
   if (xerr) return fail(-4, "exchange_dof before this fill: neighbour slot " + std::to_string(xerr - 1) + " never published its vector");

@@ -51,11 +51,20 @@ __global__ void global_h_U_kernel(const int *__restrict__ conn, int npe, int dim
       nv += 1.0;
     }
   }
+  // block partials, summed by the host in block order: the same bits run to run (the PSPG tau, and with it the
+  // whole equal-order fill, depends on these sums)
+  __shared__ double sh[4][8];
   double vals[4] = {h, cnt, vv, nv};
   for (int q = 0; q < 4; q++) {
     double v = vals[q];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&sums[q], v);
+    if ((threadIdx.x & 31) == 0) sh[q][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += sh[threadIdx.x][w];
+    sums[4 * blockIdx.x + threadIdx.x] = v;
   }
 }
 
@@ -69,8 +78,8 @@ extern "C" int goma_gpu_global_h_U(goma_gpu_ctx *c, const unsigned char *elem_ow
     d_owned = c->d_elem_owned;
     CU(cudaMemcpyAsync(d_owned, elem_owned, p.num_elems, cudaMemcpyHostToDevice, c->stream));
   }
-  if (!c->d_sums) CU(cudaMalloc((void **)&c->d_sums, 4 * sizeof(double)));
-  CU(cudaMemsetAsync(c->d_sums, 0, 4 * sizeof(double), c->stream));
+  constexpr int HU_BLOCKS_MAX = 148 * 8;
+  if (!c->d_sums) CU(cudaMalloc((void **)&c->d_sums, 4 * HU_BLOCKS_MAX * sizeof(double)));
   int ku[4] = {-1, -1, -1, -1};  // offset of U inside a node of each kind (V, W follow it)
   for (int k = 0; k < p.num_kinds && k < 4; k++) ku[k] = p.kind_slot[k][GOMA_SLOT_U];
   const int threads = 256, blocks = std::max(1, std::min(148 * 8, (std::max(p.num_elems, p.num_owned_nodes) + threads - 1) / threads));
@@ -78,8 +87,12 @@ extern "C" int goma_gpu_global_h_U(goma_gpu_ctx *c, const unsigned char *elem_ow
                                                        c->d_coord[1], c->d_coord[2], d_owned, c->d_first, c->d_kind, 0, 1, 2,
                                                        ku[0], ku[1], ku[2], ku[3], p.num_owned_nodes, c->d_x, c->d_sums);
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(sums_out, c->d_sums, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  std::vector<double> part(4 * (size_t)blocks);
+  CU(cudaMemcpyAsync(part.data(), c->d_sums, part.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  for (int q = 0; q < 4; q++) sums_out[q] = 0.0;
+  for (int b = 0; b < blocks; b++)
+    for (int q = 0; q < 4; q++) sums_out[q] += part[4 * (size_t)b + q];
   return 0;
 }
 

@@ -112,6 +112,10 @@ class MatrixFill:
     def fill_wait(self) -> int:
         return capi.check(self.lib.goma_gpu_fill_wait(self._ctx, self.flags.ctypes.data_as(capi._ip)), "goma_gpu_fill_wait")
 
+    def exchange_fence(self, which: int = 0):
+        """Owner-side fence: the stream waits until every neighbour has pulled vector ``which`` of the last exchange."""
+        capi.check(self.lib.goma_gpu_exchange_fence(self._ctx, int(which)), "goma_gpu_exchange_fence")
+
     def exchange_status(self) -> int:
         return capi.check(self.lib.goma_gpu_exchange_status(self._ctx), "goma_gpu_exchange_status")
 

@@ -260,6 +260,11 @@ int goma_gpu_exchange_dof(goma_gpu_ctx *ctx, int which);
  * epoch -- a mismatched collective -- raises an error word instead of hanging the device.  This call (and every
  * goma_gpu_fill* that follows an exchange) returns -4 with a message when that happened, 0 otherwise. */
 int goma_gpu_exchange_status(goma_gpu_ctx *ctx);
+/* Write-after-read fence for the OWNER of the values: enqueues, on the context's stream, a wait until every
+ * neighbour has pulled this rank's vector `which` of the last exchange.  Call it before anything on that stream
+ * overwrites the vector when no collective (in Goma: the linear solve) separates the exchange from the update.
+ * Bounded like the exchange itself; a time-out surfaces through goma_gpu_exchange_status / the next fill. */
+int goma_gpu_exchange_fence(goma_gpu_ctx *ctx, int which);
 
 /* timing / accounting of the last goma_gpu_fill*: device ms of the assembly kernel(s)
  * (CUDA events on the context's stream) and number of kernel launches */

@@ -97,7 +97,25 @@ def _worker(rank, world, port_no, et, n, energy, kind, skip_rank, result):
                 continue
             torch.cuda.synchronize()
             out[f"exchange{which}"] = bool(np.array_equal(d.cpu().numpy(), xg[l2g]))
-            dist.barrier()  # nobody overwrites a vector while a neighbour may still be pulling from it
+            # nobody overwrites a vector while a neighbour may still be pulling from it: the owner-side fence (instead
+            # of a host barrier), then a second round with new values straight away
+            mf.exchange_fence(which)
+            torch.cuda.synchronize()
+            mf.exchange_status()
+            xg2 = xg + 1.0 + which
+            xl = xg2[l2g].copy()
+            xl[nown:] = np.nan
+            d.copy_(torch.from_numpy(xl))
+            torch.cuda.synchronize()
+            mf.exchange_dof(which)
+            torch.cuda.synchronize()
+            out[f"exchange{which}"] = out[f"exchange{which}"] and bool(np.array_equal(d.cpu().numpy(), xg2[l2g]))
+            mf.exchange_fence(which)
+            torch.cuda.synchronize()
+            if which == 0:  # the fill below assembles the original state
+                d.copy_(torch.from_numpy(xg[l2g].copy()))
+                torch.cuda.synchronize()
+            dist.barrier()
         if skip_rank is None:
             # the fill on the exchanged state: owned rows of all ranks == the global system
             ija_g = capi.pattern_msr(p)
