@@ -101,74 +101,58 @@ extern "C" int goma_gpu_global_h_U(goma_gpu_ctx *c, const unsigned char *elem_ow
 // well as CSR rows), so a CTA stages a BATCH of rows in shared memory with asynchronous copies (cp.async: the whole
 // batch, ~25 KB, is in flight at once), sums and scales it there (one warp per row) and streams it back with
 // coalesced stores: exactly one read and one write of every value, no reliance on L1/L2 for the second sweep.
-constexpr int RSS_ROWS = 6, RSS_THREADS = 256, RSS_CAP = 3328;  // rows per batch, capacity of ONE staging buffer (doubles)
+// (A two-buffer variant that keeps the copies of the next batch in flight during the sums was slower, 27.4 vs 22.9 ms
+// at 1M hex27 elements -- smaller batches, fewer CTAs per SM; profiles/r2k_row_sum_scale_double_buffer.txt.)
+constexpr int RSS_ROWS = 8, RSS_THREADS = 256, RSS_CAP = 5120;  // rows per batch, capacity of the staging buffer (doubles)
 
 __device__ __forceinline__ void rss_cp_async8(void *dst, const void *src) {
   unsigned d = (unsigned)__cvta_generic_to_shared(dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
 }
 
-// Two staging buffers: the asynchronous copies of batch k+1 are in flight while batch k is summed, scaled and written
-// back, so a CTA always has a read request outstanding (four CTAs per SM x 26 KB).
 template <bool CSR>
 __global__ void __launch_bounds__(RSS_THREADS) row_sum_scale_kernel(int nrows, const long long *__restrict__ rowstart, long long msr0,
                                                                     const int *__restrict__ dpos, double *__restrict__ a,
                                                                     double *__restrict__ b, double *__restrict__ scale,
                                                                     int *__restrict__ zero_rows) {
-  extern __shared__ __align__(16) unsigned char rss_smem[];  // > 48 KB: dynamic
-  double (*buf)[RSS_CAP] = reinterpret_cast<double (*)[RSS_CAP]>(rss_smem);
-  long long (*rs)[RSS_ROWS + 1] = reinterpret_cast<long long (*)[RSS_ROWS + 1]>(rss_smem + 2 * RSS_CAP * sizeof(double));
+  __shared__ double buf[RSS_CAP];
+  __shared__ long long rs[RSS_ROWS + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nbatch = (nrows + RSS_ROWS - 1) / RSS_ROWS;
-  auto row_start = [&](int r) -> long long { return CSR ? rowstart[r] - msr0 + r : rowstart[r]; };
-  // stage the extent of batch bt into slot q and start its copies (every thread computes the extent itself: no
-  // barrier between the row starts and the copies)
-  auto prefetch = [&](int bt, int q) {
+  for (int bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
     const int r0 = bt * RSS_ROWS, nr = min(RSS_ROWS, nrows - r0);
-    if (tid <= nr) rs[q][tid] = row_start(r0 + tid);
-    const long long k0 = row_start(r0);
-    const int len = (int)(row_start(r0 + nr) - k0);
-    if (len <= RSS_CAP)
-      for (int k = tid; k < len; k += RSS_THREADS) rss_cp_async8(&buf[q][k], &a[k0 + k]);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  int bt = blockIdx.x, q = 0;
-  if (bt < nbatch) prefetch(bt, 0);
-  for (; bt < nbatch; bt += gridDim.x, q ^= 1) {
-    const int nxt = bt + gridDim.x;
-    if (nxt < nbatch) {
-      prefetch(nxt, q ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (tid <= nr) rs[tid] = CSR ? rowstart[r0 + tid] - msr0 + (r0 + tid) : rowstart[r0 + tid];
+    __syncthreads();
+    const long long k0 = rs[0];
+    const int len = (int)(rs[nr] - k0);
+    const bool staged = len <= RSS_CAP;  // (rows longer than the buffer go through global memory twice)
+    if (staged) {
+      for (int k = tid; k < len; k += RSS_THREADS) rss_cp_async8(&buf[k], &a[k0 + k]);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_all;" ::: "memory");
     }
     __syncthreads();
-    const int r0 = bt * RSS_ROWS, nr = min(RSS_ROWS, nrows - r0);
-    const long long k0 = rs[q][0];
-    const int len = (int)(rs[q][nr] - k0);
-    const bool staged = len <= RSS_CAP;  // (rows longer than the buffer go through global memory twice)
-    double *bq = buf[q];
     if (warp < nr) {
       const int row = r0 + warp;
-      const int o0 = (int)(rs[q][warp] - k0), o1 = (int)(rs[q][warp + 1] - k0);
+      const int o0 = (int)(rs[warp] - k0), o1 = (int)(rs[warp + 1] - k0);
       double sum = 0.0;
       if (staged)
-        for (int k = o0 + lane; k < o1; k += 32) sum += fabs(bq[k]);
+        for (int k = o0 + lane; k < o1; k += 32) sum += fabs(buf[k]);
       else
-        for (long long k = rs[q][warp] + lane; k < rs[q][warp + 1]; k += 32) sum += fabs(a[k]);
+        for (long long k = rs[warp] + lane; k < rs[warp + 1]; k += 32) sum += fabs(a[k]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       // MSR: the diagonal lives apart in a[row]; CSR: it is one of the staged entries (already in the sum)
-      const double diag = CSR ? (staged ? bq[o0 + dpos[row]] : a[rs[q][warp] + dpos[row]]) : a[row];
+      const double diag = CSR ? (staged ? buf[o0 + dpos[row]] : a[rs[warp] + dpos[row]]) : a[row];
       double row_sum = CSR ? sum : fabs(diag) + sum;
       if (fabs(diag) > 1.0e-200) row_sum = diag >= 0.0 ? row_sum : -row_sum;  // keep the diagonal positive (:547-549)
       // one reciprocal per row and a multiply per entry differ from the reference's divide by at most 1 ulp (parity
       // tolerance 1e-12) and keep the fp64 divide sequence off an HBM-bound pass
       const double inv = 1.0 / row_sum;
       if (staged)
-        for (int k = o0 + lane; k < o1; k += 32) bq[k] *= inv;
+        for (int k = o0 + lane; k < o1; k += 32) buf[k] *= inv;
       else
-        for (long long k = rs[q][warp] + lane; k < rs[q][warp + 1]; k += 32) a[k] *= inv;
+        for (long long k = rs[warp] + lane; k < rs[warp + 1]; k += 32) a[k] *= inv;
       if (lane == 0) {
         scale[row] = row_sum;
         if (row_sum == 0.0) atomicAdd(zero_rows, 1);
@@ -178,8 +162,8 @@ __global__ void __launch_bounds__(RSS_THREADS) row_sum_scale_kernel(int nrows, c
     }
     __syncthreads();
     if (staged)
-      for (int k = tid; k < len; k += RSS_THREADS) a[k0 + k] = bq[k];
-    __syncthreads();  // slot q is free for the copies of the batch after next
+      for (int k = tid; k < len; k += RSS_THREADS) a[k0 + k] = buf[k];
+    __syncthreads();
   }
 }
 
@@ -228,18 +212,18 @@ extern "C" int goma_gpu_row_sum_scale(goma_gpu_ctx *c, double *scale_out, int *z
   if (n > 0) {
     const bool csr = c->layout == GOMA_GPU_LAYOUT_CSR;
     int per_sm = 0;  // a whole number of resident waves: the batches are handed out grid-stride
-    const size_t rss_bytes = 2 * RSS_CAP * sizeof(double) + 2 * (RSS_ROWS + 1) * sizeof(long long);
-    const void *fn = csr ? (const void *)row_sum_scale_kernel<true> : (const void *)row_sum_scale_kernel<false>;
-    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rss_bytes));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, RSS_THREADS, rss_bytes));
+    if (csr)
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)row_sum_scale_kernel<true>, RSS_THREADS, 0));
+    else
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)row_sum_scale_kernel<false>, RSS_THREADS, 0));
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     const int blocks = std::max(1, std::min(sms * std::max(per_sm, 1), (n + RSS_ROWS - 1) / RSS_ROWS));
     const long long msr0 = (long long)c->prob.num_unknowns + 1;
     if (csr)
-      row_sum_scale_kernel<true><<<blocks, RSS_THREADS, rss_bytes, c->stream>>>(n, c->d_rowstart, msr0, c->d_dpos, c->d_a, c->d_resid, c->d_scale, c->d_zero_rows);
+      row_sum_scale_kernel<true><<<blocks, RSS_THREADS, 0, c->stream>>>(n, c->d_rowstart, msr0, c->d_dpos, c->d_a, c->d_resid, c->d_scale, c->d_zero_rows);
     else
-      row_sum_scale_kernel<false><<<blocks, RSS_THREADS, rss_bytes, c->stream>>>(n, c->d_rowstart, msr0, nullptr, c->d_a, c->d_resid, c->d_scale, c->d_zero_rows);
+      row_sum_scale_kernel<false><<<blocks, RSS_THREADS, 0, c->stream>>>(n, c->d_rowstart, msr0, nullptr, c->d_a, c->d_resid, c->d_scale, c->d_zero_rows);
     CU(cudaGetLastError());
   }
   int zr = 0;
