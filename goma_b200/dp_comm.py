@@ -417,8 +417,9 @@ def exchange_dof(x, sub: Subdomain, group=None, pack=None):
 
 
 def allreduce_flags(flags, group=None):
-    """The four scalar all-reduces at the end of matrix_fill_full (``mm_fill.c:271-281``): MAX of the
-    three domain-failure flags, SUM of the error count -- fused into one small tensor."""
+    """The scalar all-reduces at the end of matrix_fill_full (``mm_fill.c:271-281``), fused into one small tensor and
+    reduced with MAX: the three domain-failure flags are 0/1 (MPI_MAX in the reference), and an error count reduced
+    with MAX still answers the only question the caller asks of it -- did any rank fail."""
     import torch
     import torch.distributed as dist
 
