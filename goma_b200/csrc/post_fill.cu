@@ -101,21 +101,31 @@ extern "C" int goma_gpu_global_h_U(goma_gpu_ctx *c, const unsigned char *elem_ow
 // well as CSR rows), so a CTA stages a BATCH of rows in shared memory with asynchronous copies (cp.async: the whole
 // batch, ~25 KB, is in flight at once), sums and scales it there (one warp per row) and streams it back with
 // coalesced stores: exactly one read and one write of every value, no reliance on L1/L2 for the second sweep.
-// (A two-buffer variant that keeps the copies of the next batch in flight during the sums was slower, 27.4 vs 22.9 ms
-// at 1M hex27 elements -- smaller batches, fewer CTAs per SM; profiles/r2k_row_sum_scale_double_buffer.txt.)
-constexpr int RSS_ROWS = 8, RSS_THREADS = 256, RSS_CAP = 5120;  // rows per batch, capacity of the staging buffer (doubles)
+// The copies move 16-byte pairs: the buffer is shifted by the parity of the batch's first index so that aligned pairs
+// of a[] land on aligned slots.  ROWS rows per batch, one warp per row, 640 doubles of staging buffer per row (the
+// longest hex27 row has 532 entries).  Measured at 1M hex27 elements (profiles/r2n_row_sum_scale_variants.txt):
+// 4 rows per CTA and 16-byte copies 19.4 ms (0.70 of the copy roof; CSR layout of C3 0.81) against 22.9 ms for 8 rows
+// and 8-byte copies; slower were 2 rows (19.6), a two-buffer pipeline (27.4), one warp per row with the row held in
+// registers (19.4 MSR but 64.5 vs 56.3 ms on the longer CSR rows) and batches cut by entry count (20.8).
+#define RSS_THREADS (32 * ROWS)
+#define RSS_CAP (640 * ROWS)
+#define RSS_ROWS ROWS
 
 __device__ __forceinline__ void rss_cp_async8(void *dst, const void *src) {
   unsigned d = (unsigned)__cvta_generic_to_shared(dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
 }
+__device__ __forceinline__ void rss_cp_async16(void *dst, const void *src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
 
-template <bool CSR>
+template <bool CSR, int ROWS>
 __global__ void __launch_bounds__(RSS_THREADS) row_sum_scale_kernel(int nrows, const long long *__restrict__ rowstart, long long msr0,
                                                                     const int *__restrict__ dpos, double *__restrict__ a,
                                                                     double *__restrict__ b, double *__restrict__ scale,
                                                                     int *__restrict__ zero_rows) {
-  __shared__ double buf[RSS_CAP];
+  __shared__ __align__(16) double buf_[RSS_CAP + 2];
   __shared__ long long rs[RSS_ROWS + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nbatch = (nrows + RSS_ROWS - 1) / RSS_ROWS;
@@ -126,8 +136,15 @@ __global__ void __launch_bounds__(RSS_THREADS) row_sum_scale_kernel(int nrows, c
     const long long k0 = rs[0];
     const int len = (int)(rs[nr] - k0);
     const bool staged = len <= RSS_CAP;  // (rows longer than the buffer go through global memory twice)
+    // the buffer is shifted by the parity of k0 so that 16-byte-aligned pairs of a[] land on 16-byte-aligned slots;
+    // the first and last entries of the batch are copied alone when they do not fill a pair
+    const int sh = (int)(k0 & 1);
+    double *buf = buf_ + sh;
+    const int p_lo = sh, p_hi = (len - sh) >> 1;  // entries [p_lo, p_lo + 2 * p_hi) go as pairs
     if (staged) {
-      for (int k = tid; k < len; k += RSS_THREADS) rss_cp_async8(&buf[k], &a[k0 + k]);
+      for (int q = tid; q < p_hi; q += RSS_THREADS) rss_cp_async16(&buf[p_lo + 2 * q], &a[k0 + p_lo + 2 * q]);
+      if (tid == 0 && sh && len > 0) rss_cp_async8(&buf[0], &a[k0]);
+      if (tid == 32 % RSS_THREADS && p_lo + 2 * p_hi < len) rss_cp_async8(&buf[len - 1], &a[k0 + len - 1]);
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_all;" ::: "memory");
     }
@@ -161,8 +178,12 @@ __global__ void __launch_bounds__(RSS_THREADS) row_sum_scale_kernel(int nrows, c
       }
     }
     __syncthreads();
-    if (staged)
-      for (int k = tid; k < len; k += RSS_THREADS) a[k0 + k] = buf[k];
+    if (staged) {
+      for (int q = tid; q < p_hi; q += RSS_THREADS)
+        *reinterpret_cast<double2 *>(&a[k0 + p_lo + 2 * q]) = *reinterpret_cast<const double2 *>(&buf[p_lo + 2 * q]);
+      if (tid == 0 && sh && len > 0) a[k0] = buf[0];
+      if (tid == 32 % RSS_THREADS && p_lo + 2 * p_hi < len) a[k0 + len - 1] = buf[len - 1];
+    }
     __syncthreads();
   }
 }
@@ -211,19 +232,25 @@ extern "C" int goma_gpu_row_sum_scale(goma_gpu_ctx *c, double *scale_out, int *z
   CU(cudaMemsetAsync(c->d_zero_rows, 0, sizeof(int), c->stream));
   if (n > 0) {
     const bool csr = c->layout == GOMA_GPU_LAYOUT_CSR;
-    int per_sm = 0;  // a whole number of resident waves: the batches are handed out grid-stride
-    if (csr)
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)row_sum_scale_kernel<true>, RSS_THREADS, 0));
-    else
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)row_sum_scale_kernel<false>, RSS_THREADS, 0));
+    const long long msr0 = (long long)c->prob.num_unknowns + 1;
+    static const int rss_rows = getenv("GOMA_GPU_RSS_ROWS") ? atoi(getenv("GOMA_GPU_RSS_ROWS")) : 4;  // (2 and 8 kept for A/B runs)
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-    const int blocks = std::max(1, std::min(sms * std::max(per_sm, 1), (n + RSS_ROWS - 1) / RSS_ROWS));
-    const long long msr0 = (long long)c->prob.num_unknowns + 1;
+    auto launch = [&](auto kern, int rows) -> int {
+      int per_sm = 0;  // a whole number of resident waves: the batches are handed out grid-stride
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)kern, 32 * rows, 0));
+      const int blocks = std::max(1, std::min(sms * std::max(per_sm, 1), (n + rows - 1) / rows));
+      kern<<<blocks, 32 * rows, 0, c->stream>>>(n, c->d_rowstart, msr0, csr ? c->d_dpos : nullptr, c->d_a, c->d_resid, c->d_scale, c->d_zero_rows);
+      return 0;
+    };
+    int lrc = 0;
     if (csr)
-      row_sum_scale_kernel<true><<<blocks, RSS_THREADS, 0, c->stream>>>(n, c->d_rowstart, msr0, c->d_dpos, c->d_a, c->d_resid, c->d_scale, c->d_zero_rows);
+      lrc = rss_rows == 2 ? launch(row_sum_scale_kernel<true, 2>, 2) : rss_rows == 4 ? launch(row_sum_scale_kernel<true, 4>, 4)
+            : launch(row_sum_scale_kernel<true, 8>, 8);
     else
-      row_sum_scale_kernel<false><<<blocks, RSS_THREADS, 0, c->stream>>>(n, c->d_rowstart, msr0, nullptr, c->d_a, c->d_resid, c->d_scale, c->d_zero_rows);
+      lrc = rss_rows == 2 ? launch(row_sum_scale_kernel<false, 2>, 2) : rss_rows == 4 ? launch(row_sum_scale_kernel<false, 4>, 4)
+            : launch(row_sum_scale_kernel<false, 8>, 8);
+    if (lrc) return lrc;
     CU(cudaGetLastError());
   }
   int zr = 0;
