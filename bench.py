@@ -436,6 +436,8 @@ def main():
     ap.add_argument("--no-extra-configs", action="store_true",
                     help="N = 1, headline config: skip the device-timed C3 / C5 / C4 lines under `configs`")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--host-stream-chunks", type=int, default=8,
+                    help="N = 1 e2e leg: goma_gpu_problem.host_stream_chunks of the host-buffer context (0 = one sweep, one copy)")
     ap.add_argument("--count-flops", action="store_true", help="re-count the restatement's flops per element and exit")
     args = ap.parse_args()
     if args.count_flops:
@@ -510,7 +512,7 @@ def main():
         step_s = max_over_ranks((time.perf_counter() - t0) / steps)
         return step_s, max_over_ranks(kernel_ms / steps), launches
 
-    from goma_b200.matrix_fill import device_view
+    from goma_b200.matrix_fill import MatrixFill, device_view
 
     w = Workload(args.config, args.n, rank, world, local_rank, args.scaling, args.scatter, partition=args.partition)
     mf, sub, problem = w.mf, w.sub, w.problem
@@ -631,13 +633,31 @@ def main():
             pinned = False
         hx.numpy()[:] = x
         ptrs = (hx.data_ptr(), 0, 0, 0, 0, ha.data_ptr(), hr.data_ptr())
-        mf.fill_raw(ptrs)  # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            mf.fill_raw(ptrs)
-        barrier()
-        e2e_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+
+        def host_steps(m):
+            m.fill_raw(ptrs)  # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                m.fill_raw(ptrs)
+            barrier()
+            return max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+
+        e2e_s = host_steps(mf)
+        streamed = None
+        if world == 1 and args.host_stream_chunks > 1:
+            # the host-buffer configuration of the library (goma_gpu_problem.host_stream_chunks): finished rows leave
+            # for the host under the assembly of the later chunks.  Its own context: the class order is fixed at init.
+            single_s, single_sum = e2e_s, float(ha.numpy()[: n_unk].sum())
+            mf.close()
+            torch.cuda.empty_cache()
+            mf = MatrixFill(problem, device=local_rank, host_stream_chunks=args.host_stream_chunks)
+            mf.set_option("scatter", args.scatter)
+            bufs = mf.device_buffers()
+            ha.numpy()[: n_unk] = 0.0
+            e2e_s = host_steps(mf)
+            streamed = {"host_stream_chunks": args.host_stream_chunks, "single_copy_ms_per_step": single_s * 1e3,
+                        "diag_checksum": [single_sum, float(ha.numpy()[: n_unk].sum())]}
         # the host-copy roof beside it: what one D2H of the matrix alone takes on this link
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         d_a = device_view(bufs.d_a, nnz + 1, dev)
@@ -649,7 +669,7 @@ def main():
         e2e = {"value": total_elems / e2e_s, "unit": "elements/s", "h2d_bytes_per_step": 8 * n_unk,
                "d2h_bytes_per_step": 8 * (nnz + 1) + 8 * n_unk, "ms_per_step": e2e_s * 1e3,
                "host_buffers": "pinned" if pinned else "pageable", "steps": args.e2e_steps,
-               "resid_checksum": float(hr.numpy().sum()),
+               "resid_checksum": float(hr.numpy().sum()), "streaming": streamed,
                "host_copy_roof": {"d2h_matrix_ms": d2h_ms, "GB/s": 8e-6 * (nnz + 1) / d2h_ms,
                                   "elements_per_s_at_roof": total_elems / (d2h_ms * 1e-3),
                                   "note": "one cudaMemcpy D2H of the MSR values alone, all ranks at once (max over ranks): "

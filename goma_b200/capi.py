@@ -51,6 +51,7 @@ class GomaGpuProblem(C.Structure):
         ("heat_source", C.c_double), ("lame_mu", C.c_double), ("lame_lambda", C.c_double),
         ("dbc_flag", _bp), ("dbc_value", _dp),
         ("num_elem_blocks", C.c_int), ("num_materials", C.c_int), ("matrix_layout", C.c_int),
+        ("host_stream_chunks", C.c_int),
     ]
 
 
@@ -144,7 +145,7 @@ def _ptr(a, typ):
 LAYOUT_MSR, LAYOUT_CSR = 0, 1
 
 
-def make_problem_struct(problem, ija=None, num_owned_nodes=None, layout="msr"):
+def make_problem_struct(problem, ija=None, num_owned_nodes=None, layout="msr", host_stream_chunks=0):
     """Fill ``struct goma_gpu_problem`` from a :class:`goma_b200.problem.Problem`.
 
     Returns (struct, keepalive) -- keepalive holds the numpy arrays the struct points into.
@@ -211,6 +212,7 @@ def make_problem_struct(problem, ija=None, num_owned_nodes=None, layout="msr"):
     p.num_elem_blocks = int(getattr(m, "num_elem_blocks", 1))
     p.num_materials = int(getattr(problem, "num_materials", 1))
     p.matrix_layout = {"msr": LAYOUT_MSR, "csr": LAYOUT_CSR}[layout]
+    p.host_stream_chunks = int(host_stream_chunks)
     return p, keep
 
 

@@ -61,7 +61,15 @@ struct goma_gpu_ctx {
   int *d_dpos = nullptr;           // CSR layout: offset of the diagonal inside each owned row
   int num_colours = 0;             // element colours; class = ((border ? nchunk : 0) + chunk) * ncol + colour
   int num_chunks = 1;              // chunks of consecutive elements swept one after the other (L2-sized; 1 = off)
+  int chunk_elems = 0;             // elements per chunk in effect (pattern build)
   int chunk_elems_option = 0;      // "chunk_elems" option at init: 0 auto, > 0 elements per chunk, < 0 off
+  // host_stream_chunks: rows [0, chunk_done_row[k]) are complete once chunk k has been assembled; chunk_done_off[k] is
+  // where the entries of that row start in d_a.  Copies run on cstream behind ev_chunk[k].
+  int stream_chunks = 0;
+  std::vector<long long> chunk_done_row, chunk_done_off;
+  std::vector<cudaEvent_t> ev_chunk;
+  cudaStream_t cstream = nullptr;
+  cudaEvent_t ev_copy = nullptr;
   int first_border_class = 0;      // classes from here on touch external nodes: they wait for the ghost exchange
   cudaStream_t xstream = nullptr;  // exchange_dof runs here, overlapped with the interior classes
   cudaEvent_t ev_x = nullptr, ev_pre = nullptr;

@@ -243,6 +243,52 @@ static int validate(const goma_gpu_problem &p) {
   return 0;
 }
 
+// host_stream_chunks: which rows are final after each chunk.  A row is final once no later chunk holds an element
+// with a node at or before it: chunk_done_row[k] = min over the chunks after k of the lowest unknown they touch.
+__global__ void chunk_min_row_kernel(int ne, int npe, int chunk_elems, const int *__restrict__ conn, const int *__restrict__ first_unknown,
+                                     int *__restrict__ chunk_min) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  int m = 0x7fffffff;
+  for (int k = 0; k < npe; k++) m = min(m, first_unknown[conn[(size_t)e * npe + k]]);
+  atomicMin(&chunk_min[e / chunk_elems], m);
+}
+
+static int setup_host_streaming(goma_gpu_ctx *c) {
+  const goma_gpu_problem &p = c->prob;
+  const int K = c->num_chunks, N = p.num_unknowns;
+  int *d_min = nullptr;
+  CU(cudaMalloc((void **)&d_min, K * sizeof(int)));
+  CU(cudaMemsetAsync(d_min, 0x7f, K * sizeof(int), c->stream));
+  chunk_min_row_kernel<<<(p.num_elems + 255) / 256, 256, 0, c->stream>>>(p.num_elems, p.elem_type, c->chunk_elems, c->d_conn, c->d_first, d_min);
+  std::vector<int> h(K);
+  cudaError_t e1 = cudaMemcpyAsync(h.data(), d_min, K * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e2 = cudaStreamSynchronize(c->stream);
+  cudaFree(d_min);
+  CU(e1);
+  CU(e2);
+  const long long msr0 = (long long)N + 1;
+  const bool csr = c->layout == GOMA_GPU_LAYOUT_CSR;
+  c->chunk_done_row.assign(K, c->num_owned_unknowns);
+  c->chunk_done_off.assign(K, c->a_len);
+  long long suffix = c->num_owned_unknowns;
+  for (int k = K - 1; k >= 0; k--) {  // (the last chunk completes everything)
+    c->chunk_done_row[k] = suffix;
+    suffix = std::min<long long>(suffix, h[k]);
+  }
+  for (int k = 0; k + 1 < K; k++) {
+    long long rs = 0;
+    CU(cudaMemcpy(&rs, c->d_rowstart + c->chunk_done_row[k], sizeof(long long), cudaMemcpyDeviceToHost));
+    c->chunk_done_off[k] = csr ? rs - msr0 + c->chunk_done_row[k] : rs;
+  }
+  CU(cudaStreamCreateWithFlags(&c->cstream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+  c->ev_chunk.assign(K, nullptr);
+  for (int k = 0; k < K; k++) CU(cudaEventCreateWithFlags(&c->ev_chunk[k], cudaEventDisableTiming));
+  c->stream_chunks = K;
+  return 0;
+}
+
 extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, goma_gpu_ctx **out) {
   if (!problem || !out) return fail(-2, "null argument");
   *out = nullptr;
@@ -264,6 +310,8 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
   c->prob = p;
   c->device = device;
   if (const char *ce = getenv("GOMA_GPU_CHUNK_ELEMS")) c->chunk_elems_option = atoi(ce);  // experiments: 0 auto, < 0 off
+  const bool want_stream = p.host_stream_chunks > 1 && p.num_owned_nodes >= p.num_nodes && p.num_elems > 0;
+  if (want_stream) c->chunk_elems_option = (p.num_elems + p.host_stream_chunks - 1) / p.host_stream_chunks;
   c->num_owned_unknowns = p.num_owned_nodes < p.num_nodes ? p.first_unknown[p.num_owned_nodes] : p.num_unknowns;
   const int nn = p.num_nodes, ne = p.num_elems, npe = p.elem_type, N = p.num_unknowns;
   int rc = 0;
@@ -348,6 +396,8 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
     }
     if (ne > 0) ke.build_records<<<(ne + 127) / 128, 128, 0, c->stream>>>(P, ne);
     CU(cudaGetLastError());
+    if (want_stream && c->num_chunks > 1)
+      if (int src = setup_host_streaming(c)) return src;
     int h_flags[4] = {0, 0, 0, 0};
     CU(cudaMemcpyAsync(h_flags, c->d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -395,6 +445,10 @@ extern "C" void goma_gpu_fill_destroy(goma_gpu_ctx *c) {
   if (c->d_partials) cudaFree(c->d_partials);
   if (c->d_zero_rows) cudaFree(c->d_zero_rows);
   free_device_pattern(c, false);
+  for (cudaEvent_t e : c->ev_chunk)
+    if (e) cudaEventDestroy(e);
+  if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+  if (c->cstream) cudaStreamDestroy(c->cstream);
   if (c->ev_x) cudaEventDestroy(c->ev_x);
   if (c->ev_pre) cudaEventDestroy(c->ev_pre);
   if (c->xstream) cudaStreamDestroy(c->xstream);
@@ -616,10 +670,14 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
       P.elem_begin = c->colour_begin[col];
       P.elem_end = c->colour_begin[col + 1];
       int n = P.elem_end - P.elem_begin;
-      if (n <= 0) continue;
-      int grid = std::max(1, std::min(max_grid, n));
-      ke.fn<<<grid, ke.tpe, ke.smem, c->stream>>>(P);
-      c->last_launches++;
+      if (n > 0) {
+        int grid = std::max(1, std::min(max_grid, n));
+        ke.fn<<<grid, ke.tpe, ke.smem, c->stream>>>(P);
+        c->last_launches++;
+      }
+      // host streaming: the last colour of a chunk is done -- its finished rows may leave for the host
+      if (c->stream_chunks > 1 && (int)((col + 1) % c->num_colours) == 0 && (int)(col / c->num_colours) < c->stream_chunks)
+        CU(cudaEventRecord(c->ev_chunk[col / c->num_colours], c->stream));
     }
   }
   if (int wrc = wait_for_exchange()) return wrc;  // (no border class: nothing read the tail, keep the order anyway)
@@ -731,9 +789,29 @@ extern "C" int goma_gpu_fill(goma_gpu_ctx *c, const double *x, const double *x_o
     c->rezero = true;  // the uploaded values sit in slots the first-touch mode never rewrites
   }
   if (lrc) return lrc;
-  // one copy: the PCIe link is saturated by it (≈47 GB/s measured; two concurrent copy streams gave the same)
-  if (assemble_jacobian)
+  if (assemble_jacobian && c->stream_chunks > 1 && c->scatter_mode != 0) {
+    // rows no later chunk touches go to the host while the later chunks are still being assembled (the launches above
+    // are all enqueued; every copy waits for the event behind the last colour of its chunk)
+    const bool csr = c->layout == GOMA_GPU_LAYOUT_CSR;
+    const long long msr0 = (long long)c->prob.num_unknowns + 1;
+    long long r_prev = 0, o_prev = csr ? 0 : msr0;
+    for (int k = 0; k < c->stream_chunks; k++) {
+      const bool last = k + 1 == c->stream_chunks;
+      const long long r = last ? msr0 : c->chunk_done_row[k], o = last ? c->a_len : c->chunk_done_off[k];
+      CU(cudaStreamWaitEvent(c->cstream, c->ev_chunk[k], 0));
+      if (!csr && r > r_prev)  // MSR: the diagonal entries of those rows (and, at the end, the unused a[N])
+        CU(cudaMemcpyAsync(a + r_prev, c->d_a + r_prev, (size_t)(r - r_prev) * sizeof(double), cudaMemcpyDeviceToHost, c->cstream));
+      if (o > o_prev)
+        CU(cudaMemcpyAsync(a + o_prev, c->d_a + o_prev, (size_t)(o - o_prev) * sizeof(double), cudaMemcpyDeviceToHost, c->cstream));
+      r_prev = std::max(r_prev, r);
+      o_prev = std::max(o_prev, o);
+    }
+    CU(cudaEventRecord(c->ev_copy, c->cstream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+  } else if (assemble_jacobian) {
+    // one copy: the PCIe link is saturated by it (≈47 GB/s measured; two concurrent copy streams gave the same)
     CU(cudaMemcpyAsync(a, c->d_a, (size_t)c->a_len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
   if (assemble_residual) CU(cudaMemcpyAsync(resid_vector, c->d_resid, nb, cudaMemcpyDeviceToHost, c->stream));
   return finish_fill(c, flags_out);
 }

@@ -539,6 +539,7 @@ int build_pattern_device(goma_gpu_ctx *c) {
   c->first_border_class = split_border ? ncol * nchunk : ncls;
   c->num_colours = ncol;
   c->num_chunks = nchunk;
+  c->chunk_elems = chunk_elems;
 
   // ---- first-touch masks
   if (npe > 32) return fail(-2, "first-touch masks need <= 32 nodes per element");

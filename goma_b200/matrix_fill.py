@@ -18,14 +18,18 @@ from . import capi
 
 
 class MatrixFill:
-    def __init__(self, problem, device: int = 0, ija=None, num_owned_nodes=None, layout: str = "msr"):
+    def __init__(self, problem, device: int = 0, ija=None, num_owned_nodes=None, layout: str = "msr",
+                 host_stream_chunks: int = 0):
         """``layout``: "msr" = the reference's ``ams->val`` (default); "csr" = CSR of the owned rows with the diagonal in
-        place, assembled directly (``goma_gpu_problem.matrix_layout``)."""
+        place, assembled directly (``goma_gpu_problem.matrix_layout``).  ``host_stream_chunks`` = K > 1: host-buffer
+        fills sweep the elements in K chunks and copy finished rows to the host under the assembly of the later chunks
+        (``goma_gpu_problem.host_stream_chunks``)."""
         self.lib = capi.load_library()
         self.problem = problem
         self.device = int(device)
         self.layout = layout
-        self._struct, self._keep = capi.make_problem_struct(problem, ija=ija, num_owned_nodes=num_owned_nodes, layout=layout)
+        self._struct, self._keep = capi.make_problem_struct(problem, ija=ija, num_owned_nodes=num_owned_nodes, layout=layout,
+                                                               host_stream_chunks=host_stream_chunks)
         self._ctx = C.c_void_p()
         capi.check(self.lib.goma_gpu_fill_init(C.byref(self._struct), device, C.byref(self._ctx)),
                    "goma_gpu_fill_init")

@@ -133,6 +133,15 @@ struct goma_gpu_problem {
    * src/linalg/sparse_matrix_epetra.cpp:111-118), no second copy of the matrix: goma_gpu_fill's `a` and d_a then
    * hold goma_gpu_csr::nnz values, goma_gpu_csr_structure's d_values IS d_a and goma_gpu_csr_values is a no-op. */
   int matrix_layout;
+
+  /* Host-buffer calls (goma_gpu_fill with a in host memory) are bound by the copy of the matrix to the host.  With
+   * host_stream_chunks = K > 1 the elements are swept in K chunks of consecutive elements (all colours of a chunk
+   * before the next chunk) and the rows no later chunk touches leave for the host while the later chunks are still
+   * being assembled (the part of mm_fill.c:224 the host waits for shrinks from the whole loop to one chunk).
+   * Effective when element and node numbering advance together (any mesh generator's default order); always
+   * correct, the values are bit-identical.  0 or 1 = one sweep, one copy.  Ignored on sub-domains with ghost
+   * nodes (their classes are split interior / border for the halo exchange instead). */
+  int host_stream_chunks;
 };
 #define GOMA_GPU_LAYOUT_MSR 0
 #define GOMA_GPU_LAYOUT_CSR 1

@@ -784,3 +784,43 @@ def test_gpu_csr_layout_is_assembled_in_place(built, name, scatter):
     assert_close(r, rm, "residual, owned rows")
     mf.close()
     mf_m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["msr", "csr"])
+@pytest.mark.parametrize("name,chunks", [("c2_hex27_ns", 3), ("c3_hex27_boussinesq", 4), ("c5_hex8_pspg_global", 5),
+                                         ("irr_hex27_star_bouss", 2), ("c4_quad9_ale", 64)])
+def test_gpu_host_stream_chunks_is_bit_identical(built, name, chunks, layout):
+    """host_stream_chunks = K: the elements are swept chunk by chunk and finished rows are copied to the host under the
+    assembly of the later chunks.  The order of the contributions to a slot changes with the class order, so the
+    comparison with the one-sweep fill is at the parity tolerance; two streamed fills are bit-identical; every value
+    must have arrived (the host buffer starts as NaN) and equal the device-resident copy."""
+    p, kw, st = case_state(name)
+    fkw = dict(delta_t=kw.get("delta_t", 0.0), theta=kw.get("theta", 0.0), time_value=kw.get("time", 0.0))
+    h, U = (p.global_h_elem_siz(), p.global_velocity_norm(st["x"])) if p.pspg else (0.0, 0.0)
+    args = (st["x"], st.get("x_old"), st.get("x_older"), st.get("xdot"), st.get("xdot_old"))
+    mf0 = MatrixFill(p, layout=layout)
+    _, a0, r0 = mf0.matrix_fill_full(*args, h_elem_avg=h, U_norm=U, **fkw)
+    mf0.close()
+    mf = MatrixFill(p, layout=layout, host_stream_chunks=chunks)
+    a = np.full(mf.value_count, np.nan)
+    r = np.full(mf.num_unknowns, np.nan)
+    err, a, r = mf.matrix_fill_full(*args, h_elem_avg=h, U_norm=U, a=a, resid_vector=r, **fkw)
+    assert err == 0
+    assert not np.isnan(r).any()
+    assert not np.isnan(a).any(), "a value never reached the host"
+    ija = mf.export_msr() if layout == "msr" else None
+    if layout == "msr":
+        assert_close(a, a0, "streamed vs one sweep", ija=ija)
+    else:
+        np.testing.assert_allclose(a, a0, rtol=1e-11, atol=1e-11 * np.abs(a0).max())
+    assert_close(r, r0, "residual")
+    _, nl = mf.last_stats()
+    assert nl > 0
+    a2 = np.full(mf.value_count, np.nan)
+    err, a2, _ = mf.matrix_fill_full(*args, h_elem_avg=h, U_norm=U, a=a2, **fkw)
+    np.testing.assert_array_equal(a2, a)
+    # the device-resident copy equals what was streamed
+    ad, _ = mf.download_system()
+    np.testing.assert_array_equal(ad, a)
+    mf.close()
