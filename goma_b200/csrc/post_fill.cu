@@ -362,7 +362,15 @@ __global__ void csr_values_kernel(int num_rows, const long long *__restrict__ ro
   for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < num_rows; row += nwarp) {
     const long long k0 = rowstart[row], c0 = rowptr[row];
     const int len = (int)(rowptr[row + 1] - c0), d = dpos[row];
-    for (int t = lane; t < len; t += 32) v[c0 + t] = t < d ? a[k0 + t] : (t == d ? a[row] : a[k0 + t - 1]);
+    auto val = [&](int t) { return t < d ? a[k0 + t] : (t == d ? a[row] : a[k0 + t - 1]); };
+    // 16-byte stores on the 16-byte boundaries of v[]; the first / last entry goes alone when the row starts / ends odd
+    const int t0 = (int)(c0 & 1), np = (len - t0) >> 1;
+    for (int q = lane; q < np; q += 32) {
+      const int t = t0 + 2 * q;
+      *reinterpret_cast<double2 *>(&v[c0 + t]) = make_double2(val(t), val(t + 1));
+    }
+    if (lane == 0 && t0 && len > 0) v[c0] = val(0);
+    if (lane == 1 && t0 + 2 * np < len) v[c0 + len - 1] = val(len - 1);
   }
 }
 
