@@ -120,19 +120,36 @@ __device__ __forceinline__ void rss_cp_async16(void *dst, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
 }
 
+__device__ __forceinline__ void rss_cp_async4(void *dst, const void *src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+
+// One DRAM latency per batch instead of three: the row starts of the NEXT batch are fetched while the current one is
+// in flight, and the per-row scalars (diagonal a[row] of the MSR layout or its offset in the CSR row, b[row]) travel
+// with the same asynchronous copy group as the values instead of being loaded by lane 0 after the sums.
 template <bool CSR, int ROWS>
 __global__ void __launch_bounds__(RSS_THREADS) row_sum_scale_kernel(int nrows, const long long *__restrict__ rowstart, long long msr0,
                                                                     const int *__restrict__ dpos, double *__restrict__ a,
                                                                     double *__restrict__ b, double *__restrict__ scale,
                                                                     int *__restrict__ zero_rows) {
   __shared__ __align__(16) double buf_[RSS_CAP + 2];
-  __shared__ long long rs[RSS_ROWS + 1];
+  __shared__ long long rs_[2][RSS_ROWS + 1];
+  __shared__ double dg[RSS_ROWS], bb[RSS_ROWS];
+  __shared__ int dp[RSS_ROWS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nbatch = (nrows + RSS_ROWS - 1) / RSS_ROWS;
-  for (int bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
+  auto row_start = [&](int r) -> long long { return CSR ? rowstart[r] - msr0 + r : rowstart[r]; };
+  if ((int)blockIdx.x < nbatch && tid <= min(RSS_ROWS, nrows - (int)blockIdx.x * RSS_ROWS)) rs_[0][tid] = row_start(blockIdx.x * RSS_ROWS + tid);
+  __syncthreads();
+  int it = 0;
+  for (int bt = blockIdx.x; bt < nbatch; bt += gridDim.x, it++) {
+    const long long *rs = rs_[it & 1];
     const int r0 = bt * RSS_ROWS, nr = min(RSS_ROWS, nrows - r0);
-    if (tid <= nr) rs[tid] = CSR ? rowstart[r0 + tid] - msr0 + (r0 + tid) : rowstart[r0 + tid];
-    __syncthreads();
+    const int bt2 = bt + (int)gridDim.x;
+    const bool fetch_next = bt2 < nbatch && tid <= min(RSS_ROWS, nrows - bt2 * RSS_ROWS);
+    long long rs_next = 0;
+    if (fetch_next) rs_next = row_start(bt2 * RSS_ROWS + tid);  // lands while the copies below are in flight
     const long long k0 = rs[0];
     const int len = (int)(rs[nr] - k0);
     const bool staged = len <= RSS_CAP;  // (rows longer than the buffer go through global memory twice)
@@ -141,13 +158,21 @@ __global__ void __launch_bounds__(RSS_THREADS) row_sum_scale_kernel(int nrows, c
     const int sh = (int)(k0 & 1);
     double *buf = buf_ + sh;
     const int p_lo = sh, p_hi = (len - sh) >> 1;  // entries [p_lo, p_lo + 2 * p_hi) go as pairs
+    if (tid < nr) {
+      rss_cp_async8(&bb[tid], &b[r0 + tid]);
+      if (CSR)
+        rss_cp_async4(&dp[tid], &dpos[r0 + tid]);
+      else
+        rss_cp_async8(&dg[tid], &a[r0 + tid]);
+    }
     if (staged) {
       for (int q = tid; q < p_hi; q += RSS_THREADS) rss_cp_async16(&buf[p_lo + 2 * q], &a[k0 + p_lo + 2 * q]);
       if (tid == 0 && sh && len > 0) rss_cp_async8(&buf[0], &a[k0]);
       if (tid == 32 % RSS_THREADS && p_lo + 2 * p_hi < len) rss_cp_async8(&buf[len - 1], &a[k0 + len - 1]);
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_all;" ::: "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (fetch_next) rs_[(it & 1) ^ 1][tid] = rs_next;
     __syncthreads();
     if (warp < nr) {
       const int row = r0 + warp;
@@ -160,12 +185,13 @@ __global__ void __launch_bounds__(RSS_THREADS) row_sum_scale_kernel(int nrows, c
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       // MSR: the diagonal lives apart in a[row]; CSR: it is one of the staged entries (already in the sum)
-      const double diag = CSR ? (staged ? buf[o0 + dpos[row]] : a[rs[warp] + dpos[row]]) : a[row];
+      const double diag = CSR ? (staged ? buf[o0 + dp[warp]] : a[rs[warp] + dp[warp]]) : dg[warp];
       double row_sum = CSR ? sum : fabs(diag) + sum;
       if (fabs(diag) > 1.0e-200) row_sum = diag >= 0.0 ? row_sum : -row_sum;  // keep the diagonal positive (:547-549)
       // one reciprocal per row and a multiply per entry differ from the reference's divide by at most 1 ulp (parity
       // tolerance 1e-12) and keep the fp64 divide sequence off an HBM-bound pass
       const double inv = 1.0 / row_sum;
+      __syncwarp();  // (every lane has read the diagonal before it is scaled)
       if (staged)
         for (int k = o0 + lane; k < o1; k += 32) buf[k] *= inv;
       else
@@ -174,7 +200,7 @@ __global__ void __launch_bounds__(RSS_THREADS) row_sum_scale_kernel(int nrows, c
         scale[row] = row_sum;
         if (row_sum == 0.0) atomicAdd(zero_rows, 1);
         if (!CSR) a[row] = diag / row_sum;
-        b[row] = b[row] / row_sum;
+        b[row] = bb[warp] / row_sum;
       }
     }
     __syncthreads();
@@ -362,15 +388,7 @@ __global__ void csr_values_kernel(int num_rows, const long long *__restrict__ ro
   for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < num_rows; row += nwarp) {
     const long long k0 = rowstart[row], c0 = rowptr[row];
     const int len = (int)(rowptr[row + 1] - c0), d = dpos[row];
-    auto val = [&](int t) { return t < d ? a[k0 + t] : (t == d ? a[row] : a[k0 + t - 1]); };
-    // 16-byte stores on the 16-byte boundaries of v[]; the first / last entry goes alone when the row starts / ends odd
-    const int t0 = (int)(c0 & 1), np = (len - t0) >> 1;
-    for (int q = lane; q < np; q += 32) {
-      const int t = t0 + 2 * q;
-      *reinterpret_cast<double2 *>(&v[c0 + t]) = make_double2(val(t), val(t + 1));
-    }
-    if (lane == 0 && t0 && len > 0) v[c0] = val(0);
-    if (lane == 1 && t0 + 2 * np < len) v[c0 + len - 1] = val(len - 1);
+    for (int t = lane; t < len; t += 32) v[c0 + t] = t < d ? a[k0 + t] : (t == d ? a[row] : a[k0 + t - 1]);
   }
 }
 
