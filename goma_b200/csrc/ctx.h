@@ -58,6 +58,7 @@ struct goma_gpu_ctx {
   long long nnz_plus = 0;          // == ija[N] of the MSR graph
   int layout = 0;                  // GOMA_GPU_LAYOUT_*: how d_a is laid out
   long long a_len = 0;             // doubles in d_a: nnz_plus + 1 (MSR) or csr_nnz (CSR)
+  int rss_max_row = -1;            // longest owned row (row-sum scaling sizes its staging buffer with it); -1 = not yet known
   int *d_dpos = nullptr;           // CSR layout: offset of the diagonal inside each owned row
   int num_colours = 0;             // element colours; class = ((border ? nchunk : 0) + chunk) * ncol + colour
   int num_chunks = 1;              // chunks of consecutive elements swept one after the other (L2-sized; 1 = off)

@@ -99,16 +99,17 @@ extern "C" int goma_gpu_global_h_U(goma_gpu_ctx *c, const unsigned char *elem_ow
 // ------------------------------------------------------------------ after the fill: row-sum scaling, norms
 // row_sum_scale_MSR (src/sl_matrix_util.c:507-600).  Consecutive rows are contiguous in memory (MSR off-diagonals as
 // well as CSR rows), so a CTA stages a BATCH of rows in shared memory with asynchronous copies (cp.async: the whole
-// batch, ~25 KB, is in flight at once), sums and scales it there (one warp per row) and streams it back with
-// coalesced stores: exactly one read and one write of every value, no reliance on L1/L2 for the second sweep.
+// batch in flight at once), sums and scales it there (one warp per row) and streams it back with 16-byte stores:
+// exactly one read and one write of every value (ncu: 45.1 + 45.0 GB of DRAM traffic for 89.3 GB algorithmic,
+// profiles/r2r_row_sum_scale_4rows.txt), no reliance on L1/L2 for the second sweep.
 // The copies move 16-byte pairs: the buffer is shifted by the parity of the batch's first index so that aligned pairs
-// of a[] land on aligned slots.  ROWS rows per batch, one warp per row, 640 doubles of staging buffer per row (the
-// longest hex27 row has 532 entries).  Measured at 1M hex27 elements (profiles/r2n_row_sum_scale_variants.txt):
-// 4 rows per CTA and 16-byte copies 19.4 ms (0.70 of the copy roof; CSR layout of C3 0.81) against 22.9 ms for 8 rows
-// and 8-byte copies; slower were 2 rows (19.6), a two-buffer pipeline (27.4), one warp per row with the row held in
-// registers (19.4 MSR but 64.5 vs 56.3 ms on the longer CSR rows) and batches cut by entry count (20.8).
+// of a[] land on aligned slots.  ROWS rows per batch, one warp per row; the buffer holds ROWS x the longest row of
+// THIS matrix (dynamic shared memory).  Measured at 1M hex27 elements (profiles/r2n_row_sum_scale_variants.txt,
+// r2s_row_sum_scale_latency.txt): 22.9 ms with 8 rows and 8-byte copies -> 19.4 ms with 4 rows and 16-byte copies ->
+// 17.8-18.4 ms (0.74-0.77 of the copy roof; CSR layout of C3 0.82-0.83) once the three dependent DRAM latencies of a
+// batch (row starts, values, per-row scalars) were folded into one.  Slower: 2 rows, a two-buffer pipeline, one warp
+// per row with the row held in registers, batches cut by entry count.
 #define RSS_THREADS (32 * ROWS)
-#define RSS_CAP (640 * ROWS)
 #define RSS_ROWS ROWS
 
 __device__ __forceinline__ void rss_cp_async8(void *dst, const void *src) {
@@ -118,6 +119,15 @@ __device__ __forceinline__ void rss_cp_async8(void *dst, const void *src) {
 __device__ __forceinline__ void rss_cp_async16(void *dst, const void *src) {
   unsigned d = (unsigned)__cvta_generic_to_shared(dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+
+// longest owned row (entries staged per row: MSR off-diagonals, or the CSR row with its diagonal), once per context
+__global__ void max_row_len_kernel(int nrows, const long long *__restrict__ rowstart, int *__restrict__ out) {
+  int m = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) m = max(m, (int)(rowstart[r + 1] - rowstart[r]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
 __device__ __forceinline__ void rss_cp_async4(void *dst, const void *src) {
@@ -132,8 +142,8 @@ template <bool CSR, int ROWS>
 __global__ void __launch_bounds__(RSS_THREADS) row_sum_scale_kernel(int nrows, const long long *__restrict__ rowstart, long long msr0,
                                                                     const int *__restrict__ dpos, double *__restrict__ a,
                                                                     double *__restrict__ b, double *__restrict__ scale,
-                                                                    int *__restrict__ zero_rows) {
-  __shared__ __align__(16) double buf_[RSS_CAP + 2];
+                                                                    int *__restrict__ zero_rows, int cap) {
+  extern __shared__ __align__(16) double buf_[];  // cap + 2 doubles: ROWS x the longest row of this matrix
   __shared__ long long rs_[2][RSS_ROWS + 1];
   __shared__ double dg[RSS_ROWS], bb[RSS_ROWS];
   __shared__ int dp[RSS_ROWS];
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(RSS_THREADS) row_sum_scale_kernel(int nrows, c
     if (fetch_next) rs_next = row_start(bt2 * RSS_ROWS + tid);  // lands while the copies below are in flight
     const long long k0 = rs[0];
     const int len = (int)(rs[nr] - k0);
-    const bool staged = len <= RSS_CAP;  // (rows longer than the buffer go through global memory twice)
+    const bool staged = len <= cap;  // (always, unless the longest row outgrows the shared memory of an SM)
     // the buffer is shifted by the parity of k0 so that 16-byte-aligned pairs of a[] land on 16-byte-aligned slots;
     // the first and last entries of the batch are copied alone when they do not fill a pair
     const int sh = (int)(k0 & 1);
@@ -262,11 +272,27 @@ extern "C" int goma_gpu_row_sum_scale(goma_gpu_ctx *c, double *scale_out, int *z
     static const int rss_rows = getenv("GOMA_GPU_RSS_ROWS") ? atoi(getenv("GOMA_GPU_RSS_ROWS")) : 4;  // (2 and 8 kept for A/B runs)
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    if (c->rss_max_row < 0) {  // the staging buffer is sized for this matrix, not for the worst case: more CTAs per SM
+      CU(cudaMemsetAsync(c->d_zero_rows, 0, sizeof(int), c->stream));
+      max_row_len_kernel<<<std::min(1024, (n + 255) / 256), 256, 0, c->stream>>>(n, c->d_rowstart, c->d_zero_rows);
+      CU(cudaMemcpyAsync(&c->rss_max_row, c->d_zero_rows, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      CU(cudaMemsetAsync(c->d_zero_rows, 0, sizeof(int), c->stream));
+      if (csr) c->rss_max_row += 1;
+    }
     auto launch = [&](auto kern, int rows) -> int {
+      int cap = (rows * c->rss_max_row + 1) & ~1;
+      size_t dyn = (size_t)(cap + 2) * sizeof(double);
+      if (dyn > 200 * 1024) {  // a row of more than 200 KB / rows: those batches take the two-pass path
+        cap = 2048;
+        dyn = (size_t)(cap + 2) * sizeof(double);
+      }
+      if (dyn > 48 * 1024) CU(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
       int per_sm = 0;  // a whole number of resident waves: the batches are handed out grid-stride
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)kern, 32 * rows, 0));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)kern, 32 * rows, dyn));
       const int blocks = std::max(1, std::min(sms * std::max(per_sm, 1), (n + rows - 1) / rows));
-      kern<<<blocks, 32 * rows, 0, c->stream>>>(n, c->d_rowstart, msr0, csr ? c->d_dpos : nullptr, c->d_a, c->d_resid, c->d_scale, c->d_zero_rows);
+      kern<<<blocks, 32 * rows, dyn, c->stream>>>(n, c->d_rowstart, msr0, csr ? c->d_dpos : nullptr, c->d_a, c->d_resid, c->d_scale, c->d_zero_rows,
+                                                  cap);
       return 0;
     };
     int lrc = 0;
