@@ -411,10 +411,29 @@ __global__ void csr_values_kernel(int num_rows, const long long *__restrict__ ro
                                   const int *__restrict__ dpos, const double *__restrict__ a, double *__restrict__ v) {
   const int lane = threadIdx.x & 31;
   const int nwarp = (gridDim.x * blockDim.x) >> 5;
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < num_rows; row += nwarp) {
-    const long long k0 = rowstart[row], c0 = rowptr[row];
-    const int len = (int)(rowptr[row + 1] - c0), d = dpos[row];
-    for (int t = lane; t < len; t += 32) v[c0 + t] = t < d ? a[k0 + t] : (t == d ? a[row] : a[k0 + t - 1]);
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= num_rows) return;
+  // the row descriptors of the NEXT row are loaded under the copy of the current one (one DRAM latency per row, not two)
+  long long k0 = rowstart[row], c0 = rowptr[row], c1 = rowptr[row + 1];
+  int d = dpos[row];
+  double dg = a[row];
+  while (true) {
+    const int nxt = row + nwarp;
+    const bool more = nxt < num_rows;
+    long long k0n = 0, c0n = 0, c1n = 0;
+    int dn = 0;
+    double dgn = 0.0;
+    if (more) {
+      k0n = rowstart[nxt];
+      c0n = rowptr[nxt];
+      c1n = rowptr[nxt + 1];
+      dn = dpos[nxt];
+      dgn = a[nxt];
+    }
+    const int len = (int)(c1 - c0);
+    for (int t = lane; t < len; t += 32) v[c0 + t] = t < d ? a[k0 + t] : (t == d ? dg : a[k0 + t - 1]);
+    if (!more) break;
+    row = nxt; k0 = k0n; c0 = c0n; c1 = c1n; d = dn; dg = dgn;
   }
 }
 
