@@ -34,6 +34,18 @@ _ip = C.POINTER(C.c_int)
 _bp = C.POINTER(C.c_ubyte)
 
 
+
+class Material(C.Structure):
+    """``struct goma_gpu_material`` (include/goma_gpu_fill.h)."""
+
+    _fields_ = [
+        ("rho", C.c_double), ("mu", C.c_double), ("conductivity", C.c_double), ("heat_capacity", C.c_double),
+        ("volume_expansion", C.c_double), ("reference_temperature", C.c_double),
+        ("diffusivity", C.c_double * 4), ("momentum_source", C.c_double * 3), ("momentum_source_model", C.c_int),
+        ("heat_source", C.c_double), ("lame_mu", C.c_double), ("lame_lambda", C.c_double),
+    ]
+
+
 class GomaGpuProblem(C.Structure):
     _fields_ = [
         ("dim", C.c_int), ("elem_type", C.c_int), ("num_nodes", C.c_int), ("num_owned_nodes", C.c_int),
@@ -50,7 +62,8 @@ class GomaGpuProblem(C.Structure):
         ("diffusivity", C.c_double * 4), ("momentum_source", C.c_double * 3), ("momentum_source_model", C.c_int),
         ("heat_source", C.c_double), ("lame_mu", C.c_double), ("lame_lambda", C.c_double),
         ("dbc_flag", _bp), ("dbc_value", _dp),
-        ("num_elem_blocks", C.c_int), ("num_materials", C.c_int), ("matrix_layout", C.c_int),
+        ("num_elem_blocks", C.c_int), ("num_materials", C.c_int), ("elem_material", _ip),
+        ("materials", C.POINTER(Material)), ("matrix_layout", C.c_int),
         ("host_stream_chunks", C.c_int),
     ]
 
@@ -211,6 +224,23 @@ def make_problem_struct(problem, ija=None, num_owned_nodes=None, layout="msr", h
     p.dbc_value = _ptr(keep["dbc_value"], _dp)
     p.num_elem_blocks = int(getattr(m, "num_elem_blocks", 1))
     p.num_materials = int(getattr(problem, "num_materials", 1))
+    if p.num_materials > 1:  # material of each element = its element block (Matilda[ebn] == ebn in the decks written here)
+        keep["elem_material"] = np.ascontiguousarray(m.elem_block, np.int32)
+        mats = (Material * p.num_materials)()
+        for k in range(p.num_materials):
+            d = problem.material(k)
+            mats[k].rho, mats[k].mu, mats[k].conductivity, mats[k].heat_capacity = d["rho"], d["mu"], d["k"], d["Cp"]
+            mats[k].volume_expansion, mats[k].reference_temperature = d["beta"], d["Tref"]
+            for w in range(4):
+                mats[k].diffusivity[w] = d["diffusivity"][w]
+            for a in range(3):
+                mats[k].momentum_source[a] = d["gravity"][a]
+            mats[k].momentum_source_model = {"CONSTANT": 0, "BOUSS": 1, "BOUSSINESQ": 2}[d["ns_source"]]
+            mats[k].heat_source = d["heat_source"]
+            mats[k].lame_mu, mats[k].lame_lambda = d["lame_mu"], d["lame_lambda"]
+        keep["materials"] = mats
+        p.elem_material = _ptr(keep["elem_material"], _ip)
+        p.materials = C.cast(mats, C.POINTER(Material))
     p.matrix_layout = {"msr": LAYOUT_MSR, "csr": LAYOUT_CSR}[layout]
     p.host_stream_chunks = int(host_stream_chunks)
     return p, keep

@@ -60,7 +60,10 @@ struct goma_gpu_ctx {
   long long a_len = 0;             // doubles in d_a: nnz_plus + 1 (MSR) or csr_nnz (CSR)
   int rss_max_row = -1;            // longest owned row (row-sum scaling sizes its staging buffer with it); -1 = not yet known
   int *d_dpos = nullptr;           // CSR layout: offset of the diagonal inside each owned row
-  int num_colours = 0;             // element colours; class = ((border ? nchunk : 0) + chunk) * ncol + colour
+  int num_colours = 0;             // classes per chunk = colours x materials; class = (((border ? nchunk : 0) + chunk) * ncol + colour) * nmat + material
+  int num_mats = 1;                // materials (goma_gpu_problem::num_materials, at least 1)
+  int *d_elem_mat = nullptr;       // [num_elems] material of each element (NULL with one material)
+  std::vector<goma_gpu_material> mats;  // host copy of goma_gpu_problem::materials
   int num_chunks = 1;              // chunks of consecutive elements swept one after the other (L2-sized; 1 = off)
   int chunk_elems = 0;             // elements per chunk in effect (pattern build)
   int chunk_elems_option = 0;      // "chunk_elems" option at init: 0 auto, > 0 elements per chunk, < 0 off

@@ -179,9 +179,17 @@ static int validate(const goma_gpu_problem &p) {
     return fail(-2, "P1 pressure needs a centroid node (QUAD9/HEX27)");
   if (p.num_owned_nodes < 0 || p.num_owned_nodes > p.num_nodes) return fail(-2, "num_owned_nodes out of range");
   if (p.num_nodes < 0 || p.num_elems < 0 || p.num_unknowns < 0) return fail(-2, "negative size in goma_gpu_problem");
-  // one element block / one material (find_elemblock_index + Matilda[ebn] of mm_fill.c:224-235 are not restated)
-  if (p.num_elem_blocks > 1) return fail(-2, "meshes with more than one element block are not supported by the GPU fill");
-  if (p.num_materials > 1) return fail(-2, "more than one material is not supported by the GPU fill");
+  // several element blocks / materials: one element type, one set of equations, constants per material (the header);
+  // a host with more than one block or material must say which element has which material
+  if (p.num_materials > 64) return fail(-2, "more than 64 materials");
+  if (p.num_materials > 1 && (!p.elem_material || !p.materials))
+    return fail(-2, "num_materials > 1 needs elem_material and materials (blocks of different element types or equations are not supported)");
+  if (p.num_elem_blocks > 1 && p.num_materials <= 1 && !p.elem_material)
+    return fail(-2, "several element blocks: state num_materials, elem_material and materials (Matilda[ebn], mm_fill.c:224-235)");
+  if (p.num_materials > 1)
+    for (int e = 0; e < p.num_elems; e++)
+      if (p.elem_material[e] < 0 || p.elem_material[e] >= p.num_materials)
+        return fail(-2, "elem_material[" + std::to_string(e) + "] out of range");
   if (p.matrix_layout != GOMA_GPU_LAYOUT_MSR && p.matrix_layout != GOMA_GPU_LAYOUT_CSR)
     return fail(-2, "matrix_layout must be GOMA_GPU_LAYOUT_MSR or GOMA_GPU_LAYOUT_CSR");
 
@@ -310,7 +318,7 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
   c->prob = p;
   c->device = device;
   if (const char *ce = getenv("GOMA_GPU_CHUNK_ELEMS")) c->chunk_elems_option = atoi(ce);  // experiments: 0 auto, < 0 off
-  const bool want_stream = p.host_stream_chunks > 1 && p.num_owned_nodes >= p.num_nodes && p.num_elems > 0;
+  const bool want_stream = p.host_stream_chunks > 1 && p.num_owned_nodes >= p.num_nodes && p.num_elems > 0;  // (materials: fine, a chunk ends after its last (colour, material) class)
   if (want_stream) c->chunk_elems_option = (p.num_elems + p.host_stream_chunks - 1) / p.host_stream_chunks;
   c->num_owned_unknowns = p.num_owned_nodes < p.num_nodes ? p.first_unknown[p.num_owned_nodes] : p.num_unknowns;
   const int nn = p.num_nodes, ne = p.num_elems, npe = p.elem_type, N = p.num_unknowns;
@@ -327,6 +335,13 @@ extern "C" int goma_gpu_fill_init(const goma_gpu_problem *problem, int device, g
   CU(cudaEventCreate(&c->ev1));
   CU(cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_pre, cudaEventDisableTiming));
+  if (p.num_materials > 1) {
+    c->num_mats = p.num_materials;
+    c->mats.assign(p.materials, p.materials + p.num_materials);
+    rc |= upload(&c->d_elem_mat, p.elem_material, (size_t)ne, c);
+    c->prob.elem_material = nullptr;  // (host arrays are not kept)
+    c->prob.materials = nullptr;
+  }
   rc |= upload(&c->d_conn, p.elem_connect, (size_t)ne * npe, c);
   rc |= upload(&c->d_first, p.first_unknown, nn, c);
   for (int d = 0; d < p.dim; d++) rc |= upload(&c->d_coord[d], p.coord[d], nn, c);
@@ -441,6 +456,7 @@ extern "C" void goma_gpu_fill_destroy(goma_gpu_ctx *c) {
   if (c->d_csr_dpos) cudaFree(c->d_csr_dpos);
   if (c->d_csr_values && c->d_csr_values != c->d_a) cudaFree(c->d_csr_values);
   if (c->d_dpos) cudaFree(c->d_dpos);
+  if (c->d_elem_mat) cudaFree(c->d_elem_mat);
   if (c->d_scale) cudaFree(c->d_scale);
   if (c->d_partials) cudaFree(c->d_partials);
   if (c->d_zero_rows) cudaFree(c->d_zero_rows);
@@ -651,7 +667,23 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
     }
     return 0;
   };
-  if (mode == 0) {
+  auto set_material = [&](int m) {  // the constants of material m (mp_glob[mn], elc_glob[mn]) for the next launch
+    if (c->num_mats <= 1) return;
+    const goma_gpu_material &M = c->mats[m];
+    P.rho = M.rho;
+    P.mu = M.mu;
+    P.k = M.conductivity;
+    P.Cp = M.heat_capacity;
+    P.beta = M.volume_expansion;
+    P.Tref = M.reference_temperature;
+    P.heat_source = M.heat_source;
+    for (int d = 0; d < 3; d++) P.g[d] = M.momentum_source[d];
+    P.source_model = M.momentum_source_model;
+    for (int w = 0; w < 4; w++) P.diffusivity[w] = M.diffusivity[w];
+    P.lame_mu = M.lame_mu;
+    P.lame_lambda = M.lame_lambda;
+  };
+  if (mode == 0 && c->num_mats <= 1) {
     if (int wrc = wait_for_exchange()) return wrc;
     P.elem_list = nullptr;
     P.elem_begin = 0;
@@ -671,6 +703,7 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
       P.elem_end = c->colour_begin[col + 1];
       int n = P.elem_end - P.elem_begin;
       if (n > 0) {
+        set_material((int)(col % (size_t)c->num_mats));
         int grid = std::max(1, std::min(max_grid, n));
         ke.fn<<<grid, ke.tpe, ke.smem, c->stream>>>(P);
         c->last_launches++;

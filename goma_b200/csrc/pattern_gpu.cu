@@ -230,9 +230,10 @@ __global__ void max_colour_kernel(int ne, const signed char *__restrict__ col, i
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m >= 0) atomicMax(maxc, m);
 }
-__global__ void class_kernel(int ne, int npe, int ncol, int nchunk, int chunk_elems, int num_owned_nodes, int split_border,
-                             const int *__restrict__ conn, const signed char *__restrict__ col, unsigned *__restrict__ cls,
-                             int *__restrict__ ids, int *__restrict__ hist) {
+__global__ void class_kernel(int ne, int npe, int ncol, int nmat, const int *__restrict__ elem_mat, int nchunk, int chunk_elems,
+                             int num_owned_nodes, int split_border, const int *__restrict__ conn,
+                             const signed char *__restrict__ col, unsigned *__restrict__ cls, int *__restrict__ ids,
+                             int *__restrict__ hist) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ne) return;
   bool border = false;
@@ -240,7 +241,9 @@ __global__ void class_kernel(int ne, int npe, int ncol, int nchunk, int chunk_el
     for (int i = 0; i < npe; i++) border = border || conn[(size_t)e * npe + i] >= num_owned_nodes;
   // processing order: interior elements before border elements (the ghost exchange overlaps the former); inside each,
   // chunks of consecutive elements whose matrix rows fit the L2 cache, one colour after the other
-  const int k = ((border ? nchunk : 0) + e / chunk_elems) * ncol + col[e];
+  // ... and inside a colour one material after the other: a launch covers one class, so it runs with the constants
+  // of ONE material (mp_glob[Matilda[ebn]], mm_fill.c:224-235) in its kernel parameters
+  const int k = (((border ? nchunk : 0) + e / chunk_elems) * ncol + col[e]) * nmat + (elem_mat ? elem_mat[e] : 0);
   cls[e] = (unsigned)k;
   ids[e] = e;
   atomicAdd(&hist[k], 1);
@@ -505,7 +508,8 @@ int build_pattern_device(goma_gpu_ctx *c) {
     if (on && want < ne) chunk_elems = (int)std::max<long long>(want, 1);
   }
   const int nchunk = ne > 0 ? (ne + chunk_elems - 1) / chunk_elems : 1;
-  const long long ncls_ll = (long long)ncol * nchunk * (split_border ? 2 : 1);
+  const int nmat = std::max(1, c->num_mats);
+  const long long ncls_ll = (long long)ncol * nmat * nchunk * (split_border ? 2 : 1);
   if (ncol > 63) return fail(-2, "element colouring needs more than 63 colours");
   if (ncls_ll > (1LL << 24)) return fail(-2, "too many (chunk, colour) classes");
   const int ncls = (int)ncls_ll;
@@ -517,7 +521,7 @@ int build_pattern_device(goma_gpu_ctx *c) {
   if (dev_alloc(&c->d_elem_list, (size_t)ne, c)) return -3;
   std::vector<int> hist(std::max(ncls, 1), 0);
   if (ne > 0) {
-    class_kernel<<<(ne + 255) / 256, 256, 0, st>>>(ne, npe, ncol, nchunk, chunk_elems, p.num_owned_nodes, split_border, c->d_conn, d_colour,
+    class_kernel<<<(ne + 255) / 256, 256, 0, st>>>(ne, npe, ncol, nmat, c->d_elem_mat, nchunk, chunk_elems, p.num_owned_nodes, split_border, c->d_conn, d_colour,
                                                    d.cls, d_ids, d_hist);
     unsigned *d_cls_out = nullptr;
     CU(cudaMalloc((void **)&d_cls_out, (size_t)ne * sizeof(unsigned)));
@@ -536,8 +540,8 @@ int build_pattern_device(goma_gpu_ctx *c) {
   cudaFree(d_hist);
   c->colour_begin.assign(ncls + 1, 0);
   for (int k = 0; k < ncls; k++) c->colour_begin[k + 1] = c->colour_begin[k] + hist[k];
-  c->first_border_class = split_border ? ncol * nchunk : ncls;
-  c->num_colours = ncol;
+  c->first_border_class = split_border ? ncol * nmat * nchunk : ncls;
+  c->num_colours = ncol * nmat;  // classes per chunk: (colour, material)
   c->num_chunks = nchunk;
   c->chunk_elems = chunk_elems;
 

@@ -16,6 +16,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass, field
 
+from typing import Optional
+
 import numpy as np
 
 # (s,t[,u]) lattice offsets in {0,1,2} of each local node
@@ -50,6 +52,13 @@ class Mesh:
     node_sets: dict = field(default_factory=dict)  # id -> sorted int32 node list
     shape: tuple = ()  # elements per direction
     lattice: tuple = ()  # nodes per direction
+    # element block of each element (exo->eb: blocks hold consecutive elements, so the array is non-decreasing);
+    # None = one block.  Block b carries material b of the Problem (Matilda[ebn] == ebn in the decks written here).
+    elem_block: Optional[np.ndarray] = None
+
+    @property
+    def num_elem_blocks(self) -> int:
+        return 1 if self.elem_block is None else int(self.elem_block.max()) + 1
 
     @property
     def num_nodes(self) -> int:

@@ -83,6 +83,34 @@ class Problem:
     pspg: Optional[str] = None  # None | "global" | "local"
     ps_scaling: float = 0.1
     bcs: list = field(default_factory=list)
+    # materials 1.. of a multi-block mesh (``mesh.elem_block``): dicts overriding the constants above (rho, mu, k, Cp,
+    # beta, Tref, diffusivity, gravity, ns_source, heat_source, lame_mu, lame_lambda); material 0 = the fields above.
+    # Same equations in every material (mp_glob[Matilda[ebn]] picked per element block, mm_fill.c:224-235).
+    extra_materials: list = field(default_factory=list)
+
+    MATERIAL_KEYS = ("rho", "mu", "k", "Cp", "beta", "Tref", "diffusivity", "gravity", "ns_source", "heat_source",
+                     "lame_mu", "lame_lambda")
+
+    @property
+    def num_materials(self) -> int:
+        return 1 + len(self.extra_materials)
+
+    def material(self, m: int) -> dict:
+        """Constants of material ``m`` (0 = the Problem's own fields)."""
+        d = {k: getattr(self, k) for k in self.MATERIAL_KEYS}
+        if m > 0:
+            unknown = set(self.extra_materials[m - 1]) - set(self.MATERIAL_KEYS)
+            if unknown:
+                raise ValueError(f"unknown material constants {sorted(unknown)}")
+            d.update(self.extra_materials[m - 1])
+        return d
+
+    def single_material(self, m: int):
+        """The same problem with material ``m``'s constants everywhere (no extra materials)."""
+        import dataclasses
+
+        mesh = dataclasses.replace(self.mesh, elem_block=None)
+        return dataclasses.replace(self, mesh=mesh, extra_materials=[], **self.material(m))
 
     # ------------------------------------------------------------------ layout
     @property
@@ -250,9 +278,7 @@ class Problem:
                 L.append(f"BC = Y NS {bc.ns_id} {bc.species} {bc.value!r}{relax}")
             else:
                 L.append(f"BC = {bc.var} NS {bc.ns_id} {bc.value!r}{relax}")
-        L += ["END OF BC", "", "Problem Description", "Number of Materials = 1", "MAT = fluid 1",
-              "Coordinate System = CARTESIAN", "Element Mapping = isoparametric",
-              f"Mesh Motion = ARBITRARY", f"Number of bulk species = {self.n_species}"]
+        L += ["END OF BC", "", "Problem Description", f"Number of Materials = {self.num_materials}"]
         eqs = []
         fm = lambda t: " ".join(repr(float(v)) for v in t)
         if self.ale:
@@ -265,11 +291,19 @@ class Problem:
         if self.n_species:
             eqs.append(f"EQ = species_bulk {q} Y {q} {fm(self.etm_species)}")
         eqs.append(f"EQ = continuity {pq} P {pq} {fm(self.etm_continuity)}")
-        L += [f"Number of EQ = {len(eqs)}"] + eqs + ["END OF EQ", "END OF MAT", "",
-              "Post Processing Specifications", "Stream Function = no", ""]
+        for m in range(self.num_materials):  # one MAT section per element block, the same equations in each
+            L += [f"MAT = {self.mat_name(m)} {m + 1}", "Coordinate System = CARTESIAN", "Element Mapping = isoparametric",
+                  "Mesh Motion = ARBITRARY", f"Number of bulk species = {self.n_species}",
+                  f"Number of EQ = {len(eqs)}"] + eqs + ["END OF EQ"]
+        L += ["END OF MAT", "", "Post Processing Specifications", "Stream Function = no", ""]
         return "\n".join(L)
 
-    def mat_file(self) -> str:
+    def mat_name(self, m: int) -> str:
+        return "fluid" if m == 0 else f"fluid{m + 1}"
+
+    def mat_file(self, m: int = 0) -> str:
+        if m > 0 or self.extra_materials:
+            return self.single_material(m).mat_file()
         g = self.gravity
         L = ["---Physical Properties", f"Density = CONSTANT {self.rho!r}",
              "---Mechanical Properties and Constitutive Equations",

@@ -67,6 +67,16 @@ enum {
 #define GOMA_PRESSURE_P1 1 /* discontinuous {1,s,t[,u]} on the centroid node (I_P1) */
 #define GOMA_PRESSURE_EQ 2 /* same basis as velocity (Q1/Q1, needs PSPG)            */
 
+/* mp_glob[mn] / elc_glob[mn] constants of one material (CONSTANT models only), see the fields of the same names below */
+struct goma_gpu_material {
+  double rho, mu, conductivity, heat_capacity, volume_expansion, reference_temperature;
+  double diffusivity[4];
+  double momentum_source[3];
+  int momentum_source_model;
+  double heat_source;
+  double lame_mu, lame_lambda;
+};
+
 /* Plain-C snapshot of the host state the element loop depends on. */
 struct goma_gpu_problem {
   /* mesh: Exo_DB / rd_mesh.c:397-507 globals */
@@ -120,11 +130,16 @@ struct goma_gpu_problem {
   const unsigned char *dbc_flag; /* [num_unknowns] 0 none, 1 residual = x - value, 2 hard set (residual 0) */
   const double *dbc_value; /* [num_unknowns] */
 
-  /* exo->num_elem_blocks and upd->Num_Mat of the host: the element loop here covers ONE element block with ONE
-   * material (find_elemblock_index / Matilda[ebn], src/mm_fill.c:224-235, are not restated); values > 1 are
-   * refused by goma_gpu_fill_init instead of being assembled with the wrong material.  0 = not stated. */
+  /* exo->num_elem_blocks and upd->Num_Mat of the host.  Several element blocks / materials are assembled when
+   * they share ONE element type and ONE set of active equations and differ in the material constants only (the
+   * reference's loop picks mp = mp_glob[Matilda[ebn]] per element block, src/mm_fill.c:224-235, 621-640):
+   * `materials[m]` then overrides the scalar constants above for the elements with elem_material[e] == m.
+   * With num_materials <= 1 (or 0 = not stated) both pointers may be NULL.  Anything else (blocks of different
+   * element types, materials with different equations) is refused by goma_gpu_fill_init. */
   int num_elem_blocks;
   int num_materials;
+  const int *elem_material;                 /* [num_elems] material index = Matilda[block of the element]; NULL = all 0 */
+  const struct goma_gpu_material *materials; /* [num_materials]; NULL = the scalar constants above for every element */
 
   /* Layout of the assembled values.  GOMA_GPU_LAYOUT_MSR (0): the reference's ams->val -- diagonal a[0..N), a[N]
    * unused, off-diagonals of row r at a[ija[r]..ija[r+1]) (src/mm_fill_util.c:2865-3031).  GOMA_GPU_LAYOUT_CSR (1):

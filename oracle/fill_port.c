@@ -108,10 +108,12 @@ static long msr_pos(const int *ija, int ie, int je) {
   return -1;
 }
 
-/* Returns 0, or -2 if a (row,col) the element block touches is missing from ija. */
-int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const double *x, const double *x_old,
-                   const double *xdot, double delta_t, double theta, double time_value, double h_elem_avg,
-                   double U_norm, int assemble_residual, int assemble_jacobian, double *a, double *resid) {
+/* Returns 0, or -2 if a (row,col) the element block touches is missing from ija.  `only_mat` >= 0 restricts the loop
+ * to the elements of that material (p then carries its constants). */
+static int port_fill_elems(const struct goma_gpu_problem *p, int only_mat, const int *elem_mat, const int *ija, const double *x,
+                           const double *x_old, const double *xdot, double delta_t, double theta, double time_value,
+                           double h_elem_avg, double U_norm, int assemble_residual, int assemble_jacobian, double *a,
+                           double *resid) {
   (void)x_old; (void)time_value;
   const int dim = p->dim, et = p->elem_type, nn = et;
   const int n1 = (et == 4 || et == 8) ? 2 : 3;
@@ -149,6 +151,7 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
   int rc = 0;
 
   for (int e = 0; e < p->num_elems; e++) {
+    if (only_mat >= 0 && elem_mat[e] != only_mat) continue;
     const int *c = p->elem_connect + (size_t)e * nn;
     double X[3][MAXN], U[MAXF][MAXN], Ud[MAXF][MAXN], Pd[4] = {0, 0, 0, 0};
     /* local dof numbering: dof(f,i) = f*nn + i ; P1 dofs = nf*nn + q */
@@ -552,4 +555,28 @@ int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const doubl
 done:
   free(R); free(J); free(gun); free(lnode);
   return rc;
+}
+
+/* The reference's element loop takes mp = mp_glob[Matilda[ebn]] per element block (mm_fill.c:224-235, 621-640).  Element
+ * blocks hold consecutive elements, so sweeping material by material adds the element contributions in the same order. */
+int goma_port_fill(const struct goma_gpu_problem *p, const int *ija, const double *x, const double *x_old,
+                   const double *xdot, double delta_t, double theta, double time_value, double h_elem_avg,
+                   double U_norm, int assemble_residual, int assemble_jacobian, double *a, double *resid) {
+  if (p->num_materials <= 1 || !p->materials || !p->elem_material)
+    return port_fill_elems(p, -1, NULL, ija, x, x_old, xdot, delta_t, theta, time_value, h_elem_avg, U_norm,
+                           assemble_residual, assemble_jacobian, a, resid);
+  for (int m = 0; m < p->num_materials; m++) {
+    struct goma_gpu_problem pm = *p;
+    const struct goma_gpu_material *M = &p->materials[m];
+    pm.rho = M->rho; pm.mu = M->mu; pm.conductivity = M->conductivity; pm.heat_capacity = M->heat_capacity;
+    pm.volume_expansion = M->volume_expansion; pm.reference_temperature = M->reference_temperature;
+    memcpy(pm.diffusivity, M->diffusivity, sizeof(pm.diffusivity));
+    memcpy(pm.momentum_source, M->momentum_source, sizeof(pm.momentum_source));
+    pm.momentum_source_model = M->momentum_source_model;
+    pm.heat_source = M->heat_source; pm.lame_mu = M->lame_mu; pm.lame_lambda = M->lame_lambda;
+    int rc = port_fill_elems(&pm, m, p->elem_material, ija, x, x_old, xdot, delta_t, theta, time_value, h_elem_avg, U_norm,
+                             assemble_residual, assemble_jacobian, a, resid);
+    if (rc) return rc;
+  }
+  return 0;
 }

@@ -62,6 +62,7 @@
 
 extern void fake_exodus_set_mesh(int, int, const double *, const double *, const double *, int, int,
                                  const char *, const int *, int, const int *, const int *, const int *);
+extern void fake_exodus_set_blocks(int, const int *);
 extern char **Argv;
 extern int Argc;
 extern double time_goma_started;
@@ -97,8 +98,16 @@ static void load_mesh(const char *fn) {
   double *x = xread(f, nn, 8), *y = dim > 1 ? xread(f, nn, 8) : NULL, *z = dim > 2 ? xread(f, nn, 8) : NULL;
   int *conn = xread(f, (size_t)ne * npe, 4);
   int *ns_ids = xread(f, nns, 4), *ns_ptr = xread(f, nns + 1, 4), *ns_nodes = xread(f, nsl, 4);
+  /* optional trailer: element blocks (consecutive elements), one material each */
+  int nb = 0, *counts = NULL;
+  if (fread(&nb, sizeof(int), 1, f) == 1 && nb > 0)
+    counts = xread(f, nb, 4);
+  else
+    nb = 0;
   fclose(f);
   fake_exodus_set_mesh(dim, nn, x, y, z, ne, npe, et, conn, nns, ns_ids, ns_ptr, ns_nodes);
+  if (nb > 0)
+    fake_exodus_set_blocks(nb, counts);
 }
 
 static Exo_DB *exo;

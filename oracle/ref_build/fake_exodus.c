@@ -14,7 +14,20 @@ struct fake_mesh {
   const int *conn; /* 1-based, num_elems*npe */
   int num_ns;
   const int *ns_ids, *ns_ptr, *ns_nodes; /* 1-based node ids */
+  int num_eb;          /* element blocks: block b (id b+1) = eb_count[b] consecutive elements */
+  const int *eb_count;
 } g_fake;
+
+void fake_exodus_set_blocks(int num_eb, const int *counts) {
+  g_fake.num_eb = num_eb;
+  g_fake.eb_count = counts;
+}
+static int eb_first(int blk_id) { /* first element of the block with id blk_id (1-based ids) */
+  int first = 0;
+  for (int b = 0; b + 1 < blk_id && b < g_fake.num_eb; b++) first += g_fake.eb_count[b];
+  return first;
+}
+static int eb_size(int blk_id) { return g_fake.num_eb ? g_fake.eb_count[blk_id - 1] : g_fake.num_elems; }
 
 void fake_exodus_set_mesh(int dim, int num_nodes, const double *x, const double *y, const double *z,
                           int num_elems, int npe, const char *elem_type, const int *conn,
@@ -40,7 +53,7 @@ int ex_get_init(int id, char *title, int *num_dim, int *num_nodes, int *num_elem
   (void)id;
   strcpy(title, "goma_b200 oracle in-memory mesh");
   *num_dim = g_fake.dim; *num_nodes = g_fake.num_nodes; *num_elems = g_fake.num_elems;
-  *num_eb = 1; *num_ns = g_fake.num_ns; *num_ss = 0;
+  *num_eb = g_fake.num_eb ? g_fake.num_eb : 1; *num_ns = g_fake.num_ns; *num_ss = 0;
   return 0;
 }
 int ex_inquire(int id, int what, int *ri, float *rf, char *rc) {
@@ -69,19 +82,19 @@ int ex_get_coord_names(int id, char **names) {
 }
 int ex_get_ids(int id, int type, int *ids) {
   (void)id;
-  if (type == EX_ELEM_BLOCK) ids[0] = 1;
+  if (type == EX_ELEM_BLOCK) for (int b = 0; b < (g_fake.num_eb ? g_fake.num_eb : 1); b++) ids[b] = b + 1;
   else if (type == EX_NODE_SET) for (int i = 0; i < g_fake.num_ns; i++) ids[i] = g_fake.ns_ids[i];
   return 0;
 }
 int ex_get_block(int id, int type, int blk, char *etype, int *nel, int *npe, int *nedge, int *nface, int *nattr) {
-  (void)id; (void)type; (void)blk; (void)nedge; (void)nface;
+  (void)id; (void)type; (void)nedge; (void)nface;
   strcpy(etype, g_fake.elem_type);
-  *nel = g_fake.num_elems; *npe = g_fake.npe; *nattr = 0;
+  *nel = eb_size(blk); *npe = g_fake.npe; *nattr = 0;
   return 0;
 }
 int ex_get_conn(int id, int type, int blk, int *conn, int *e, int *f) {
-  (void)id; (void)type; (void)blk; (void)e; (void)f;
-  memcpy(conn, g_fake.conn, (size_t)g_fake.num_elems * g_fake.npe * sizeof(int));
+  (void)id; (void)type; (void)e; (void)f;
+  memcpy(conn, g_fake.conn + (size_t)eb_first(blk) * g_fake.npe, (size_t)eb_size(blk) * g_fake.npe * sizeof(int));
   return 0;
 }
 int ex_get_concat_sets(int id, int type, ex_set_specs *s) {

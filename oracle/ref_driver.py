@@ -39,14 +39,24 @@ def write_mesh(mesh, path):
         f.write(np.array(ns_ids, np.int32).tobytes())
         f.write(np.array(ns_ptr, np.int32).tobytes())
         f.write(ns_nodes.tobytes())
+        # element blocks (optional trailer): count, then the number of (consecutive) elements of each block
+        eb = getattr(mesh, "elem_block", None)
+        if eb is not None:
+            eb = np.asarray(eb)
+            if (np.diff(eb) < 0).any():
+                raise ValueError("elements must be ordered block by block (EXODUS II stores them that way)")
+            counts = np.bincount(eb)
+            f.write(np.array([len(counts)], np.int32).tobytes())
+            f.write(counts.astype(np.int32).tobytes())
 
 
 def write_workdir(problem, workdir):
     os.makedirs(workdir, exist_ok=True)
     with open(os.path.join(workdir, "input"), "w") as f:
         f.write(problem.deck())
-    with open(os.path.join(workdir, "fluid.mat"), "w") as f:
-        f.write(problem.mat_file())
+    for m in range(getattr(problem, "num_materials", 1)):
+        with open(os.path.join(workdir, problem.mat_name(m) + ".mat"), "w") as f:
+            f.write(problem.mat_file(m))
     write_mesh(problem.mesh, os.path.join(workdir, "mesh.bin"))
 
 

@@ -147,10 +147,46 @@ def build_case(name):
             return Problem(m, interp="Q1Q1", pspg="local", ps_scaling=0.1, energy=True, n_species=2, rho=1.2, mu=0.3,
                            k=0.2, Cp=1.5, beta=0.4, Tref=0.2, diffusivity=(0.05, 0.11, 1.0, 1.0),
                            gravity=(0.1, -0.2, -1.0), ns_source="BOUSSINESQ", heat_source=0.3, bcs=bcs), {}
+    if name.startswith("mm_"):
+        # several element blocks, one material each (mp_glob[Matilda[ebn]], mm_fill.c:224-235): same equations,
+        # every constant different; blocks hold consecutive elements as in an EXODUS II file
+        def blocks(m, nb):
+            m.elem_block = (np.arange(m.num_elems) * nb // m.num_elems).astype(np.int32)
+            return m
+
+        if name == "mm_hex27_bouss_2mat":
+            m = blocks(box_mesh("HEX27", (2, 2, 3), perturb=0.12, seed=11), 2)
+            return Problem(m, energy=True, rho=1.1, mu=0.05, k=0.07, Cp=1.4, beta=0.8, Tref=0.3, gravity=(0.0, 0.1, -1.0),
+                           ns_source="BOUSSINESQ", heat_source=0.6, bcs=_bcs(3, True),
+                           extra_materials=[dict(rho=2.3, mu=0.4, k=0.31, Cp=0.9, beta=0.25, Tref=-0.2,
+                                                 gravity=(0.3, -0.2, -0.5), ns_source="BOUSS", heat_source=-0.4)]), {}
+        if name == "mm_quad9_ale_3mat":
+            m = blocks(box_mesh("QUAD9", (6, 3), lo=(0, 0), hi=(2, 1), perturb=0.1, seed=12), 3)
+            bcs = _bcs(2) + [Dirichlet("DX", 1, 0.0), Dirichlet("DY", 1, 0.0), Dirichlet("DY", 4, 0.02, relax=1.0)]
+            return Problem(m, ale=True, rho=1.3, mu=0.7, gravity=(0.3, -0.2, 0.0), lame_mu=0.9, lame_lambda=1.7, bcs=bcs,
+                           extra_materials=[dict(rho=0.6, mu=1.9, gravity=(0.0, -1.0, 0.0), lame_mu=2.5, lame_lambda=0.4),
+                                            dict(rho=3.0, mu=0.2, lame_mu=0.3, lame_lambda=3.1)]), {}
+        if name == "mm_hex8_pspg_2mat_transient":
+            m = blocks(box_mesh("HEX8", (3, 3, 2), perturb=0.12, seed=13), 2)
+            bcs = [Dirichlet("U", 1, 1.0), Dirichlet("V", 1, 0.0), Dirichlet("U", 4, 0.0, relax=1.0), Dirichlet("T", 1, 1.0),
+                   Dirichlet("Y", 2, 0.3, species=1), Dirichlet("P", 7, 0.0)]
+            return Problem(m, interp="Q1Q1", pspg="local", ps_scaling=0.1, energy=True, n_species=2, transient=True,
+                           etm_momentum=(1.0, 1.0, 1.0, 1.0, 1.0, 0.0), etm_energy=(1.0,) * 5, etm_species=(1.0,) * 5,
+                           rho=1.2, mu=0.3, k=0.2, Cp=1.5, beta=0.4, Tref=0.2, diffusivity=(0.05, 0.11, 1.0, 1.0),
+                           gravity=(0.1, -0.2, -1.0), ns_source="BOUSSINESQ", heat_source=0.3, bcs=bcs,
+                           extra_materials=[dict(rho=0.4, mu=1.1, k=0.9, Cp=0.6, beta=0.1, Tref=0.0,
+                                                 diffusivity=(0.4, 0.02, 1.0, 1.0), gravity=(0.0, 0.0, -0.3),
+                                                 heat_source=0.0)]), {"delta_t": 0.02, "theta": 0.5, "time": 0.1}
+        if name == "mm_hex27_star_2mat":
+            m = blocks(star_mesh("HEX27", refine=0, nz=2, perturb=0.3, seed=14), 2)
+            bcs = [Dirichlet("U", 1, 0.0), Dirichlet("V", 1, 0.5, relax=1.0), Dirichlet("W", 5, 0.0), Dirichlet("P", 7, 0.0)]
+            return Problem(m, rho=1.1, mu=0.3, gravity=(0.1, -0.2, 0.3), bcs=bcs,
+                           extra_materials=[dict(rho=4.0, mu=0.02, gravity=(0.0, 0.0, -2.0))]), {}
     raise KeyError(name)
 
 
-GOLDEN_CASES = ["irr_quad9_star_ns", "irr_hex27_star_bouss", "irr_hex8_star_pspg","c1_quad9_ns", "c1_quad9_ns_transient", "c2_hex27_ns", "c3_hex27_boussinesq",
+GOLDEN_CASES = ["mm_hex27_bouss_2mat", "mm_quad9_ale_3mat", "mm_hex8_pspg_2mat_transient", "mm_hex27_star_2mat",
+                "irr_quad9_star_ns", "irr_hex27_star_bouss", "irr_hex8_star_pspg","c1_quad9_ns", "c1_quad9_ns_transient", "c2_hex27_ns", "c3_hex27_boussinesq",
                 "c3_quad9_bouss_transient", "c5_hex8_pspg_local_transient", "c5_hex8_pspg_global",
                 "c5_quad4_pspg_local", "c4_quad9_ale", "c4_hex27_ale", "c4_quad9_ale_energy_transient",
                 "q2p1_quad9_species_ale_transient", "c2_hex27_ns_transient", "c4_hex27_ale_energy_transient",

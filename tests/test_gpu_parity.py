@@ -726,7 +726,8 @@ def test_gpu_zero_row_scaling_does_not_poison_later_fills(built):
 
 
 @pytest.mark.parametrize("name", ["c2_hex27_ns", "c3_hex27_boussinesq", "c5_hex8_pspg_global", "c4_quad9_ale",
-                                  "c1_quad9_ns_transient", "irr_hex27_star_bouss", "q2p1_quad9_species_ale_transient"])
+                                  "c1_quad9_ns_transient", "irr_hex27_star_bouss", "q2p1_quad9_species_ale_transient",
+                                  "mm_hex27_bouss_2mat", "mm_hex8_pspg_2mat_transient"])
 @pytest.mark.parametrize("scatter", [0, 2], ids=["atomic", "first_touch"])
 def test_gpu_csr_layout_is_assembled_in_place(built, name, scatter):
     """matrix_layout = CSR: the element blocks are scattered straight into the CSR value array (diagonal at its sorted
@@ -789,7 +790,8 @@ def test_gpu_csr_layout_is_assembled_in_place(built, name, scatter):
 @pytest.mark.gpu
 @pytest.mark.parametrize("layout", ["msr", "csr"])
 @pytest.mark.parametrize("name,chunks", [("c2_hex27_ns", 3), ("c3_hex27_boussinesq", 4), ("c5_hex8_pspg_global", 5),
-                                         ("irr_hex27_star_bouss", 2), ("c4_quad9_ale", 64)])
+                                         ("irr_hex27_star_bouss", 2), ("c4_quad9_ale", 64), ("mm_quad9_ale_3mat", 2),
+                                         ("mm_hex27_star_2mat", 3)])
 def test_gpu_host_stream_chunks_is_bit_identical(built, name, chunks, layout):
     """host_stream_chunks = K: the elements are swept chunk by chunk and finished rows are copied to the host under the
     assembly of the later chunks.  The order of the contributions to a slot changes with the class order, so the
@@ -824,3 +826,27 @@ def test_gpu_host_stream_chunks_is_bit_identical(built, name, chunks, layout):
     ad, _ = mf.download_system()
     np.testing.assert_array_equal(ad, a)
     mf.close()
+
+
+def test_gpu_materials_with_equal_constants_equal_one_material(built):
+    """Two element blocks whose materials carry the same constants: the launches are split by material, the values
+    must equal the one-material fill to the parity tolerance (the order of the contributions to a slot changes) and
+    the residual likewise; a material index out of range is refused."""
+    import dataclasses
+
+    p, kw, st = case_state("mm_hex27_bouss_2mat")
+    same = dataclasses.replace(p, extra_materials=[{}])
+    one = p.single_material(0)
+    mf2, mf1 = MatrixFill(same), MatrixFill(one)
+    _, a2, r2 = mf2.matrix_fill_full(st["x"])
+    _, a1, r1 = mf1.matrix_fill_full(st["x"])
+    assert_close(a2, a1, "two equal materials vs one", ija=mf1.export_msr())
+    assert_close(r2, r1, "residual")
+    _, nl2 = mf2.last_stats()
+    _, nl1 = mf1.last_stats()
+    assert nl2 > nl1  # one launch per (colour, material)
+    mf2.close()
+    mf1.close()
+    bad = dataclasses.replace(p, mesh=dataclasses.replace(p.mesh, elem_block=p.mesh.elem_block + 1))
+    with pytest.raises(RuntimeError, match="elem_material"):
+        MatrixFill(bad)
