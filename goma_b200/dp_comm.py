@@ -93,6 +93,8 @@ def decompose(problem: Problem, elem_rank: np.ndarray, nranks: int):
             loc = g2l[nodes]
             node_sets[k] = np.sort(loc[loc >= 0]).astype(np.int32)
         lmesh = Mesh(m.elem_type, m.dim, np.ascontiguousarray(m.coords[:, order]), conn, node_sets, m.shape, m.lattice)
+        if m.elem_block is not None:  # the material of an element travels with it (mp_glob[Matilda[ebn]])
+            lmesh.elem_block = np.ascontiguousarray(m.elem_block[le])
         sub = Subdomain(rank=r, problem=_sub_problem(problem, lmesh), num_owned_nodes=len(internal) + len(boundary),
                         num_internal_nodes=len(internal), node_global=order, elem_global=le,
                         elem_owned=owner_of_conn[le].min(axis=1) == r)

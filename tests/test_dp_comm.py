@@ -29,11 +29,18 @@ def _local_to_global_dofs(sub, first_g):
     return out
 
 
-@pytest.mark.parametrize("et,n,nranks", [("QUAD9", (6, 4), 2), ("QUAD9", (9, 3), 3), ("HEX27", (4, 2, 2), 2)])
-def test_subdomain_assembly_reproduces_global_rows(built, et, n, nranks):
+@pytest.mark.parametrize("et,n,nranks,nmat", [("QUAD9", (6, 4), 2, 1), ("QUAD9", (9, 3), 3, 1), ("HEX27", (4, 2, 2), 2, 1),
+                                              ("QUAD9", (6, 4), 3, 2)])
+def test_subdomain_assembly_reproduces_global_rows(built, et, n, nranks, nmat):
     """Each rank assembles all its local elements but loads only owned rows (mm_fill.c:5374); the
-    owned rows of all ranks together are exactly the global matrix and residual."""
+    owned rows of all ranks together are exactly the global matrix and residual.  With two materials (element blocks
+    cut across the slabs) every local element keeps the material of its block."""
     p = _problem(et, n)
+    if nmat > 1:
+        import dataclasses
+
+        p.mesh.elem_block = (np.arange(p.mesh.num_elems) % n[0] * nmat // n[0]).astype(np.int32)  # blocks = x ranges
+        p = dataclasses.replace(p, extra_materials=[dict(rho=2.7, mu=0.9, gravity=(0.0, -1.0, 0.0))])
     st = make_state(p, seed=3)
     first_g = p.unknown_map()[0]
     ija_g = capi.pattern_msr(p)
