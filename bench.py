@@ -563,6 +563,20 @@ def main():
         ms = min(ts[1:])
         post = {"row_sum_scale_ms": ms, "GB/s": 16.0 * nnz / ms / 1e6, "bytes": 16 * nnz,
                 "note": "row_sum_scaling_scale on device: one read + one write of the MSR values"}
+        # w = A v of the Newton line search (mm_sol_nonlinear.c:442-449) on the device-resident matrix: columns from
+        # the node-level neighbour lists, the values streamed once
+        vv = torch.ones(n_unk, dtype=torch.float64, device=dev)
+        ts = []
+        for _ in range(3):
+            ev0.record(st_lib)
+            mf.matvec(vv)
+            ev1.record(st_lib)
+            torch.cuda.synchronize(dev)
+            ts.append(ev0.elapsed_time(ev1))
+        post["matvec_ms"] = min(ts[1:])
+        post["matvec_GB/s"] = 8.0 * nnz / post["matvec_ms"] / 1e6
+        post["matvec_note"] = "goma_gpu_matvec: one read of the values (8 B per entry), no column-index array"
+        del vv
         # CSR hand-off to a GPU solver (§8f-2): structure once, values re-gathered after every fill
         free_b, _ = torch.cuda.mem_get_info(dev)
         if 12.0 * (nnz + n_unk) > 0.9 * free_b:  # colind + values

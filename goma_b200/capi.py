@@ -24,7 +24,7 @@ EXPORTED = [
     "goma_gpu_fill", "goma_gpu_fill_device_buffers", "goma_gpu_fill_device", "goma_gpu_global_h_U",
     "goma_gpu_pack_dofs", "goma_gpu_unpack_dofs", "goma_gpu_fill_last_stats", "goma_gpu_fill_set_option",
     "goma_gpu_last_error", "goma_gpu_pattern_msr", "goma_gpu_exchange_export", "goma_gpu_exchange_setup",
-    "goma_gpu_exchange_dof", "goma_gpu_row_sum_scale", "goma_gpu_scale_buffer", "goma_gpu_vector_norms", "goma_gpu_csr_structure",
+    "goma_gpu_exchange_dof", "goma_gpu_matvec", "goma_gpu_row_sum_scale", "goma_gpu_scale_buffer", "goma_gpu_vector_norms", "goma_gpu_csr_structure",
     "goma_gpu_csr_values", "goma_gpu_exchange_status", "goma_gpu_fill_device_async", "goma_gpu_fill_wait", "goma_gpu_fill_setup_stats",
     "goma_gpu_fill_value_count", "goma_gpu_csr_rows", "goma_gpu_node_graph", "goma_gpu_exchange_fence",
 ]
@@ -123,6 +123,7 @@ def load_library():
     lib.goma_gpu_exchange_status.argtypes = [C.c_void_p]
     lib.goma_gpu_exchange_fence.argtypes = [C.c_void_p, C.c_int]
     lib.goma_gpu_row_sum_scale.argtypes = [C.c_void_p, _dp, _ip]
+    lib.goma_gpu_matvec.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.goma_gpu_scale_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _ip]
     lib.goma_gpu_vector_norms.argtypes = [C.c_void_p, C.c_int, _dp]
     lib.goma_gpu_csr_structure.argtypes = [C.c_void_p, C.POINTER(GomaGpuProblem), C.POINTER(Csr)]

@@ -519,6 +519,89 @@ extern "C" int goma_gpu_csr_rows(goma_gpu_ctx *c, goma_gpu_csr *out) {
   return 0;
 }
 
+// ------------------------------------------------------------------ w = A v on the device-resident matrix
+// The product the Newton line search takes after a fill (mm_sol_nonlinear.c:442-449: AZ_MSR_matvec_mult for "msr",
+// GomaSparseMatrix::matrix_vector_mult otherwise).  No column-index array is read: all rows of a node share the node's
+// sorted neighbour list (exo_conn.c build_node_node) and their columns are the unknowns of those neighbours in node
+// order -- energy rows skip the pressure unknowns (Inter_Mask) -- so the indices cost 4 bytes per NODE pair instead of
+// 4 bytes per entry, and the pass streams the values once (8 bytes per entry).  One warp per row, lanes over the
+// neighbour nodes (column offsets by a warp scan of the neighbours' unknown counts); MSR: the diagonal lives in a[row]
+// and the entries behind it sit one slot earlier.
+template <bool CSR>
+__global__ void __launch_bounds__(256) node_graph_matvec_kernel(int num_owned_nodes, const long long *__restrict__ nn_ptr,
+                                                                const int *__restrict__ nn_list, const int *__restrict__ first_unknown,
+                                                                const unsigned char *__restrict__ node_kind,
+                                                                const __grid_constant__ KindInfo K, const long long *__restrict__ rowstart,
+                                                                long long msr0, const double *__restrict__ a,
+                                                                const double *__restrict__ v, double *__restrict__ w) {
+  const int lane = threadIdx.x & 31;
+  const int nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int nd = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; nd < num_owned_nodes; nd += nwarp) {
+    const int kd = node_kind[nd], fu = first_unknown[nd], nu = K.nunk[kd], ts = K.tslot[kd];
+    const long long b = nn_ptr[nd], e = nn_ptr[nd + 1];
+    for (int s = 0; s < nu; s++) {
+      const int row = fu + s;
+      const bool nop = ts >= 0 && s == ts;  // energy row: no pressure columns
+      const long long base = CSR ? rowstart[row] - msr0 + row : rowstart[row];
+      double sum = 0.0;
+      int carry = 0;  // columns of the neighbours before this group of 32
+      for (long long q0 = b; q0 < e; q0 += 32) {
+        const long long q = q0 + lane;
+        int m = -1, fm = 0, ncol = 0;
+        if (q < e) {
+          m = nn_list[q];
+          const int km = node_kind[m];
+          fm = first_unknown[m];
+          ncol = K.nunk[km] - (nop ? K.npress[km] : 0);
+        }
+        int incl = ncol;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int off = carry + incl - ncol;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+        if (CSR) {
+          for (int c = 0; c < ncol; c++) sum += a[base + off + c] * v[fm + c];
+        } else {
+          for (int c = 0; c < ncol; c++) {
+            const int col = fm + c;
+            const double val = col == row ? a[row] : a[base + off + c - (col > row ? 1 : 0)];
+            sum += val * v[col];
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) w[row] = sum;
+    }
+  }
+}
+
+extern "C" int goma_gpu_matvec(goma_gpu_ctx *c, const double *d_v, double *d_w) {
+  if (!c || !d_v || !d_w) return fail(-2, "null argument");
+  if (!c->dpat.nn_ptr || !c->dpat.nn_list) return fail(-2, "node-node lists are not resident");
+  CU(cudaSetDevice(c->device));
+  const int nown = c->prob.num_owned_nodes;
+  if (nown > 0) {
+    const KindInfo K = make_kind_info(c->prob);
+    const long long msr0 = (long long)c->prob.num_unknowns + 1;
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    const int blocks = std::max(1, std::min(sms * 8, (nown + 7) / 8));
+    if (c->layout == GOMA_GPU_LAYOUT_CSR)
+      node_graph_matvec_kernel<true><<<blocks, 256, 0, c->stream>>>(nown, c->dpat.nn_ptr, c->dpat.nn_list, c->d_first, c->d_kind, K,
+                                                                   c->d_rowstart, msr0, c->d_a, d_v, d_w);
+    else
+      node_graph_matvec_kernel<false><<<blocks, 256, 0, c->stream>>>(nown, c->dpat.nn_ptr, c->dpat.nn_list, c->d_first, c->d_kind, K,
+                                                                    c->d_rowstart, msr0, c->d_a, d_v, d_w);
+    CU(cudaGetLastError());
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 extern "C" int goma_gpu_node_graph(goma_gpu_ctx *c, long long **d_nn_ptr, int **d_nn_list) {
   if (!c) return fail(-2, "null context");
   if (!c->dpat.nn_ptr) return fail(-2, "node-node lists are not resident");

@@ -145,6 +145,18 @@ class MatrixFill:
                    "goma_gpu_row_sum_scale")
         return scale, int(zr.value)
 
+    def matvec(self, v):
+        """w = A v with the device-resident matrix of the last fill (``goma_gpu_matvec``; the product of the Newton line
+        search, ``mm_sol_nonlinear.c:442-449``).  ``v``: torch float64 CUDA tensor over all local unknowns; returns a
+        tensor of the same length whose owned rows hold the product (the others are zero)."""
+        import torch
+
+        assert v.is_cuda and v.dtype == torch.float64 and v.numel() == self.num_unknowns and v.is_contiguous()
+        w = torch.zeros_like(v)
+        torch.cuda.synchronize(v.device)
+        capi.check(self.lib.goma_gpu_matvec(self._ctx, C.c_void_p(v.data_ptr()), C.c_void_p(w.data_ptr())), "goma_gpu_matvec")
+        return w
+
     def vector_norms(self, which: int = 0):
         """(Loo, L1, L2, index) of the owned part of resid (0), x (1) or xdot (2) -- local values; a distributed
         host combines them with MPI_MAXLOC / MPI_SUM before the square root (``mm_sol_nonlinear.c:3177-3375``)."""

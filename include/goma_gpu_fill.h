@@ -252,6 +252,12 @@ int goma_gpu_csr_structure(goma_gpu_ctx *ctx, const struct goma_gpu_problem *pro
 int goma_gpu_csr_rows(goma_gpu_ctx *ctx, struct goma_gpu_csr *out);
 int goma_gpu_node_graph(goma_gpu_ctx *ctx, long long **d_nn_ptr, int **d_nn_list);
 int goma_gpu_csr_values(goma_gpu_ctx *ctx);
+/* w = A v with the device-resident matrix of the last fill (either layout): the product the Newton line search takes
+ * right after a fill (src/mm_sol_nonlinear.c:442-449, AZ_MSR_matvec_mult / GomaSparseMatrix::matrix_vector_mult,
+ * include/linalg/sparse_matrix.h:76-78).  d_v: device vector over all local unknowns (owned + external columns),
+ * d_w: device vector, the entries of the owned rows are written.  Needs no column-index array: the columns come
+ * from the node-level neighbour lists (goma_gpu_node_graph). */
+int goma_gpu_matvec(goma_gpu_ctx *ctx, const double *d_v, double *d_w);
 
 /* exchange_dof() (src/dp_comm.c:48-102) over NVLink peer memory, one rank per GPU of one node.
  * Every rank exports CUDA IPC handles of its state vectors and of a small flag block

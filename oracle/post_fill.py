@@ -43,3 +43,21 @@ def norms(v, N):
     for t in w:
         l1 += t
     return (float(w[k]) if N else -1.0), float(l1), float(np.sqrt(l2)), k
+
+
+def msr_matvec(N, a, ija, v):
+    """w = A v for the owned rows of an MSR matrix: the product of the Newton line search, src/mm_sol_nonlinear.c:442-446
+    (``AZ_MSR_matvec_mult``).  Aztec is a third-party dependency that is not vendored in the reference tree (AztecOO of
+    Trilinos, ``az_aztec.h``); its published algorithm (Aztec 2.1 user's guide, SAND99-8801J, section 3.1 "DMSR format";
+    ``az_matvec_mult.c``) is, per row i, ``val[i] * b[i] + sum_{k = bindx[i]}^{bindx[i+1]-1} val[k] * b[bindx[k]]`` with
+    the off-diagonals accumulated in storage order.  Parity unpinned against Aztec itself (no source, no vectors in the
+    reference); anchored on the reference's MSR graph and values of the fixtures."""
+    ija = np.asarray(ija, np.int64)
+    w = np.zeros(len(v))
+    for i in range(N):
+        acc = 0.0
+        for k in range(ija[i], ija[i + 1]):
+            acc += a[k] * v[ija[k]]
+        w[i] = a[i] * v[i] + acc
+    return w
+

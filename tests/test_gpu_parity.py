@@ -850,3 +850,43 @@ def test_gpu_materials_with_equal_constants_equal_one_material(built):
     bad = dataclasses.replace(p, mesh=dataclasses.replace(p.mesh, elem_block=p.mesh.elem_block + 1))
     with pytest.raises(RuntimeError, match="elem_material"):
         MatrixFill(bad)
+
+
+@pytest.mark.parametrize("layout", ["msr", "csr"])
+@pytest.mark.parametrize("name", ["c1_quad9_ns", "c3_hex27_boussinesq", "c5_hex8_pspg_global", "c4_quad9_ale_energy_transient",
+                                  "irr_hex27_star_bouss", "mm_hex8_pspg_2mat_transient"])
+def test_gpu_matvec_matches_msr_oracle(built, name, layout):
+    """w = A v on the device-resident matrix, columns taken from the node-level neighbour lists (no column-index array):
+    equals the MSR product of the Newton line search (mm_sol_nonlinear.c:442-446, oracle/post_fill.py::msr_matvec) on the
+    REFERENCE's graph and values -- energy rows (no pressure columns), P1 and equal-order pressure, ghost rows."""
+    import torch
+
+    from oracle import post_fill
+
+    p, kw, st = case_state(name)
+    g = golden(name)
+    n = len(g["resid"])
+    fkw = dict(delta_t=kw.get("delta_t", 0.0), theta=kw.get("theta", 0.0), time_value=kw.get("time", 0.0))
+    h, U = (p.global_h_elem_siz(), p.global_velocity_norm(st["x"])) if p.pspg else (0.0, 0.0)
+    args = (st["x"], st.get("x_old"), st.get("x_older"), st.get("xdot"), st.get("xdot_old"))
+    rng = np.random.default_rng(7)
+    v = rng.standard_normal(n)
+    want = post_fill.msr_matvec(n, g["a"], g["ija"], v)
+    rows = np.repeat(np.arange(n), np.diff(np.asarray(g["ija"][: n + 1], np.int64)))
+    rowscale = np.abs(g["a"][:n] * v)
+    np.add.at(rowscale, rows, np.abs(g["a"][n + 1: int(g["ija"][n])] * v[np.asarray(g["ija"][n + 1: int(g["ija"][n])], np.int64)]))
+    mf = MatrixFill(p, layout=layout)
+    err, _, _ = mf.matrix_fill_full(*args, h_elem_avg=h, U_norm=U, **fkw)
+    assert err == 0
+    w = mf.matvec(torch.from_numpy(v).cuda()).cpu().numpy()
+    assert (np.abs(w - want) <= 1e-12 * np.maximum(rowscale, 1e-300)).all(), "w = A v vs the MSR product of the reference values"
+    mf.close()
+    # owned rows only: the rows of ghost nodes are not written
+    owned = p.mesh.num_nodes - 5
+    n_owned = int(p.unknown_map()[0][owned])
+    mf = MatrixFill(p, num_owned_nodes=owned, layout=layout)
+    mf.matrix_fill_full(*args, h_elem_avg=h, U_norm=U, **fkw)
+    w = mf.matvec(torch.from_numpy(v).cuda()).cpu().numpy()
+    assert (np.abs(w[:n_owned] - want[:n_owned]) <= 1e-12 * np.maximum(rowscale[:n_owned], 1e-300)).all()
+    assert not w[n_owned:].any()
+    mf.close()
