@@ -528,6 +528,10 @@ extern "C" int goma_gpu_fill_set_option(goma_gpu_ctx *c, const char *name, int v
     c->exchange_spin_limit = (long long)std::max(1, value) * 2000000LL;
     return 0;
   }
+  if (!strcmp(name, "matvec_cap")) {  // goma_gpu_matvec: longest column list staged in shared memory (tests)
+    c->matvec_cap = value;
+    return 0;
+  }
   if (!strcmp(name, "rezero")) {  // the next first-touch fill zeroes the whole matrix / residual storage first
     c->rezero = value != 0;
     return 0;

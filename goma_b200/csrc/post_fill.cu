@@ -527,47 +527,133 @@ extern "C" int goma_gpu_csr_rows(goma_gpu_ctx *c, goma_gpu_csr *out) {
 // 4 bytes per entry, and the pass streams the values once (8 bytes per entry).  One warp per row, lanes over the
 // neighbour nodes (column offsets by a warp scan of the neighbours' unknown counts); MSR: the diagonal lives in a[row]
 // and the entries behind it sit one slot earlier.
+#define MV_WARPS 4    // warps per CTA, one node each
+#define MV_CAP 1024   // columns of a node's rows staged per warp (hex27 NS + energy: 532); longer lists take the slow path
 template <bool CSR>
-__global__ void __launch_bounds__(256) node_graph_matvec_kernel(int num_owned_nodes, const long long *__restrict__ nn_ptr,
-                                                                const int *__restrict__ nn_list, const int *__restrict__ first_unknown,
-                                                                const unsigned char *__restrict__ node_kind,
-                                                                const __grid_constant__ KindInfo K, const long long *__restrict__ rowstart,
-                                                                long long msr0, const double *__restrict__ a,
-                                                                const double *__restrict__ v, double *__restrict__ w) {
-  const int lane = threadIdx.x & 31;
-  const int nwarp = (gridDim.x * blockDim.x) >> 5;
-  for (int nd = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; nd < num_owned_nodes; nd += nwarp) {
+__global__ void __launch_bounds__(32 * MV_WARPS, 12) node_graph_matvec_kernel(int num_owned_nodes, const long long *__restrict__ nn_ptr,
+                                                                          const int *__restrict__ nn_list,
+                                                                          const int *__restrict__ first_unknown,
+                                                                          const unsigned char *__restrict__ node_kind,
+                                                                          const __grid_constant__ KindInfo K,
+                                                                          const long long *__restrict__ rowstart, long long msr0,
+                                                                          const double *__restrict__ a, const double *__restrict__ v,
+                                                                          double *__restrict__ w, int cap, int nlist) {
+  // the column list of the node's rows, expanded once per node into shared memory (all its rows share it; the energy
+  // row has its own, without the pressure unknowns): the values are then read in storage order, every byte once
+  extern __shared__ int cols_[];  // [MV_WARPS][2 (1 without an energy equation)][cap]
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  const int nwarp = gridDim.x * MV_WARPS;
+  int *colf = cols_ + (size_t)wl * nlist * cap, *coln = colf + (nlist > 1 ? cap : 0);
+  for (int nd = blockIdx.x * MV_WARPS + wl; nd < num_owned_nodes; nd += nwarp) {
     const int kd = node_kind[nd], fu = first_unknown[nd], nu = K.nunk[kd], ts = K.tslot[kd];
     const long long b = nn_ptr[nd], e = nn_ptr[nd + 1];
+    int totf = 0, totn = 0;  // columns of a full row / of the energy row
+    bool fits = true;
+    for (long long q0 = b; q0 < e; q0 += 32) {
+      const long long q = q0 + lane;
+      int fm = 0, nf = 0, np = 0;
+      if (q < e) {
+        const int m = nn_list[q], km = node_kind[m];
+        fm = first_unknown[m];
+        nf = K.nunk[km];
+        np = ts >= 0 ? K.npress[km] : 0;
+      }
+      int incf = nf, incp = np;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incf, o), u = __shfl_up_sync(0xffffffffu, incp, o);
+        if (lane >= o) {
+          incf += t;
+          incp += u;
+        }
+      }
+      const int of = totf + incf - nf, on = totn + (incf - incp) - (nf - np);
+      totf += __shfl_sync(0xffffffffu, incf, 31);
+      totn += __shfl_sync(0xffffffffu, incf - incp, 31);
+      fits = fits && totf <= cap;
+      if (fits) {
+        for (int c = 0; c < nf; c++) colf[of + c] = fm + c;
+        if (ts >= 0)
+          for (int c = 0; c < nf - np; c++) coln[on + c] = fm + c;
+      }
+    }
+    __syncwarp();
+    if (fits) {
+      // four rows of the node per sweep over the column list: one shared-memory read and one gather of v per column,
+      // four independent loads of a in flight per lane (the rows of a node are neighbours in memory)
+      for (int s0 = 0; s0 < nu; s0 += 4) {
+        long long base[4];
+        int rw[4];
+        bool on[4];
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const int sr = s0 + r;
+          on[r] = sr < nu && sr != ts;  // (the energy row has its own list, below)
+          rw[r] = fu + min(sr, nu - 1);
+          base[r] = CSR ? rowstart[rw[r]] - msr0 + rw[r] : rowstart[rw[r]];
+        }
+#pragma unroll 2
+        for (int t = lane; t < totf; t += 32) {
+          const int col = colf[t];
+          const double x = v[col];
+#pragma unroll
+          for (int r = 0; r < 4; r++) {
+            const long long idx = CSR ? base[r] + t : (col == rw[r] ? (long long)rw[r] : base[r] + t - (col > rw[r] ? 1 : 0));
+            if (on[r]) acc[r] += a[idx] * x;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          double sum = acc[r];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (lane == 0 && on[r]) w[rw[r]] = sum;
+        }
+      }
+      if (ts >= 0) {  // energy row: no pressure columns
+        const int row = fu + ts;
+        const long long base = CSR ? rowstart[row] - msr0 + row : rowstart[row];
+        double sum = 0.0;
+#pragma unroll 4
+        for (int t = lane; t < totn; t += 32) {
+          const int col = coln[t];
+          const long long idx = CSR ? base + t : (col == row ? (long long)row : base + t - (col > row ? 1 : 0));
+          sum += a[idx] * v[col];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) w[row] = sum;
+      }
+      __syncwarp();
+      continue;
+    }
     for (int s = 0; s < nu; s++) {
       const int row = fu + s;
       const bool nop = ts >= 0 && s == ts;  // energy row: no pressure columns
       const long long base = CSR ? rowstart[row] - msr0 + row : rowstart[row];
       double sum = 0.0;
-      int carry = 0;  // columns of the neighbours before this group of 32
-      for (long long q0 = b; q0 < e; q0 += 32) {
-        const long long q = q0 + lane;
-        int m = -1, fm = 0, ncol = 0;
-        if (q < e) {
-          m = nn_list[q];
-          const int km = node_kind[m];
-          fm = first_unknown[m];
-          ncol = K.nunk[km] - (nop ? K.npress[km] : 0);
-        }
-        int incl = ncol;
+      {  // slow path: lanes over the neighbour nodes, offsets by a warp scan per row
+        int carry = 0;
+        for (long long q0 = b; q0 < e; q0 += 32) {
+          const long long q = q0 + lane;
+          int fm = 0, ncol = 0;
+          if (q < e) {
+            const int m = nn_list[q], km = node_kind[m];
+            fm = first_unknown[m];
+            ncol = K.nunk[km] - (nop ? K.npress[km] : 0);
+          }
+          int incl = ncol;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const int off = carry + incl - ncol;
-        carry += __shfl_sync(0xffffffffu, incl, 31);
-        if (CSR) {
-          for (int c = 0; c < ncol; c++) sum += a[base + off + c] * v[fm + c];
-        } else {
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          const int off = carry + incl - ncol;
+          carry += __shfl_sync(0xffffffffu, incl, 31);
           for (int c = 0; c < ncol; c++) {
             const int col = fm + c;
-            const double val = col == row ? a[row] : a[base + off + c - (col > row ? 1 : 0)];
+            const double val = CSR ? a[base + off + c] : (col == row ? a[row] : a[base + off + c - (col > row ? 1 : 0)]);
             sum += val * v[col];
           }
         }
@@ -576,6 +662,7 @@ __global__ void __launch_bounds__(256) node_graph_matvec_kernel(int num_owned_no
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       if (lane == 0) w[row] = sum;
     }
+    __syncwarp();
   }
 }
 
@@ -589,13 +676,30 @@ extern "C" int goma_gpu_matvec(goma_gpu_ctx *c, const double *d_v, double *d_w) 
     const long long msr0 = (long long)c->prob.num_unknowns + 1;
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-    const int blocks = std::max(1, std::min(sms * 8, (nown + 7) / 8));
-    if (c->layout == GOMA_GPU_LAYOUT_CSR)
-      node_graph_matvec_kernel<true><<<blocks, 256, 0, c->stream>>>(nown, c->dpat.nn_ptr, c->dpat.nn_list, c->d_first, c->d_kind, K,
-                                                                   c->d_rowstart, msr0, c->d_a, d_v, d_w);
-    else
-      node_graph_matvec_kernel<false><<<blocks, 256, 0, c->stream>>>(nown, c->dpat.nn_ptr, c->dpat.nn_list, c->d_first, c->d_kind, K,
-                                                                    c->d_rowstart, msr0, c->d_a, d_v, d_w);
+    // staging buffer per warp: the longest column list of this matrix (an energy problem keeps a second list without
+    // the pressure unknowns); lists beyond MV_CAP columns take the path without shared memory
+    if (c->rss_max_row < 0) {
+      if (!c->d_zero_rows) CU(cudaMalloc((void **)&c->d_zero_rows, sizeof(int)));
+      CU(cudaMemsetAsync(c->d_zero_rows, 0, sizeof(int), c->stream));
+      max_row_len_kernel<<<std::min(1024, (c->num_owned_unknowns + 255) / 256), 256, 0, c->stream>>>(c->num_owned_unknowns, c->d_rowstart, c->d_zero_rows);
+      CU(cudaMemcpyAsync(&c->rss_max_row, c->d_zero_rows, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      if (c->layout == GOMA_GPU_LAYOUT_CSR) c->rss_max_row += 1;
+    }
+    const int longest = c->rss_max_row + (c->layout == GOMA_GPU_LAYOUT_CSR ? 0 : 1);  // columns of a row, diagonal included
+    int cap = std::min(MV_CAP, (longest + 3) & ~3);
+    if (c->matvec_cap > 0) cap = std::min(cap, c->matvec_cap);  // (option "matvec_cap": tests of the slow path)
+    const int nlist = c->prob.energy ? 2 : 1;
+    const size_t dyn = (size_t)MV_WARPS * nlist * cap * sizeof(int);
+    auto launch = [&](auto kern) -> int {
+      int per_sm = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)kern, 32 * MV_WARPS, dyn));
+      const int blocks = std::max(1, std::min(sms * std::max(per_sm, 1), (nown + MV_WARPS - 1) / MV_WARPS));
+      kern<<<blocks, 32 * MV_WARPS, dyn, c->stream>>>(nown, c->dpat.nn_ptr, c->dpat.nn_list, c->d_first, c->d_kind, K, c->d_rowstart, msr0,
+                                                       c->d_a, d_v, d_w, cap, nlist);
+      return 0;
+    };
+    if (int lrc = c->layout == GOMA_GPU_LAYOUT_CSR ? launch(node_graph_matvec_kernel<true>) : launch(node_graph_matvec_kernel<false>)) return lrc;
     CU(cudaGetLastError());
   }
   CU(cudaStreamSynchronize(c->stream));

@@ -880,6 +880,9 @@ def test_gpu_matvec_matches_msr_oracle(built, name, layout):
     assert err == 0
     w = mf.matvec(torch.from_numpy(v).cuda()).cpu().numpy()
     assert (np.abs(w - want) <= 1e-12 * np.maximum(rowscale, 1e-300)).all(), "w = A v vs the MSR product of the reference values"
+    mf.set_option("matvec_cap", 20)  # column lists longer than the staging buffer: the path without shared memory
+    w = mf.matvec(torch.from_numpy(v).cuda()).cpu().numpy()
+    assert (np.abs(w - want) <= 1e-12 * np.maximum(rowscale, 1e-300)).all(), "w = A v, unstaged path"
     mf.close()
     # owned rows only: the rows of ghost nodes are not written
     owned = p.mesh.num_nodes - 5
