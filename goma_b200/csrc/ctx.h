@@ -58,6 +58,7 @@ struct goma_gpu_ctx {
   long long nnz_plus = 0;          // == ija[N] of the MSR graph
   int layout = 0;                  // GOMA_GPU_LAYOUT_*: how d_a is laid out
   long long a_len = 0;             // doubles in d_a: nnz_plus + 1 (MSR) or csr_nnz (CSR)
+  int *d_work = nullptr;           // one hand-out counter per class launch (dynamic element distribution)
   int matvec_cap = 0;              // option "matvec_cap": columns staged per node in goma_gpu_matvec (0 = default)
   int rss_max_row = -1;            // longest owned row (row-sum scaling sizes its staging buffer with it); -1 = not yet known
   int *d_dpos = nullptr;           // CSR layout: offset of the diagonal inside each owned row

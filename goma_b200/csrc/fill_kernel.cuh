@@ -78,6 +78,8 @@ struct FillParams {
   int pspg;  // 0 off, 1 global, 2 local (calc_pspg)
   double ps_scaling;
   long long *prof;  // optional per-CTA phase cycle counters (profiling build), 8 per CTA
+  int *work;        // per-launch counter: the elements after the first static_rounds * gridDim.x are handed out dynamically (NULL: grid-stride)
+  int static_rounds;  // >= 1
   int debug;        // experiments only: bit0 = drop the matrix stores, bit1 = skip the Gauss loop
 };
 
@@ -233,6 +235,7 @@ struct alignas(16) Smem {
   unsigned long long mbar;
   unsigned long long mbar_rec[C::NRECB];
   unsigned long long full[2], empty[2];  // WS: operand buffer hand-off between builders and multipliers
+  int next_ee;  // index of the element this CTA takes next (dynamic hand-out)
 };
 
 static_assert(sizeof(double2) == 16, "double2 layout");
@@ -1840,22 +1843,35 @@ __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_cons
   long long stamps_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long *stamps = (P.prof && tid == 0) ? stamps_ : nullptr;
   int count = 0;
+  int pending = 0;  // (thread 0) the index the counter handed out for the element after the next
+  if (tid == 0 && P.work) pending = P.elem_begin + P.static_rounds * (int)gridDim.x + atomicAdd(P.work, 1);
 #pragma unroll 1
-  for (; ee < P.elem_end; ee += gridDim.x, count++) {
+  for (; ee < P.elem_end; count++) {
     const int buf = count & 1;
-    const bool has_next = ee + (int)gridDim.x < P.elem_end;
-    // the record of the next element starts its way into the other buffer (free since the barrier that
-    // closed the previous iteration)
-    if (has_next && tid == 0) {
-      const int nxt = P.elem_list ? P.elem_list[ee + gridDim.x] : ee + (int)gridDim.x;
-      mbar_expect_tx(&s.mbar_rec[buf ^ 1], REC_BYTES);
-      tma_bulk_g2s(&s.rec[buf ^ 1], P.erec + (size_t)nxt * REC_BYTES, REC_BYTES, &s.mbar_rec[buf ^ 1]);
+    // Which element comes next: the first static_rounds * gridDim.x elements of the launch are taken by block index,
+    // the rest from a counter, so that a CTA on a slower SM takes fewer elements and the launch ends without a tail (elements of one
+    // launch share no slot: the result does not depend on who assembles which).  The record of that element starts
+    // its way into the other buffer (free since the barrier that closed the previous iteration).
+    if (tid == 0) {
+      int nx = ee + (int)gridDim.x;              // the first static_rounds elements of a CTA go by block index ...
+      if (P.work && count + 1 >= P.static_rounds) {  // ... the later ones come from the counter, asked for one element
+        nx = pending;                                // ahead: the round trip of the atomic is over when it is needed
+        pending = P.elem_begin + P.static_rounds * (int)gridDim.x + atomicAdd(P.work, 1);
+      }
+      s.next_ee = nx;
+      if (nx < P.elem_end) {
+        const int nxt = P.elem_list ? P.elem_list[nx] : nx;
+        mbar_expect_tx(&s.mbar_rec[buf ^ 1], REC_BYTES);
+        tma_bulk_g2s(&s.rec[buf ^ 1], P.erec + (size_t)nxt * REC_BYTES, REC_BYTES, &s.mbar_rec[buf ^ 1]);
+      }
     }
     long long c0 = GOMA_CLOCK();
     build_element<C>(P, s, buf, 0, tid, stamps);
     long long c1 = GOMA_CLOCK();
     element_rows<C>(P, s, buf, 0, tid);
     long long c2 = GOMA_CLOCK();
+    const int ee_next = s.next_ee;  // (written before the barriers of the phases above)
+    const bool has_next = ee_next < P.elem_end;
     // ... and, once it has landed, the gather of the next element's unknowns runs under the Gauss loop
     if (has_next) {
       mbar_wait(&s.mbar_rec[buf ^ 1], ((count + 1) >> 1) & 1);
@@ -1892,6 +1908,7 @@ __global__ void __launch_bounds__(C::TPE, C::MINB) fill_kernel(const __grid_cons
     }
     cp_async_wait_all();
     __syncthreads();
+    ee = ee_next;
     t_loop += GOMA_CLOCK() - c2;
     t_build += c1 - c0;
     t_rows += c2 - c1;

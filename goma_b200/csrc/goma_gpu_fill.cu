@@ -457,6 +457,7 @@ extern "C" void goma_gpu_fill_destroy(goma_gpu_ctx *c) {
   if (c->d_csr_values && c->d_csr_values != c->d_a) cudaFree(c->d_csr_values);
   if (c->d_dpos) cudaFree(c->d_dpos);
   if (c->d_elem_mat) cudaFree(c->d_elem_mat);
+  if (c->d_work) cudaFree(c->d_work);
   if (c->d_scale) cudaFree(c->d_scale);
   if (c->d_partials) cudaFree(c->d_partials);
   if (c->d_zero_rows) cudaFree(c->d_zero_rows);
@@ -671,6 +672,16 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
     }
     return 0;
   };
+  // dynamic hand-out of the elements inside a launch (fill_kernel): one counter per class, zeroed here
+  static const bool static_stride = getenv("GOMA_GPU_STATIC") && atoi(getenv("GOMA_GPU_STATIC")) != 0;  // A/B runs
+  // share of a launch handed out by block index before the counter takes over (per cent)
+  static const int static_pct = getenv("GOMA_GPU_STATIC_PCT") ? std::max(0, std::min(100, atoi(getenv("GOMA_GPU_STATIC_PCT")))) : 75;
+  const size_t nctr = std::max<size_t>(c->colour_begin.size(), 2);
+  if (!static_stride) {
+    if (!c->d_work) CU(cudaMalloc((void **)&c->d_work, nctr * sizeof(int)));
+    CU(cudaMemsetAsync(c->d_work, 0, nctr * sizeof(int), c->stream));
+  }
+  P.work = nullptr;
   auto set_material = [&](int m) {  // the constants of material m (mp_glob[mn], elc_glob[mn]) for the next launch
     if (c->num_mats <= 1) return;
     const goma_gpu_material &M = c->mats[m];
@@ -693,6 +704,8 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
     P.elem_begin = 0;
     P.elem_end = p.num_elems;
     int grid = std::max(1, std::min(max_grid, p.num_elems));
+    P.work = static_stride ? nullptr : c->d_work;
+    P.static_rounds = std::max(1, (int)((long long)static_pct * p.num_elems / 100 / grid));
     ke.fn<<<grid, ke.tpe, ke.smem, c->stream>>>(P);
     c->last_launches++;
   } else {
@@ -708,7 +721,9 @@ static int launch_fill(goma_gpu_ctx *c, double delta_t, double theta, double tim
       int n = P.elem_end - P.elem_begin;
       if (n > 0) {
         set_material((int)(col % (size_t)c->num_mats));
+        P.work = static_stride ? nullptr : c->d_work + col;
         int grid = std::max(1, std::min(max_grid, n));
+        P.static_rounds = std::max(1, (int)((long long)static_pct * n / 100 / grid));
         ke.fn<<<grid, ke.tpe, ke.smem, c->stream>>>(P);
         c->last_launches++;
       }
