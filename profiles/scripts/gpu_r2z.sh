@@ -2,7 +2,7 @@
 # r2z: dynamic hand-out of the elements inside a launch against the grid-stride distribution
 O=gpurun_out/r2z; mkdir -p $O
 python -m pytest tests/test_gpu_parity.py -q -x -k "fixture or reproducible or full_size or tiny or ghost" > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest.log
-for st in 0 0; do
+for st in 0 1 0 1; do
 GOMA_GPU_STATIC=$st python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > $O/bench_static${st}_$RANDOM.json 2>> $O/bench.err
 done
 python - <<'PY'
