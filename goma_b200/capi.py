@@ -223,6 +223,8 @@ def make_problem_struct(problem, ija=None, num_owned_nodes=None, layout="msr", h
     p.lame_mu, p.lame_lambda = problem.lame_mu, problem.lame_lambda
     p.dbc_flag = _ptr(keep["dbc_flag"], _bp)
     p.dbc_value = _ptr(keep["dbc_value"], _dp)
+    if getattr(problem, "extra_bc_cards", None):
+        raise GomaGpuError("integrated boundary conditions (BC cards on side sets) are not assembled by the GPU fill (SURVEY.md §8f-3)")
     p.num_elem_blocks = int(getattr(m, "num_elem_blocks", 1))
     p.num_materials = int(getattr(problem, "num_materials", 1))
     if p.num_materials > 1:  # material of each element = its element block (Matilda[ebn] == ebn in the decks written here)

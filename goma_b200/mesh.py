@@ -55,6 +55,9 @@ class Mesh:
     # element block of each element (exo->eb: blocks hold consecutive elements, so the array is non-decreasing);
     # None = one block.  Block b carries material b of the Problem (Matilda[ebn] == ebn in the decks written here).
     elem_block: Optional[np.ndarray] = None
+    # side sets (exo->ss_*): id -> (elements [k] 0-based, EXODUS II side numbers [k] 1-based); the reference's integrated
+    # boundary conditions (BC = ... SS <id>) hang off them.  Only the reference driver of the oracle consumes them so far.
+    side_sets: dict = field(default_factory=dict)
 
     @property
     def num_elem_blocks(self) -> int:
@@ -121,7 +124,18 @@ def box_mesh(elem_type: str, n, lo=None, hi=None, perturb: float = 0.0, seed: in
         for d in range(dim):
             h = (hi[d] - lo[d]) / (lat[d] - 1)
             coords[d, interior] += perturb * h * rng.uniform(-1, 1, interior.sum())
-    return Mesh(elem_type, dim, np.ascontiguousarray(coords), conn, node_sets, n, lat)
+    # side sets with the ids of the node sets 1..6: the element sides on that face of the box (EXODUS II side numbers of
+    # QUAD: 1 bottom, 2 right, 3 top, 4 left; HEX: 1 y-min, 2 x-max, 3 y-max, 4 x-min, 5 z-min, 6 z-max)
+    side_of = {2: {1: 4, 2: 2, 3: 1, 4: 3}, 3: {1: 4, 2: 2, 3: 1, 4: 3, 5: 5, 6: 6}}[dim]
+    side_sets = {}
+    eid = np.arange(conn.shape[0])
+    for d in range(dim):
+        for hi_side in (0, 1):
+            sel = eid[idx[d] == (n[d] - 1 if hi_side else 0)]
+            side_sets[2 * d + 1 + hi_side] = (sel.astype(np.int32), np.full(len(sel), side_of[2 * d + 1 + hi_side], np.int32))
+    m = Mesh(elem_type, dim, np.ascontiguousarray(coords), conn, node_sets, n, lat)
+    m.side_sets = side_sets
+    return m
 
 
 def patch_mesh(elem_type: str, verts, quads, refine: int = 0, nz: int = 0, height: float = 1.0) -> Mesh:

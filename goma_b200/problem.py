@@ -87,6 +87,9 @@ class Problem:
     # beta, Tref, diffusivity, gravity, ns_source, heat_source, lame_mu, lame_lambda); material 0 = the fields above.
     # Same equations in every material (mp_glob[Matilda[ebn]] picked per element block, mm_fill.c:224-235).
     extra_materials: list = field(default_factory=list)
+    # raw ``BC = ...`` cards of conditions the GPU path does not assemble (integrated conditions on side sets):
+    # written into the deck for the reference driver of the oracle; the C-ABI marshalling refuses such a problem
+    extra_bc_cards: list = field(default_factory=list)
 
     MATERIAL_KEYS = ("rho", "mu", "k", "Cp", "beta", "Tref", "diffusivity", "gravity", "ns_source", "heat_source",
                      "lame_mu", "lame_lambda")
@@ -271,13 +274,14 @@ class Problem:
         if self.pspg:
             L += [f"Pressure Stabilization = {'yes' if self.pspg == 'global' else 'local'}",
                   f"Pressure Stabilization Scaling = {self.ps_scaling!r}"]
-        L += ["", "Boundary Condition Specifications", f"Number of BC = {len(self.bcs)}"]
+        L += ["", "Boundary Condition Specifications", f"Number of BC = {len(self.bcs) + len(self.extra_bc_cards)}"]
         for bc in self.bcs:
             relax = "" if bc.relax is None else f" {bc.relax!r}"
             if bc.var == "Y":
                 L.append(f"BC = Y NS {bc.ns_id} {bc.species} {bc.value!r}{relax}")
             else:
                 L.append(f"BC = {bc.var} NS {bc.ns_id} {bc.value!r}{relax}")
+        L += list(self.extra_bc_cards)
         L += ["END OF BC", "", "Problem Description", f"Number of Materials = {self.num_materials}"]
         eqs = []
         fm = lambda t: " ".join(repr(float(v)) for v in t)

@@ -63,6 +63,7 @@
 extern void fake_exodus_set_mesh(int, int, const double *, const double *, const double *, int, int,
                                  const char *, const int *, int, const int *, const int *, const int *);
 extern void fake_exodus_set_blocks(int, const int *);
+extern void fake_exodus_set_side_sets(int, const int *, const int *, const int *, const int *);
 extern char **Argv;
 extern int Argc;
 extern double time_goma_started;
@@ -100,14 +101,25 @@ static void load_mesh(const char *fn) {
   int *ns_ids = xread(f, nns, 4), *ns_ptr = xread(f, nns + 1, 4), *ns_nodes = xread(f, nsl, 4);
   /* optional trailer: element blocks (consecutive elements), one material each */
   int nb = 0, *counts = NULL;
-  if (fread(&nb, sizeof(int), 1, f) == 1 && nb > 0)
-    counts = xread(f, nb, 4);
-  else
+  if (fread(&nb, sizeof(int), 1, f) == 1) {
+    if (nb > 0) counts = xread(f, nb, 4);
+  } else
     nb = 0;
+  /* second optional trailer: side sets -- count, ids, ptr[count+1], then 1-based element and EXODUS side numbers */
+  int nss = 0, *ss_ids = NULL, *ss_ptr = NULL, *ss_elem = NULL, *ss_side = NULL;
+  if (fread(&nss, sizeof(int), 1, f) == 1 && nss > 0) {
+    ss_ids = xread(f, nss, 4);
+    ss_ptr = xread(f, nss + 1, 4);
+    ss_elem = xread(f, ss_ptr[nss], 4);
+    ss_side = xread(f, ss_ptr[nss], 4);
+  } else
+    nss = 0;
   fclose(f);
   fake_exodus_set_mesh(dim, nn, x, y, z, ne, npe, et, conn, nns, ns_ids, ns_ptr, ns_nodes);
   if (nb > 0)
     fake_exodus_set_blocks(nb, counts);
+  if (nss > 0)
+    fake_exodus_set_side_sets(nss, ss_ids, ss_ptr, ss_elem, ss_side);
 }
 
 static Exo_DB *exo;

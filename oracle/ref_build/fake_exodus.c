@@ -16,7 +16,51 @@ struct fake_mesh {
   const int *ns_ids, *ns_ptr, *ns_nodes; /* 1-based node ids */
   int num_eb;          /* element blocks: block b (id b+1) = eb_count[b] consecutive elements */
   const int *eb_count;
+  int num_ss;          /* side sets: ss_ptr[i]..ss_ptr[i+1] index ss_elem (1-based element) / ss_side (1-based EXODUS side) */
+  const int *ss_ids, *ss_ptr, *ss_elem, *ss_side;
 } g_fake;
+
+void fake_exodus_set_side_sets(int num_ss, const int *ids, const int *ptr, const int *elem, const int *side) {
+  g_fake.num_ss = num_ss; g_fake.ss_ids = ids; g_fake.ss_ptr = ptr; g_fake.ss_elem = elem; g_fake.ss_side = side;
+}
+/* nodes of one element side in EXODUS II order (corners counter-clockwise seen from outside, then the mid-side /
+ * mid-face nodes), as local 0-based node numbers; returns the count */
+static int side_nodes(int side, int *ln) {
+  const int s = side - 1;
+  if (g_fake.dim == 2) {
+    ln[0] = s; ln[1] = (s + 1) % 4;
+    if (g_fake.npe == 9) { ln[2] = 4 + s; return 3; }
+    return 2;
+  }
+  static const int hexc[6][4] = {{0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {0, 4, 7, 3}, {0, 3, 2, 1}, {4, 5, 6, 7}};
+  static const int hexm[6][5] = {{8, 13, 16, 12, 25}, {9, 14, 17, 13, 24}, {10, 15, 18, 14, 26},
+                                 {12, 19, 15, 11, 23}, {11, 10, 9, 8, 21}, {16, 17, 18, 19, 22}};
+  for (int k = 0; k < 4; k++) ln[k] = hexc[s][k];
+  if (g_fake.npe == 27) { for (int k = 0; k < 5; k++) ln[4 + k] = hexm[s][k]; return 9; }
+  return 4;
+}
+static int ss_index(int ss_id) {
+  for (int i = 0; i < g_fake.num_ss; i++) if (g_fake.ss_ids[i] == ss_id) return i;
+  return -1;
+}
+int ex_get_side_set_node_list_len(int id, int ss_id, int *len) {
+  (void)id;
+  int ln[9], i = ss_index(ss_id);
+  *len = i < 0 ? 0 : (g_fake.ss_ptr[i + 1] - g_fake.ss_ptr[i]) * side_nodes(1, ln);
+  return 0;
+}
+int ex_get_side_set_node_list(int id, int ss_id, int *cnt, int *list) {
+  (void)id;
+  int i = ss_index(ss_id), pos = 0;
+  if (i < 0) return -1;
+  for (int k = g_fake.ss_ptr[i]; k < g_fake.ss_ptr[i + 1]; k++) {
+    int ln[9], n = side_nodes(g_fake.ss_side[k], ln);
+    const int *c = g_fake.conn + (size_t)(g_fake.ss_elem[k] - 1) * g_fake.npe;
+    cnt[k - g_fake.ss_ptr[i]] = n;
+    for (int q = 0; q < n; q++) list[pos++] = c[ln[q]];
+  }
+  return 0;
+}
 
 void fake_exodus_set_blocks(int num_eb, const int *counts) {
   g_fake.num_eb = num_eb;
@@ -53,7 +97,7 @@ int ex_get_init(int id, char *title, int *num_dim, int *num_nodes, int *num_elem
   (void)id;
   strcpy(title, "goma_b200 oracle in-memory mesh");
   *num_dim = g_fake.dim; *num_nodes = g_fake.num_nodes; *num_elems = g_fake.num_elems;
-  *num_eb = g_fake.num_eb ? g_fake.num_eb : 1; *num_ns = g_fake.num_ns; *num_ss = 0;
+  *num_eb = g_fake.num_eb ? g_fake.num_eb : 1; *num_ns = g_fake.num_ns; *num_ss = g_fake.num_ss;
   return 0;
 }
 int ex_inquire(int id, int what, int *ri, float *rf, char *rc) {
@@ -62,6 +106,9 @@ int ex_inquire(int id, int what, int *ri, float *rf, char *rc) {
   switch (what) {
   case EX_INQ_API_VERS: case EX_INQ_DB_VERS: *rf = 8.03f; break;
   case EX_INQ_NS_NODE_LEN: *ri = g_fake.num_ns ? g_fake.ns_ptr[g_fake.num_ns] : 0; break;
+  case EX_INQ_SS_ELEM_LEN: *ri = g_fake.num_ss ? g_fake.ss_ptr[g_fake.num_ss] : 0; break;
+  case EX_INQ_SS_NODE_LEN: { int ln[9]; *ri = g_fake.num_ss ? g_fake.ss_ptr[g_fake.num_ss] * side_nodes(1, ln) : 0; break; }
+  case EX_INQ_SS_DF_LEN: *ri = 0; break;
   default: break; /* no QA, info, dist-factors, side sets, properties, time planes */
   }
   return 0;
@@ -84,6 +131,7 @@ int ex_get_ids(int id, int type, int *ids) {
   (void)id;
   if (type == EX_ELEM_BLOCK) for (int b = 0; b < (g_fake.num_eb ? g_fake.num_eb : 1); b++) ids[b] = b + 1;
   else if (type == EX_NODE_SET) for (int i = 0; i < g_fake.num_ns; i++) ids[i] = g_fake.ns_ids[i];
+  else if (type == EX_SIDE_SET) for (int i = 0; i < g_fake.num_ss; i++) ids[i] = g_fake.ss_ids[i];
   return 0;
 }
 int ex_get_block(int id, int type, int blk, char *etype, int *nel, int *npe, int *nedge, int *nface, int *nattr) {
@@ -99,6 +147,20 @@ int ex_get_conn(int id, int type, int blk, int *conn, int *e, int *f) {
 }
 int ex_get_concat_sets(int id, int type, ex_set_specs *s) {
   (void)id;
+  if (type == EX_SIDE_SET) {
+    int *ids = s->sets_ids, *cnt = s->num_entries_per_set, *ndf = s->num_dist_per_set;
+    int *idx = s->sets_entry_index, *dfi = s->sets_dist_index, *lst = s->sets_entry_list, *ext = s->sets_extra_list;
+    for (int i = 0; i < g_fake.num_ss; i++) {
+      ids[i] = g_fake.ss_ids[i];
+      cnt[i] = g_fake.ss_ptr[i + 1] - g_fake.ss_ptr[i];
+      ndf[i] = 0; idx[i] = g_fake.ss_ptr[i]; dfi[i] = 0;
+    }
+    if (g_fake.num_ss) {
+      memcpy(lst, g_fake.ss_elem, (size_t)g_fake.ss_ptr[g_fake.num_ss] * sizeof(int));
+      memcpy(ext, g_fake.ss_side, (size_t)g_fake.ss_ptr[g_fake.num_ss] * sizeof(int));
+    }
+    return 0;
+  }
   if (type != EX_NODE_SET) return 0;
   int *ids = s->sets_ids, *cnt = s->num_entries_per_set, *ndf = s->num_dist_per_set;
   int *idx = s->sets_entry_index, *dfi = s->sets_dist_index, *lst = s->sets_entry_list;

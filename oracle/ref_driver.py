@@ -41,6 +41,7 @@ def write_mesh(mesh, path):
         f.write(ns_nodes.tobytes())
         # element blocks (optional trailer): count, then the number of (consecutive) elements of each block
         eb = getattr(mesh, "elem_block", None)
+        ss = getattr(mesh, "side_sets", None) or {}
         if eb is not None:
             eb = np.asarray(eb)
             if (np.diff(eb) < 0).any():
@@ -48,6 +49,17 @@ def write_mesh(mesh, path):
             counts = np.bincount(eb)
             f.write(np.array([len(counts)], np.int32).tobytes())
             f.write(counts.astype(np.int32).tobytes())
+        elif ss:
+            f.write(np.array([0], np.int32).tobytes())
+        # side sets (second optional trailer): id -> (elements, EXODUS side numbers 1..), both 0-based here / 1-based on file
+        if ss:
+            ids = sorted(ss)
+            ptr = np.cumsum([0] + [len(ss[k][0]) for k in ids]).astype(np.int32)
+            f.write(np.array([len(ids)], np.int32).tobytes())
+            f.write(np.array(ids, np.int32).tobytes())
+            f.write(ptr.tobytes())
+            f.write((np.concatenate([np.asarray(ss[k][0]) for k in ids]) + 1).astype(np.int32).tobytes())
+            f.write(np.concatenate([np.asarray(ss[k][1]) for k in ids]).astype(np.int32).tobytes())
 
 
 def write_workdir(problem, workdir):

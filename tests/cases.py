@@ -182,8 +182,22 @@ def build_case(name):
             bcs = [Dirichlet("U", 1, 0.0), Dirichlet("V", 1, 0.5, relax=1.0), Dirichlet("W", 5, 0.0), Dirichlet("P", 7, 0.0)]
             return Problem(m, rho=1.1, mu=0.3, gravity=(0.1, -0.2, 0.3), bcs=bcs,
                            extra_materials=[dict(rho=4.0, mu=0.02, gravity=(0.0, 0.0, -2.0))]), {}
+    if name == "f3_quad9_free_surface":
+        # SURVEY.md §8f-3, reference side only: the C4 strip with a free surface on top (KINEMATIC on the mesh normal,
+        # CAPILLARY traction) and a slip wall below (VELO_NORMAL) -- integrated conditions on side sets, applied by the
+        # reference's apply_integrated_bc (mm_fill.c:2945-3033, bc_integ.c) incl. the rotation of the equations.  The
+        # GPU path does not assemble them yet; the fixture pins WHICH rows they change and what they must become.
+        import dataclasses
+
+        p, kw = build_case("c4_quad9_ale")
+        return dataclasses.replace(p, bcs=[b for b in p.bcs if b.ns_id != 4],
+                                   extra_bc_cards=["BC = KINEMATIC SS 4 0.", "BC = CAPILLARY SS 4 1.0 0.0 0.0",
+                                                   "BC = VELO_NORMAL SS 3 0.0"]), kw
     raise KeyError(name)
 
+
+# fixtures of what the GPU path does not assemble yet (reference output only)
+REFERENCE_ONLY_CASES = ["f3_quad9_free_surface"]
 
 GOLDEN_CASES = ["mm_hex27_bouss_2mat", "mm_quad9_ale_3mat", "mm_hex8_pspg_2mat_transient", "mm_hex27_star_2mat",
                 "irr_quad9_star_ns", "irr_hex27_star_bouss", "irr_hex8_star_pspg","c1_quad9_ns", "c1_quad9_ns_transient", "c2_hex27_ns", "c3_hex27_boussinesq",

@@ -345,3 +345,42 @@ def test_msr_matvec_oracle_equals_dense_product():
     v = np.random.default_rng(3).standard_normal(n)
     w = post_fill.msr_matvec(n, a, ija, v)
     np.testing.assert_allclose(w, dense @ v, rtol=0, atol=1e-12 * np.abs(dense).sum(1).max() * np.abs(v).max())
+
+
+def test_f3_integrated_bcs_change_only_the_rows_of_their_side_set_nodes():
+    """SURVEY.md §8f-3 groundwork.  The fixture is the reference's own assembly of the C4 strip with KINEMATIC + CAPILLARY
+    on the free surface (side set 4) and VELO_NORMAL on the wall below (side set 3), parsed from a real deck by the
+    reference and applied by its apply_integrated_bc (mm_fill.c:2945-3033) with the rotation of the equations.
+    Everything OUTSIDE the rows of the nodes on those two side sets equals the volumetric assembly of the restatement
+    (what the GPU path reproduces); inside them the integrated conditions replace or add to it -- those rows are what
+    §8f-3 still has to build.  The C-ABI marshalling refuses such a problem instead of assembling it without them."""
+    import dataclasses
+
+    p, kw, st = case_state("f3_quad9_free_surface")
+    g = golden("f3_quad9_free_surface")
+    vol = dataclasses.replace(p, extra_bc_cards=[])
+    ija = capi.pattern_msr(vol)
+    np.testing.assert_array_equal(ija, g["ija"])  # the integrated conditions add no couplings to the graph
+    rc, a, r = port.port_fill(vol, ija, st)
+    assert rc == 0
+    n = len(r)
+    first, kind, kinds = p.unknown_map()
+    bc_nodes = np.unique(np.concatenate([p.mesh.node_sets[3], p.mesh.node_sets[4]]))
+    bc_rows = np.zeros(n, bool)
+    for nd in bc_nodes:
+        bc_rows[first[nd]:first[nd + 1]] = True
+    rows = np.repeat(np.arange(n), np.diff(np.asarray(ija[: n + 1], np.int64)))
+    scale = np.abs(g["a"][:n]).copy()
+    np.maximum.at(scale, rows, np.abs(g["a"][n + 1: int(ija[n])]))
+    dd = np.abs(a[:n] - g["a"][:n])
+    do = np.abs(a[n + 1: int(ija[n])] - g["a"][n + 1: int(ija[n])])
+    free = ~bc_rows
+    assert (dd[free] <= 1e-12 * scale[free]).all() and (do[free[rows]] <= 1e-12 * scale[rows][free[rows]]).all()
+    assert (np.abs(r - g["resid"])[free] <= 1e-12 * np.abs(g["resid"]).max()).all()
+    changed = np.zeros(n, bool)
+    changed[np.nonzero(dd > 1e-9 * np.maximum(scale, 1e-300))[0]] = True
+    changed[rows[do > 1e-9 * np.maximum(scale[rows], 1e-300)]] = True
+    assert changed.any() and not changed[free].any()
+    assert np.abs(g["a"]).max() > 1e11  # BIG_PENALTY rows of the strongly integrated conditions (rf_bc_const.h)
+    with pytest.raises(capi.GomaGpuError, match="integrated boundary conditions"):
+        capi.make_problem_struct(p)
